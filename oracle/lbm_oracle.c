@@ -1,0 +1,418 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE.  See lbm_oracle.h for the contract and parity status.
+ *
+ * Everything here works on a per-site local copy  p[0..nc-1]  of the populations (p[0] = f0),
+ * gathered from / scattered to the reference layout.  Each primitive exists in the operation
+ * order of the reference's AVX overloads ("_avx") and, where it differs, of its scalar templates
+ * ("_sc"); the collides pick per site exactly as the reference does (packed sites vs tail sites).
+ */
+#define _GNU_SOURCE
+#include "lbm_oracle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* lattice constants: d2q9.h:160-163, d3q15.h:251-254                                          */
+static const double CX2[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+static const double CY2[9] = {0, 0, 1, 0, -1, 1, 1, -1, -1};
+static const double CZ2[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+static const double EI2[9] = {4.0/9.0, 1.0/9.0, 1.0/9.0, 1.0/9.0, 1.0/9.0, 1.0/36.0, 1.0/36.0, 1.0/36.0, 1.0/36.0};
+static const double CX3[15] = {0, 1, 0, 0, -1, 0, 0, 1, -1, 1, 1, -1, 1, -1, -1};
+static const double CY3[15] = {0, 0, 1, 0, 0, -1, 0, 1, 1, -1, 1, -1, -1, 1, -1};
+static const double CZ3[15] = {0, 0, 0, 1, 0, 0, -1, 1, 1, 1, -1, -1, -1, -1, 1};
+static const double EI3[15] = {2.0/9.0, 1.0/9.0, 1.0/9.0, 1.0/9.0, 1.0/9.0, 1.0/9.0, 1.0/9.0,
+                               1.0/72.0, 1.0/72.0, 1.0/72.0, 1.0/72.0, 1.0/72.0, 1.0/72.0, 1.0/72.0, 1.0/72.0};
+#define NCMAX 15
+
+struct orc_lattice {
+    int nd, nc;
+    int lx, ly, lz, peid, mx, my, mz, pex, pey, pez, nx, ny, nz, nxyz, offx, offy, offz;
+    const double *cx, *cy, *cz, *ei;
+    int ci[NCMAX][3];  /* integer velocities */
+    int opp[NCMAX];    /* opposite direction */
+    double *f0, *f, *fnext;
+};
+typedef struct orc_lattice L;
+
+static int find_dir(const L* l, int x, int y, int z) {
+    for (int c = 0; c < l->nc; ++c) if (l->ci[c][0] == x && l->ci[c][1] == y && l->ci[c][2] == z) return c;
+    return -1;
+}
+
+/* block decomposition rule: d3q15.h:29-35, d2q9.h:29-35 */
+orc_lattice* orc_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz) {
+    L* l = (L*)calloc(1, sizeof(L));
+    l->nd = kind; l->nc = kind == 2 ? 9 : 15;
+    if (kind == 2) { lz = 1; mz = 1; }
+    l->lx = lx; l->ly = ly; l->lz = lz; l->peid = peid; l->mx = mx; l->my = my; l->mz = mz;
+    l->pex = peid%mx;
+    l->pey = kind == 2 ? peid/mx : (peid/mx)%my;
+    l->pez = kind == 2 ? 0 : peid/(mx*my);
+    l->nx = (lx + l->pex)/mx; l->ny = (ly + l->pey)/my; l->nz = kind == 2 ? 1 : (lz + l->pez)/mz;
+    l->nxyz = l->nx*l->ny*l->nz;
+    l->offx = mx - l->pex > lx%mx ? l->pex*l->nx : lx - (mx - l->pex)*l->nx;
+    l->offy = my - l->pey > ly%my ? l->pey*l->ny : ly - (my - l->pey)*l->ny;
+    l->offz = kind == 2 ? 0 : (mz - l->pez > lz%mz ? l->pez*l->nz : lz - (mz - l->pez)*l->nz);
+    l->cx = kind == 2 ? CX2 : CX3; l->cy = kind == 2 ? CY2 : CY3; l->cz = kind == 2 ? CZ2 : CZ3; l->ei = kind == 2 ? EI2 : EI3;
+    for (int c = 0; c < l->nc; ++c) { l->ci[c][0] = (int)l->cx[c]; l->ci[c][1] = (int)l->cy[c]; l->ci[c][2] = (int)l->cz[c]; }
+    for (int c = 0; c < l->nc; ++c) l->opp[c] = find_dir(l, -l->ci[c][0], -l->ci[c][1], -l->ci[c][2]);
+    size_t n = (size_t)l->nxyz;
+    l->f0 = (double*)calloc(n, sizeof(double));
+    l->f = (double*)calloc(n*(l->nc - 1), sizeof(double));
+    l->fnext = (double*)calloc(n*(l->nc - 1), sizeof(double));
+    return l;
+}
+void orc_lattice_destroy(orc_lattice* l) { free(l->f0); free(l->f); free(l->fnext); free(l); }
+void orc_lattice_info(const orc_lattice* l, int* o) {
+    int v[18] = {l->lx, l->ly, l->lz, l->peid, l->mx, l->my, l->mz, l->pex, l->pey, l->pez, l->nx, l->ny, l->nz, l->nxyz, l->offx, l->offy, l->offz, l->nc};
+    memcpy(o, v, sizeof(v));
+}
+void orc_lattice_get(const orc_lattice* l, double* f0, double* f) {
+    memcpy(f0, l->f0, sizeof(double)*l->nxyz); memcpy(f, l->f, sizeof(double)*(size_t)l->nxyz*(l->nc - 1));
+}
+void orc_lattice_set(orc_lattice* l, const double* f0, const double* f) {
+    memcpy(l->f0, f0, sizeof(double)*l->nxyz); memcpy(l->f, f, sizeof(double)*(size_t)l->nxyz*(l->nc - 1));
+}
+
+/* periodic-wrap index: d3q15.h:136-141 */
+static inline int wrap(int v, int n) { return v == -1 ? n - 1 : (v == n ? 0 : v); }
+static inline int IDX(const L* l, int i, int j, int k) { return wrap(i, l->nx) + l->nx*(wrap(j, l->ny) + l->ny*wrap(k, l->nz)); }
+static inline size_t IF(const L* l, int idx, int c) { return (size_t)(l->nc - 1)*idx + (c - 1); }
+static inline int GIDX(const L* l, int i, int j, int k) { return (i + l->offx) + l->lx*((j + l->offy) + l->ly*(k + l->offz)); }
+
+static inline void gather(const L* l, int idx, double* p) {
+    p[0] = l->f0[idx];
+    for (int c = 1; c < l->nc; ++c) p[c] = l->f[IF(l, idx, c)];
+}
+static inline void scatter(L* l, int idx, const double* p) {
+    l->f0[idx] = p[0];
+    for (int c = 1; c < l->nc; ++c) l->f[IF(l, idx, c)] = p[c];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Stream / iStream (single-rank path): d3q15.h:601-616, 964-979; d2q9.h:284-295                */
+static void stream_dir(L* l, int sgn) {
+    #pragma omp parallel for
+    for (int k = 0; k < l->nz; ++k)
+        for (int j = 0; j < l->ny; ++j)
+            for (int i = 0; i < l->nx; ++i) {
+                int idx = IDX(l, i, j, k);
+                for (int c = 1; c < l->nc; ++c) {
+                    int src = IDX(l, i - sgn*l->ci[c][0], j - sgn*l->ci[c][1], k - sgn*l->ci[c][2]);
+                    l->fnext[IF(l, idx, c)] = l->f[IF(l, src, c)];
+                }
+            }
+    double* t = l->f; l->f = l->fnext; l->fnext = t;
+}
+void orc_stream(orc_lattice* l) { stream_dir(l, 1); }
+void orc_istream(orc_lattice* l) { stream_dir(l, -1); }
+
+/* Iterate the local sites of the global plane  axis = coord  in the reference's loop order and
+ * call fn(l, idx, gidx, ctx).  (d3q15.h:984-990 etc.: X face loops j then k, Y face k then i, Z face
+ * i then j; the order is irrelevant to the result because every update is site-local.) */
+typedef void (*site_fn)(L* l, int idx, int gidx, int axis, int dir, void* ctx);
+static void for_plane(L* l, int axis, int coord, int dir, site_fn fn, void* ctx) {
+    int off[3] = {l->offx, l->offy, l->offz}, n[3] = {l->nx, l->ny, l->nz};
+    int loc = coord - off[axis];
+    if (!(0 <= loc && loc < n[axis])) return;
+    int a1 = (axis + 1)%3, a2 = (axis + 2)%3;
+    if (l->nd == 2) { a1 = 1 - axis; a2 = 2; }
+    for (int p = 0; p < n[a1]; ++p)
+        for (int q = 0; q < n[a2]; ++q) {
+            int ijk[3]; ijk[axis] = loc; ijk[a1] = p; ijk[a2] = q;
+            fn(l, IDX(l, ijk[0], ijk[1], ijk[2]), GIDX(l, ijk[0], ijk[1], ijk[2]), axis, dir, ctx);
+        }
+}
+/* the 4 (2D) / 6 (3D) outer planes in the reference's order xmin,xmax,ymin,ymax,zmin,zmax (d3q15.h:182-189) */
+static void for_all_faces(L* l, site_fn fn, void* ctx) {
+    int ext[3] = {l->lx, l->ly, l->lz};
+    for (int axis = 0; axis < l->nd; ++axis) {
+        for_plane(l, axis, 0, -1, fn, ctx);
+        for_plane(l, axis, ext[axis] - 1, 1, fn, ctx);
+    }
+}
+
+/* bounce-back (BARRIER=1) / specular (MIRROR=2): d3q15.h:984-1239, d2q9.h:431-575.
+ * forward: the populations entering the domain (c_axis == -dir) are rebuilt from their partners;
+ * inverse: the ones leaving (c_axis == dir). */
+typedef struct { const int* bct; int inverse; } bounce_ctx;
+static void bounce_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    bounce_ctx* b = (bounce_ctx*)vctx;
+    int t = b->bct[gidx];
+    if (t != 1 && t != 2) return;
+    int want = b->inverse ? dir : -dir;
+    /* quirk: MIRROR on an X face with direction +1 always addresses the plane i = nx-1 (d3q15.h:1013) —
+       identical to idx whenever the plane is the xmax face, which is the only way the drivers call it. */
+    for (int c = 1; c < l->nc; ++c) {
+        if (l->ci[c][axis] != want) continue;
+        int src;
+        if (t == 1) src = l->opp[c];
+        else { int v[3] = {l->ci[c][0], l->ci[c][1], l->ci[c][2]}; v[axis] = -v[axis]; src = find_dir(l, v[0], v[1], v[2]); }
+        l->f[IF(l, idx, c)] = l->f[IF(l, idx, src)];
+    }
+}
+void orc_bc(orc_lattice* l, const int* bct, int inverse) { bounce_ctx b = {bct, inverse}; for_all_faces(l, bounce_site, &b); }
+void orc_bc_plane(orc_lattice* l, int axis, int coord, int dir, const int* bct, int inverse) {
+    bounce_ctx b = {bct, inverse}; for_plane(l, axis, coord, dir, bounce_site, &b);
+}
+
+/* SmoothCorner: d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587 */
+static void smooth2(L* l, int idx, int a, int b) {
+    l->f0[idx] = 0.5*(l->f0[a] + l->f0[b]);
+    for (int c = 1; c < l->nc; ++c) l->f[IF(l, idx, c)] = 0.5*(l->f[IF(l, a, c)] + l->f[IF(l, b, c)]);
+}
+static void smooth3(L* l, int idx, int a, int b, int d) {
+    l->f0[idx] = (l->f0[a] + l->f0[b] + l->f0[d])/3.0;
+    for (int c = 1; c < l->nc; ++c) l->f[IF(l, idx, c)] = (l->f[IF(l, a, c)] + l->f[IF(l, b, c)] + l->f[IF(l, d, c)])/3.0;
+}
+static int inloc(int v, int n) { return 0 <= v && v < n; }
+void orc_smooth_corner(orc_lattice* l) {
+    int X0 = 0 - l->offx, X1 = l->lx - 1 - l->offx, Y0 = 0 - l->offy, Y1 = l->ly - 1 - l->offy, Z0 = 0 - l->offz, Z1 = l->lz - 1 - l->offz;
+    if (l->nd == 2) {
+        /* order: (xmin,ymin) (xmin,ymax) (xmax,ymin) (xmax,ymax) */
+        int cs[4][4] = {{X0, Y0, -1, -1}, {X0, Y1, -1, 1}, {X1, Y0, 1, -1}, {X1, Y1, 1, 1}};
+        for (int n = 0; n < 4; ++n) {
+            int i = cs[n][0], j = cs[n][1], dx = cs[n][2], dy = cs[n][3];
+            if (inloc(i, l->nx) && inloc(j, l->ny)) smooth2(l, IDX(l, i, j, 0), IDX(l, i - dx, j, 0), IDX(l, i, j - dy, 0));
+        }
+        return;
+    }
+    /* 12 edges: YZ lines, ZX lines, XY lines, each (min,min) (max,min) (max,max) (min,max) */
+    int yz[4][4] = {{Y0, Z0, -1, -1}, {Y1, Z0, 1, -1}, {Y1, Z1, 1, 1}, {Y0, Z1, -1, 1}};
+    for (int n = 0; n < 4; ++n) {
+        int j = yz[n][0], k = yz[n][1], dy = yz[n][2], dz = yz[n][3];
+        if (inloc(j, l->ny) && inloc(k, l->nz))
+            for (int i = 0; i < l->nx; ++i) smooth2(l, IDX(l, i, j, k), IDX(l, i, j - dy, k), IDX(l, i, j, k - dz));
+    }
+    int zx[4][4] = {{Z0, X0, -1, -1}, {Z1, X0, 1, -1}, {Z1, X1, 1, 1}, {Z0, X1, -1, 1}};
+    for (int n = 0; n < 4; ++n) {
+        int k = zx[n][0], i = zx[n][1], dz = zx[n][2], dx = zx[n][3];
+        if (inloc(k, l->nz) && inloc(i, l->nx))
+            for (int j = 0; j < l->ny; ++j) smooth2(l, IDX(l, i, j, k), IDX(l, i, j, k - dz), IDX(l, i - dx, j, k));
+    }
+    int xy[4][4] = {{X0, Y0, -1, -1}, {X1, Y0, 1, -1}, {X1, Y1, 1, 1}, {X0, Y1, -1, 1}};
+    for (int n = 0; n < 4; ++n) {
+        int i = xy[n][0], j = xy[n][1], dx = xy[n][2], dy = xy[n][3];
+        if (inloc(i, l->nx) && inloc(j, l->ny))
+            for (int k = 0; k < l->nz; ++k) smooth2(l, IDX(l, i, j, k), IDX(l, i - dx, j, k), IDX(l, i, j - dy, k));
+    }
+    int cn[8][6] = {{X0, Y0, Z0, -1, -1, -1}, {X1, Y0, Z0, 1, -1, -1}, {X1, Y1, Z0, 1, 1, -1}, {X0, Y1, Z0, -1, 1, -1},
+                    {X0, Y0, Z1, -1, -1, 1}, {X1, Y0, Z1, 1, -1, 1}, {X1, Y1, Z1, 1, 1, 1}, {X0, Y1, Z1, -1, 1, 1}};
+    for (int n = 0; n < 8; ++n) {
+        int i = cn[n][0], j = cn[n][1], k = cn[n][2];
+        if (inloc(i, l->nx) && inloc(j, l->ny) && inloc(k, l->nz))
+            smooth3(l, IDX(l, i, j, k), IDX(l, i - cn[n][3], j, k), IDX(l, i, j - cn[n][4], k), IDX(l, i, j, k - cn[n][5]));
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* shared helpers                                                                              */
+/* (ax*bx + ay*by) [+ az*bz] in the reference's association */
+static inline double dot3(const L* l, double ax, double ay, double az, double bx, double by, double bz) {
+    double s = ax*bx + ay*by;
+    if (l->nd == 3) s = s + az*bz;
+    return s;
+}
+static inline double cdot(const L* l, int c, double vx, double vy, double vz) { return dot3(l, l->cx[c], l->cy[c], l->cz[c], vx, vy, vz); }
+static inline int npacked(const L* l) { return 4*(l->nxyz/4); }  /* sites handled by the AVX overloads */
+static inline void relax(const L* l, double* p, const double* eq, double omega, double iomega) {
+    for (int c = 0; c < l->nc; ++c) p[c] = iomega*p[c] + omega*eq[c];
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* NS primitives                                                                               */
+/* Macro: navierstokes.h:17-50 == navierstokes_avx.h:24-55 (same order) */
+static void ns_macro(const L* l, const double* p, double* rho, double* ux, double* uy, double* uz) {
+    double r = p[0], x = 0.0, y = 0.0, z = 0.0;
+    for (int c = 1; c < l->nc; ++c) {
+        r = r + p[c];
+        x = x + p[c]*l->cx[c];
+        y = y + p[c]*l->cy[c];
+        if (l->nd == 3) z = z + p[c]*l->cz[c];
+    }
+    double inv = 1.0/r;
+    *rho = r; *ux = x*inv; *uy = y*inv; *uz = z*inv;
+}
+/* Equilibrium, AVX order: navierstokes_avx.h:58-75 */
+static void ns_eq_avx(const L* l, double* feq, double rho, double ux, double uy, double uz) {
+    double a = 1.0 - 1.5*dot3(l, ux, uy, uz, ux, uy, uz);
+    for (int c = 0; c < l->nc; ++c) {
+        double cu = cdot(l, c, ux, uy, uz);
+        feq[c] = l->ei[c]*(rho*(a + (3.0*cu + 4.5*(cu*cu))));
+    }
+}
+/* Equilibrium, scalar order: navierstokes.h:53-70 */
+static void ns_eq_sc(const L* l, double* feq, double rho, double ux, double uy, double uz) {
+    double uu = 1.0 - 1.5*dot3(l, ux, uy, uz, ux, uy, uz);
+    for (int c = 0; c < l->nc; ++c) {
+        double ciu = cdot(l, c, ux, uy, uz);
+        feq[c] = l->ei[c]*rho*(3.0*ciu + 4.5*ciu*ciu + uu);
+    }
+}
+/* Brinkman force: navierstokes.h:73-88 == navierstokes_avx.h:77-91 */
+static void ns_brinkman(const L* l, double* p, double rho, double ux, double uy, double uz, double alpha) {
+    double coef = 3.0*alpha*rho/(rho + alpha);
+    for (int c = 1; c < l->nc; ++c) p[c] = p[c] - coef*l->ei[c]*cdot(l, c, ux, uy, uz);
+}
+
+void orc_ns_init(orc_lattice* l, const double* rho, const double* ux, const double* uy, const double* uz) {
+    double feq[NCMAX];
+    for (int idx = 0; idx < l->nxyz; ++idx) {   /* navierstokes.h:550-572 (scalar Equilibrium) */
+        ns_eq_sc(l, feq, rho[idx], ux[idx], uy[idx], l->nd == 3 ? uz[idx] : 0.0);
+        scatter(l, idx, feq);
+    }
+}
+
+/* MacroCollide / MacroBrinkmanCollide: navierstokes_avx.h:93-329 */
+static void ns_collide(L* l, double* rho, double* ux, double* uy, double* uz, double nu, const double* alpha, int issave) {
+    double omega = 1.0/(3.0*nu + 0.5), iomega = 1.0 - omega;
+    int ne = npacked(l);
+    #pragma omp parallel for
+    for (int idx = 0; idx < l->nxyz; ++idx) {
+        double p[NCMAX], feq[NCMAX], r, x, y, z;
+        int tail = idx >= ne;
+        gather(l, idx, p);
+        ns_macro(l, p, &r, &x, &y, &z);
+        /* quirk: the 2-D Brinkman tail saves the macros BEFORE the force (navierstokes_avx.h:246-254) */
+        int save_early = alpha && tail && l->nd == 2;
+        if (issave && save_early) { rho[idx] = r; ux[idx] = x; uy[idx] = y; }
+        if (alpha) {
+            ns_brinkman(l, p, r, x, y, z, alpha[idx]);
+            ns_macro(l, p, &r, &x, &y, &z);
+        }
+        if (issave && !save_early) { rho[idx] = r; ux[idx] = x; uy[idx] = y; if (l->nd == 3) uz[idx] = z; }
+        if (tail) ns_eq_sc(l, feq, r, x, y, z); else ns_eq_avx(l, feq, r, x, y, z);
+        relax(l, p, feq, omega, iomega);
+        scatter(l, idx, p);
+    }
+}
+void orc_ns_macro_collide(orc_lattice* l, double* rho, double* ux, double* uy, double* uz, double nu, int issave) {
+    ns_collide(l, rho, ux, uy, uz, nu, NULL, issave);
+}
+void orc_ns_macro_brinkman_collide(orc_lattice* l, double* rho, double* ux, double* uy, double* uz, double nu, const double* alpha, int issave) {
+    ns_collide(l, rho, ux, uy, uz, nu, alpha, issave);
+}
+
+/* ---- velocity / pressure closures on a face: navierstokes.h:90-426 ------------------------------
+ * Face with normal axis a and outward direction dir.  "in" = populations entering the domain
+ * (c_a == -dir, the unknowns), "out" = their opposites, "tan" = populations with c_a == 0 (c != 0).
+ *   SetU:   rho0 = (f0 + sum(tan) + 2*sum(out)) / (1 + dir*u_a)
+ *   SetRho: u_a  = -dir*(1 - (f0 + sum(tan) + 2*sum(out))/rho)
+ *   m_a = rho0*u_a/(6|12);  m_t = (0.5|0.25)*(f_{+t} - f_{-t} - rho0*u_t)
+ *   f_in(axis pop) = f_out -dir*(4|8)*m_a ;  f_in(diag) = f_opp + sum_d s_d*m_d, s_a = c_a, s_t = -c_t,
+ * all sums in ascending c and x,y,z order exactly as written in the reference. */
+typedef struct { const double *v0, *v1, *v2; const int* mask; int setrho; } nsbc_ctx;
+static void ns_bc_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    nsbc_ctx* b = (nsbc_ctx*)vctx;
+    if (!b->mask[gidx]) return;
+    double p[NCMAX];
+    gather(l, idx, p);
+    double s = p[0];
+    for (int c = 1; c < l->nc; ++c) if (l->ci[c][axis] == 0) s = s + p[c];
+    double o = 0.0; int first = 1;
+    for (int c = 1; c < l->nc; ++c) if (l->ci[c][axis] == dir) { o = first ? p[c] : o + p[c]; first = 0; }
+    double tot = s + 2.0*o;
+    double u[3], rho0;
+    int t1 = l->nd == 2 ? 1 - axis : (axis + 1)%3, t2 = l->nd == 2 ? -1 : (axis + 2)%3;
+    if (!b->setrho) {
+        u[0] = b->v0[gidx]; u[1] = b->v1[gidx]; u[2] = l->nd == 3 ? b->v2[gidx] : 0.0;
+        rho0 = dir == -1 ? tot/(1.0 - u[axis]) : tot/(1.0 + u[axis]);
+    } else {
+        /* reference argument order: (rho, us, ut) with (us,ut) = (uy,uz) on X, (uz,ux) on Y, (ux,uy) on Z faces
+           (navierstokes.h:326, 363, 400); in 2-D the single tangential velocity (navierstokes.h:267, 296) */
+        rho0 = b->v0[gidx];
+        u[0] = u[1] = u[2] = 0.0;
+        if (l->nd == 2) u[t1] = b->v1[gidx];
+        else { u[t1] = b->v1[gidx]; u[t2] = b->v2[gidx]; }
+        u[axis] = dir == -1 ? 1.0 - tot/rho0 : -1.0 + tot/rho0;
+    }
+    double m[3] = {0.0, 0.0, 0.0};
+    double kn = l->nd == 2 ? 6.0 : 12.0, kt = l->nd == 2 ? 0.5 : 0.25, ka = l->nd == 2 ? 4.0 : 8.0;
+    m[axis] = rho0*u[axis]/kn;
+    for (int d = 0; d < l->nd; ++d) if (d != axis) {
+        int v[3] = {0, 0, 0}; v[d] = 1; int cp = find_dir(l, v[0], v[1], v[2]); v[d] = -1; int cm = find_dir(l, v[0], v[1], v[2]);
+        m[d] = kt*(p[cp] - p[cm] - rho0*u[d]);
+    }
+    for (int c = 1; c < l->nc; ++c) {
+        if (l->ci[c][axis] != -dir) continue;
+        int nz = abs(l->ci[c][0]) + abs(l->ci[c][1]) + abs(l->ci[c][2]);
+        double val;
+        if (nz == 1) val = dir == -1 ? p[l->opp[c]] + ka*m[axis] : p[l->opp[c]] - ka*m[axis];
+        else {
+            val = p[l->opp[c]];
+            for (int d = 0; d < l->nd; ++d) {
+                int sgn = d == axis ? l->ci[c][d] : -l->ci[c][d];
+                val = sgn > 0 ? val + m[d] : val - m[d];
+            }
+        }
+        l->f[IF(l, idx, c)] = val;
+    }
+}
+void orc_ns_bc_set_u(orc_lattice* l, const double* uxg, const double* uyg, const double* uzg, const int* mask) {
+    nsbc_ctx b = {uxg, uyg, uzg, mask, 0}; for_all_faces(l, ns_bc_site, &b);
+}
+void orc_ns_bc_set_rho(orc_lattice* l, const double* v0, const double* v1, const double* v2, const int* mask) {
+    nsbc_ctx b = {v0, v1, v2, mask, 1}; for_all_faces(l, ns_bc_site, &b);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* utilities: residual.h:8-50, normalize.h:8-24 (serial loops)                                  */
+double orc_residual3(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, int n) {
+    double unorm = 0.0, dunorm = 0.0;
+    for (int i = 0; i < n; ++i) {
+        unorm += pow(ux[i], 2.0) + pow(uy[i], 2.0) + pow(uz[i], 2.0);
+        dunorm += pow(ux[i] - uxp[i], 2.0) + pow(uy[i] - uyp[i], 2.0) + pow(uz[i] - uzp[i], 2.0);
+    }
+    return sqrt(dunorm/unorm);
+}
+double orc_residual2(const double* ux, const double* uy, const double* uxp, const double* uyp, int n) {
+    double unorm = 0.0, dunorm = 0.0;
+    for (int i = 0; i < n; ++i) {
+        unorm += pow(ux[i], 2.0) + pow(uy[i], 2.0);
+        dunorm += pow(ux[i] - uxp[i], 2.0) + pow(uy[i] - uyp[i], 2.0);
+    }
+    return sqrt(dunorm/unorm);
+}
+double orc_residual1(const double* ux, const double* uxp, int n) {
+    double unorm = 0.0, dunorm = 0.0;
+    for (int i = 0; i < n; ++i) { dunorm += pow(ux[i] - uxp[i], 2.0); unorm += pow(ux[i], 2.0); }
+    return sqrt(dunorm/unorm);
+}
+void orc_normalize(double* v, int n) {
+    double m = 0.0;
+    for (int i = 0; i < n; ++i) if (m < fabs(v[i])) m = fabs(v[i]);
+    for (int i = 0; i < n; ++i) v[i] /= m;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* cpu_baseline: the test/cavityflow3D.cpp:44-59 call sequence on the oracle port              */
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9*ts.tv_nsec; }
+double orc_time_cavity3d(int lx, int ly, int lz, int steps, int warmup, double* rho, double* ux, double* uy, double* uz) {
+    L* l = orc_lattice_create(3, lx, ly, lz, 0, 1, 1, 1);
+    size_t n = (size_t)l->nxyz;
+    int* bct = (int*)malloc(n*sizeof(int)); int* lid = (int*)malloc(n*sizeof(int));
+    double* uxg = (double*)malloc(n*sizeof(double)); double* uyg = (double*)malloc(n*sizeof(double)); double* uzg = (double*)malloc(n*sizeof(double));
+    double u0 = 0.1, theta = 90.0, nu = 0.1;
+    for (int k = 0; k < lz; ++k) for (int j = 0; j < ly; ++j) for (int i = 0; i < lx; ++i) {
+        size_t g = i + (size_t)lx*(j + (size_t)ly*k);
+        bct[g] = (i == 0 || i == lx - 1 || j == 0 || j == ly - 1 || k == 0) ? 1 : 0;
+        lid[g] = k == lz - 1;
+        uxg[g] = u0*cos(theta*M_PI/180.0); uyg[g] = u0*sin(theta*M_PI/180.0); uzg[g] = 0.0;
+        rho[g] = 1.0; ux[g] = 0.0; uy[g] = 0.0; uz[g] = 0.0;
+    }
+    orc_ns_init(l, rho, ux, uy, uz);
+    double t0 = 0.0;
+    for (int t = 0; t < warmup + steps; ++t) {
+        if (t == warmup) t0 = now_s();
+        orc_ns_macro_collide(l, rho, ux, uy, uz, nu, 1);
+        orc_stream(l);
+        orc_bc(l, bct, 0);
+        orc_ns_bc_set_u(l, uxg, uyg, uzg, lid);
+        orc_smooth_corner(l);
+    }
+    double t1 = now_s();
+    free(bct); free(lid); free(uxg); free(uyg); free(uzg);
+    orc_lattice_destroy(l);
+    return t1 - t0;
+}
