@@ -1,0 +1,212 @@
+/* panslbm_c.h — C-ABI of libpanslbm_b200.so: the B200 (sm_100a) implementation of the PANSLBM2
+ * lattice-Boltzmann forward/adjoint sweep.
+ *
+ * The reference (PANFACTORY/PANSLBM2) has no FFI: its "plugin API" is the header-only C++ template surface
+ * in src/particle and src/equation.  The drop-in headers in panslbm2_b200/src/ keep that surface (same names,
+ * argument order and defaults) and forward every call to the entry points below; each entry point cites the
+ * reference interface it replaces.  Plain C types only; every per-site array argument is a DEVICE pointer to
+ * nxyz doubles unless a parameter is explicitly named *_host.  All calls are asynchronous on the library's
+ * stream unless they return data to the host.  Single-threaded callers, one CUDA device per process (rank).
+ *
+ * Return convention: 0 = success, non-zero = failure with a message available from pl_last_error().
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with PL_ERR_CUDA.
+ */
+#ifndef PANSLBM_C_H
+#define PANSLBM_C_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PL_OK 0
+#define PL_ERR_ARG 1
+#define PL_ERR_CUDA 2
+#define PL_ERR_UNSUPPORTED 3
+
+typedef struct pl_lattice pl_lattice;
+typedef struct pl_bc pl_bc;
+typedef struct pl_plan pl_plan;
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* pl_last_error(void);
+const char* pl_version(void);
+int pl_device_count(void);
+int pl_set_device(int device);
+int pl_synchronize(void);
+/* The CUstream all work is queued on (as a void*); callers that share buffers with another runtime
+ * (e.g. torch) must order against it. pl_set_stream(NULL) restores the library's own stream. */
+void* pl_get_stream(void);
+int pl_set_stream(void* custream);
+/* Number of kernels this library has launched since load / since the last reset (bench.py "gpu_launches"). */
+uint64_t pl_launch_count(void);
+void pl_launch_count_reset(void);
+
+/* ---- device arrays (caller-owned macroscopic fields: `new double[nxyz]` in the drivers,
+ *      e.g. production/heatsink3D.cpp:50-59) ------------------------------------------------- */
+double* pl_array_alloc(size_t n);                 /* NULL on failure */
+int pl_array_free(double* dev);
+int pl_array_upload(double* dev, const double* host, size_t n);     /* synchronous wrt the host buffer */
+int pl_array_download(double* host, const double* dev, size_t n);   /* synchronises the stream */
+int pl_array_fill(double* dev, double value, size_t n);
+
+/* ---- lattices: D2Q9<double> (src/particle/d2q9.h:24-158), D3Q15<double> (src/particle/d3q15.h:24-249) ---- */
+#define PL_D2Q9 2
+#define PL_D3Q15 3
+/* ctor (d2q9.h:28, d3q15.h:28): same block-decomposition rule (d3q15.h:29-35). For PL_D2Q9 pass lz=mz=1. */
+pl_lattice* pl_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz);
+int pl_lattice_destroy(pl_lattice*);
+/* out[0..17] = lx ly lz PEid mx my mz PEx PEy PEz nx ny nz nxyz offsetx offsety offsetz nc (d3q15.h:222-223) */
+int pl_lattice_info(const pl_lattice*, int* out18);
+/* Host view in the reference layout f0[nxyz], f[(nc-1)*idx + (c-1)] (d3q15.h:142-144, public members f0/f:225).
+ * Device storage is fp64 SoA [c][nxyz]; these two convert (test/d2q9.cpp, test/d3q15.cpp touch f0/f directly). */
+int pl_lattice_set_host(pl_lattice*, const double* f0_host, const double* f_host);
+int pl_lattice_get_host(pl_lattice*, double* f0_host, double* f_host);
+/* Device SoA view of the current populations: c-th plane at base + c*pitch (pitch in doubles). */
+int pl_lattice_device_view(pl_lattice*, double** base, size_t* pitch);
+
+/* Stream()/iStream() single-rank path (d3q15.h:601-616, 964-979; d2q9.h:284-295): pull with periodic wrap. */
+int pl_stream(pl_lattice*, int inverse);
+/* SmoothCorner() (d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587) */
+int pl_smooth_corner(pl_lattice*);
+
+/* ---- boundary conditions ------------------------------------------------------------------------
+ * One pl_bc = one call of a reference "...AlongXFace/YFace/ZFace (XEdge/YEdge)" helper: the plane
+ * `axis` = `coord` (GLOBAL coordinate, may be interior: production/ncpump.cpp:155-170), outward `dir` = -1/+1.
+ * The host callables of the reference (bctype / value lambdas, evaluated with global coordinates,
+ * navierstokes.h:155-157) are baked by the caller into per-plane arrays over the LOCAL plane sites in
+ * natural order (lower axis fastest): X plane [j + ny*k], Y plane [i + nx*k], Z plane [i + nx*j].
+ * mask_host: uint8 per plane site. BOUNCE/IBOUNCE: 0 none, 1 BARRIER, 2 MIRROR (d3q15.h:19-22); others: 0/1.
+ * v0..v2_host: fp64 per plane site, meaning by type (unused = NULL). The arrays are copied at creation.
+ * A plane that does not intersect this rank's block, or whose mask is all zero, yields an empty pl_bc
+ * whose application is a no-op — exactly the reference's `if (0 <= i && i < nx)` guard (d3q15.h:987). */
+#define PL_BC_BOUNCE 1        /* P::BoundaryConditionAlong*      d3q15.h:984-1110, d2q9.h:431-501 */
+#define PL_BC_IBOUNCE 2       /* P::iBoundaryConditionAlong*     d3q15.h:1114-1239, d2q9.h:505-575 */
+#define PL_BC_NS_SET_U 3      /* NS::BoundaryConditionSetUAlong*   navierstokes.h:92-257;  v0,v1,v2 = ux,uy,uz */
+#define PL_BC_NS_SET_RHO 4    /* NS::BoundaryConditionSetRhoAlong* navierstokes.h:261-426; v0=rho, v1=_usbc, v2=_utbc */
+#define PL_BC_AD_SET_T 5      /* AD::BoundaryConditionSetTAlong*   advection.h:99-238;  v0 = T; aux ux,uy,uz */
+#define PL_BC_AD_SET_Q 6      /* AD::BoundaryConditionSetQAlong*   advection.h:242-524; v0 = qn; aux ux,uy,uz,diffusivity */
+#define PL_BC_ANS_ISET_U 7    /* ANS::iBoundaryConditionSetUAlong* adjointnavierstokes.h:97-254; v0,v1,v2 = ux,uy,uz; eps */
+#define PL_BC_ANS_ISET_RHO 8  /* ANS::iBoundaryConditionSetRhoAlong* adjointnavierstokes.h:258-392 */
+#define PL_BC_AAD_ISET_T 9    /* AAD::iBoundaryConditionSetTAlong* adjointadvection.h:154-300; aux ux,uy,uz */
+#define PL_BC_AAD_ISET_Q 10   /* AAD::iBoundaryConditionSetQAlong* adjointadvection.h:304-484; aux ux,uy,uz; eps */
+#define PL_BC_AAD_ISET_RHO 11 /* AAD::iBoundaryConditionSetRhoAlong*Edge (D2Q9 only) adjointadvection.h:488-575 */
+
+pl_bc* pl_bc_create(pl_lattice*, int type, int axis, int coord, int dir,
+                    const uint8_t* mask_host, const double* v0_host, const double* v1_host, const double* v2_host);
+int pl_bc_destroy(pl_bc*);
+int pl_bc_is_empty(const pl_bc*);
+
+/* Per-site fields some closures read at the boundary site (device pointers, nxyz doubles; unused = NULL):
+ * the velocities saved by the collide of the same step (advection.h:1083-1090), the per-cell diffusivity
+ * (advection.h:1114-1130) or its scalar overload (advection.h:1094-1110), eps (adjointadvection.h:1405). */
+typedef struct pl_bc_aux {
+    const double *rho, *ux, *uy, *uz, *tem, *diffusivity;
+    double diffusivity_const;   /* used when diffusivity == NULL */
+    double eps;
+} pl_bc_aux;
+/* Apply one plane closure to the lattice's current populations. `other` is the second lattice for
+ * PL_BC_AAD_ISET_RHO (f first, g second as in adjointadvection.h:1425) and NULL otherwise. */
+int pl_bc_apply(pl_lattice*, pl_lattice* other, const pl_bc*, const pl_bc_aux* aux);
+
+/* ---- collides -----------------------------------------------------------------------------------
+ * One entry point for every Macro*Collide* of the reference; `model` selects the function. */
+#define PL_NS_COLLIDE 1                  /* NS::MacroCollide                         navierstokes_avx.h:93-201 */
+#define PL_NS_BRINKMAN 2                 /* NS::MacroBrinkmanCollide                 navierstokes_avx.h:203-329 */
+#define PL_AD_FORCE_CONV 3               /* AD::MacroCollideForceConvection          advection_avx.h:104-270 */
+#define PL_AD_NAT_CONV 4                 /* AD::MacroCollideNaturalConvection        advection_avx.h:272-460 */
+#define PL_AD_BRINKMAN_HEATEX 5          /* AD::MacroBrinkmanCollideHeatExchange     advection_avx.h:462-654 */
+#define PL_AD_BRINKMAN_FORCE_CONV 6      /* AD::MacroBrinkmanCollideForceConvection  advection_avx.h:656-882 */
+#define PL_AD_BRINKMAN_NAT_CONV 7        /* AD::MacroBrinkmanCollideNaturalConvection advection_avx.h:884-1116 */
+#define PL_ANS_BRINKMAN 8                /* ANS::MacroBrinkmanCollide                adjointnavierstokes_avx.h:112-259 */
+#define PL_AAD_HEATEX 9                  /* AAD::MacroBrinkmanCollideHeatExchange    adjointadvection_avx.h:324-528 */
+#define PL_AAD_FORCE_CONV 10             /* AAD::MacroBrinkmanCollideForceConvection adjointadvection_avx.h:530-761 */
+#define PL_AAD_NAT_CONV 11               /* AAD::MacroBrinkmanCollideNaturalConvection adjointadvection_avx.h:763-1005 */
+#define PL_AAD_NAT_CONV_MASSFLOW 12      /* AAD::...NaturalConvectionMassFlow (D2Q9)  adjointadvection_avx.h:1007-1129 */
+
+typedef struct pl_collide_args {
+    int model;
+    int issave;                      /* _issave */
+    double viscosity;                /* _viscosity */
+    double diffusivity_const;        /* scalar _diffusivity overloads (models 3,4,5,9) */
+    double gx, gy, gz, tem0;         /* buoyancy / reference temperature */
+    const double *alpha;             /* Brinkman coefficient field */
+    const double *diffusivity;       /* per-cell diffusivity field (models 6,7,10,11,12) */
+    const double *beta;              /* heat-exchange coefficient field (models 5,9) */
+    const double *dirx, *diry, *dirz;/* mass-flow direction fields (model 12) */
+    /* forward macros: outputs of models 1-7 (written when issave), inputs of models 8-12 */
+    double *rho, *ux, *uy, *uz, *tem, *qx, *qy, *qz;
+    /* adjoint macros: outputs of models 8-12 (written when issave) */
+    double *ip, *iux, *iuy, *iuz, *imx, *imy, *imz, *item, *iqx, *iqy, *iqz;
+    /* optional snapshot of the thermal populations before relaxation (`_g` / `_ig`, advection_avx.h:1047-1052):
+     * device buffer of nc*nxyz doubles, SoA [c][nxyz]; opaque to callers exactly as in the reference. */
+    double *snapshot;
+} pl_collide_args;
+/* f = flow lattice (or the only lattice), g = thermal lattice (NULL for models 1,2,8). */
+int pl_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args*);
+
+/* Export a device snapshot (SoA) into the reference's host layout ([pack][c][lane] for idx < 4*(nxyz/4),
+ * [idx][c] for the tail; adjointadvection_avx.h:20-22) — used only by parity tests. */
+int pl_snapshot_to_host(const pl_lattice*, const double* snapshot_dev, double* out_host);
+
+/* InitialCondition of NS / AD / ANS / AAD (navierstokes.h:550-572, advection.h:1048-1070,
+ * adjointnavierstokes.h:474-498, adjointadvection.h:1359-1381). family: 1=NS(rho,ux,uy,uz) 2=AD(tem,ux,uy,uz)
+ * 3=ANS(ux,uy,uz,ip,iux,iuy,iuz) 4=AAD(ux,uy,uz,item,iqx,iqy,iqz); a[] holds the device arrays in that order. */
+int pl_initial_condition(pl_lattice*, int family, const double* const* a, int na);
+
+/* ---- fused time stepping ------------------------------------------------------------------------
+ * A plan records one iteration of a driver time loop — collide; Stream/iStream; closures in call order;
+ * SmoothCorner (test/cavityflow3D.cpp:48-58, production/heatsink3D.cpp:150-176, 194-216) — and advances it
+ * with ONE fused stream+closure+collide pass per step instead of one pass per call. Results are identical
+ * to issuing the calls one by one. args[2]/aux[2]: the two argument sets a driver alternates between by
+ * std::swap of its array pointers (heatsink3D.cpp:178-183); pass the same pointer twice if it does not swap. */
+pl_plan* pl_plan_create(pl_lattice* f, pl_lattice* g);
+int pl_plan_destroy(pl_plan*);
+int pl_plan_set_collide(pl_plan*, const pl_collide_args* even, const pl_collide_args* odd);
+int pl_plan_set_stream(pl_plan*, int inverse);
+int pl_plan_add_bc(pl_plan*, int on_g, const pl_bc*, const pl_bc_aux* even, const pl_bc_aux* odd);
+int pl_plan_set_smooth_corner(pl_plan*, int on_f, int on_g);
+int pl_plan_finalize(pl_plan*);
+/* Execute `ncollides` collides starting from the lattices' current phase (streamed or just collided);
+ * every stream+closures+SmoothCorner between two collides is fused with the collide that follows.
+ * end_streamed != 0 appends the trailing Stream+closures+SmoothCorner (loop ran to nt);
+ * end_streamed == 0 stops right after the last collide (the drivers' convergence `break`). */
+int pl_plan_advance(pl_plan*, int ncollides, int end_streamed);
+/* 0/1: the argument set of the last collide if the lattices are in the just-collided phase, else of the next one */
+int pl_plan_parity(const pl_plan*);
+/* Measurement hook (bench.py "roofline"): when enabled, every launch of the fused interior kernel is bracketed by CUDA
+ * events on the launching stream.  pl_plan_profile_read synchronises, returns the accumulated kernel milliseconds, the
+ * number of launches and the total number of lattice sites those launches updated, and clears the accumulators. */
+int pl_plan_profile(pl_plan*, int enable);
+int pl_plan_profile_read(pl_plan*, double* total_ms, int* launches, long long* total_sites);
+
+/* ---- reductions and sensitivities ---------------------------------------------------------------- */
+/* Residual (src/utility/residual.h:8-50): sqrt(sum|u-up|^2 / sum|u|^2) over 1, 2 or 3 components. */
+int pl_residual(const double* ux, const double* uy, const double* uz,
+                const double* uxp, const double* uyp, const double* uzp, size_t n, double* out_host);
+int pl_reduce_sum(const double* v, size_t n, double* out_host);
+int pl_reduce_absmax(const double* v, size_t n, double* out_host);
+/* Normalize (src/utility/normalize.h:8-24) */
+int pl_normalize(double* v, size_t n);
+
+#define PL_SENS_ANS_BRINKMAN 1            /* ANS::SensitivityBrinkman              adjointnavierstokes_avx.h:262-293 */
+#define PL_SENS_AAD_HEATEX 2              /* AAD::SensitivityHeatExchange          adjointadvection_avx.h:1257-1300 */
+#define PL_SENS_AAD_BRINKMAN_DIFF 3       /* AAD::SensitivityBrinkmanDiffusivity   adjointadvection_avx.h:1302-1401 */
+typedef struct pl_sens_args {
+    int kind;
+    double* dfds;
+    const double *ux, *uy, *uz, *imx, *imy, *imz, *dads, *tem, *item, *iqx, *iqy, *iqz;
+    const double *gsnap, *igsnap;   /* device snapshots, SoA */
+    const double *diffusivity, *dkds, *dbds;
+} pl_sens_args;
+int pl_sensitivity(pl_lattice*, const pl_sens_args*);
+/* Heat-source boundary term of AAD::SensitivityTemperatureAtHeatSource (adjointadvection_avx.h:16-185): one
+ * plane per call like a closure; mask/qn baked on the host. The volume term is PL_SENS_AAD_BRINKMAN_DIFF. */
+int pl_sensitivity_heat_source_plane(pl_lattice*, int axis, int coord, int dir, const uint8_t* mask_host, const double* qn_host,
+                                     double* dfds, const double* ux, const double* uy, const double* uz,
+                                     const double* igsnap, const double* diffusivity, const double* dkds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,13 @@
+"""panslbm2_b200 — B200 (sm_100a) implementation of the PANSLBM2 lattice-Boltzmann forward/adjoint sweep.
+
+The product is `libpanslbm_b200.so` (hand-written CUDA behind the C-ABI of include/panslbm_c.h) plus two host
+surfaces over it: the drop-in C++ headers in `panslbm2_b200/src/` (same template surface as the reference) and the
+Python mirror in `panslbm2_b200.api`.  There is no CPU fallback; importing works without a GPU, computing does not.
+"""
+from . import _lib
+from ._lib import PanslbmError
+from .api import (BARRIER, MIRROR, D2Q9, D3Q15, NS, DeviceArray, Normalize, Residual, StepPlan, bc_aux, collide_args,
+                  synchronize)
+
+__all__ = ["BARRIER", "MIRROR", "D2Q9", "D3Q15", "NS", "DeviceArray", "Normalize", "Residual", "StepPlan", "bc_aux",
+           "collide_args", "synchronize", "PanslbmError"]

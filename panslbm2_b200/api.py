@@ -1,0 +1,425 @@
+"""Host-side mirror of the PANSLBM2 C++ surface for the hot path, over the C-ABI (include/panslbm_c.h).
+
+Same names, argument order and defaults as the reference so that callers (and the parity tests) read like the
+reference's own programs:
+
+    pf = D3Q15(lx, ly, lz)                                   # src/particle/d3q15.h:28
+    NS.InitialCondition(pf, rho, ux, uy, uz)                 # src/equation/navierstokes.h:562
+    NS.MacroCollide(pf, rho, ux, uy, uz, nu, True)           # src/equation_avx/navierstokes_avx.h:149
+    pf.Stream()                                              # d3q15.h:257
+    pf.BoundaryCondition(lambda i, j, k: ...)                # d3q15.h:182
+    NS.BoundaryConditionSetU(pf, fux, fuy, fuz, fmask)       # navierstokes.h:585
+    pf.SmoothCorner()                                        # d3q15.h:199
+
+Differences forced by the device boundary, and nothing else:
+  * macroscopic arrays are `DeviceArray`s (or CUDA fp64 torch tensors) instead of `new double[nxyz]`;
+  * boundary callables are evaluated ONCE per call on the host, vectorised: they receive numpy integer arrays of
+    GLOBAL coordinates (the reference passes global coordinates too, navierstokes.h:155-157) and return arrays/scalars;
+    the baked planes are cached per (lattice, plane, content).
+There is no CPU fallback: every call ends in a CUDA kernel of libpanslbm_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+
+import numpy as np
+
+from . import _lib
+from ._lib import BcAux, CollideArgs, SensArgs, check
+
+BARRIER, MIRROR = 1, 2   # d3q15.h:19-22
+
+# pl_bc types / collide models (include/panslbm_c.h)
+BC_BOUNCE, BC_IBOUNCE, BC_NS_SET_U, BC_NS_SET_RHO, BC_AD_SET_T, BC_AD_SET_Q = 1, 2, 3, 4, 5, 6
+BC_ANS_ISET_U, BC_ANS_ISET_RHO, BC_AAD_ISET_T, BC_AAD_ISET_Q, BC_AAD_ISET_RHO = 7, 8, 9, 10, 11
+(M_NS_COLLIDE, M_NS_BRINKMAN, M_AD_FORCE_CONV, M_AD_NAT_CONV, M_AD_BRINKMAN_HEATEX, M_AD_BRINKMAN_FORCE_CONV,
+ M_AD_BRINKMAN_NAT_CONV, M_ANS_BRINKMAN, M_AAD_HEATEX, M_AAD_FORCE_CONV, M_AAD_NAT_CONV, M_AAD_NAT_CONV_MASSFLOW) = range(1, 13)
+
+
+# ----------------------------------------------------------------------------------------------------------
+class DeviceArray:
+    """n fp64 values in HBM (the drivers' `new double[nxyz]`, e.g. production/heatsink3D.cpp:50-59)."""
+
+    def __init__(self, n: int, fill: float | None = None):
+        self.n = int(n)
+        self.ptr = _lib.lib().pl_array_alloc(self.n)
+        if not self.ptr:
+            raise _lib.PanslbmError(_lib.lib().pl_last_error().decode())
+        if fill is not None:
+            self.fill(fill)
+
+    @classmethod
+    def from_host(cls, a) -> "DeviceArray":
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        d = cls(a.size)
+        check(_lib.lib().pl_array_upload(d.ptr, a.ctypes.data, a.size))
+        return d
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+        assert a.size == self.n
+        check(_lib.lib().pl_array_upload(self.ptr, a.ctypes.data, a.size))
+        return self
+
+    def to_host(self, out=None) -> np.ndarray:
+        out = np.empty(self.n) if out is None else out
+        check(_lib.lib().pl_array_download(out.ctypes.data, self.ptr, self.n))
+        return out
+
+    def fill(self, v: float):
+        check(_lib.lib().pl_array_fill(self.ptr, float(v), self.n))
+        return self
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            _lib.lib().pl_array_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def dptr(x):
+    """device pointer of a DeviceArray / CUDA fp64 torch tensor / None"""
+    if x is None:
+        return None
+    if isinstance(x, DeviceArray):
+        return x.ptr
+    if hasattr(x, "data_ptr"):   # torch tensor
+        assert x.is_cuda and x.is_contiguous() and str(x.dtype) == "torch.float64", "need a contiguous CUDA float64 tensor"
+        return x.data_ptr()
+    if isinstance(x, int):
+        return x
+    raise TypeError(f"not a device array: {type(x)}")
+
+
+def synchronize():
+    check(_lib.lib().pl_synchronize())
+
+
+# ----------------------------------------------------------------------------------------------------------
+class _Lattice:
+    kind = 0
+    nc = 0
+    nd = 0
+
+    def __init__(self, lx, ly, lz=1, PEid=0, mx=1, my=1, mz=1):
+        L = _lib.lib()
+        _lib.require_device()
+        self._h = L.pl_lattice_create(self.kind, lx, ly, lz, PEid, mx, my, mz)
+        if not self._h:
+            raise _lib.PanslbmError(L.pl_last_error().decode())
+        info = np.zeros(18, dtype=np.int32)
+        check(L.pl_lattice_info(self._h, info.ctypes.data))
+        (self.lx, self.ly, self.lz, self.PEid, self.mx, self.my, self.mz, self.PEx, self.PEy, self.PEz,
+         self.nx, self.ny, self.nz, self.nxyz, self.offsetx, self.offsety, self.offsetz, _nc) = [int(v) for v in info]
+        self._bc_cache = {}
+
+    # -- reference public helpers (d3q15.h:136-150)
+    def Index(self, i, j, k=0):
+        i = self.nx - 1 if i == -1 else (0 if i == self.nx else i)
+        j = self.ny - 1 if j == -1 else (0 if j == self.ny else j)
+        k = self.nz - 1 if k == -1 else (0 if k == self.nz else k)
+        return i + self.nx*(j + self.ny*k)
+
+    @classmethod
+    def IndexF(cls, idx, c):
+        return (cls.nc - 1)*idx + (c - 1)
+
+    # -- populations in the reference host layout (public members f0/f, d3q15.h:225)
+    def set_populations(self, f0, f):
+        f0 = np.ascontiguousarray(f0, dtype=np.float64); f = np.ascontiguousarray(f, dtype=np.float64)
+        assert f0.size == self.nxyz and f.size == self.nxyz*(self.nc - 1)
+        check(_lib.lib().pl_lattice_set_host(self._h, f0.ctypes.data, f.ctypes.data))
+
+    def get_populations(self):
+        f0 = np.empty(self.nxyz); f = np.empty(self.nxyz*(self.nc - 1))
+        check(_lib.lib().pl_lattice_get_host(self._h, f0.ctypes.data, f.ctypes.data))
+        return f0, f
+
+    # -- particle ops
+    def Stream(self):
+        check(_lib.lib().pl_stream(self._h, 0))
+
+    def iStream(self):
+        check(_lib.lib().pl_stream(self._h, 1))
+
+    def SmoothCorner(self):
+        check(_lib.lib().pl_smooth_corner(self._h))
+
+    def _faces(self):
+        ext = (self.lx, self.ly, self.lz)
+        for axis in range(self.nd):   # xmin, xmax, ymin, ymax, zmin, zmax (d3q15.h:182-189)
+            yield axis, 0, -1
+            yield axis, ext[axis] - 1, 1
+
+    def plane_coords(self, axis, coord):
+        """global (i, j, k) of the local sites of plane axis=coord in the C-ABI's natural order, or None if not local"""
+        off = (self.offsetx, self.offsety, self.offsetz); n = (self.nx, self.ny, self.nz)
+        loc = coord - off[axis]
+        if not (0 <= loc < n[axis]):
+            return None
+        a1 = 1 if axis == 0 else 0
+        a2 = 1 if axis == 2 else 2
+        b, a = np.meshgrid(np.arange(n[a2]), np.arange(n[a1]), indexing="ij")   # a (lower axis) fastest
+        c = [None, None, None]
+        c[axis] = np.full(a.size, coord, dtype=np.int64)
+        c[a1] = a.reshape(-1) + off[a1]
+        c[a2] = b.reshape(-1) + off[a2]
+        return c[0], c[1], c[2]
+
+    def _eval(self, fn, coords, dtype):
+        i, j, k = coords
+        v = fn(i, j) if self.nd == 2 else fn(i, j, k)
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(v), i.shape), dtype=dtype)
+
+    def make_bc(self, bctype_id, axis, coord, direction, maskfn, valfns=()):
+        """Bake one plane closure (cached by content). Returns a pl_bc handle (int) — possibly an empty one."""
+        L = _lib.lib()
+        coords = self.plane_coords(axis, coord)
+        if coords is None:
+            key = (bctype_id, axis, coord, direction, None)
+            if key not in self._bc_cache:
+                h = L.pl_bc_create(self._h, bctype_id, axis, coord, direction, None, None, None, None)
+                if not h:
+                    raise _lib.PanslbmError(L.pl_last_error().decode())
+                self._bc_cache[key] = h
+            return self._bc_cache[key]
+        mask = self._eval(maskfn, coords, np.uint8) if bctype_id in (BC_BOUNCE, BC_IBOUNCE) else \
+            np.ascontiguousarray(self._eval(maskfn, coords, np.float64) != 0, dtype=np.uint8)
+        vals = [self._eval(f, coords, np.float64) if f is not None else None for f in valfns]
+        hsh = hashlib.blake2b(mask.tobytes(), digest_size=16)
+        for v in vals:
+            hsh.update(b"|" if v is None else v.tobytes())
+        key = (bctype_id, axis, coord, direction, hsh.hexdigest())
+        if key not in self._bc_cache:
+            vp = [v.ctypes.data if v is not None else None for v in vals] + [None]*(3 - len(vals))
+            h = L.pl_bc_create(self._h, bctype_id, axis, coord, direction, mask.ctypes.data, vp[0], vp[1], vp[2])
+            if not h:
+                raise _lib.PanslbmError(L.pl_last_error().decode())
+            self._bc_cache[key] = h
+        return self._bc_cache[key]
+
+    def _apply(self, h, aux=None, other=None):
+        check(_lib.lib().pl_bc_apply(self._h, other._h if other is not None else None, h, C.byref(aux) if aux is not None else None))
+
+    def _bounce_plane(self, axis, coord, direction, bctype, inverse):
+        self._apply(self.make_bc(BC_IBOUNCE if inverse else BC_BOUNCE, axis, coord, direction, bctype))
+
+    def BoundaryCondition(self, bctype):
+        for axis, coord, d in self._faces():
+            self._bounce_plane(axis, coord, d, bctype, False)
+
+    def iBoundaryCondition(self, bctype):
+        for axis, coord, d in self._faces():
+            self._bounce_plane(axis, coord, d, bctype, True)
+
+    def free(self):
+        L = _lib.lib()
+        for h in self._bc_cache.values():
+            L.pl_bc_destroy(h)
+        self._bc_cache = {}
+        if getattr(self, "_h", None):
+            L.pl_lattice_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class D2Q9(_Lattice):
+    """src/particle/d2q9.h:24-158"""
+    kind, nc, nd = 2, 9, 2
+    cx = (0, 1, 0, -1, 0, 1, -1, -1, 1)
+    cy = (0, 0, 1, 0, -1, 1, 1, -1, -1)
+    cz = (0,)*9
+    ei = (4/9,) + (1/9,)*4 + (1/36,)*4
+
+    def __init__(self, lx, ly, PEid=0, mx=1, my=1):
+        super().__init__(lx, ly, 1, PEid, mx, my, 1)
+
+    def BoundaryConditionAlongXEdge(self, i, directionx, bctype): self._bounce_plane(0, i, directionx, bctype, False)
+    def BoundaryConditionAlongYEdge(self, j, directiony, bctype): self._bounce_plane(1, j, directiony, bctype, False)
+    def iBoundaryConditionAlongXEdge(self, i, directionx, bctype): self._bounce_plane(0, i, directionx, bctype, True)
+    def iBoundaryConditionAlongYEdge(self, j, directiony, bctype): self._bounce_plane(1, j, directiony, bctype, True)
+
+
+class D3Q15(_Lattice):
+    """src/particle/d3q15.h:24-249"""
+    kind, nc, nd = 3, 15, 3
+    cx = (0, 1, 0, 0, -1, 0, 0, 1, -1, 1, 1, -1, 1, -1, -1)
+    cy = (0, 0, 1, 0, 0, -1, 0, 1, 1, -1, 1, -1, -1, 1, -1)
+    cz = (0, 0, 0, 1, 0, 0, -1, 1, 1, 1, -1, -1, -1, -1, 1)
+    ei = (2/9,) + (1/9,)*6 + (1/72,)*8
+
+    def __init__(self, lx, ly, lz, PEid=0, mx=1, my=1, mz=1):
+        super().__init__(lx, ly, lz, PEid, mx, my, mz)
+
+    def BoundaryConditionAlongXFace(self, i, d, bctype): self._bounce_plane(0, i, d, bctype, False)
+    def BoundaryConditionAlongYFace(self, j, d, bctype): self._bounce_plane(1, j, d, bctype, False)
+    def BoundaryConditionAlongZFace(self, k, d, bctype): self._bounce_plane(2, k, d, bctype, False)
+    def iBoundaryConditionAlongXFace(self, i, d, bctype): self._bounce_plane(0, i, d, bctype, True)
+    def iBoundaryConditionAlongYFace(self, j, d, bctype): self._bounce_plane(1, j, d, bctype, True)
+    def iBoundaryConditionAlongZFace(self, k, d, bctype): self._bounce_plane(2, k, d, bctype, True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def collide_args(model, issave=False, viscosity=0.0, diffusivity_const=0.0, gx=0.0, gy=0.0, gz=0.0, tem0=0.0, **arrays) -> CollideArgs:
+    a = CollideArgs()
+    a.model, a.issave, a.viscosity, a.diffusivity_const = int(model), int(bool(issave)), float(viscosity), float(diffusivity_const)
+    a.gx, a.gy, a.gz, a.tem0 = float(gx), float(gy), float(gz), float(tem0)
+    a._keep = arrays   # keep the device arrays alive as long as the argument block
+    for k, v in arrays.items():
+        setattr(a, k, dptr(v))
+    return a
+
+
+def _collide(p, q, a: CollideArgs):
+    check(_lib.lib().pl_collide(p._h, q._h if q is not None else None, C.byref(a)))
+
+
+def _init(p, family, arrs):
+    n = len(arrs)
+    arr = (C.c_void_p*n)(*[dptr(a) for a in arrs])
+    check(_lib.lib().pl_initial_condition(p._h, family, arr, n))
+
+
+def _z(p, lst3, lst2):
+    return lst3 if p.nd == 3 else lst2
+
+
+def _closure_faces(p, bctype_id, maskfn, valfns, aux=None, other=None, planes=None):
+    for axis, coord, d in (planes if planes is not None else p._faces()):
+        p._apply(p.make_bc(bctype_id, axis, coord, d, maskfn, valfns), aux, other)
+
+
+def bc_aux(rho=None, ux=None, uy=None, uz=None, tem=None, diffusivity=None, diffusivity_const=0.0, eps=0.0) -> BcAux:
+    a = BcAux()
+    a._keep = (rho, ux, uy, uz, tem, diffusivity)
+    a.rho, a.ux, a.uy, a.uz, a.tem, a.diffusivity = dptr(rho), dptr(ux), dptr(uy), dptr(uz), dptr(tem), dptr(diffusivity)
+    a.diffusivity_const, a.eps = float(diffusivity_const), float(eps)
+    return a
+
+
+class NS:
+    """src/equation/navierstokes.h + src/equation_avx/navierstokes_avx.h"""
+
+    @staticmethod
+    def InitialCondition(p, rho, ux, uy, uz=None):
+        _init(p, 1, [rho, ux, uy, uz])
+
+    @staticmethod
+    def MacroCollide(p, *args):
+        # (rho, ux, uy, [uz,] viscosity, issave=False)
+        m = _z(p, ["rho", "ux", "uy", "uz", "viscosity", "issave"], ["rho", "ux", "uy", "viscosity", "issave"])
+        kw = dict(zip(m, args))
+        _collide(p, None, collide_args(M_NS_COLLIDE, kw.pop("issave", False), kw.pop("viscosity"), **kw))
+
+    @staticmethod
+    def MacroBrinkmanCollide(p, *args):
+        # (rho, ux, uy, [uz,] viscosity, alpha, issave=False)
+        m = _z(p, ["rho", "ux", "uy", "uz", "viscosity", "alpha", "issave"], ["rho", "ux", "uy", "viscosity", "alpha", "issave"])
+        kw = dict(zip(m, args))
+        _collide(p, None, collide_args(M_NS_BRINKMAN, kw.pop("issave", False), kw.pop("viscosity"), **kw))
+
+    @staticmethod
+    def BoundaryConditionSetU(p, *fns):
+        # (uxbc, uybc, [uzbc,] bctype)
+        *vals, mask = fns
+        _closure_faces(p, BC_NS_SET_U, mask, vals)
+
+    @staticmethod
+    def BoundaryConditionSetRho(p, *fns):
+        # (rhobc, usbc, [utbc,] bctype)
+        *vals, mask = fns
+        _closure_faces(p, BC_NS_SET_RHO, mask, vals)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def Residual(*arrays):
+    """src/utility/residual.h:8-50 — Residual(ux,[uy,[uz,]] uxp,[uyp,[uzp,]] n)"""
+    *arrs, n = arrays
+    h = len(arrs)//2
+    cur = list(arrs[:h]) + [None]*(3 - h)
+    prev = list(arrs[h:]) + [None]*(3 - h)
+    out = C.c_double(0.0)
+    check(_lib.lib().pl_residual(dptr(cur[0]), dptr(cur[1]), dptr(cur[2]), dptr(prev[0]), dptr(prev[1]), dptr(prev[2]), int(n), C.byref(out)))
+    return out.value
+
+
+def Normalize(v, n):
+    """src/utility/normalize.h:8-24"""
+    check(_lib.lib().pl_normalize(dptr(v), int(n)))
+
+
+# ----------------------------------------------------------------------------------------------------------
+class StepPlan:
+    """Fused time stepping (pl_plan_*): record one loop iteration, then advance it with one fused
+    stream+closures+collide pass per step.  Results are identical to issuing the calls one by one."""
+
+    def __init__(self, pf, pg=None):
+        L = _lib.lib()
+        self.pf, self.pg = pf, pg
+        self._h = L.pl_plan_create(pf._h, pg._h if pg is not None else None)
+        if not self._h:
+            raise _lib.PanslbmError(L.pl_last_error().decode())
+        self._keep = []
+
+    def set_collide(self, even: CollideArgs, odd: CollideArgs | None = None):
+        self._keep += [even, odd]
+        check(_lib.lib().pl_plan_set_collide(self._h, C.byref(even), C.byref(odd) if odd is not None else None))
+        return self
+
+    def set_stream(self, inverse=False):
+        check(_lib.lib().pl_plan_set_stream(self._h, int(bool(inverse))))
+        return self
+
+    def add_bc(self, lattice, bc_handle, aux_even: BcAux | None = None, aux_odd: BcAux | None = None):
+        self._keep += [aux_even, aux_odd]
+        on_g = 1 if (self.pg is not None and lattice is self.pg) else 0
+        check(_lib.lib().pl_plan_add_bc(self._h, on_g, bc_handle, C.byref(aux_even) if aux_even is not None else None,
+                                        C.byref(aux_odd) if aux_odd is not None else None))
+        return self
+
+    def add_bounce(self, lattice, bctype, inverse=False):
+        for axis, coord, d in lattice._faces():
+            self.add_bc(lattice, lattice.make_bc(BC_IBOUNCE if inverse else BC_BOUNCE, axis, coord, d, bctype))
+        return self
+
+    def add_closure(self, lattice, bctype_id, maskfn, valfns=(), aux_even=None, aux_odd=None):
+        for axis, coord, d in lattice._faces():
+            self.add_bc(lattice, lattice.make_bc(bctype_id, axis, coord, d, maskfn, valfns), aux_even, aux_odd)
+        return self
+
+    def set_smooth_corner(self, on_f=True, on_g=False):
+        check(_lib.lib().pl_plan_set_smooth_corner(self._h, int(bool(on_f)), int(bool(on_g))))
+        return self
+
+    def finalize(self):
+        check(_lib.lib().pl_plan_finalize(self._h))
+        return self
+
+    def advance(self, ncollides, end_streamed=True):
+        check(_lib.lib().pl_plan_advance(self._h, int(ncollides), int(bool(end_streamed))))
+
+    @property
+    def parity(self):
+        return _lib.lib().pl_plan_parity(self._h)
+
+    def free(self):
+        if getattr(self, "_h", None):
+            _lib.lib().pl_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

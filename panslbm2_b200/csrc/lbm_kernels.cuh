@@ -1,0 +1,246 @@
+// CUDA kernels of the sweep: population streaming, the fused stream+collide pass, in-place collide,
+// bounce-back / specular planes, SmoothCorner, layout conversion.  fp64 SoA: population c of site idx lives at
+// base[c*pitch + idx], idx = i + nx*(j + ny*k)  (same site order as the reference, d3q15.h:136-141).
+#pragma once
+#include "lbm_equations.cuh"
+
+namespace plb {
+
+// Shell membership = union of axis-aligned planes; byte per coordinate, non-zero = plane is in the shell.
+struct ShellMask {
+    const uint8_t *x, *y, *z;   // x == nullptr: no shell (the interior kernel takes every packed site)
+};
+
+// signed index deltas to the periodic neighbours of one site (reference Index(): d3q15.h:136-141)
+struct Nbr {
+    long long m[3], p[3];   // delta to coordinate-1 / coordinate+1 along x,y,z
+};
+PL_D void decompose(const Geom& G, long long idx, int& i, int& j, int& k) {
+    unsigned u = (unsigned)idx, nxy = (unsigned)(G.nx*G.ny);
+    unsigned kk = u/nxy, r = u - kk*nxy, jj = r/(unsigned)G.nx;
+    k = (int)kk; j = (int)jj; i = (int)(r - jj*(unsigned)G.nx);
+}
+PL_D Nbr neighbours(const Geom& G, int i, int j, int k) {
+    Nbr n;
+    long long sx = 1, sy = G.nx, sz = (long long)G.nx*G.ny;
+    n.m[0] = i == 0 ? (G.nx - 1)*sx : -sx;  n.p[0] = i == G.nx - 1 ? -(G.nx - 1)*sx : sx;
+    n.m[1] = j == 0 ? (G.ny - 1)*sy : -sy;  n.p[1] = j == G.ny - 1 ? -(G.ny - 1)*sy : sy;
+    n.m[2] = k == 0 ? (G.nz - 1)*sz : -sz;  n.p[2] = k == G.nz - 1 ? -(G.nz - 1)*sz : sz;
+    return n;
+}
+// offset of the site population c is pulled from: x - c (Stream) or x + c (iStream, n has m/p swapped by the caller)
+template <int D, int c> PL_D long long pull_offset(const Nbr& n) {
+    constexpr int X = LT<D>::cx(c), Y = LT<D>::cy(c), Z = LT<D>::cz(c);
+    long long o = 0;
+    if constexpr (X > 0) o += n.m[0]; else if constexpr (X < 0) o += n.p[0];
+    if constexpr (Y > 0) o += n.m[1]; else if constexpr (Y < 0) o += n.p[1];
+    if constexpr (Z > 0) o += n.m[2]; else if constexpr (Z < 0) o += n.p[2];
+    return o;
+}
+PL_D void orient(Nbr& n, int inverse) {
+    if (inverse) {
+        for (int d = 0; d < 3; ++d) { long long t = n.m[d]; n.m[d] = n.p[d]; n.p[d] = t; }
+    }
+}
+
+template <int D> PL_D void pull(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx, const Nbr& n) {
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        f[c] = __ldg(src + (size_t)c*pitch + (size_t)(idx + pull_offset<D, c>(n)));
+    });
+}
+template <int D> PL_D void load_site(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx) {
+    sfor<0, LT<D>::nc>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = src[(size_t)c*pitch + (size_t)idx]; });
+}
+template <int D> PL_D void store_site(const double (&f)[LT<D>::nc], double* __restrict__ dst, size_t pitch, long long idx) {
+    sfor<0, LT<D>::nc>([&](auto C) { constexpr int c = decltype(C)::value; dst[(size_t)c*pitch + (size_t)idx] = f[c]; });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Stream()/iStream(): dst(x,c) = src(x -/+ c, c) for every site (d3q15.h:601-616, 964-979)
+template <int D>
+__global__ void __launch_bounds__(256) k_stream(Geom G, const double* __restrict__ src, double* __restrict__ dst, int inverse) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    Nbr n = neighbours(G, i, j, k);
+    orient(n, inverse);
+    double f[LT<D>::nc];
+    pull<D>(f, src, G.pitch, idx, n);
+    store_site<D>(f, dst, G.pitch, idx);
+}
+// the same for a list of sites (shell of a fused step)
+template <int D>
+__global__ void __launch_bounds__(256) k_stream_list(Geom G, const double* __restrict__ src, double* __restrict__ dst, int inverse,
+                                                     const int* __restrict__ list, int nlist) {
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= nlist) return;
+    long long idx = list[t];
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    Nbr n = neighbours(G, i, j, k);
+    orient(n, inverse);
+    double f[LT<D>::nc];
+    pull<D>(f, src, G.pitch, idx, n);
+    store_site<D>(f, dst, G.pitch, idx);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// In-place Macro*Collide* over all sites (list == nullptr) or over a site list.  Tail sites
+// (idx >= 4*(nxyz/4)) take the scalar operation order exactly as the reference does (navierstokes_avx.h:180-200).
+template <int D, int M>
+__global__ void __launch_bounds__(256) k_collide(Geom G, double* __restrict__ fb, double* __restrict__ gb, CollideParams P,
+                                                 const int* __restrict__ list, long long count) {
+    constexpr unsigned FL = ModelFlags<M>::v;
+    long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    long long idx = list ? (long long)list[t] : t;
+    double f[LT<D>::nc], g[LT<D>::nc];
+    load_site<D>(f, fb, G.pitch, idx);
+    if constexpr ((FL & F_G) != 0) load_site<D>(g, gb, G.pitch, idx);
+    if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
+    else collide_site<D, FL, true>(f, g, P, (size_t)idx);
+    store_site<D>(f, fb, G.pitch, idx);
+    if constexpr ((FL & F_G) != 0) store_site<D>(g, gb, G.pitch, idx);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The hot kernel: one fused Stream + Macro*Collide* pass, source buffer -> destination buffer, for every
+// packed site that is not in the shell (shell = planes carrying closures / SmoothCorner, handled by the
+// plane kernels around k_stream_list and k_collide).  Each population is read once and written once.
+template <int D, int M>
+__global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
+                                               const double* __restrict__ gs, double* __restrict__ gd,
+                                               CollideParams P, ShellMask S, int inverse) {
+    constexpr unsigned FL = ModelFlags<M>::v;
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.npacked) return;
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    if (S.x != nullptr && (S.x[i] | S.y[j] | S.z[k])) return;
+    Nbr n = neighbours(G, i, j, k);
+    orient(n, inverse);
+    double f[LT<D>::nc], g[LT<D>::nc];
+    pull<D>(f, fs, G.pitch, idx, n);
+    if constexpr ((FL & F_G) != 0) pull<D>(g, gs, G.pitch, idx, n);
+    collide_site<D, FL, false>(f, g, P, (size_t)idx);
+    store_site<D>(f, fd, G.pitch, idx);
+    if constexpr ((FL & F_G) != 0) store_site<D>(g, gd, G.pitch, idx);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Plane descriptor shared by every closure kernel.  n1 x n2 local plane sites, site index = base + a*s1 + b*s2.
+struct Plane {
+    int axis, dir;          // normal axis 0/1/2, outward direction -1/+1
+    int n1, n2;             // extents of the two in-plane axes (lower axis first)
+    long long base, s1, s2; // index of plane site (0,0) and the strides of the in-plane axes
+};
+
+// BARRIER / MIRROR (d3q15.h:984-1239, d2q9.h:431-575): forward rebuilds the populations entering the
+// domain (c_axis == -dir) from their opposite (BARRIER=1) or mirror image (MIRROR=2); inverse the leaving ones.
+template <int D>
+__global__ void __launch_bounds__(128) k_bounce(Geom G, double* __restrict__ fb, Plane pl, const uint8_t* __restrict__ mask, int inverse) {
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= pl.n1*pl.n2) return;
+    int type = mask[t];
+    if (type != 1 && type != 2) return;
+    int a = t%pl.n1, b = t/pl.n1;
+    long long idx = pl.base + a*pl.s1 + b*pl.s2;
+    int want = inverse ? pl.dir : -pl.dir;
+    double v[LT<D>::nc];
+    #pragma unroll
+    for (int c = 1; c < LT<D>::nc; ++c) v[c] = fb[(size_t)c*G.pitch + idx];
+    #pragma unroll
+    for (int c = 1; c < LT<D>::nc; ++c) {
+        if (cdir<D>(c, pl.axis) != want) continue;
+        int src;
+        if (type == 1) src = LT<D>::opp(c);
+        else {
+            int x = LT<D>::cx(c), y = LT<D>::cy(c), z = LT<D>::cz(c);
+            if (pl.axis == 0) x = -x; else if (pl.axis == 1) y = -y; else z = -z;
+            src = find_dir<D>(x, y, z);
+        }
+        fb[(size_t)c*G.pitch + idx] = v[src];
+    }
+}
+
+// SmoothCorner (d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587).  A line/point list is built on the host.
+struct SmoothItem {
+    long long base, stride;   // first site of the line and stride along it (corner: a single site)
+    int len;                  // number of sites on the line (1 for a corner)
+    long long n0, n1, n2;     // index deltas to the 2 (edge / 2-D corner) or 3 (3-D corner) inward neighbours; n2 == 0: two neighbours
+};
+struct SmoothList { SmoothItem it[12]; int count; int maxlen; };
+template <int D>
+__global__ void __launch_bounds__(128) k_smooth(Geom G, double* __restrict__ fb, SmoothList L) {
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    int which = blockIdx.y;
+    if (which >= L.count) return;
+    const SmoothItem it = L.it[which];
+    if (t >= it.len) return;
+    long long idx = it.base + (long long)t*it.stride;
+    #pragma unroll
+    for (int c = 0; c < LT<D>::nc; ++c) {
+        double* p = fb + (size_t)c*G.pitch;
+        if (it.n2 == 0) p[idx] = 0.5*(p[idx + it.n0] + p[idx + it.n1]);
+        else p[idx] = (p[idx + it.n0] + p[idx + it.n1] + p[idx + it.n2])/3.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layout conversion host(reference AoS) <-> device SoA:  f0[idx], f[(nc-1)*idx + c-1]
+template <int D>
+__global__ void k_from_aos(Geom G, const double* __restrict__ f0, const double* __restrict__ f, double* __restrict__ dst) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    dst[idx] = f0[idx];
+    #pragma unroll
+    for (int c = 1; c < LT<D>::nc; ++c) dst[(size_t)c*G.pitch + idx] = f[(size_t)(LT<D>::nc - 1)*idx + (c - 1)];
+}
+template <int D>
+__global__ void k_to_aos(Geom G, const double* __restrict__ src, double* __restrict__ f0, double* __restrict__ f) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    f0[idx] = src[idx];
+    #pragma unroll
+    for (int c = 1; c < LT<D>::nc; ++c) f[(size_t)(LT<D>::nc - 1)*idx + (c - 1)] = src[(size_t)c*G.pitch + idx];
+}
+// snapshot SoA -> reference host layout: [pack][c][lane] for packed sites, [idx][c] for the tail (adjointadvection_avx.h:20-22)
+template <int D>
+__global__ void k_snapshot_to_ref(Geom G, const double* __restrict__ snap, size_t spitch, double* __restrict__ out) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    constexpr int NC = LT<D>::nc;
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        size_t o = idx < G.npacked ? (size_t)(idx/4)*4*NC + 4*c + idx%4 : (size_t)NC*idx + c;
+        out[o] = snap[(size_t)c*spitch + idx];
+    }
+}
+
+// InitialCondition: populations = scalar-order equilibrium (navierstokes.h:550-572, advection.h:1048-1070,
+// adjointnavierstokes.h:474-498, adjointadvection.h:1359-1381).  a0..a6 by family as in pl_initial_condition.
+template <int D>
+__global__ void __launch_bounds__(256) k_init(Geom G, double* __restrict__ dst, int family, const double* a0, const double* a1, const double* a2,
+                                              const double* a3, const double* a4, const double* a5, const double* a6) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    double eq[LT<D>::nc];
+    if (family == 1) {          // NS: rho, ux, uy, uz
+        ns_eq_sc<D>(eq, a0[idx], a1[idx], a2[idx], D == 3 ? a3[idx] : 0.0);
+    } else if (family == 2) {   // AD: tem, ux, uy, uz
+        ad_eq_sc<D>(eq, a0[idx], a1[idx], a2[idx], D == 3 ? a3[idx] : 0.0);
+    } else if (family == 3) {   // ANS: ux, uy, uz, ip, iux, iuy, iuz
+        ans_eq<D>(eq, a0[idx], a1[idx], D == 3 ? a2[idx] : 0.0, a3[idx], a4[idx], a5[idx], D == 3 ? a6[idx] : 0.0);
+    } else {                    // AAD: ux, uy, uz, item, iqx, iqy, iqz
+        double ux = a0[idx], uy = a1[idx], uz = D == 3 ? a2[idx] : 0.0;
+        // scalar order: item + 3*(ux*iqx + uy*iqy + uz*iqz)  (adjointadvection.h:54-68)
+        double ge = a3[idx] + 3.0*dot<D>(ux, uy, uz, a4[idx], a5[idx], D == 3 ? a6[idx] : 0.0);
+        #pragma unroll
+        for (int c = 0; c < LT<D>::nc; ++c) eq[c] = ge;
+    }
+    store_site<D>(eq, dst, G.pitch, idx);
+}
+
+}  // namespace plb

@@ -1,0 +1,98 @@
+// Reductions: Residual (src/utility/residual.h:8-50), Normalize (src/utility/normalize.h:8-24), sums.
+// Grid-stride accumulation per thread, warp-shuffle + shared-memory block reduction, fixed grid => the
+// summation order (and therefore the result) is deterministic from run to run.
+#pragma once
+#include "lbm_traits.cuh"
+
+namespace plb {
+
+PL_D double warp_sum(double v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+PL_D double warp_max(double v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// sum over the block; result valid in thread 0
+PL_D double block_sum(double v) {
+    __shared__ double sh[32];
+    __syncthreads();
+    v = warp_sum(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = threadIdx.x < nw ? sh[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    return v;
+}
+PL_D double block_max(double v) {
+    __shared__ double shm[32];
+    __syncthreads();
+    v = warp_max(v);
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) shm[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    v = threadIdx.x < nw ? shm[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_max(v);
+    return v;
+}
+
+__global__ void k_fill(double* __restrict__ p, double v, long long n) {
+    long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_divide(double* __restrict__ p, double d, long long n) {
+    long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) p[i] = p[i]/d;
+}
+
+// out[2*b+0] = sum |u-up|^2, out[2*b+1] = sum |u|^2 over this block's share; uy/uz may be null (1- and 2-component overloads)
+__global__ void __launch_bounds__(256) k_residual_partial(const double* __restrict__ ux, const double* __restrict__ uy, const double* __restrict__ uz,
+                                                          const double* __restrict__ uxp, const double* __restrict__ uyp, const double* __restrict__ uzp,
+                                                          long long n, double* __restrict__ out) {
+    double d = 0.0, s = 0.0;
+    for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) {
+        double a = ux[i], e = a - uxp[i];
+        double dd = e*e, ss = a*a;
+        if (uy) { double b = uy[i], eb = b - uyp[i]; dd = dd + eb*eb; ss = ss + b*b; }
+        if (uz) { double c = uz[i], ec = c - uzp[i]; dd = dd + ec*ec; ss = ss + c*c; }
+        d += dd; s += ss;
+    }
+    d = block_sum(d);
+    s = block_sum(s);
+    if (threadIdx.x == 0) { out[2*blockIdx.x] = d; out[2*blockIdx.x + 1] = s; }
+}
+__global__ void __launch_bounds__(256) k_sum_partial(const double* __restrict__ v, long long n, double* __restrict__ out) {
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) s += v[i];
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+// final pass: `ncomp` interleaved partials per block -> out[0..ncomp)
+__global__ void __launch_bounds__(256) k_sum_final(const double* __restrict__ part, int nb, int ncomp, double* __restrict__ out) {
+    for (int c = 0; c < ncomp; ++c) {
+        double s = 0.0;
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) s += part[(size_t)ncomp*b + c];
+        s = block_sum(s);
+        if (threadIdx.x == 0) out[c] = s;
+    }
+}
+__global__ void __launch_bounds__(256) k_absmax_partial(const double* __restrict__ v, long long n, double* __restrict__ out) {
+    double m = 0.0;
+    for (long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x*blockDim.x) m = fmax(m, fabs(v[i]));
+    m = block_max(m);
+    if (threadIdx.x == 0) out[blockIdx.x] = m;
+}
+__global__ void __launch_bounds__(256) k_absmax_final(const double* __restrict__ part, int nb, double* __restrict__ out) {
+    double m = 0.0;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) m = fmax(m, part[b]);
+    m = block_max(m);
+    if (threadIdx.x == 0) out[0] = m;
+}
+
+}  // namespace plb

@@ -1,0 +1,783 @@
+// C-ABI of libpanslbm_b200.so (see include/panslbm_c.h).  Host-side orchestration only: every numerical
+// operation is a CUDA kernel from lbm_kernels.cuh / lbm_closures.cuh / lbm_reduce.cuh.  No CPU fallback.
+#include "../../include/panslbm_c.h"
+#include "lbm_closures.cuh"
+#include "lbm_reduce.cuh"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace plb;
+
+// -------------------------------------------------------------------------------------------------
+namespace {
+thread_local std::string g_err;
+cudaStream_t g_stream = 0;          // legacy default stream unless the caller installs another one
+uint64_t g_launches = 0;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(PL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+#define CUP(call)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            fail(PL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));                     \
+            return nullptr;                                                                             \
+        }                                                                                               \
+    } while (0)
+#define LAUNCH(kernel, grid, block, ...)                                                                \
+    do {                                                                                                \
+        kernel<<<(grid), (block), 0, g_stream>>>(__VA_ARGS__);                                          \
+        ++g_launches;                                                                                   \
+        CU(cudaGetLastError());                                                                         \
+    } while (0)
+
+inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1)/bs); }
+}  // namespace
+
+struct pl_lattice {
+    int kind;                      // 2 / 3
+    int nc;
+    int lx, ly, lz, peid, mx, my, mz, pex, pey, pez;
+    Geom g;
+    double* buf[2] = {nullptr, nullptr};
+    int cur = 0;
+    int streamed = 1;              // phase: 1 = populations are "pre-collision" (after init / Stream+closures), 0 = just collided
+    double* current() const { return buf[cur]; }
+    double* other() const { return buf[cur ^ 1]; }
+};
+
+struct pl_bc {
+    pl_lattice* lat;
+    int type, axis, coord, dir;
+    bool empty;
+    Plane pl;
+    uint8_t* mask = nullptr;
+    double *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;
+};
+
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* pl_last_error(void) { return g_err.c_str(); }
+const char* pl_version(void) { return "panslbm_b200 0.1 (sm_100a, fp64, fmad=off)"; }
+int pl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int pl_set_device(int device) { CU(cudaSetDevice(device)); return PL_OK; }
+int pl_synchronize(void) { CU(cudaStreamSynchronize(g_stream)); return PL_OK; }
+void* pl_get_stream(void) { return (void*)g_stream; }
+int pl_set_stream(void* s) { g_stream = (cudaStream_t)s; return PL_OK; }
+uint64_t pl_launch_count(void) { return g_launches; }
+void pl_launch_count_reset(void) { g_launches = 0; }
+
+double* pl_array_alloc(size_t n) {
+    double* p = nullptr;
+    CUP(cudaMalloc(&p, std::max<size_t>(n, 1)*sizeof(double)));
+    return p;
+}
+int pl_array_free(double* dev) { CU(cudaFree(dev)); return PL_OK; }
+int pl_array_upload(double* dev, const double* host, size_t n) {
+    CU(cudaMemcpyAsync(dev, host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return PL_OK;
+}
+int pl_array_download(double* host, const double* dev, size_t n) {
+    CU(cudaMemcpyAsync(host, dev, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return PL_OK;
+}
+int pl_array_fill(double* dev, double value, size_t n) {
+    if (n == 0) return PL_OK;
+    LAUNCH(k_fill, blocks_for((long long)n, 256), 256, dev, value, (long long)n);
+    return PL_OK;
+}
+
+// ---- lattices -------------------------------------------------------------------------------------
+pl_lattice* pl_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz) {
+    if ((kind != PL_D2Q9 && kind != PL_D3Q15) || lx <= 0 || ly <= 0 || lz <= 0 || peid < 0 || mx <= 0 || my <= 0 || mz <= 0) {
+        fail(PL_ERR_ARG, "pl_lattice_create: bad arguments");   // the reference asserts (d3q15.h:37)
+        return nullptr;
+    }
+    if (kind == PL_D2Q9) { lz = 1; mz = 1; }
+    if (peid >= mx*my*mz) { fail(PL_ERR_ARG, "pl_lattice_create: PEid outside the PE grid"); return nullptr; }
+    pl_lattice* l = new pl_lattice();
+    l->kind = kind; l->nc = kind == PL_D2Q9 ? 9 : 15;
+    l->lx = lx; l->ly = ly; l->lz = lz; l->peid = peid; l->mx = mx; l->my = my; l->mz = mz;
+    // block decomposition: d3q15.h:29-35, d2q9.h:29-35
+    l->pex = peid%mx;
+    l->pey = kind == PL_D2Q9 ? peid/mx : (peid/mx)%my;
+    l->pez = kind == PL_D2Q9 ? 0 : peid/(mx*my);
+    Geom& g = l->g;
+    g.lx = lx; g.ly = ly; g.lz = lz;
+    g.nx = (lx + l->pex)/mx; g.ny = (ly + l->pey)/my; g.nz = kind == PL_D2Q9 ? 1 : (lz + l->pez)/mz;
+    g.offx = mx - l->pex > lx%mx ? l->pex*g.nx : lx - (mx - l->pex)*g.nx;
+    g.offy = my - l->pey > ly%my ? l->pey*g.ny : ly - (my - l->pey)*g.ny;
+    g.offz = kind == PL_D2Q9 ? 0 : (mz - l->pez > lz%mz ? l->pez*g.nz : lz - (mz - l->pez)*g.nz);
+    g.nxyz = (long long)g.nx*g.ny*g.nz;
+    if (g.nxyz <= 0 || g.nxyz >= (1LL << 31)) { delete l; fail(PL_ERR_ARG, "pl_lattice_create: block must hold 1..2^31-1 sites"); return nullptr; }
+    g.npacked = 4*(g.nxyz/4);
+    g.pitch = (size_t)((g.nxyz + 15)/16*16);
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaMalloc(&l->buf[b], g.pitch*l->nc*sizeof(double));
+        if (e != cudaSuccess) {
+            fail(PL_ERR_CUDA, std::string("pl_lattice_create: cudaMalloc: ") + cudaGetErrorString(e));
+            if (l->buf[0]) cudaFree(l->buf[0]);
+            delete l;
+            return nullptr;
+        }
+    }
+    cudaMemsetAsync(l->buf[0], 0, g.pitch*l->nc*sizeof(double), g_stream);
+    cudaMemsetAsync(l->buf[1], 0, g.pitch*l->nc*sizeof(double), g_stream);
+    return l;
+}
+int pl_lattice_destroy(pl_lattice* l) {
+    if (!l) return PL_OK;
+    cudaStreamSynchronize(g_stream);
+    cudaFree(l->buf[0]); cudaFree(l->buf[1]);
+    delete l;
+    return PL_OK;
+}
+int pl_lattice_info(const pl_lattice* l, int* o) {
+    if (!l || !o) return fail(PL_ERR_ARG, "pl_lattice_info: null");
+    int v[18] = {l->lx, l->ly, l->lz, l->peid, l->mx, l->my, l->mz, l->pex, l->pey, l->pez, l->g.nx, l->g.ny, l->g.nz, (int)l->g.nxyz,
+                 l->g.offx, l->g.offy, l->g.offz, l->nc};
+    memcpy(o, v, sizeof(v));
+    return PL_OK;
+}
+int pl_lattice_set_host(pl_lattice* l, const double* f0, const double* f) {
+    if (!l || !f0 || !f) return fail(PL_ERR_ARG, "pl_lattice_set_host: null");
+    size_t n = (size_t)l->g.nxyz, nf = n*(l->nc - 1);
+    double *d0 = nullptr, *d1 = nullptr;
+    CU(cudaMalloc(&d0, n*sizeof(double)));
+    CU(cudaMalloc(&d1, nf*sizeof(double)));
+    CU(cudaMemcpyAsync(d0, f0, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaMemcpyAsync(d1, f, nf*sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    if (l->kind == PL_D2Q9) LAUNCH(k_from_aos<2>, blocks_for(l->g.nxyz, 256), 256, l->g, d0, d1, l->current());
+    else LAUNCH(k_from_aos<3>, blocks_for(l->g.nxyz, 256), 256, l->g, d0, d1, l->current());
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(d0); cudaFree(d1);
+    return PL_OK;
+}
+int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
+    if (!l || !f0 || !f) return fail(PL_ERR_ARG, "pl_lattice_get_host: null");
+    size_t n = (size_t)l->g.nxyz, nf = n*(l->nc - 1);
+    double *d0 = nullptr, *d1 = nullptr;
+    CU(cudaMalloc(&d0, n*sizeof(double)));
+    CU(cudaMalloc(&d1, nf*sizeof(double)));
+    if (l->kind == PL_D2Q9) LAUNCH(k_to_aos<2>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), d0, d1);
+    else LAUNCH(k_to_aos<3>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), d0, d1);
+    CU(cudaMemcpyAsync(f0, d0, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaMemcpyAsync(f, d1, nf*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(d0); cudaFree(d1);
+    return PL_OK;
+}
+int pl_lattice_device_view(pl_lattice* l, double** base, size_t* pitch) {
+    if (!l) return fail(PL_ERR_ARG, "pl_lattice_device_view: null");
+    if (base) *base = l->current();
+    if (pitch) *pitch = l->g.pitch;
+    return PL_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// internal launch helpers (C++ linkage)
+namespace {
+
+int do_stream_all(pl_lattice* l, int inverse) {
+    if (l->kind == PL_D2Q9) LAUNCH(k_stream<2>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse);
+    else LAUNCH(k_stream<3>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse);
+    l->cur ^= 1;
+    return PL_OK;
+}
+int do_stream_list(pl_lattice* l, int inverse, const int* list, int n) {   // does NOT flip
+    if (n == 0) return PL_OK;
+    if (l->kind == PL_D2Q9) LAUNCH(k_stream_list<2>, blocks_for(n, 256), 256, l->g, l->current(), l->other(), inverse, list, n);
+    else LAUNCH(k_stream_list<3>, blocks_for(n, 256), 256, l->g, l->current(), l->other(), inverse, list, n);
+    return PL_OK;
+}
+
+// the local sites of the global plane axis=coord
+bool make_plane(const pl_lattice* l, int axis, int coord, int dir, Plane& pl) {
+    const Geom& g = l->g;
+    int off[3] = {g.offx, g.offy, g.offz}, n[3] = {g.nx, g.ny, g.nz};
+    long long st[3] = {1, g.nx, (long long)g.nx*g.ny};
+    if (axis < 0 || axis >= l->kind) return false;
+    int loc = coord - off[axis];
+    if (loc < 0 || loc >= n[axis]) return false;
+    int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+    pl.axis = axis; pl.dir = dir;
+    pl.n1 = n[a1]; pl.s1 = st[a1];
+    pl.n2 = n[a2]; pl.s2 = st[a2];
+    pl.base = loc*st[axis];
+    return true;
+}
+
+int smooth_lists(const pl_lattice* l, SmoothList& edges, SmoothList& corners) {
+    const Geom& g = l->g;
+    edges.count = 0; edges.maxlen = 0; corners.count = 0; corners.maxlen = 1;
+    long long st[3] = {1, g.nx, (long long)g.nx*g.ny};
+    int n[3] = {g.nx, g.ny, g.nz};
+    int lo[3] = {0 - g.offx, 0 - g.offy, 0 - g.offz};                       // local coordinate of the global min faces
+    int hi[3] = {g.lx - 1 - g.offx, g.ly - 1 - g.offy, g.lz - 1 - g.offz};  // ... of the global max faces
+    auto in = [&](int d, int v) { return 0 <= v && v < n[d]; };
+    // inward neighbour delta along axis d for a site on the min (dirn=-1) / max (dirn=+1) face: x - dirn (periodic wrap as Index())
+    auto inward = [&](int d, int v, int dirn) -> long long {
+        int w = v - dirn;
+        if (w == -1) w = n[d] - 1; else if (w == n[d]) w = 0;
+        return (long long)(w - v)*st[d];
+    };
+    if (l->kind == PL_D2Q9) {
+        int cs[4][4] = {{lo[0], lo[1], -1, -1}, {lo[0], hi[1], -1, 1}, {hi[0], lo[1], 1, -1}, {hi[0], hi[1], 1, 1}};
+        for (auto& c : cs) if (in(0, c[0]) && in(1, c[1])) {
+            SmoothItem it{};
+            it.base = c[0] + c[1]*st[1]; it.stride = 0; it.len = 1;
+            it.n0 = inward(0, c[0], c[2]); it.n1 = inward(1, c[1], c[3]); it.n2 = 0;
+            corners.it[corners.count++] = it;
+        }
+        return PL_OK;
+    }
+    // 12 edges (d3q15.h:200-211): line along axis `al`, fixed on the faces of the two other axes (p, q)
+    for (int al = 0; al < 3; ++al) {
+        int p = (al + 1)%3, q = (al + 2)%3;
+        int combos[4][2] = {{-1, -1}, {1, -1}, {1, 1}, {-1, 1}};
+        for (auto& cb : combos) {
+            int vp = cb[0] < 0 ? lo[p] : hi[p], vq = cb[1] < 0 ? lo[q] : hi[q];
+            if (!in(p, vp) || !in(q, vq)) continue;
+            // skip the global corner sites at the ends: they are overwritten by SmoothCornerAt afterwards (d3q15.h:212-219)
+            int a0 = 0, a1 = n[al] - 1;
+            if (lo[al] == 0) a0 = 1;
+            if (hi[al] == n[al] - 1) a1 = n[al] - 2;
+            if (a1 < a0) continue;
+            SmoothItem it{};
+            it.base = vp*st[p] + vq*st[q] + a0*st[al]; it.stride = st[al]; it.len = a1 - a0 + 1;
+            it.n0 = inward(p, vp, cb[0]); it.n1 = inward(q, vq, cb[1]); it.n2 = 0;
+            edges.it[edges.count++] = it;
+            edges.maxlen = std::max(edges.maxlen, it.len);
+        }
+    }
+    int dirs[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+    for (auto& d : dirs) {
+        int v[3];
+        for (int a = 0; a < 3; ++a) v[a] = d[a] < 0 ? lo[a] : hi[a];
+        if (!in(0, v[0]) || !in(1, v[1]) || !in(2, v[2])) continue;
+        SmoothItem it{};
+        it.base = v[0] + v[1]*st[1] + v[2]*st[2]; it.stride = 0; it.len = 1;
+        it.n0 = inward(0, v[0], d[0]); it.n1 = inward(1, v[1], d[1]); it.n2 = inward(2, v[2], d[2]);
+        corners.it[corners.count++] = it;
+    }
+    return PL_OK;
+}
+
+int do_smooth(pl_lattice* l) {
+    SmoothList e, c;
+    smooth_lists(l, e, c);
+    double* fb = l->current();
+    if (e.count > 0) {
+        dim3 grid(blocks_for(e.maxlen, 128), e.count);
+        if (l->kind == PL_D2Q9) LAUNCH(k_smooth<2>, grid, 128, l->g, fb, e); else LAUNCH(k_smooth<3>, grid, 128, l->g, fb, e);
+    }
+    if (c.count > 0) {
+        dim3 grid(1, c.count);
+        if (l->kind == PL_D2Q9) LAUNCH(k_smooth<2>, grid, 128, l->g, fb, c); else LAUNCH(k_smooth<3>, grid, 128, l->g, fb, c);
+    }
+    return PL_OK;
+}
+
+int do_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* aux) {
+    if (bc->empty) return PL_OK;
+    if (bc->lat != l && !(bc->lat->kind == l->kind && bc->lat->g.nxyz == l->g.nxyz && bc->lat->g.nx == l->g.nx && bc->lat->g.ny == l->g.ny
+                          && bc->lat->g.offx == l->g.offx && bc->lat->g.offy == l->g.offy && bc->lat->g.offz == l->g.offz))
+        return fail(PL_ERR_ARG, "pl_bc_apply: closure was created for a lattice of another shape");
+    int np = bc->pl.n1*bc->pl.n2;
+    if (bc->type == PL_BC_BOUNCE || bc->type == PL_BC_IBOUNCE) {
+        int inv = bc->type == PL_BC_IBOUNCE;
+        if (l->kind == PL_D2Q9) LAUNCH(k_bounce<2>, blocks_for(np, 128), 128, l->g, l->current(), bc->pl, bc->mask, inv);
+        else LAUNCH(k_bounce<3>, blocks_for(np, 128), 128, l->g, l->current(), bc->pl, bc->mask, inv);
+        return PL_OK;
+    }
+    ClosureArgs A{};
+    A.type = bc->type; A.pl = bc->pl; A.mask = bc->mask; A.v0 = bc->v0; A.v1 = bc->v1; A.v2 = bc->v2;
+    if (aux) {
+        A.rho = aux->rho; A.ux = aux->ux; A.uy = aux->uy; A.uz = aux->uz; A.tem = aux->tem; A.kappa = aux->diffusivity;
+        A.kconst = aux->diffusivity_const; A.eps = aux->eps;
+    }
+    switch (bc->type) {
+        case PL_BC_NS_SET_U:
+            if (!bc->v0 || !bc->v1 || (l->kind == PL_D3Q15 && !bc->v2)) return fail(PL_ERR_ARG, "pl_bc_apply: SetU needs ux,uy(,uz) plane values");
+            break;
+        case PL_BC_NS_SET_RHO:
+            if (!bc->v0 || !bc->v1 || (l->kind == PL_D3Q15 && !bc->v2)) return fail(PL_ERR_ARG, "pl_bc_apply: SetRho needs rho,us(,ut) plane values");
+            break;
+        default:
+            return fail(PL_ERR_UNSUPPORTED, "pl_bc_apply: closure type not implemented");
+    }
+    double* gb = other ? other->current() : nullptr;
+    if (l->kind == PL_D2Q9) LAUNCH(k_closure<2>, blocks_for(np, 128), 128, l->g, l->current(), gb, A);
+    else LAUNCH(k_closure<3>, blocks_for(np, 128), 128, l->g, l->current(), gb, A);
+    return PL_OK;
+}
+
+// pl_collide_args -> kernel argument block
+int make_params(const pl_lattice* f, const pl_lattice* g, const pl_collide_args* a, CollideParams& P, unsigned& flags) {
+    static const unsigned FLAGS[13] = {0, ModelFlags<1>::v, ModelFlags<2>::v, ModelFlags<3>::v, ModelFlags<4>::v, ModelFlags<5>::v, ModelFlags<6>::v,
+                                       ModelFlags<7>::v, ModelFlags<8>::v, ModelFlags<9>::v, ModelFlags<10>::v, ModelFlags<11>::v, ModelFlags<12>::v};
+    if (!f || !a) return fail(PL_ERR_ARG, "pl_collide: null");
+    if (a->model < 1 || a->model > 12) return fail(PL_ERR_ARG, "pl_collide: unknown model");
+    flags = FLAGS[a->model];
+    const bool d3 = f->kind == PL_D3Q15;
+    if (a->model == PL_AAD_NAT_CONV_MASSFLOW && d3)
+        return fail(PL_ERR_UNSUPPORTED, "pl_collide: the reference's D3Q15 NaturalConvectionMassFlow does not compile (adjointadvection_avx.h:1161); D2Q9 only");
+    if ((flags & F_G) && (!g || g->kind != f->kind || g->g.nxyz != f->g.nxyz)) return fail(PL_ERR_ARG, "pl_collide: model needs a thermal lattice of the same shape");
+    memset(&P, 0, sizeof(P));
+    P.issave = a->issave;
+    P.omegaf = 1.0/(3.0*a->viscosity + 0.5); P.iomegaf = 1.0 - P.omegaf;
+    P.omegag = 1.0/(3.0*a->diffusivity_const + 0.5); P.iomegag = 1.0 - P.omegag;
+    P.gx = a->gx; P.gy = a->gy; P.gz = d3 ? a->gz : 0.0; P.tem0 = a->tem0;
+    for (int c = 0; c < f->nc; ++c) {
+        double cx = d3 ? LT<3>::cx(c) : LT<2>::cx(c), cy = d3 ? LT<3>::cy(c) : LT<2>::cy(c), cz = d3 ? LT<3>::cz(c) : 0;
+        double ei = d3 ? LT<3>::ei(c) : LT<2>::ei(c);
+        volatile double px = cx*P.gx, py = cy*P.gy, pz = cz*P.gz;   // volatile: keep the host compiler from contracting
+        volatile double s = px + py;
+        if (d3) s = s + pz;
+        P.cg[c] = s;
+        volatile double e = ei*s;
+        P.eicg[c] = e;
+    }
+    P.alpha = a->alpha; P.kappa = a->diffusivity; P.beta = a->beta; P.dirx = a->dirx; P.diry = a->diry; P.dirz = a->dirz;
+    P.rho = a->rho; P.ux = a->ux; P.uy = a->uy; P.uz = a->uz; P.tem = a->tem; P.qx = a->qx; P.qy = a->qy; P.qz = a->qz;
+    P.ip = a->ip; P.iux = a->iux; P.iuy = a->iuy; P.iuz = a->iuz; P.imx = a->imx; P.imy = a->imy; P.imz = a->imz;
+    P.item = a->item; P.iqx = a->iqx; P.iqy = a->iqy; P.iqz = a->iqz;
+    P.snap = (flags & F_SNAP) ? a->snapshot : nullptr; P.snap_pitch = f->g.pitch;
+    // argument validation: every array the selected model dereferences must be present
+    auto need = [&](const void* p, const char* what) { if (!p) { g_err = std::string("pl_collide: missing array ") + what; return false; } return true; };
+    bool ok = true;
+    const bool adj = flags & F_ADJ, two = flags & F_G;
+    if (adj || a->issave) {
+        ok = ok && need(a->rho, "rho") && need(a->ux, "ux") && need(a->uy, "uy") && (!d3 || need(a->uz, "uz"));
+        if (two && (adj ? true : a->issave)) ok = ok && need(a->tem, "tem");
+    }
+    if (!adj && two && a->issave) ok = ok && need(a->qx, "qx") && need(a->qy, "qy") && (!d3 || need(a->qz, "qz"));
+    if (adj && a->issave) {
+        ok = ok && need(a->ip, "ip") && need(a->iux, "iux") && need(a->iuy, "iuy") && need(a->imx, "imx") && need(a->imy, "imy") && (!d3 || (need(a->iuz, "iuz") && need(a->imz, "imz")));
+        if (two) ok = ok && need(a->item, "item") && need(a->iqx, "iqx") && need(a->iqy, "iqy") && (!d3 || need(a->iqz, "iqz"));
+    }
+    if ((flags & F_BRINK) || (adj && two)) ok = ok && need(a->alpha, "alpha");
+    if (flags & F_KFIELD) ok = ok && need(a->diffusivity, "diffusivity");
+    if (flags & F_HEATEX) ok = ok && need(a->beta, "beta");
+    if (flags & F_MASSFLOW) ok = ok && need(a->dirx, "dirx") && need(a->diry, "diry");
+    return ok ? PL_OK : PL_ERR_ARG;
+}
+
+template <int D, int M> int launch_collide(pl_lattice* f, pl_lattice* g, const CollideParams& P, const int* list, long long count) {
+    if (count == 0) return PL_OK;
+    LAUNCH((k_collide<D, M>), blocks_for(count, 256), 256, f->g, f->current(), g ? g->current() : nullptr, P, list, count);
+    return PL_OK;
+}
+template <int D, int M> int launch_fused(pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, int inverse) {
+    if (f->g.npacked == 0) return PL_OK;
+    LAUNCH((k_fused<D, M>), blocks_for(f->g.npacked, 256), 256, f->g, f->current(), f->other(), g ? g->current() : nullptr, g ? g->other() : nullptr, P, S, inverse);
+    return PL_OK;
+}
+#define MODEL_SWITCH(D, FN, ...)                                                     \
+    switch (model) {                                                                 \
+        case 1: return FN<D, 1>(__VA_ARGS__);                                        \
+        case 2: return FN<D, 2>(__VA_ARGS__);                                        \
+        case 3: return FN<D, 3>(__VA_ARGS__);                                        \
+        case 4: return FN<D, 4>(__VA_ARGS__);                                        \
+        case 5: return FN<D, 5>(__VA_ARGS__);                                        \
+        case 6: return FN<D, 6>(__VA_ARGS__);                                        \
+        case 7: return FN<D, 7>(__VA_ARGS__);                                        \
+        case 8: return FN<D, 8>(__VA_ARGS__);                                        \
+        case 9: return FN<D, 9>(__VA_ARGS__);                                        \
+        case 10: return FN<D, 10>(__VA_ARGS__);                                      \
+        case 11: return FN<D, 11>(__VA_ARGS__);                                      \
+        default: break;                                                              \
+    }
+int dispatch_collide(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, const int* list, long long count) {
+    if (f->kind == PL_D2Q9) {
+        MODEL_SWITCH(2, launch_collide, f, g, P, list, count)
+        if (model == 12) return launch_collide<2, 12>(f, g, P, list, count);
+    } else {
+        MODEL_SWITCH(3, launch_collide, f, g, P, list, count)
+    }
+    return fail(PL_ERR_UNSUPPORTED, "collide: model not available for this lattice");
+}
+int dispatch_fused(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, int inverse) {
+    if (f->kind == PL_D2Q9) {
+        MODEL_SWITCH(2, launch_fused, f, g, P, S, inverse)
+        if (model == 12) return launch_fused<2, 12>(f, g, P, S, inverse);
+    } else {
+        MODEL_SWITCH(3, launch_fused, f, g, P, S, inverse)
+    }
+    return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pl_stream(pl_lattice* l, int inverse) {
+    if (!l) return fail(PL_ERR_ARG, "pl_stream: null");
+    int r = do_stream_all(l, inverse);
+    l->streamed = 1;
+    return r;
+}
+int pl_smooth_corner(pl_lattice* l) {
+    if (!l) return fail(PL_ERR_ARG, "pl_smooth_corner: null");
+    return do_smooth(l);
+}
+
+pl_bc* pl_bc_create(pl_lattice* l, int type, int axis, int coord, int dir, const uint8_t* mask, const double* v0, const double* v1, const double* v2) {
+    if (!l || type < 1 || type > 11 || (dir != -1 && dir != 1) || axis < 0 || axis >= l->kind) { fail(PL_ERR_ARG, "pl_bc_create: bad arguments"); return nullptr; }
+    if (type == PL_BC_AAD_ISET_RHO && l->kind == PL_D3Q15) {
+        fail(PL_ERR_UNSUPPORTED, "pl_bc_create: the reference's D3Q15 AAD::iBoundaryConditionSetRho does not compile (adjointadvection.h:583); D2Q9 only");
+        return nullptr;
+    }
+    pl_bc* bc = new pl_bc();
+    bc->lat = l; bc->type = type; bc->axis = axis; bc->coord = coord; bc->dir = dir;
+    bc->empty = !make_plane(l, axis, coord, dir, bc->pl);
+    if (!bc->empty) {
+        if (!mask) { delete bc; fail(PL_ERR_ARG, "pl_bc_create: mask is required"); return nullptr; }
+        size_t np = (size_t)bc->pl.n1*bc->pl.n2;
+        bool any = false;
+        for (size_t t = 0; t < np; ++t) any = any || mask[t] != 0;
+        if (!any) bc->empty = true;
+        else {
+            auto up8 = [&](const uint8_t* h) -> uint8_t* { uint8_t* d = nullptr; if (cudaMalloc(&d, np) != cudaSuccess) return nullptr; cudaMemcpy(d, h, np, cudaMemcpyHostToDevice); return d; };
+            auto upd = [&](const double* h) -> double* { if (!h) return nullptr; double* d = nullptr; if (cudaMalloc(&d, np*sizeof(double)) != cudaSuccess) return nullptr; cudaMemcpy(d, h, np*sizeof(double), cudaMemcpyHostToDevice); return d; };
+            bc->mask = up8(mask); bc->v0 = upd(v0); bc->v1 = upd(v1); bc->v2 = upd(v2);
+            if (!bc->mask || (v0 && !bc->v0) || (v1 && !bc->v1) || (v2 && !bc->v2)) { pl_bc_destroy(bc); fail(PL_ERR_CUDA, "pl_bc_create: device allocation failed"); return nullptr; }
+        }
+    }
+    return bc;
+}
+int pl_bc_destroy(pl_bc* bc) {
+    if (!bc) return PL_OK;
+    cudaStreamSynchronize(g_stream);
+    cudaFree(bc->mask); cudaFree(bc->v0); cudaFree(bc->v1); cudaFree(bc->v2);
+    delete bc;
+    return PL_OK;
+}
+int pl_bc_is_empty(const pl_bc* bc) { return bc ? (bc->empty ? 1 : 0) : 1; }
+int pl_bc_apply(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* aux) {
+    if (!l || !bc) return fail(PL_ERR_ARG, "pl_bc_apply: null");
+    return do_bc(l, other, bc, aux);
+}
+
+int pl_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* a) {
+    CollideParams P; unsigned flags;
+    int r = make_params(f, g, a, P, flags);
+    if (r) return r;
+    if (!(flags & F_G)) g = nullptr;
+    r = dispatch_collide(a->model, f, g, P, nullptr, f->g.nxyz);
+    if (r) return r;
+    f->streamed = 0; if (g) g->streamed = 0;
+    return PL_OK;
+}
+
+int pl_snapshot_to_host(const pl_lattice* l, const double* snap, double* out) {
+    if (!l || !snap || !out) return fail(PL_ERR_ARG, "pl_snapshot_to_host: null");
+    size_t n = (size_t)l->g.nxyz*l->nc;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, n*sizeof(double)));
+    if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_to_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, l->g.pitch, d);
+    else LAUNCH(k_snapshot_to_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, l->g.pitch, d);
+    CU(cudaMemcpyAsync(out, d, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(d);
+    return PL_OK;
+}
+
+int pl_initial_condition(pl_lattice* l, int family, const double* const* a, int na) {
+    if (!l || !a || family < 1 || family > 4) return fail(PL_ERR_ARG, "pl_initial_condition: bad arguments");
+    const int want = family <= 2 ? 4 : 7;
+    if (na < want) return fail(PL_ERR_ARG, "pl_initial_condition: too few arrays");
+    const double* p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int n = 0; n < want; ++n) p[n] = a[n];
+    const bool d3 = l->kind == PL_D3Q15;
+    // z-components may be null on D2Q9
+    for (int n = 0; n < want; ++n) {
+        bool zslot = family <= 2 ? n == 3 : (n == 2 || n == 6);
+        if (!p[n] && !(zslot && !d3)) return fail(PL_ERR_ARG, "pl_initial_condition: null array");
+    }
+    if (d3) LAUNCH(k_init<3>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), family, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+    else LAUNCH(k_init<2>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), family, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+    l->streamed = 1;
+    return PL_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// plans
+struct PlanBC { int on_g; const pl_bc* bc; pl_bc_aux aux[2]; bool has_aux; };
+struct pl_plan {
+    pl_lattice *f, *g;
+    pl_collide_args args[2];
+    bool have_collide = false;
+    int inverse = 0;
+    std::vector<PlanBC> bcs;
+    int smooth_f = 0, smooth_g = 0;
+    bool finalized = false;
+    int parity = 0;
+    // shell
+    uint8_t *mx = nullptr, *my = nullptr, *mz = nullptr;
+    int* list = nullptr;
+    int nlist = 0;
+    // measurement hook
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+    long long profiled_sites = 0;
+};
+
+namespace {
+int plan_stream_bc_smooth_full(pl_plan* p, int parity) {     // standalone S: every site
+    int r;
+    if ((r = do_stream_all(p->f, p->inverse))) return r;
+    if (p->g && (r = do_stream_all(p->g, p->inverse))) return r;
+    for (auto& b : p->bcs) {
+        pl_lattice* l = b.on_g ? p->g : p->f;
+        pl_lattice* o = b.bc->type == PL_BC_AAD_ISET_RHO ? p->g : nullptr;
+        if ((r = do_bc(l, o, b.bc, b.has_aux ? &b.aux[parity] : nullptr))) return r;
+    }
+    if (p->smooth_f && (r = do_smooth(p->f))) return r;
+    if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
+    p->f->streamed = 1; if (p->g) p->g->streamed = 1;
+    return PL_OK;
+}
+int plan_collide_full(pl_plan* p, int parity) {              // standalone C: every site, in place
+    CollideParams P; unsigned flags;
+    int r = make_params(p->f, p->g, &p->args[parity], P, flags);
+    if (r) return r;
+    pl_lattice* g = (flags & F_G) ? p->g : nullptr;
+    if ((r = dispatch_collide(p->args[parity].model, p->f, g, P, nullptr, p->f->g.nxyz))) return r;
+    p->f->streamed = 0; if (p->g) p->g->streamed = 0;
+    return PL_OK;
+}
+// fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1
+int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
+    CollideParams P; unsigned flags;
+    int r = make_params(p->f, p->g, &p->args[col_parity], P, flags);
+    if (r) return r;
+    pl_lattice* g = (flags & F_G) ? p->g : nullptr;
+    ShellMask S{p->mx, p->my, p->mz};
+    // interior: one pass, source -> destination
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (p->profile) {
+        CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+        CU(cudaEventRecord(ev0, g_stream));
+    }
+    if ((r = dispatch_fused(p->args[col_parity].model, p->f, g, P, S, p->inverse))) return r;
+    if (p->profile) {
+        CU(cudaEventRecord(ev1, g_stream));
+        p->events.emplace_back(ev0, ev1);
+        p->profiled_sites += p->f->g.nxyz - p->nlist;
+    }
+    // shell: stream the listed sites, then closures / SmoothCorner / collide in place on the destination
+    if ((r = do_stream_list(p->f, p->inverse, p->list, p->nlist))) return r;
+    if (p->g && (r = do_stream_list(p->g, p->inverse, p->list, p->nlist))) return r;
+    p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
+    for (auto& b : p->bcs) {
+        pl_lattice* l = b.on_g ? p->g : p->f;
+        pl_lattice* o = b.bc->type == PL_BC_AAD_ISET_RHO ? p->g : nullptr;
+        if ((r = do_bc(l, o, b.bc, b.has_aux ? &b.aux[bc_parity] : nullptr))) return r;
+    }
+    if (p->smooth_f && (r = do_smooth(p->f))) return r;
+    if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
+    if ((r = dispatch_collide(p->args[col_parity].model, p->f, g, P, p->list, p->nlist))) return r;
+    p->f->streamed = 0; if (p->g) p->g->streamed = 0;
+    return PL_OK;
+}
+}  // namespace
+
+extern "C" {
+
+pl_plan* pl_plan_create(pl_lattice* f, pl_lattice* g) {
+    if (!f) { fail(PL_ERR_ARG, "pl_plan_create: null lattice"); return nullptr; }
+    if (g && (g->kind != f->kind || g->g.nxyz != f->g.nxyz || g->g.nx != f->g.nx || g->g.ny != f->g.ny)) { fail(PL_ERR_ARG, "pl_plan_create: lattices differ in shape"); return nullptr; }
+    pl_plan* p = new pl_plan();
+    p->f = f; p->g = g;
+    return p;
+}
+int pl_plan_destroy(pl_plan* p) {
+    if (!p) return PL_OK;
+    cudaStreamSynchronize(g_stream);
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list);
+    delete p;
+    return PL_OK;
+}
+int pl_plan_set_collide(pl_plan* p, const pl_collide_args* even, const pl_collide_args* odd) {
+    if (!p || !even) return fail(PL_ERR_ARG, "pl_plan_set_collide: null");
+    p->args[0] = *even; p->args[1] = odd ? *odd : *even;
+    if (p->args[0].model != p->args[1].model) return fail(PL_ERR_ARG, "pl_plan_set_collide: the two argument sets must use the same model");
+    p->have_collide = true;
+    return PL_OK;
+}
+int pl_plan_set_stream(pl_plan* p, int inverse) { if (!p) return fail(PL_ERR_ARG, "null plan"); p->inverse = inverse ? 1 : 0; return PL_OK; }
+int pl_plan_add_bc(pl_plan* p, int on_g, const pl_bc* bc, const pl_bc_aux* even, const pl_bc_aux* odd) {
+    if (!p || !bc) return fail(PL_ERR_ARG, "pl_plan_add_bc: null");
+    if (p->finalized) return fail(PL_ERR_ARG, "pl_plan_add_bc: plan already finalized");
+    if (on_g && !p->g) return fail(PL_ERR_ARG, "pl_plan_add_bc: plan has no thermal lattice");
+    PlanBC b{};
+    b.on_g = on_g ? 1 : 0; b.bc = bc; b.has_aux = even != nullptr;
+    if (even) { b.aux[0] = *even; b.aux[1] = odd ? *odd : *even; }
+    p->bcs.push_back(b);
+    return PL_OK;
+}
+int pl_plan_set_smooth_corner(pl_plan* p, int on_f, int on_g) {
+    if (!p) return fail(PL_ERR_ARG, "null plan");
+    if (p->finalized) return fail(PL_ERR_ARG, "pl_plan_set_smooth_corner: plan already finalized");
+    p->smooth_f = on_f; p->smooth_g = on_g;
+    return PL_OK;
+}
+int pl_plan_finalize(pl_plan* p) {
+    if (!p || !p->have_collide) return fail(PL_ERR_ARG, "pl_plan_finalize: no collide set");
+    const Geom& g = p->f->g;
+    std::vector<uint8_t> hx(g.nx, 0), hy(g.ny, 0), hz(g.nz, 0);
+    std::vector<uint8_t>* h[3] = {&hx, &hy, &hz};
+    int off[3] = {g.offx, g.offy, g.offz}, n[3] = {g.nx, g.ny, g.nz}, ext[3] = {g.lx, g.ly, g.lz};
+    for (auto& b : p->bcs) if (!b.bc->empty) (*h[b.bc->axis])[b.bc->coord - off[b.bc->axis]] = 1;
+    if (p->smooth_f || p->smooth_g) {
+        for (int a = 0; a < p->f->kind; ++a) {
+            int lo = 0 - off[a], hi = ext[a] - 1 - off[a];
+            if (0 <= lo && lo < n[a]) (*h[a])[lo] = 1;
+            if (0 <= hi && hi < n[a]) (*h[a])[hi] = 1;
+        }
+    }
+    std::vector<int> list;
+    for (int k = 0; k < g.nz; ++k)
+        for (int j = 0; j < g.ny; ++j) {
+            if (hy[j] || hz[k]) { for (int i = 0; i < g.nx; ++i) list.push_back(i + g.nx*(j + g.ny*k)); }
+            else { for (int i = 0; i < g.nx; ++i) if (hx[i]) list.push_back(i + g.nx*(j + g.ny*k)); }
+        }
+    // tail sites always go through the list so that the interior kernel only ever runs the packed operation order
+    for (long long idx = g.npacked; idx < g.nxyz; ++idx) {
+        int k = (int)(idx/((long long)g.nx*g.ny)), r = (int)(idx - (long long)k*g.nx*g.ny), j = r/g.nx, i = r - j*g.nx;
+        if (!(hx[i] || hy[j] || hz[k])) list.push_back((int)idx);
+    }
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list);
+    p->mx = p->my = p->mz = nullptr; p->list = nullptr;
+    CU(cudaMalloc(&p->mx, g.nx)); CU(cudaMalloc(&p->my, g.ny)); CU(cudaMalloc(&p->mz, g.nz));
+    CU(cudaMemcpy(p->mx, hx.data(), g.nx, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->my, hy.data(), g.ny, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->mz, hz.data(), g.nz, cudaMemcpyHostToDevice));
+    p->nlist = (int)list.size();
+    if (p->nlist) {
+        CU(cudaMalloc(&p->list, list.size()*sizeof(int)));
+        CU(cudaMemcpy(p->list, list.data(), list.size()*sizeof(int), cudaMemcpyHostToDevice));
+    }
+    p->finalized = true;
+    return PL_OK;
+}
+int pl_plan_parity(const pl_plan* p) { return p ? p->parity : 0; }
+int pl_plan_profile(pl_plan* p, int enable) { if (!p) return fail(PL_ERR_ARG, "null plan"); p->profile = enable != 0; return PL_OK; }
+int pl_plan_profile_read(pl_plan* p, double* total_ms, int* launches, long long* total_sites) {
+    if (!p) return fail(PL_ERR_ARG, "null plan");
+    CU(cudaStreamSynchronize(g_stream));
+    double ms = 0.0;
+    for (auto& e : p->events) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, e.first, e.second));
+        ms += t;
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (int)p->events.size();
+    if (total_sites) *total_sites = p->profiled_sites;
+    p->events.clear(); p->profiled_sites = 0;
+    return PL_OK;
+}
+
+int pl_plan_advance(pl_plan* p, int ncollides, int end_streamed) {
+    if (!p || !p->finalized) return fail(PL_ERR_ARG, "pl_plan_advance: plan not finalized");
+    if (ncollides < 0) return fail(PL_ERR_ARG, "pl_plan_advance: negative count");
+    int r;
+    int done = 0;
+    // The argument set of step t serves its collide and the closures that follow it (they read the velocities that
+    // collide saved, production/heatsink3D.cpp:164-173); the driver swaps sets after the closures (:178-183).
+    if (ncollides > 0 && p->f->streamed) {
+        if ((r = plan_collide_full(p, p->parity))) return r;
+        done = 1;
+    }
+    while (done < ncollides) {
+        // state: just collided with set `parity`; fuse S(parity) with C(parity^1)
+        if ((r = plan_fused(p, p->parity, p->parity ^ 1))) return r;
+        p->parity ^= 1;
+        ++done;
+    }
+    if (end_streamed && !p->f->streamed) {
+        if ((r = plan_stream_bc_smooth_full(p, p->parity))) return r;
+        p->parity ^= 1;
+    }
+    return PL_OK;
+}
+
+// ---- reductions ---------------------------------------------------------------------------------
+int pl_residual(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, size_t n, double* out) {
+    if (!ux || !uxp || !out) return fail(PL_ERR_ARG, "pl_residual: null");
+    double* scratch = nullptr;
+    const int nb = 1024;
+    CU(cudaMalloc(&scratch, 2*(nb + 1)*sizeof(double)));
+    LAUNCH(k_residual_partial, nb, 256, ux, uy, uz, uxp, uyp, uzp, (long long)n, scratch);
+    LAUNCH(k_sum_final, 1, 256, scratch, nb, 2, scratch + 2*nb);
+    double h[2];
+    CU(cudaMemcpyAsync(h, scratch + 2*nb, 2*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(scratch);
+    *out = sqrt(h[0]/h[1]);
+    return PL_OK;
+}
+int pl_reduce_sum(const double* v, size_t n, double* out) {
+    if (!v || !out) return fail(PL_ERR_ARG, "pl_reduce_sum: null");
+    double* scratch = nullptr;
+    const int nb = 1024;
+    CU(cudaMalloc(&scratch, (nb + 1)*sizeof(double)));
+    LAUNCH(k_sum_partial, nb, 256, v, (long long)n, scratch);
+    LAUNCH(k_sum_final, 1, 256, scratch, nb, 1, scratch + nb);
+    CU(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(scratch);
+    return PL_OK;
+}
+int pl_reduce_absmax(const double* v, size_t n, double* out) {
+    if (!v || !out) return fail(PL_ERR_ARG, "pl_reduce_absmax: null");
+    double* scratch = nullptr;
+    const int nb = 1024;
+    CU(cudaMalloc(&scratch, (nb + 1)*sizeof(double)));
+    LAUNCH(k_absmax_partial, nb, 256, v, (long long)n, scratch);
+    LAUNCH(k_absmax_final, 1, 256, scratch, nb, scratch + nb);
+    CU(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(scratch);
+    return PL_OK;
+}
+int pl_normalize(double* v, size_t n) {
+    double m = 0.0;
+    int r = pl_reduce_absmax(v, n, &m);
+    if (r) return r;
+    LAUNCH(k_divide, blocks_for((long long)n, 256), 256, v, m, (long long)n);
+    return PL_OK;
+}
+
+int pl_sensitivity(pl_lattice*, const pl_sens_args*) { return fail(PL_ERR_UNSUPPORTED, "pl_sensitivity: not implemented yet"); }
+int pl_sensitivity_heat_source_plane(pl_lattice*, int, int, int, const uint8_t*, const double*, double*, const double*, const double*, const double*,
+                                     const double*, const double*, const double*) {
+    return fail(PL_ERR_UNSUPPORTED, "pl_sensitivity_heat_source_plane: not implemented yet");
+}
+
+}  // extern "C"
