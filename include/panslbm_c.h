@@ -139,7 +139,8 @@ typedef struct pl_collide_args {
     /* adjoint macros: outputs of models 8-12 (written when issave) */
     double *ip, *iux, *iuy, *iuz, *imx, *imy, *imz, *item, *iqx, *iqy, *iqz;
     /* optional snapshot of the thermal populations before relaxation (`_g` / `_ig`, advection_avx.h:1047-1052):
-     * device buffer of nc*nxyz doubles, SoA [c][nxyz]; opaque to callers exactly as in the reference. */
+     * device buffer of nc*nxyz doubles (the size the drivers allocate, production/heatsink3D.cpp:59), stored SoA
+     * [c][nxyz]; opaque to callers exactly as in the reference. */
     double *snapshot;
 } pl_collide_args;
 /* f = flow lattice (or the only lattice), g = thermal lattice (NULL for models 1,2,8). */

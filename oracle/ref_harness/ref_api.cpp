@@ -230,7 +230,7 @@ void ref_aad_macro_brinkman_collide_natural_convection_massflow(void* hf, const 
 // undeclared `_bctype` (adjointadvection.h:583,642,701).
 void ref_aad_ibc_set_rho(void* hf, void* hg, const double* rho, const double* ux, const double* uy, const double* tem, const int* mask, double eps) {
     GDEF(L(hf));
-    AAD::iBoundaryConditionSetRho(*L(hf)->p, *L(hg)->p, rho, ux, uy, tem, FM(mask), eps);
+    AAD::iBoundaryConditionSetRho(*L(hf)->p, *L(hg)->p, rho, ux, uy, tem, FV(mask), eps);   // 0 / SetT=1 / SetQ=2 (adjointadvection.h:16-17)
 }
 #endif
 void ref_aad_ibc_set_t(void* hg, const double* ux, const double* uy, const double* uz, const int* mask) {

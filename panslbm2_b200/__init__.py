@@ -6,8 +6,8 @@ Python mirror in `panslbm2_b200.api`.  There is no CPU fallback; importing works
 """
 from . import _lib
 from ._lib import PanslbmError
-from .api import (BARRIER, MIRROR, D2Q9, D3Q15, NS, DeviceArray, Normalize, Residual, StepPlan, bc_aux, collide_args,
+from .api import (AAD, AD, ANS, BARRIER, MIRROR, D2Q9, D3Q15, NS, DeviceArray, Normalize, Residual, StepPlan, bc_aux, collide_args,
                   synchronize)
 
-__all__ = ["BARRIER", "MIRROR", "D2Q9", "D3Q15", "NS", "DeviceArray", "Normalize", "Residual", "StepPlan", "bc_aux",
+__all__ = ["AAD", "AD", "ANS", "BARRIER", "MIRROR", "D2Q9", "D3Q15", "NS", "DeviceArray", "Normalize", "Residual", "StepPlan", "bc_aux",
            "collide_args", "synchronize", "PanslbmError"]

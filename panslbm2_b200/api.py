@@ -189,7 +189,7 @@ class _Lattice:
                     raise _lib.PanslbmError(L.pl_last_error().decode())
                 self._bc_cache[key] = h
             return self._bc_cache[key]
-        mask = self._eval(maskfn, coords, np.uint8) if bctype_id in (BC_BOUNCE, BC_IBOUNCE) else \
+        mask = self._eval(maskfn, coords, np.uint8) if bctype_id in (BC_BOUNCE, BC_IBOUNCE, BC_AAD_ISET_RHO) else \
             np.ascontiguousarray(self._eval(maskfn, coords, np.float64) != 0, dtype=np.uint8)
         vals = [self._eval(f, coords, np.float64) if f is not None else None for f in valfns]
         hsh = hashlib.blake2b(mask.tobytes(), digest_size=16)
@@ -340,6 +340,235 @@ class NS:
         # (rhobc, usbc, [utbc,] bctype)
         *vals, mask = fns
         _closure_faces(p, BC_NS_SET_RHO, mask, vals)
+
+
+_ZNAMES = {"uz", "qz", "iuz", "imz", "iqz", "gz", "dirz"}
+
+
+def _bind(p, names3, args, defaults=None):
+    """map the reference's positional argument list (3-D names; the z entries do not exist for D2Q9) to a dict"""
+    names = names3 if p.nd == 3 else [n for n in names3 if n not in _ZNAMES]
+    if len(args) > len(names):
+        raise TypeError(f"too many arguments: expected at most {len(names)} ({names})")
+    kw = dict(defaults or {})
+    kw.update(zip(names, args))
+    missing = [n for n in names if n not in kw]
+    if missing:
+        raise TypeError(f"missing arguments {missing}")
+    return kw
+
+
+_SCALARS = ("viscosity", "diffusivity_const", "gx", "gy", "gz", "tem0", "issave")
+
+
+def _collide_kw(model, p, q, kw):
+    sc = {k: kw.pop(k) for k in list(kw) if k in _SCALARS}
+    kw = {k: v for k, v in kw.items() if v is not None}
+    _collide(p, q, collide_args(model, sc.pop("issave", False), sc.pop("viscosity"), **sc, **kw))
+
+
+_F = ["rho", "ux", "uy", "uz"]
+_Q = ["tem", "qx", "qy", "qz"]
+_A = ["ip", "iux", "iuy", "iuz", "imx", "imy", "imz"]
+_IQ = ["item", "iqx", "iqy", "iqz"]
+
+
+class AD:
+    """src/equation/advection.h + src/equation_avx/advection_avx.h — thermal lattice q next to the flow lattice p"""
+
+    @staticmethod
+    def InitialCondition(q, tem, ux, uy, uz=None):
+        _init(q, 2, [tem, ux, uy, uz])
+
+    @staticmethod
+    def MacroCollideForceConvection(p, *args):
+        # (rho,u..,viscosity, q, tem,q..,diffusivity, issave=False)
+        n = 5 if p.nd == 3 else 4
+        kw = _bind(p, _F + ["viscosity"], args[:n]); q = args[n]
+        kw.update(_bind(p, _Q + ["diffusivity_const", "issave"], args[n + 1:], {"issave": False}))
+        _collide_kw(M_AD_FORCE_CONV, p, q, kw)
+
+    @staticmethod
+    def MacroCollideNaturalConvection(p, *args):
+        # (rho,u..,viscosity, q, tem,q..,diffusivity, gx,gy[,gz], tem0, issave=False)
+        n = 5 if p.nd == 3 else 4
+        kw = _bind(p, _F + ["viscosity"], args[:n]); q = args[n]
+        kw.update(_bind(p, _Q + ["diffusivity_const", "gx", "gy", "gz", "tem0", "issave"], args[n + 1:], {"issave": False}))
+        _collide_kw(M_AD_NAT_CONV, p, q, kw)
+
+    @staticmethod
+    def MacroBrinkmanCollideHeatExchange(p, *args):
+        # (rho,u..,alpha,viscosity, q, tem,q..,beta,diffusivity, issave=False)
+        n = 6 if p.nd == 3 else 5
+        kw = _bind(p, _F + ["alpha", "viscosity"], args[:n]); q = args[n]
+        kw.update(_bind(p, _Q + ["beta", "diffusivity_const", "issave"], args[n + 1:], {"issave": False}))
+        _collide_kw(M_AD_BRINKMAN_HEATEX, p, q, kw)
+
+    @staticmethod
+    def MacroBrinkmanCollideForceConvection(p, *args):
+        # (rho,u..,alpha,viscosity, q, tem,q..,diffusivity[], issave=False, g=None)
+        n = 6 if p.nd == 3 else 5
+        kw = _bind(p, _F + ["alpha", "viscosity"], args[:n]); q = args[n]
+        kw.update(_bind(p, _Q + ["diffusivity", "issave", "snapshot"], args[n + 1:], {"issave": False, "snapshot": None}))
+        _collide_kw(M_AD_BRINKMAN_FORCE_CONV, p, q, kw)
+
+    @staticmethod
+    def MacroBrinkmanCollideNaturalConvection(p, *args):
+        # (rho,u..,alpha,viscosity, q, tem,q..,diffusivity[], gx,gy[,gz], tem0, issave=False, g=None)   advection_avx.h:1001
+        n = 6 if p.nd == 3 else 5
+        kw = _bind(p, _F + ["alpha", "viscosity"], args[:n]); q = args[n]
+        kw.update(_bind(p, _Q + ["diffusivity", "gx", "gy", "gz", "tem0", "issave", "snapshot"], args[n + 1:], {"issave": False, "snapshot": None}))
+        _collide_kw(M_AD_BRINKMAN_NAT_CONV, p, q, kw)
+
+    @staticmethod
+    def BoundaryConditionSetT(q, tembc, *args):
+        # (tembc, ux, uy, [uz,] bctype)   advection.h:1074-1090
+        *u, mask = args
+        _closure_faces(q, BC_AD_SET_T, mask, [tembc], bc_aux(ux=u[0], uy=u[1], uz=u[2] if q.nd == 3 else None))
+
+    @staticmethod
+    def BoundaryConditionSetQ(q, qnbc, *args):
+        # (qnbc, ux, uy, [uz,] diffusivity (scalar or per-cell array), bctype)   advection.h:1094-1130
+        *u, k, mask = args
+        kf, kc = (None, float(k)) if isinstance(k, (int, float)) else (k, 0.0)
+        _closure_faces(q, BC_AD_SET_Q, mask, [qnbc], bc_aux(ux=u[0], uy=u[1], uz=u[2] if q.nd == 3 else None, diffusivity=kf, diffusivity_const=kc))
+
+
+class ANS:
+    """src/equation/adjointnavierstokes.h + src/equation_avx/adjointnavierstokes_avx.h"""
+
+    @staticmethod
+    def InitialCondition(p, *args):
+        # (ux,uy[,uz], ip, iux,iuy[,iuz])
+        kw = _bind(p, ["ux", "uy", "uz", "ip", "iux", "iuy", "iuz"], args)
+        _init(p, 3, [kw["ux"], kw["uy"], kw.get("uz"), kw["ip"], kw["iux"], kw["iuy"], kw.get("iuz")])
+
+    @staticmethod
+    def MacroBrinkmanCollide(p, *args):
+        # (rho,u.., ip,iu..,im.., viscosity, alpha, issave=False)
+        kw = _bind(p, _F + _A + ["viscosity", "alpha", "issave"], args, {"issave": False})
+        _collide_kw(M_ANS_BRINKMAN, p, None, kw)
+
+    @staticmethod
+    def iBoundaryConditionSetU(p, *fns, eps=0.0):
+        # (uxbc, uybc, [uzbc,] bctype, eps=0)
+        fns = list(fns)
+        if isinstance(fns[-1], (int, float)) and not callable(fns[-1]):
+            eps = float(fns.pop())
+        *vals, mask = fns
+        _closure_faces(p, BC_ANS_ISET_U, mask, vals, bc_aux(eps=eps))
+
+    @staticmethod
+    def iBoundaryConditionSetRho(p, bctype):
+        _closure_faces(p, BC_ANS_ISET_RHO, bctype, [])
+
+    iBoundaryConditionSetRho2D = iBoundaryConditionSetRho
+    iBoundaryConditionSetRho3D = iBoundaryConditionSetRho
+
+    @staticmethod
+    def SensitivityBrinkman(p, dfds, *args):
+        kw = _bind(p, ["ux", "uy", "uz", "imx", "imy", "imz", "dads"], args)
+        _sens(p, 1, dfds, kw)
+
+
+class AAD:
+    """src/equation/adjointadvection.h + src/equation_avx/adjointadvection_avx.h"""
+
+    @staticmethod
+    def InitialCondition(q, *args):
+        # (ux,uy[,uz], item, iqx,iqy[,iqz])
+        kw = _bind(q, ["ux", "uy", "uz", "item", "iqx", "iqy", "iqz"], args)
+        _init(q, 4, [kw["ux"], kw["uy"], kw.get("uz"), kw["item"], kw["iqx"], kw["iqy"], kw.get("iqz")])
+
+    @staticmethod
+    def _two(model, p, args, tail, defaults):
+        n = 13 if p.nd == 3 else 10
+        kw = _bind(p, _F + _A + ["alpha", "viscosity"], args[:n]); q = args[n]
+        kw.update(_bind(p, ["tem"] + _IQ + tail, args[n + 1:], defaults))
+        _collide_kw(model, p, q, kw)
+
+    @staticmethod
+    def MacroBrinkmanCollideHeatExchange(p, *args):
+        # (rho,u.., ip,iu..,im.., alpha,viscosity, q, tem,item,iq.., beta, diffusivity, issave=False)
+        AAD._two(M_AAD_HEATEX, p, args, ["beta", "diffusivity_const", "issave"], {"issave": False})
+
+    @staticmethod
+    def MacroBrinkmanCollideForceConvection(p, *args):
+        AAD._two(M_AAD_FORCE_CONV, p, args, ["diffusivity", "issave", "snapshot"], {"issave": False, "snapshot": None})
+
+    @staticmethod
+    def MacroBrinkmanCollideNaturalConvection(p, *args):
+        # (..., q, tem,item,iq.., diffusivity[], gx,gy[,gz], issave=False, ig=None)   adjointadvection_avx.h:884
+        AAD._two(M_AAD_NAT_CONV, p, args, ["diffusivity", "gx", "gy", "gz", "issave", "snapshot"], {"issave": False, "snapshot": None})
+
+    @staticmethod
+    def MacroBrinkmanCollideNaturalConvectionMassFlow(p, *args):
+        # D2Q9 only: (..., diffusivity[], gx,gy, dirx,diry, issave=False, ig=None)   adjointadvection_avx.h:1009
+        AAD._two(M_AAD_NAT_CONV_MASSFLOW, p, args, ["diffusivity", "gx", "gy", "gz", "dirx", "diry", "dirz", "issave", "snapshot"],
+                 {"issave": False, "snapshot": None})
+
+    @staticmethod
+    def iBoundaryConditionSetT(q, *args):
+        # (ux, uy, [uz,] bctype)
+        *u, mask = args
+        _closure_faces(q, BC_AAD_ISET_T, mask, [], bc_aux(ux=u[0], uy=u[1], uz=u[2] if q.nd == 3 else None))
+
+    @staticmethod
+    def iBoundaryConditionSetQ(q, *args):
+        # (ux, uy, [uz,] bctype, eps=0)
+        args = list(args)
+        eps = float(args.pop()) if isinstance(args[-1], (int, float)) and not callable(args[-1]) else 0.0
+        *u, mask = args
+        _closure_faces(q, BC_AAD_ISET_Q, mask, [], bc_aux(ux=u[0], uy=u[1], uz=u[2] if q.nd == 3 else None, eps=eps))
+
+    @staticmethod
+    def iBoundaryConditionSetRho(p, q, rho, ux, uy, tem, bctype, eps=0.0):
+        # D2Q9 only (adjointadvection.h:1422-1430); bctype returns 0 / SetT=1 / SetQ=2
+        _closure_faces(p, BC_AAD_ISET_RHO, bctype, [], bc_aux(rho=rho, ux=ux, uy=uy, tem=tem, eps=eps), other=q)
+
+    @staticmethod
+    def SensitivityHeatExchange(q, dfds, *args):
+        kw = _bind(q, ["ux", "uy", "uz", "imx", "imy", "imz", "dads", "tem", "item", "dbds"], args)
+        _sens(q, 2, dfds, kw)
+
+    @staticmethod
+    def SensitivityBrinkmanDiffusivity(q, dfds, *args):
+        kw = _bind(q, ["ux", "uy", "uz", "imx", "imy", "imz", "dads", "tem", "item", "iqx", "iqy", "iqz", "gsnap", "igsnap", "diffusivity", "dkds"], args)
+        _sens(q, 3, dfds, kw)
+
+    @staticmethod
+    def SensitivityTemperatureAtHeatSource(q, dfds, *args):
+        # (..., g, ig, diffusivity, dkds, qnbc, bctype)   adjointadvection_avx.h:1403-1513
+        *rest, qnbc, bctype = args
+        kw = _bind(q, ["ux", "uy", "uz", "imx", "imy", "imz", "dads", "tem", "item", "iqx", "iqy", "iqz", "gsnap", "igsnap", "diffusivity", "dkds"], rest)
+        _sens(q, 3, dfds, kw)
+        L = _lib.lib()
+        for axis, coord, d in q._faces():
+            coords = q.plane_coords(axis, coord)
+            if coords is None:
+                continue
+            mask = np.ascontiguousarray(q._eval(bctype, coords, np.float64) != 0, dtype=np.uint8)
+            if not mask.any():
+                continue
+            qn = q._eval(qnbc, coords, np.float64)
+            check(L.pl_sensitivity_heat_source_plane(q._h, axis, coord, d, mask.ctypes.data, qn.ctypes.data, dptr(dfds), dptr(kw["ux"]), dptr(kw["uy"]),
+                                                     dptr(kw.get("uz")), dptr(kw["igsnap"]), dptr(kw["diffusivity"]), dptr(kw["dkds"])))
+
+
+def _sens(p, kind, dfds, kw):
+    a = SensArgs()
+    a.kind = kind
+    a.dfds = dptr(dfds)
+    for k, v in kw.items():
+        setattr(a, k, dptr(v))
+    check(_lib.lib().pl_sensitivity(p._h, C.byref(a)))
+
+
+def snapshot_to_host(p, snap):
+    """device snapshot (SoA) -> the reference's host layout of `_g` / `_ig` (parity tests only)"""
+    out = np.empty(p.nxyz*p.nc)
+    check(_lib.lib().pl_snapshot_to_host(p._h, dptr(snap), out.ctypes.data))
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -334,7 +334,12 @@ PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Col
         if constexpr (G && (FL & (F_HEATEX | F_NATCONV)) != 0) aad_macro<D>(g, item, iqx, iqy, iqz);
         if (P.issave) {
             P.ip[idx] = ip; P.iux[idx] = iux; P.iuy[idx] = iuy; P.imx[idx] = imx; P.imy[idx] = imy;
-            if constexpr (D == 3) { P.iuz[idx] = iuz; P.imz[idx] = imz; }
+            if constexpr (D == 3) {
+                // quirk: the 3-D scalar tail of AAD::MacroBrinkmanCollideForceConvection does not store _iuz (adjointadvection_avx.h:725-735)
+                constexpr bool skip_iuz = SC && FL == ModelFlags<10>::v;
+                if constexpr (!skip_iuz) P.iuz[idx] = iuz;
+                P.imz[idx] = imz;
+            }
             if constexpr (G) {
                 P.item[idx] = item; P.iqx[idx] = iqx; P.iqy[idx] = iqy;
                 if constexpr (D == 3) P.iqz[idx] = iqz;

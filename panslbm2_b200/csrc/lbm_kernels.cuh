@@ -2,7 +2,7 @@
 // bounce-back / specular planes, SmoothCorner, layout conversion.  fp64 SoA: population c of site idx lives at
 // base[c*pitch + idx], idx = i + nx*(j + ny*k)  (same site order as the reference, d3q15.h:136-141).
 #pragma once
-#include "lbm_equations.cuh"
+#include "lbm_sens.cuh"
 
 namespace plb {
 
@@ -70,22 +70,6 @@ __global__ void __launch_bounds__(256) k_stream(Geom G, const double* __restrict
     pull<D>(f, src, G.pitch, idx, n);
     store_site<D>(f, dst, G.pitch, idx);
 }
-// the same for a list of sites (shell of a fused step)
-template <int D>
-__global__ void __launch_bounds__(256) k_stream_list(Geom G, const double* __restrict__ src, double* __restrict__ dst, int inverse,
-                                                     const int* __restrict__ list, int nlist) {
-    int t = blockIdx.x*blockDim.x + threadIdx.x;
-    if (t >= nlist) return;
-    long long idx = list[t];
-    int i, j, k;
-    decompose(G, idx, i, j, k);
-    Nbr n = neighbours(G, i, j, k);
-    orient(n, inverse);
-    double f[LT<D>::nc];
-    pull<D>(f, src, G.pitch, idx, n);
-    store_site<D>(f, dst, G.pitch, idx);
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // In-place Macro*Collide* over all sites (list == nullptr) or over a site list.  Tail sites
 // (idx >= 4*(nxyz/4)) take the scalar operation order exactly as the reference does (navierstokes_avx.h:180-200).
@@ -108,7 +92,7 @@ __global__ void __launch_bounds__(256) k_collide(Geom G, double* __restrict__ fb
 // ---------------------------------------------------------------------------------------------------------
 // The hot kernel: one fused Stream + Macro*Collide* pass, source buffer -> destination buffer, for every
 // packed site that is not in the shell (shell = planes carrying closures / SmoothCorner, handled by the
-// plane kernels around k_stream_list and k_collide).  Each population is read once and written once.
+// boundary pass k_shell).  Each population is read once and written once.
 template <int D, int M>
 __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
                                                const double* __restrict__ gs, double* __restrict__ gd,
@@ -137,32 +121,100 @@ struct Plane {
     long long base, s1, s2; // index of plane site (0,0) and the strides of the in-plane axes
 };
 
-// BARRIER / MIRROR (d3q15.h:984-1239, d2q9.h:431-575): forward rebuilds the populations entering the
-// domain (c_axis == -dir) from their opposite (BARRIER=1) or mirror image (MIRROR=2); inverse the leaving ones.
+// Arguments of one plane closure launch (k_closure) / one entry of a plan's closure program (k_shell).
+struct ClosureArgs {
+    int type;                      // BC_* (PL_BC_* of the C-ABI)
+    int on_g;                      // program entries only: 0 = acts on the flow lattice, 1 = on the thermal lattice
+    int loc;                       // program entries only: local coordinate of the plane along its axis
+    Plane pl;
+    const uint8_t* mask;           // per plane site
+    const double *v0, *v1, *v2;    // per plane site values
+    const double *rho, *ux, *uy, *uz, *tem, *kappa;   // per lattice site fields (device, may be null)
+    double kconst, eps;
+};
+PL_D SiteVals site_vals(const ClosureArgs& A, int t, long long idx) {
+    SiteVals V;
+    V.v0 = A.v0 ? A.v0[t] : 0.0; V.v1 = A.v1 ? A.v1[t] : 0.0; V.v2 = A.v2 ? A.v2[t] : 0.0;
+    V.rho = A.rho ? A.rho[idx] : 0.0; V.ux = A.ux ? A.ux[idx] : 0.0; V.uy = A.uy ? A.uy[idx] : 0.0; V.uz = A.uz ? A.uz[idx] : 0.0;
+    V.tem = A.tem ? A.tem[idx] : 0.0;
+    V.kappa = A.kappa ? A.kappa[idx] : A.kconst;
+    V.eps = A.eps;
+    return V;
+}
+
+// One closure on one plane, in place (the call-by-call path: P::BoundaryConditionAlong*, NS::BoundaryConditionSetU, ...).
+// pb = populations of the lattice the closure acts on, qb = the other lattice (BC_AAD_ISET_RHO only, else null).
 template <int D>
-__global__ void __launch_bounds__(128) k_bounce(Geom G, double* __restrict__ fb, Plane pl, const uint8_t* __restrict__ mask, int inverse) {
+__global__ void __launch_bounds__(128) k_closure(Geom G, double* __restrict__ pb, const double* __restrict__ qb, ClosureArgs A) {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
-    if (t >= pl.n1*pl.n2) return;
-    int type = mask[t];
-    if (type != 1 && type != 2) return;
-    int a = t%pl.n1, b = t/pl.n1;
-    long long idx = pl.base + a*pl.s1 + b*pl.s2;
-    int want = inverse ? pl.dir : -pl.dir;
-    double v[LT<D>::nc];
+    if (t >= A.pl.n1*A.pl.n2) return;
+    const int m = A.mask[t];
+    if (!m) return;
+    int a = t%A.pl.n1, b = t/A.pl.n1;
+    long long idx = A.pl.base + a*A.pl.s1 + b*A.pl.s2;
+    double p[LT<D>::nc], q[LT<D>::nc];
     #pragma unroll
-    for (int c = 1; c < LT<D>::nc; ++c) v[c] = fb[(size_t)c*G.pitch + idx];
+    for (int c = 0; c < LT<D>::nc; ++c) { p[c] = pb[(size_t)c*G.pitch + idx]; q[c] = qb ? qb[(size_t)c*G.pitch + idx] : 0.0; }
+    apply_closure<D>(A.type, A.pl.axis, A.pl.dir, m, p, q, site_vals(A, t, idx));
     #pragma unroll
-    for (int c = 1; c < LT<D>::nc; ++c) {
-        if (cdir<D>(c, pl.axis) != want) continue;
-        int src;
-        if (type == 1) src = LT<D>::opp(c);
-        else {
-            int x = LT<D>::cx(c), y = LT<D>::cy(c), z = LT<D>::cz(c);
-            if (pl.axis == 0) x = -x; else if (pl.axis == 1) y = -y; else z = -z;
-            src = find_dir<D>(x, y, z);
-        }
-        fb[(size_t)c*G.pitch + idx] = v[src];
+    for (int c = 1; c < LT<D>::nc; ++c) pb[(size_t)c*G.pitch + idx] = p[c];
+}
+
+// heat-source boundary term of AAD::SensitivityTemperatureAtHeatSource on one plane (adjointadvection_avx.h:16-185);
+// A.v0 = qn, A.ux/uy/uz/kappa = fields; igsnap = adjoint thermal snapshot (SoA [c][nxyz]).
+template <int D>
+__global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A, const double* __restrict__ igsnap, const double* __restrict__ dkds,
+                                                          double* __restrict__ dfds) {
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= A.pl.n1*A.pl.n2) return;
+    if (!A.mask[t]) return;
+    int a = t%A.pl.n1, b = t/A.pl.n1;
+    long long idx = A.pl.base + a*A.pl.s1 + b*A.pl.s2;
+    double ig[LT<D>::nc];
+    #pragma unroll
+    for (int c = 0; c < LT<D>::nc; ++c) ig[c] = igsnap[(size_t)c*(size_t)G.nxyz + idx];
+    dfds[idx] = dfds[idx] + sens_heat_source_term<D>(ig, A.pl.axis, A.pl.dir, site_vals(A, t, idx), dkds[idx]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The boundary pass of a fused step: one thread per listed site does Stream (pull from the source buffers), the plan's
+// closure program in call order on the register copy, and then either the collide of the next step (t < ndirect) or,
+// for the sites SmoothCorner reads or writes (t >= ndirect), a plain store of the streamed+closed populations; those
+// few sites are finished by k_smooth + k_collide on the destination buffer.
+template <int D, int M>
+__global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
+                                               const double* __restrict__ gs, double* __restrict__ gd, CollideParams P,
+                                               const ClosureArgs* __restrict__ prog, int nprog,
+                                               const int* __restrict__ list, int nlist, int ndirect, int inverse) {
+    constexpr unsigned FL = ModelFlags<M>::v;
+    constexpr bool HASG = (FL & F_G) != 0;
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= nlist) return;
+    const long long idx = list[t];
+    int co[3];
+    decompose(G, idx, co[0], co[1], co[2]);
+    Nbr n = neighbours(G, co[0], co[1], co[2]);
+    orient(n, inverse);
+    double f[LT<D>::nc], g[LT<D>::nc];
+    pull<D>(f, fs, G.pitch, idx, n);
+    if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
+    else { for (int c = 0; c < LT<D>::nc; ++c) g[c] = 0.0; }
+    for (int e = 0; e < nprog; ++e) {
+        const ClosureArgs& A = prog[e];
+        if (co[A.pl.axis] != A.loc) continue;
+        const int a1 = A.pl.axis == 0 ? 1 : 0, a2 = A.pl.axis == 2 ? 1 : 2;
+        const int pt = co[a1] + A.pl.n1*(D == 2 ? 0 : co[a2]);
+        const int m = A.mask[pt];
+        if (!m) continue;
+        if (A.on_g) { if constexpr (HASG) apply_closure<D>(A.type, A.pl.axis, A.pl.dir, m, g, f, site_vals(A, pt, idx)); }
+        else apply_closure<D>(A.type, A.pl.axis, A.pl.dir, m, f, g, site_vals(A, pt, idx));
     }
+    if (t < ndirect) {
+        if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
+        else collide_site<D, FL, true>(f, g, P, (size_t)idx);
+    }
+    store_site<D>(f, fd, G.pitch, idx);
+    if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
 }
 
 // SmoothCorner (d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587).  A line/point list is built on the host.

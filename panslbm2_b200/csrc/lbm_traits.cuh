@@ -5,8 +5,16 @@
 #include <cstdint>
 #include <type_traits>
 
+// The site-local math (this header, lbm_equations.cuh, lbm_closures.cuh, lbm_sens.cuh) also compiles as plain
+// host C++ (tests/hostmath: the not-gpu suite checks the arithmetic of the product code against the reference
+// build); kernels are guarded by __CUDACC__.
+#ifdef __CUDACC__
 #define PL_HD __host__ __device__ __forceinline__
 #define PL_D __device__ __forceinline__
+#else
+#define PL_HD inline
+#define PL_D inline
+#endif
 
 namespace plb {
 

@@ -1,7 +1,7 @@
 // C-ABI of libpanslbm_b200.so (see include/panslbm_c.h).  Host-side orchestration only: every numerical
 // operation is a CUDA kernel from lbm_kernels.cuh / lbm_closures.cuh / lbm_reduce.cuh.  No CPU fallback.
 #include "../../include/panslbm_c.h"
-#include "lbm_closures.cuh"
+#include "lbm_kernels.cuh"
 #include "lbm_reduce.cuh"
 
 #include <cuda_runtime.h>
@@ -203,13 +203,6 @@ int do_stream_all(pl_lattice* l, int inverse) {
     l->cur ^= 1;
     return PL_OK;
 }
-int do_stream_list(pl_lattice* l, int inverse, const int* list, int n) {   // does NOT flip
-    if (n == 0) return PL_OK;
-    if (l->kind == PL_D2Q9) LAUNCH(k_stream_list<2>, blocks_for(n, 256), 256, l->g, l->current(), l->other(), inverse, list, n);
-    else LAUNCH(k_stream_list<3>, blocks_for(n, 256), 256, l->g, l->current(), l->other(), inverse, list, n);
-    return PL_OK;
-}
-
 // the local sites of the global plane axis=coord
 bool make_plane(const pl_lattice* l, int axis, int coord, int dir, Plane& pl) {
     const Geom& g = l->g;
@@ -297,37 +290,57 @@ int do_smooth(pl_lattice* l) {
     return PL_OK;
 }
 
-int do_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* aux) {
-    if (bc->empty) return PL_OK;
-    if (bc->lat != l && !(bc->lat->kind == l->kind && bc->lat->g.nxyz == l->g.nxyz && bc->lat->g.nx == l->g.nx && bc->lat->g.ny == l->g.ny
-                          && bc->lat->g.offx == l->g.offx && bc->lat->g.offy == l->g.offy && bc->lat->g.offz == l->g.offz))
-        return fail(PL_ERR_ARG, "pl_bc_apply: closure was created for a lattice of another shape");
-    int np = bc->pl.n1*bc->pl.n2;
-    if (bc->type == PL_BC_BOUNCE || bc->type == PL_BC_IBOUNCE) {
-        int inv = bc->type == PL_BC_IBOUNCE;
-        if (l->kind == PL_D2Q9) LAUNCH(k_bounce<2>, blocks_for(np, 128), 128, l->g, l->current(), bc->pl, bc->mask, inv);
-        else LAUNCH(k_bounce<3>, blocks_for(np, 128), 128, l->g, l->current(), bc->pl, bc->mask, inv);
-        return PL_OK;
-    }
-    ClosureArgs A{};
+// plane closure -> kernel argument block (+ validation of the arrays the closure type dereferences)
+int make_closure_args(const pl_lattice* l, const pl_lattice* other, const pl_bc* bc, const pl_bc_aux* aux, ClosureArgs& A) {
+    memset(&A, 0, sizeof(A));
     A.type = bc->type; A.pl = bc->pl; A.mask = bc->mask; A.v0 = bc->v0; A.v1 = bc->v1; A.v2 = bc->v2;
     if (aux) {
         A.rho = aux->rho; A.ux = aux->ux; A.uy = aux->uy; A.uz = aux->uz; A.tem = aux->tem; A.kappa = aux->diffusivity;
         A.kconst = aux->diffusivity_const; A.eps = aux->eps;
     }
+    const bool d3 = l->kind == PL_D3Q15;
+    const bool vel = A.ux && A.uy && (!d3 || A.uz);
     switch (bc->type) {
-        case PL_BC_NS_SET_U:
-            if (!bc->v0 || !bc->v1 || (l->kind == PL_D3Q15 && !bc->v2)) return fail(PL_ERR_ARG, "pl_bc_apply: SetU needs ux,uy(,uz) plane values");
+        case PL_BC_BOUNCE: case PL_BC_IBOUNCE: case PL_BC_ANS_ISET_RHO: break;
+        case PL_BC_NS_SET_U: case PL_BC_ANS_ISET_U:
+            if (!bc->v0 || !bc->v1 || (d3 && !bc->v2)) return fail(PL_ERR_ARG, "closure: SetU needs ux,uy(,uz) plane values");
             break;
         case PL_BC_NS_SET_RHO:
-            if (!bc->v0 || !bc->v1 || (l->kind == PL_D3Q15 && !bc->v2)) return fail(PL_ERR_ARG, "pl_bc_apply: SetRho needs rho,us(,ut) plane values");
+            if (!bc->v0 || !bc->v1 || (d3 && !bc->v2)) return fail(PL_ERR_ARG, "closure: SetRho needs rho,us(,ut) plane values");
             break;
-        default:
-            return fail(PL_ERR_UNSUPPORTED, "pl_bc_apply: closure type not implemented");
+        case PL_BC_AD_SET_T: case PL_BC_AD_SET_Q:
+            if (!bc->v0) return fail(PL_ERR_ARG, "closure: SetT/SetQ needs the plane values of T / qn");
+            if (!vel) return fail(PL_ERR_ARG, "closure: SetT/SetQ needs the velocity fields (pl_bc_aux ux,uy(,uz))");
+            break;
+        case PL_BC_AAD_ISET_T: case PL_BC_AAD_ISET_Q:
+            if (!vel) return fail(PL_ERR_ARG, "closure: iSetT/iSetQ needs the velocity fields (pl_bc_aux ux,uy(,uz))");
+            break;
+        case PL_BC_AAD_ISET_RHO:
+            if (d3) return fail(PL_ERR_UNSUPPORTED, "closure: AAD::iBoundaryConditionSetRho is D2Q9 only");
+            if (!vel || !A.rho || !A.tem) return fail(PL_ERR_ARG, "closure: AAD iSetRho needs rho,ux,uy,tem fields");
+            if (!other) return fail(PL_ERR_ARG, "closure: AAD iSetRho needs the thermal lattice");
+            break;
+        default: return fail(PL_ERR_ARG, "closure: unknown type");
     }
-    double* gb = other ? other->current() : nullptr;
-    if (l->kind == PL_D2Q9) LAUNCH(k_closure<2>, blocks_for(np, 128), 128, l->g, l->current(), gb, A);
-    else LAUNCH(k_closure<3>, blocks_for(np, 128), 128, l->g, l->current(), gb, A);
+    return PL_OK;
+}
+
+bool same_shape(const pl_lattice* a, const pl_lattice* b) {
+    return a->kind == b->kind && a->g.nxyz == b->g.nxyz && a->g.nx == b->g.nx && a->g.ny == b->g.ny && a->g.offx == b->g.offx &&
+           a->g.offy == b->g.offy && a->g.offz == b->g.offz;
+}
+
+int do_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* aux) {
+    if (bc->empty) return PL_OK;
+    if (bc->lat != l && !same_shape(bc->lat, l)) return fail(PL_ERR_ARG, "pl_bc_apply: closure was created for a lattice of another shape");
+    if (other && !same_shape(other, l)) return fail(PL_ERR_ARG, "pl_bc_apply: the two lattices differ in shape");
+    ClosureArgs A;
+    int r = make_closure_args(l, other, bc, aux, A);
+    if (r) return r;
+    int np = bc->pl.n1*bc->pl.n2;
+    const double* qb = (other && bc->type == PL_BC_AAD_ISET_RHO) ? other->current() : nullptr;
+    if (l->kind == PL_D2Q9) LAUNCH(k_closure<2>, blocks_for(np, 128), 128, l->g, l->current(), qb, A);
+    else LAUNCH(k_closure<3>, blocks_for(np, 128), 128, l->g, l->current(), qb, A);
     return PL_OK;
 }
 
@@ -361,7 +374,7 @@ int make_params(const pl_lattice* f, const pl_lattice* g, const pl_collide_args*
     P.rho = a->rho; P.ux = a->ux; P.uy = a->uy; P.uz = a->uz; P.tem = a->tem; P.qx = a->qx; P.qy = a->qy; P.qz = a->qz;
     P.ip = a->ip; P.iux = a->iux; P.iuy = a->iuy; P.iuz = a->iuz; P.imx = a->imx; P.imy = a->imy; P.imz = a->imz;
     P.item = a->item; P.iqx = a->iqx; P.iqy = a->iqy; P.iqz = a->iqz;
-    P.snap = (flags & F_SNAP) ? a->snapshot : nullptr; P.snap_pitch = f->g.pitch;
+    P.snap = (flags & F_SNAP) ? a->snapshot : nullptr; P.snap_pitch = (size_t)f->g.nxyz;
     // argument validation: every array the selected model dereferences must be present
     auto need = [&](const void* p, const char* what) { if (!p) { g_err = std::string("pl_collide: missing array ") + what; return false; } return true; };
     bool ok = true;
@@ -495,8 +508,8 @@ int pl_snapshot_to_host(const pl_lattice* l, const double* snap, double* out) {
     size_t n = (size_t)l->g.nxyz*l->nc;
     double* d = nullptr;
     CU(cudaMalloc(&d, n*sizeof(double)));
-    if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_to_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, l->g.pitch, d);
-    else LAUNCH(k_snapshot_to_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, l->g.pitch, d);
+    if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_to_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, (size_t)l->g.nxyz, d);
+    else LAUNCH(k_snapshot_to_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, (size_t)l->g.nxyz, d);
     CU(cudaMemcpyAsync(out, d, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     cudaFree(d);
@@ -535,10 +548,13 @@ struct pl_plan {
     int smooth_f = 0, smooth_g = 0;
     bool finalized = false;
     int parity = 0;
-    // shell
+    // boundary pass: plane masks for the interior kernel, site list (direct sites first, SmoothCorner-coupled sites last),
+    // closure program per argument-set parity
     uint8_t *mx = nullptr, *my = nullptr, *mz = nullptr;
     int* list = nullptr;
-    int nlist = 0;
+    int nlist = 0, ndirect = 0;
+    ClosureArgs* prog[2] = {nullptr, nullptr};
+    int nprog = 0;
     // measurement hook
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -569,12 +585,29 @@ int plan_collide_full(pl_plan* p, int parity) {              // standalone C: ev
     p->f->streamed = 0; if (p->g) p->g->streamed = 0;
     return PL_OK;
 }
+template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
+    if (p->nlist == 0) return PL_OK;
+    LAUNCH((k_shell<D, M>), blocks_for(p->nlist, 128), 128, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
+           g ? g->other() : nullptr, P, p->prog[bc_parity], p->nprog, p->list, p->nlist, p->ndirect, p->inverse);
+    return PL_OK;
+}
+int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
+    if (p->f->kind == PL_D2Q9) {
+        MODEL_SWITCH(2, launch_shell, p, g, P, bc_parity)
+        if (model == 12) return launch_shell<2, 12>(p, g, P, bc_parity);
+    } else {
+        MODEL_SWITCH(3, launch_shell, p, g, P, bc_parity)
+    }
+    return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
+}
 // fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1
 int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     CollideParams P; unsigned flags;
     int r = make_params(p->f, p->g, &p->args[col_parity], P, flags);
     if (r) return r;
+    const int model = p->args[col_parity].model;
     pl_lattice* g = (flags & F_G) ? p->g : nullptr;
+    if (p->g && !g) return fail(PL_ERR_ARG, "plan: a single-lattice collide cannot drive a two-lattice plan");
     ShellMask S{p->mx, p->my, p->mz};
     // interior: one pass, source -> destination
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -582,24 +615,19 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
         CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, g_stream));
     }
-    if ((r = dispatch_fused(p->args[col_parity].model, p->f, g, P, S, p->inverse))) return r;
+    if ((r = dispatch_fused(model, p->f, g, P, S, p->inverse))) return r;
     if (p->profile) {
         CU(cudaEventRecord(ev1, g_stream));
         p->events.emplace_back(ev0, ev1);
         p->profiled_sites += p->f->g.nxyz - p->nlist;
     }
-    // shell: stream the listed sites, then closures / SmoothCorner / collide in place on the destination
-    if ((r = do_stream_list(p->f, p->inverse, p->list, p->nlist))) return r;
-    if (p->g && (r = do_stream_list(p->g, p->inverse, p->list, p->nlist))) return r;
+    // boundary pass: Stream + closure program (+ collide for the sites SmoothCorner does not touch), source -> destination
+    if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
     p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
-    for (auto& b : p->bcs) {
-        pl_lattice* l = b.on_g ? p->g : p->f;
-        pl_lattice* o = b.bc->type == PL_BC_AAD_ISET_RHO ? p->g : nullptr;
-        if ((r = do_bc(l, o, b.bc, b.has_aux ? &b.aux[bc_parity] : nullptr))) return r;
-    }
+    // SmoothCorner and the collide of the sites it couples, in place on the destination
     if (p->smooth_f && (r = do_smooth(p->f))) return r;
     if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
-    if ((r = dispatch_collide(p->args[col_parity].model, p->f, g, P, p->list, p->nlist))) return r;
+    if ((r = dispatch_collide(model, p->f, g, P, p->list + p->ndirect, p->nlist - p->ndirect))) return r;
     p->f->streamed = 0; if (p->g) p->g->streamed = 0;
     return PL_OK;
 }
@@ -609,7 +637,7 @@ extern "C" {
 
 pl_plan* pl_plan_create(pl_lattice* f, pl_lattice* g) {
     if (!f) { fail(PL_ERR_ARG, "pl_plan_create: null lattice"); return nullptr; }
-    if (g && (g->kind != f->kind || g->g.nxyz != f->g.nxyz || g->g.nx != f->g.nx || g->g.ny != f->g.ny)) { fail(PL_ERR_ARG, "pl_plan_create: lattices differ in shape"); return nullptr; }
+    if (g && !same_shape(f, g)) { fail(PL_ERR_ARG, "pl_plan_create: lattices differ in shape"); return nullptr; }
     pl_plan* p = new pl_plan();
     p->f = f; p->g = g;
     return p;
@@ -617,7 +645,8 @@ pl_plan* pl_plan_create(pl_lattice* f, pl_lattice* g) {
 int pl_plan_destroy(pl_plan* p) {
     if (!p) return PL_OK;
     cudaStreamSynchronize(g_stream);
-    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list);
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    for (auto& e : p->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     delete p;
     return PL_OK;
 }
@@ -633,6 +662,8 @@ int pl_plan_add_bc(pl_plan* p, int on_g, const pl_bc* bc, const pl_bc_aux* even,
     if (!p || !bc) return fail(PL_ERR_ARG, "pl_plan_add_bc: null");
     if (p->finalized) return fail(PL_ERR_ARG, "pl_plan_add_bc: plan already finalized");
     if (on_g && !p->g) return fail(PL_ERR_ARG, "pl_plan_add_bc: plan has no thermal lattice");
+    if (bc->type == PL_BC_AAD_ISET_RHO && (on_g || !p->g)) return fail(PL_ERR_ARG, "pl_plan_add_bc: AAD iSetRho acts on the flow lattice of a two-lattice plan");
+    if (!same_shape(bc->lat, p->f)) return fail(PL_ERR_ARG, "pl_plan_add_bc: closure was created for a lattice of another shape");
     PlanBC b{};
     b.on_g = on_g ? 1 : 0; b.bc = bc; b.has_aux = even != nullptr;
     if (even) { b.aux[0] = *even; b.aux[1] = odd ? *odd : *even; }
@@ -650,28 +681,63 @@ int pl_plan_finalize(pl_plan* p) {
     const Geom& g = p->f->g;
     std::vector<uint8_t> hx(g.nx, 0), hy(g.ny, 0), hz(g.nz, 0);
     std::vector<uint8_t>* h[3] = {&hx, &hy, &hz};
-    int off[3] = {g.offx, g.offy, g.offz}, n[3] = {g.nx, g.ny, g.nz}, ext[3] = {g.lx, g.ly, g.lz};
-    for (auto& b : p->bcs) if (!b.bc->empty) (*h[b.bc->axis])[b.bc->coord - off[b.bc->axis]] = 1;
+    int off[3] = {g.offx, g.offy, g.offz};
+    // closure program: the non-empty closures in call order, one copy per argument-set parity
+    std::vector<ClosureArgs> prog[2];
+    for (auto& b : p->bcs) {
+        if (b.bc->empty) continue;
+        (*h[b.bc->axis])[b.bc->coord - off[b.bc->axis]] = 1;
+        for (int par = 0; par < 2; ++par) {
+            ClosureArgs A;
+            pl_lattice* l = b.on_g ? p->g : p->f;
+            int r = make_closure_args(l, b.bc->type == PL_BC_AAD_ISET_RHO ? p->g : nullptr, b.bc, b.has_aux ? &b.aux[par] : nullptr, A);
+            if (r) return r;
+            A.on_g = b.on_g; A.loc = b.bc->coord - off[b.bc->axis];
+            prog[par].push_back(A);
+        }
+    }
+    // sites SmoothCorner writes (edge lines, corners) or reads (their inward neighbours): collide is deferred for them
+    std::vector<long long> coupled;
     if (p->smooth_f || p->smooth_g) {
+        int n[3] = {g.nx, g.ny, g.nz}, ext[3] = {g.lx, g.ly, g.lz};
         for (int a = 0; a < p->f->kind; ++a) {
             int lo = 0 - off[a], hi = ext[a] - 1 - off[a];
             if (0 <= lo && lo < n[a]) (*h[a])[lo] = 1;
             if (0 <= hi && hi < n[a]) (*h[a])[hi] = 1;
         }
+        SmoothList e, c;
+        smooth_lists(p->f, e, c);
+        for (SmoothList* L : {&e, &c})
+            for (int n = 0; n < L->count; ++n) {
+                const SmoothItem& it = L->it[n];
+                for (int t = 0; t < it.len; ++t) {
+                    long long idx = it.base + (long long)t*it.stride;
+                    coupled.push_back(idx); coupled.push_back(idx + it.n0); coupled.push_back(idx + it.n1);
+                    if (it.n2 != 0) coupled.push_back(idx + it.n2);
+                }
+            }
+        std::sort(coupled.begin(), coupled.end());
+        coupled.erase(std::unique(coupled.begin(), coupled.end()), coupled.end());
     }
+    auto is_coupled = [&](long long idx) { return std::binary_search(coupled.begin(), coupled.end(), idx); };
+    // the interior kernel skips whole planes: every coupled site must lie on a marked plane (they all lie on the global
+    // boundary planes marked above; the fallback keeps the two kernels disjoint in any case)
+    for (long long idx : coupled) {
+        int k = (int)(idx/((long long)g.nx*g.ny)), r = (int)(idx - (long long)k*g.nx*g.ny), j = r/g.nx, i = r - j*g.nx;
+        if (!(hx[i] || hy[j] || hz[k])) hx[i] = 1;
+    }
+    // list = [sites on marked planes and AVX-tail sites that SmoothCorner does not couple | coupled sites]
     std::vector<int> list;
     for (int k = 0; k < g.nz; ++k)
-        for (int j = 0; j < g.ny; ++j) {
-            if (hy[j] || hz[k]) { for (int i = 0; i < g.nx; ++i) list.push_back(i + g.nx*(j + g.ny*k)); }
-            else { for (int i = 0; i < g.nx; ++i) if (hx[i]) list.push_back(i + g.nx*(j + g.ny*k)); }
-        }
-    // tail sites always go through the list so that the interior kernel only ever runs the packed operation order
-    for (long long idx = g.npacked; idx < g.nxyz; ++idx) {
-        int k = (int)(idx/((long long)g.nx*g.ny)), r = (int)(idx - (long long)k*g.nx*g.ny), j = r/g.nx, i = r - j*g.nx;
-        if (!(hx[i] || hy[j] || hz[k])) list.push_back((int)idx);
-    }
-    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list);
-    p->mx = p->my = p->mz = nullptr; p->list = nullptr;
+        for (int j = 0; j < g.ny; ++j)
+            for (int i = 0; i < g.nx; ++i) {
+                long long idx = i + (long long)g.nx*(j + (long long)g.ny*k);
+                if ((hx[i] || hy[j] || hz[k] || idx >= g.npacked) && !is_coupled(idx)) list.push_back((int)idx);
+            }
+    p->ndirect = (int)list.size();
+    for (long long idx : coupled) list.push_back((int)idx);
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    p->mx = p->my = p->mz = nullptr; p->list = nullptr; p->prog[0] = p->prog[1] = nullptr;
     CU(cudaMalloc(&p->mx, g.nx)); CU(cudaMalloc(&p->my, g.ny)); CU(cudaMalloc(&p->mz, g.nz));
     CU(cudaMemcpy(p->mx, hx.data(), g.nx, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->my, hy.data(), g.ny, cudaMemcpyHostToDevice));
@@ -680,6 +746,11 @@ int pl_plan_finalize(pl_plan* p) {
     if (p->nlist) {
         CU(cudaMalloc(&p->list, list.size()*sizeof(int)));
         CU(cudaMemcpy(p->list, list.data(), list.size()*sizeof(int), cudaMemcpyHostToDevice));
+    }
+    p->nprog = (int)prog[0].size();
+    for (int par = 0; par < 2; ++par) {
+        CU(cudaMalloc(&p->prog[par], std::max<size_t>(1, prog[par].size())*sizeof(ClosureArgs)));
+        if (p->nprog) CU(cudaMemcpy(p->prog[par], prog[par].data(), prog[par].size()*sizeof(ClosureArgs), cudaMemcpyHostToDevice));
     }
     p->finalized = true;
     return PL_OK;
@@ -774,10 +845,46 @@ int pl_normalize(double* v, size_t n) {
     return PL_OK;
 }
 
-int pl_sensitivity(pl_lattice*, const pl_sens_args*) { return fail(PL_ERR_UNSUPPORTED, "pl_sensitivity: not implemented yet"); }
-int pl_sensitivity_heat_source_plane(pl_lattice*, int, int, int, const uint8_t*, const double*, double*, const double*, const double*, const double*,
-                                     const double*, const double*, const double*) {
-    return fail(PL_ERR_UNSUPPORTED, "pl_sensitivity_heat_source_plane: not implemented yet");
+int pl_sensitivity(pl_lattice* l, const pl_sens_args* a) {
+    if (!l || !a) return fail(PL_ERR_ARG, "pl_sensitivity: null");
+    const bool d3 = l->kind == PL_D3Q15;
+    if (a->kind < 1 || a->kind > 3) return fail(PL_ERR_ARG, "pl_sensitivity: unknown kind");
+    if (!a->dfds || !a->ux || !a->uy || !a->imx || !a->imy || !a->dads || (d3 && (!a->uz || !a->imz)))
+        return fail(PL_ERR_ARG, "pl_sensitivity: missing dfds / u / im / dads arrays");
+    if (a->kind == PL_SENS_AAD_HEATEX && (!a->tem || !a->item || !a->dbds)) return fail(PL_ERR_ARG, "pl_sensitivity: HeatExchange needs tem, item, dbds");
+    if (a->kind == PL_SENS_AAD_BRINKMAN_DIFF &&
+        (!a->tem || !a->item || !a->iqx || !a->iqy || (d3 && !a->iqz) || !a->gsnap || !a->igsnap || !a->diffusivity || !a->dkds))
+        return fail(PL_ERR_ARG, "pl_sensitivity: BrinkmanDiffusivity needs tem, item, iq, the two snapshots, diffusivity and dkds");
+    SensArgs A{};
+    A.kind = a->kind; A.dfds = a->dfds; A.ux = a->ux; A.uy = a->uy; A.uz = a->uz; A.imx = a->imx; A.imy = a->imy; A.imz = a->imz; A.dads = a->dads;
+    A.tem = a->tem; A.item = a->item; A.iqx = a->iqx; A.iqy = a->iqy; A.iqz = a->iqz; A.gsnap = a->gsnap; A.igsnap = a->igsnap;
+    A.kappa = a->diffusivity; A.dkds = a->dkds; A.dbds = a->dbds; A.pitch = (size_t)l->g.nxyz;
+    if (d3) LAUNCH(k_sensitivity<3>, blocks_for(l->g.nxyz, 256), 256, l->g, A);
+    else LAUNCH(k_sensitivity<2>, blocks_for(l->g.nxyz, 256), 256, l->g, A);
+    return PL_OK;
+}
+int pl_sensitivity_heat_source_plane(pl_lattice* l, int axis, int coord, int dir, const uint8_t* mask_host, const double* qn_host, double* dfds,
+                                     const double* ux, const double* uy, const double* uz, const double* igsnap, const double* diffusivity,
+                                     const double* dkds) {
+    if (!l || !dfds || !ux || !uy || (l->kind == PL_D3Q15 && !uz) || !igsnap || !diffusivity || !dkds)
+        return fail(PL_ERR_ARG, "pl_sensitivity_heat_source_plane: null argument");
+    pl_bc* bc = pl_bc_create(l, PL_BC_AD_SET_Q, axis, coord, dir, mask_host, qn_host, nullptr, nullptr);
+    if (!bc) return PL_ERR_ARG;
+    int r = PL_OK;
+    if (!bc->empty) {
+        if (!bc->v0) { pl_bc_destroy(bc); return fail(PL_ERR_ARG, "pl_sensitivity_heat_source_plane: qn values are required"); }
+        ClosureArgs A{};
+        A.type = 0; A.pl = bc->pl; A.mask = bc->mask; A.v0 = bc->v0; A.ux = ux; A.uy = uy; A.uz = uz; A.kappa = diffusivity;
+        int np = bc->pl.n1*bc->pl.n2;
+        cudaError_t e;
+        if (l->kind == PL_D2Q9) k_sens_heat_source<2><<<blocks_for(np, 128), 128, 0, g_stream>>>(l->g, A, igsnap, dkds, dfds);
+        else k_sens_heat_source<3><<<blocks_for(np, 128), 128, 0, g_stream>>>(l->g, A, igsnap, dkds, dfds);
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) r = fail(PL_ERR_CUDA, std::string("k_sens_heat_source: ") + cudaGetErrorString(e));
+    }
+    pl_bc_destroy(bc);   // synchronises the stream before freeing the baked arrays
+    return r;
 }
 
 }  // extern "C"

@@ -43,6 +43,47 @@ def cavity3d():
     np.savez_compressed(os.path.join(HERE, "cavity3d.npz"), **out)
 
 
+def ops():
+    """every op-level scenario of tests/scenarios.py on the reference build -> sha256 digests (values only: -0.0 == +0.0)"""
+    import json
+    sys.path.insert(0, os.path.dirname(HERE))
+    import scenarios as S
+    out = {}
+    for dim, size in ((2, (7, 5, 1)), (3, (5, 3, 3)), (3, (6, 4, 4))):
+        ref = O.Backend("ref", dim)
+        tag = f"d{dim}_{size[0]}x{size[1]}x{size[2]}"
+        for model in S.FORWARD_MODELS + S.ADJOINT_MODELS:
+            if model.endswith("massflow") and dim == 3:
+                continue
+            out[f"{tag}/collide/{model}"] = digest(*[a + 0.0 for _, a in S.collide(ref, dim, model, size, 3)])
+        for kind in S.CLOSURES:
+            if kind == "aad_iset_rho" and dim == 3:
+                continue
+            out[f"{tag}/closure/{kind}"] = digest(*[a + 0.0 for _, a in S.closure(ref, dim, kind, size, 5)])
+        for kind in S.SENSITIVITIES:
+            out[f"{tag}/sensitivity/{kind}"] = digest(*[a + 0.0 for _, a in S.sensitivity(ref, dim, kind, size, 9)])
+        out[f"{tag}/inits"] = digest(*[a + 0.0 for _, a in S.inits(ref, dim, size, 2)])
+    json.dump(out, open(os.path.join(HERE, "ops_digests.json"), "w"), indent=1, sort_keys=True)
+
+
+HEATSINK_CASES = {"hs3d": (3, (13, 17, 9), 40), "hs2d": (2, (23, 29, 1), 40), "hs3d_tail": (3, (7, 9, 5), 15)}
+
+
+def heatsink():
+    """one heatsink optimisation iteration (tests/heatsink_case.py) on the reference build: digests + strided samples"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import heatsink_case as H
+    out = {}
+    for tag, (dim, size, nt) in HEATSINK_CASES.items():
+        r = H.run_oplevel(O.Backend("ref", dim), dim, size, nt)
+        for k, a in r.items():
+            out[f"{tag}/{k}/s5"] = (a + 0.0)[::5].copy()
+            out[f"{tag}/{k}/sha"] = np.frombuffer(bytes.fromhex(digest(a + 0.0)), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "heatsink.npz"), **out)
+
+
 if __name__ == "__main__":
     cavity3d()
+    ops()
+    heatsink()
     print("wrote", os.listdir(HERE))

@@ -42,3 +42,29 @@ def relinf(a, b):
     d = np.max(np.abs(a - b)) if a.size else 0.0
     s = np.max(np.abs(b)) if b.size else 0.0
     return d / s if s > 0 else d
+
+
+def hostmath_backend(dim):
+    """the product's site math compiled for the host (tests/hostmath), driven like an oracle backend"""
+    import ctypes as C
+    import importlib.util
+    import os
+    from oracle import oracle as O
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("hostmath_build", os.path.join(here, "hostmath", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class HostMath(O.Backend):
+        def __init__(self, dim):
+            self.kind, self.dim = "hm", dim
+            self.lib = C.CDLL(mod.build())
+            self.prefix = "hm_"
+
+        def lattice(self, lx, ly, lz=1, peid=0, mx=1, my=1, mz=1):
+            h = self._call("lattice_create", self.dim, lx, ly, lz, peid, mx, my, mz, restype=C.c_void_p)
+            info = np.zeros(18, dtype=np.int32)
+            self._fn("lattice_info")(C.c_void_p(h), info.ctypes.data_as(C.c_void_p))
+            return O.Lattice(self, h, info)
+
+    return HostMath(dim)
