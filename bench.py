@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — MLUPS of the fused D3Q15 stream+collide sweep on B200 (BASELINE.json configs[2]:
-test/cavityflow3D.cpp scaled to 512^3), with the HBM roofline of the dominant kernel and the reference's own
-CPU path timed beside it.
+"""bench.py — MLUPS (fp64, forward + adjoint) of the D3Q15 NS+AD lattice-Boltzmann sweep on B200, with the HBM roofline
+of the dominant kernel and the reference's own CPU path timed beside it.
 
-    python bench.py --gpus 1 --steps 50 --warmup 5            # our arm
+    python bench.py --gpus 1 --steps 30 --warmup 3            # our arm
     python bench.py --impl reference --steps 5 --warmup 1     # reference arm (oracle/_ref on the host cores)
 
-One "step" = one lattice update of the whole domain: Stream + wall/lid closures + SmoothCorner + MacroCollide,
-executed as one fused pass (pl_plan_advance).  Prints ONE JSON line on rank 0.
+Workload: the forward ("Direct analyse") and adjoint ("Inverse analyse") time loops of production/heatsink3D.cpp
+(:148-184, :191-224; the physics of BASELINE configs[3]) on a synthetic S^3 block per GPU (the synthetic-domain scaling of
+configs[2]), grey closed-form design, convergence `break` disabled.  One "step" = one forward lattice update
+(AD::MacroBrinkmanCollideNaturalConvection + 2x Stream + wall/SetT/SetQ closures + 2x SmoothCorner, macros and the g
+snapshot saved) plus one adjoint lattice update (AAD::MacroBrinkmanCollideNaturalConvection + 2x iStream + iSetT/iSetQ/
+iSetQ(eps)/walls + SmoothCorner), each executed as one fused pass (pl_plan_advance).  MLUPS = 2*sites*steps/seconds.
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -21,8 +26,13 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-B_ALG_NS_SAVE = 272.0   # bytes / lattice update: 15 pops read + 15 written + rho,ux,uy,uz written
+# algorithmic bytes per lattice update (SURVEY.md §8d / DESIGN.md): every population read once and written once, per-site
+# coefficient fields read, saved macros and the thermal snapshot written
+B_NS_SAVE = 272.0     # D3Q15 NS: 15r+15w + rho,u (4w)
+B_FWD = 680.0         # D3Q15 NS+AD forward: 30r+30w + alpha,kappa (2r) + rho,u,T,q (8w) + g snapshot (15w)
+B_ADJ = 744.0         # D3Q15 NS+AD adjoint: 30r+30w + rho,u,T,alpha,kappa (7r) + ip,iu,im,iT,iq (11w) + ig snapshot (15w)
 METRIC = "MLUPS"
 
 
@@ -50,7 +60,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
@@ -61,58 +71,159 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(self.samples)}
 
 
-def cavity_plan(pl, api, pf, rho, u, nu=0.1, u0=0.1, theta=90.0):
-    """record the loop body of test/cavityflow3D.cpp:48-58"""
-    import math
-    import numpy as np
-    lx, ly, lz = pf.lx, pf.ly, pf.lz
-    wall = lambda i, j, k: np.where((i == 0) | (i == lx - 1) | (j == 0) | (j == ly - 1) | (k == 0), 1, 0)
-    lid = lambda i, j, k: k == lz - 1
-    uvals = [lambda i, j, k: u0*math.cos(theta*math.pi/180.0), lambda i, j, k: u0*math.sin(theta*math.pi/180.0), lambda i, j, k: 0.0]
-    plan = pl.StepPlan(pf)
-    plan.set_collide(pl.collide_args(api.M_NS_COLLIDE, True, nu, rho=rho, ux=u[0], uy=u[1], uz=u[2]))
-    plan.add_bounce(pf, wall)
-    plan.add_closure(pf, api.BC_NS_SET_U, lid, uvals)
-    plan.set_smooth_corner(True).finalize()
-    return plan
+# ---------------------------------------------------------------------------------------------------------
+class HeatsinkSweep:
+    """forward + adjoint plans of the heatsink3D loop bodies on one block (tests/heatsink_case.py holds the same sequence
+    call by call for the parity tests)"""
+
+    def __init__(self, pl, api, size, peid=0, m=(1, 1, 1)):
+        import heatsink_case as H
+        import numpy as np
+        self.pl, self.api, self.H = pl, api, H
+        self.p = p = H.params(3, size)
+        self.f = pl.D3Q15(*size, peid, *m)
+        self.g = pl.D3Q15(*size, peid, *m)
+        self.n = n = self.f.nxyz
+        f = self.f
+
+        class _L:
+            nx, ny, nz, offx, offy, offz = f.nx, f.ny, f.nz, f.offsetx, f.offsety, f.offsetz
+        self.host_design = [np.ascontiguousarray(a) for a in H.design_fields(p, *H.local_coords(_L))]   # alpha, kappa, dads, dkds
+        self.alpha, self.kappa, self.dads, self.dkds = [pl.DeviceArray(n) for _ in range(4)]
+        names = H.FWD + H.ADJ + ["uxp", "uyp", "uzp", "qxp", "qyp", "qzp", "iuxp", "iuyp", "iuzp", "iqxp", "iqyp", "iqzp"]
+        self.A = {k: pl.DeviceArray(n, 0.0) for k in names}
+        self.gsnap, self.igsnap = pl.DeviceArray(n*15), pl.DeviceArray(n*15)
+        self.dfdss = pl.DeviceArray(n, 0.0)
+        self.P = H.predicates(p)
+        self.fplan = self.aplan = None
+
+    def upload_design(self, pinned=None):
+        src = pinned if pinned is not None else self.host_design
+        for d, h in zip((self.alpha, self.kappa, self.dads, self.dkds), src):
+            d.upload(h) if pinned is None else self._up(d, h)
+
+    def _up(self, d, t):
+        from panslbm2_b200 import _lib
+        _lib.check(_lib.lib().pl_array_upload(d.ptr, t.data_ptr(), d.n))
+
+    def init_forward(self):
+        pl, A = self.pl, self.A
+        A["rho"].fill(1.0)
+        for k in ("ux", "uy", "uz", "tem"):
+            A[k].fill(0.0)
+        pl.NS.InitialCondition(self.f, A["rho"], A["ux"], A["uy"], A["uz"])
+        pl.AD.InitialCondition(self.g, A["tem"], A["ux"], A["uy"], A["uz"])
+        if self.fplan is None:
+            self.fplan = self._forward_plan()
+
+    def _forward_plan(self):
+        pl, api, p, A, P, f, g = self.pl, self.api, self.p, self.A, self.P, self.f, self.g
+
+        def args(sw):
+            s = "p" if sw else ""
+            arrs = dict(ux=A["ux" + s], uy=A["uy" + s], uz=A["uz" + s], qx=A["qx" + s], qy=A["qy" + s], qz=A["qz" + s])
+            ca = pl.collide_args(api.M_AD_BRINKMAN_NAT_CONV, True, p["nu"], gx=p["gx"], gy=p["gy"], gz=p["gz"], tem0=p["tem0"], rho=A["rho"], tem=A["tem"],
+                                 alpha=self.alpha, diffusivity=self.kappa, snapshot=self.gsnap, **arrs)
+            return ca, pl.bc_aux(ux=arrs["ux"], uy=arrs["uy"], uz=arrs["uz"], diffusivity=self.kappa)
+        (c0, a0), (c1, a1) = args(False), args(True)
+        plan = pl.StepPlan(f, g).set_collide(c0, c1).set_stream(False)
+        plan.add_bounce(f, P["f_wall"])
+        plan.add_closure(g, api.BC_AD_SET_T, P["setT"], [P["tem"]], a0, a1)
+        plan.add_closure(g, api.BC_AD_SET_Q, P["setQ"], [P["qn"]], a0, a1)
+        plan.add_bounce(g, P["g_wall"])
+        return plan.set_smooth_corner(True, True).finalize()
+
+    def init_adjoint(self):
+        pl, A = self.pl, self.A
+        for k in ("ip", "iux", "iuy", "iuz", "item", "iqx", "iqy", "iqz"):
+            A[k].fill(0.0)
+        pl.ANS.InitialCondition(self.f, A["ux"], A["uy"], A["uz"], A["ip"], A["iux"], A["iuy"], A["iuz"])
+        pl.AAD.InitialCondition(self.g, A["ux"], A["uy"], A["uz"], A["item"], A["iqx"], A["iqy"], A["iqz"])
+        if self.aplan is None:
+            self.aplan = self._adjoint_plan()
+
+    def _adjoint_plan(self):
+        pl, api, p, A, P, f, g = self.pl, self.api, self.p, self.A, self.P, self.f, self.g
+
+        def args(sw):
+            s = "p" if sw else ""
+            arrs = dict(iux=A["iux" + s], iuy=A["iuy" + s], iuz=A["iuz" + s], iqx=A["iqx" + s], iqy=A["iqy" + s], iqz=A["iqz" + s])
+            fixed = {k: A[k] for k in ("rho", "ux", "uy", "uz", "tem", "ip", "imx", "imy", "imz", "item")}
+            return pl.collide_args(api.M_AAD_NAT_CONV, True, p["nu"], gx=p["gx"], gy=p["gy"], gz=p["gz"], alpha=self.alpha, diffusivity=self.kappa,
+                                   snapshot=self.igsnap, **fixed, **arrs)
+        aux0 = pl.bc_aux(ux=A["ux"], uy=A["uy"], uz=A["uz"])
+        aux1 = pl.bc_aux(ux=A["ux"], uy=A["uy"], uz=A["uz"], eps=1.0)
+        plan = pl.StepPlan(f, g).set_collide(args(False), args(True)).set_stream(True)
+        plan.add_closure(g, api.BC_AAD_ISET_T, P["setT"], [], aux0, aux0)
+        plan.add_closure(g, api.BC_AAD_ISET_Q, P["setQ"], [], aux0, aux0)
+        plan.add_closure(g, api.BC_AAD_ISET_Q, P["source"], [], aux1, aux1)
+        plan.add_bounce(g, P["g_wall"], inverse=True)
+        plan.add_bounce(f, P["f_wall"], inverse=True)
+        return plan.set_smooth_corner(True, True).finalize()
+
+    def sensitivity(self):
+        pl, A, P = self.pl, self.A, self.P
+        self.dfdss.fill(0.0)
+        pl.AAD.SensitivityTemperatureAtHeatSource(self.g, self.dfdss, A["ux"], A["uy"], A["uz"], A["imx"], A["imy"], A["imz"], self.dads, A["tem"], A["item"],
+                                                  A["iqx"], A["iqy"], A["iqz"], self.gsnap, self.igsnap, self.kappa, self.dkds, P["qn"], P["source"])
 
 
+def read_profile(L, plan):
+    kms, kn, ksites = C.c_double(0), C.c_int(0), C.c_longlong(0)
+    L.pl_plan_profile_read(plan._h, C.byref(kms), C.byref(kn), C.byref(ksites))
+    return kms.value, kn.value, ksites.value
+
+
+def roofline(kernel, bytes_per_site, prof, peak, peak_src, step_ms_total):
+    kms, kn, ksites = prof
+    if not kn:
+        return None
+    avg_ms = kms/kn
+    achieved = bytes_per_site*(ksites/kn)/(avg_ms*1e-3)/1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": None, "kernel": kernel,
+            "avg_kernel_ms": avg_ms, "sites_per_launch": ksites/kn, "algorithmic_bytes_per_site": bytes_per_site, "peak_source": peak_src,
+            "kernel_share_of_timed_region": kms/step_ms_total if step_ms_total else None}
+
+
+# ---------------------------------------------------------------------------------------------------------
 def cpu_reference(size, steps, warmup, threads=None):
-    """reference's own OpenMP+AVX path (oracle/_ref) on the host cores; falls back to the C port when _ref is absent"""
-    from oracle import oracle as O
-    kind = "reference" if O.have_ref(3) else "port"
-    be = O.Backend("ref" if kind == "reference" else "orc", 3)
-    if kind == "reference":
-        cores = be.lib.ref_max_threads()
-        if threads:
-            be.lib.ref_set_threads(int(threads)); cores = int(threads)
-    else:
-        cores = os.cpu_count() or 1
+    """the reference's own OpenMP+AVX forward+adjoint loops (oracle/_ref, built from the unmodified headers) on the host cores"""
     import numpy as np
+    import heatsink_case as H
+    from oracle import oracle as O
+    if not O.have_ref(3):
+        raise RuntimeError("oracle/_ref/libpanslbm_ref3d.so is absent (it is built by __graft_entry__.build() where /root/reference exists)")
+    be = O.Backend("ref", 3)
+    cores = be.lib.ref_max_threads()
+    if threads:
+        be.lib.ref_set_threads(int(threads)); cores = int(threads)
+    sz = (size, size, size)
+    p = H.params(3, sz)
+    alpha, kappa, _, _ = [np.ascontiguousarray(a) for a in H.design_fields(p, *H.gcoords(*sz))]
+    secs = np.zeros(2)
+    be.time_heatsink(size, size, size, alpha, kappa, p["nu"], p["gx"], p["gy"], p["gz"], p["tem0"], p["qn0"], p["L"], int(steps), int(warmup), secs)
     n = size**3
-    m = [np.zeros(n) for _ in range(4)]
-    sec = be.time_cavity3d(size, size, size, steps, warmup, *m)
-    return {"value": n*steps/sec/1e6, "unit": "MLUPS", "cores": int(cores), "kind": kind,
-            "sample": f"cavityflow3D D3Q15 NS {size}^3, {steps} steps after {warmup} warm-up, {sec:.2f} s"}, sec
+    tot = float(secs.sum())
+    return {"value": 2*n*steps/tot/1e6, "unit": "MLUPS", "cores": int(cores), "kind": "reference",
+            "sample": f"heatsink3D forward+adjoint loops, D3Q15 NS+AD {size}^3, {steps}+{steps} steps after {warmup}+{warmup} warm-up, "
+                      f"{tot:.2f} s (forward {n*steps/secs[0]/1e6:.1f} / adjoint {n*steps/secs[1]/1e6:.1f} MLUPS)"}, tot
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    # bounded sample: probe one step at 96^3, then pick the largest cube <= 256 whose (steps+warmup) fit in ~90 s
-    probe, psec = cpu_reference(96, 1, 1)
-    rate = probe["value"]*1e6   # sites/s
-    budget = 90.0
-    size = 96
-    for s in (128, 160, 192, 224, 256):
-        if s**3*(args.steps + args.warmup)/rate <= budget:
+    # bounded sample: probe at 64^3, then the largest cube whose (steps + warmup) forward+adjoint steps fit in ~100 s
+    probe, _ = cpu_reference(64, 2, 1)
+    rate = probe["value"]*1e6
+    size = 64
+    for s in (96, 128, 160, 192, 224, 256):
+        if 2*s**3*(args.steps + args.warmup)/rate <= 100.0:
             size = s
     cb, sec = cpu_reference(size, args.steps, args.warmup)
     line = {"metric": METRIC, "value": cb["value"], "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3*sec/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "test/cavityflow3D.cpp D3Q15 NS lid-driven cavity (BASELINE configs[2]), CPU sample " + f"{size}^3",
+            "config": {"workload": f"production/heatsink3D.cpp forward+adjoint time loops (D3Q15 NS+AD), CPU sample {size}^3 of the S^3-per-GPU workload",
                        "global_sites": size**3, "parallelism": "OpenMP+AVX host threads"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -120,7 +231,6 @@ def run_reference(args):
 
 
 def run_ours(args):
-    import numpy as np
     import torch
     import panslbm2_b200 as pl
     from panslbm2_b200 import _lib, api
@@ -139,84 +249,103 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    S = args.size
-    pf = pl.D3Q15(S, S, S)
-    N = pf.nxyz
-    rho = pl.DeviceArray(N, 1.0)
-    u = [pl.DeviceArray(N, 0.0) for _ in range(3)]
-    pl.NS.InitialCondition(pf, rho, *u)
-    plan = cavity_plan(pl, api, pf, rho, u)
-    L = _lib.lib()
+    def maxms(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
 
-    # ---- device-resident throughput ----------------------------------------------------------------
-    plan.advance(args.warmup, end_streamed=False)
+    L = _lib.lib()
+    S, K, W = args.size, args.steps, args.warmup
+    sw = HeatsinkSweep(pl, api, (S, S, S))
+    N = sw.n
+    sw.upload_design()
+
+    # ---- device-resident throughput: K forward + K adjoint fused steps -----------------------------------------
+    # two timed segments (the adjoint loop starts from the forward loop's final fields, heatsink3D.cpp:191-192): each is W
+    # untimed steps, then EXACTLY K steps between a barrier+synchronize on both sides; ms = forward segment + adjoint segment.
+    sampler = ClockSampler(local); sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    sw.init_forward()
+    sw.fplan.advance(W, end_streamed=False)
+    L.pl_plan_profile(sw.fplan._h, 1)
     barrier()
     L.pl_launch_count_reset()
-    sampler = ClockSampler(local); sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    L.pl_plan_profile(plan._h, 1)
-    e0.record()
-    plan.advance(args.steps, end_streamed=False)
-    e1.record()
+    ev[0].record()
+    sw.fplan.advance(K, end_streamed=False)
+    ev[1].record()
     barrier()
-    sampler.stop_flag = True
-    ms = e0.elapsed_time(e1)
     launches = int(L.pl_launch_count())
-    import ctypes as C
-    kms, kn, ksites = C.c_double(0), C.c_int(0), C.c_longlong(0)
-    L.pl_plan_profile_read(plan._h, C.byref(kms), C.byref(kn), C.byref(ksites))
-    L.pl_plan_profile(plan._h, 0)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world*N*args.steps/(ms*1e-3)/1e6
-
-    # ---- end to end through the public API with host buffers ---------------------------------------------
-    # what test/cavityflow3D.cpp does around its loop: fields start on the host, results are read on the host.
-    hrho = torch.ones(N, dtype=torch.float64).pin_memory()
-    hu = [torch.zeros(N, dtype=torch.float64).pin_memory() for _ in range(3)]
+    sw.fplan.advance(0, end_streamed=True)     # close the last forward step (Stream + closures), as the loop running to nt does
+    sw.init_adjoint()
+    sw.aplan.advance(W, end_streamed=False)
+    L.pl_plan_profile(sw.aplan._h, 1)
     barrier()
-    t0 = time.perf_counter()
-    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    L.pl_launch_count_reset()
+    ev[2].record()
+    sw.aplan.advance(K, end_streamed=False)
+    ev[3].record()
+    barrier()
+    launches += int(L.pl_launch_count())
+    sampler.stop_flag = True
+    fwd_ms, adj_ms = maxms(ev[0].elapsed_time(ev[1])), maxms(ev[2].elapsed_time(ev[3]))
+    fprof, aprof = read_profile(L, sw.fplan), read_profile(L, sw.aplan)
+    L.pl_plan_profile(sw.fplan._h, 0); L.pl_plan_profile(sw.aplan._h, 0)
+    ms = fwd_ms + adj_ms
+    value = world*2*N*K/(ms*1e-3)/1e6
+
+    # ---- end to end through the public API with HOST buffers --------------------------------------------------
+    # one optimisation-iteration shape (heatsink3D.cpp:114-246): design fields arrive from the host, the loops run, the
+    # sensitivity and the temperature field go back to the host.
+    hdesign = [torch.from_numpy(a).pin_memory() for a in sw.host_design]
+    hout = [torch.empty(N, dtype=torch.float64).pin_memory() for _ in range(2)]
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for d, h in zip([rho] + u, [hrho] + hu):
-        _lib.check(L.pl_array_upload(d.ptr, h.data_ptr(), N))
-    pl.NS.InitialCondition(pf, rho, *u)
-    plan2 = cavity_plan(pl, api, pf, rho, u)
-    plan2.advance(args.steps, end_streamed=True)
-    for d, h in zip([rho] + u, [hrho] + hu):
-        _lib.check(L.pl_array_download(h.data_ptr(), d.ptr, N))
+    sw.upload_design(hdesign)
+    sw.init_forward()
+    sw.fplan.advance(K, end_streamed=True)
+    sw.init_adjoint()
+    sw.aplan.advance(K, end_streamed=True)
+    sw.sensitivity()
+    _lib.check(L.pl_array_download(hout[0].data_ptr(), sw.dfdss.ptr, N))
+    _lib.check(L.pl_array_download(hout[1].data_ptr(), sw.A["tem"].ptr, N))
     f1.record()
     barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world*N*args.steps/(e2e_ms*1e-3)/1e6
-    checksum = float(hu[0].abs().max())
+    e2e_ms = maxms(f0.elapsed_time(f1))
+    e2e_value = world*2*N*K/(e2e_ms*1e-3)/1e6
+    checks = {"max_abs_dfdss": float(hout[0].abs().max()), "max_tem": float(hout[1].max())}
+
+    # ---- secondary sweep: pure NS roofline case (BASELINE configs[2], test/cavityflow3D.cpp scaled) -------------
+    extra = {}
+    if args.ns_size > 0:
+        del sw
+        import gc
+        gc.collect()
+        extra["ns_cavity"] = ns_cavity(pl, api, L, torch, args.ns_size, max(10, K//2), W, barrier, maxms, world)
 
     if rank != 0:
         return
     peak, peak_src = peaks()
-    k_avg_ms = kms.value/max(kn.value, 1)
-    achieved = B_ALG_NS_SAVE*ksites.value/max(kn.value, 1)/(k_avg_ms*1e-3)/1e9 if kn.value else None
+    rf = roofline("k_fused<3,7> (AD::MacroBrinkmanCollideNaturalConvection + Stream x2, fused)", B_FWD, fprof, peak, peak_src, fwd_ms)
+    ra = roofline("k_fused<3,11> (AAD::MacroBrinkmanCollideNaturalConvection + iStream x2, fused)", B_ADJ, aprof, peak, peak_src, adj_ms)
     line = {
-        "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms/args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms/K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"test/cavityflow3D.cpp D3Q15 NS lid-driven cavity scaled to {S}^3 per GPU (BASELINE configs[2])",
-                   "global_sites": world*N, "sites_per_gpu": N, "bytes_per_site_update": B_ALG_NS_SAVE,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (halo exchange not wired into bench yet)",
-                   "l2": "two 16 GB population buffers per GPU >> 126 MB L2, no flush needed"},
+        "config": {"workload": f"production/heatsink3D.cpp forward+adjoint time loops (D3Q15 NS+AD, BASELINE configs[3] physics) on a synthetic {S}^3 block per GPU "
+                               "(configs[2] synthetic-domain scaling); 1 step = 1 forward + 1 adjoint lattice update",
+                   "global_sites": world*N, "sites_per_gpu": N, "lattice_updates_per_step": 2,
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
+                   "l2": f"population buffers {4*15*8*N/1e9:.1f} GB per GPU >> 126 MB L2, no flush needed"},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": 4*N*8/args.steps, "d2h_bytes_per_step": 4*N*8/args.steps,
-                "note": "host rho,u -> H2D -> InitialCondition -> plan -> steps -> D2H rho,u (bytes amortised per step)", "max_abs_ux": checksum},
+        "sweeps": {"forward_mlups": world*N*K/(fwd_ms*1e-3)/1e6, "adjoint_mlups": world*N*K/(adj_ms*1e-3)/1e6, **extra},
+        "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": 4*N*8/K, "d2h_bytes_per_step": 2*N*8/K,
+                "note": "pinned host alpha,kappa,dads,dkds -> H2D -> InitialCondition -> K forward -> adjoint InitialCondition -> K adjoint -> "
+                        "SensitivityTemperatureAtHeatSource -> D2H dfdss,tem (bytes amortised per step)", **checks},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved/peak if achieved else None),
-                     "traffic": None, "kernel": "k_fused<3,1>", "avg_kernel_ms": k_avg_ms, "peak_source": peak_src,
-                     "kernel_share_of_step": (kms.value/ms if ms else None)},
+        "roofline": rf, "roofline_adjoint": ra,
     }
     if world == 1 and not args.no_cpu:
         try:
@@ -229,15 +358,46 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def ns_cavity(pl, api, L, torch, S, K, W, barrier, maxms, world):
+    """test/cavityflow3D.cpp:44-59 scaled to S^3: NS::MacroCollide(save) + Stream + 5 BARRIER walls + lid SetU + SmoothCorner"""
+    import math
+    import numpy as np
+    pf = pl.D3Q15(S, S, S)
+    N = pf.nxyz
+    rho = pl.DeviceArray(N, 1.0)
+    u = [pl.DeviceArray(N, 0.0) for _ in range(3)]
+    pl.NS.InitialCondition(pf, rho, *u)
+    nu, u0, theta = 0.1, 0.1, 90.0
+    wall = lambda i, j, k: np.where((i == 0) | (i == S - 1) | (j == 0) | (j == S - 1) | (k == 0), 1, 0)
+    lid = lambda i, j, k: k == S - 1
+    uv = [lambda i, j, k: u0*math.cos(theta*math.pi/180.0), lambda i, j, k: u0*math.sin(theta*math.pi/180.0), lambda i, j, k: 0.0]
+    plan = pl.StepPlan(pf).set_collide(pl.collide_args(api.M_NS_COLLIDE, True, nu, rho=rho, ux=u[0], uy=u[1], uz=u[2]))
+    plan.add_bounce(pf, wall).add_closure(pf, api.BC_NS_SET_U, lid, uv).set_smooth_corner(True).finalize()
+    plan.advance(W, end_streamed=False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L.pl_plan_profile(plan._h, 1)
+    e0.record()
+    plan.advance(K, end_streamed=False)
+    e1.record()
+    barrier()
+    ms = maxms(e0.elapsed_time(e1))
+    prof = read_profile(L, plan)
+    peak, src = peaks()
+    r = roofline("k_fused<3,1> (NS::MacroCollide + Stream, fused)", B_NS_SAVE, prof, peak, src, ms)
+    return {"workload": f"test/cavityflow3D.cpp scaled to {S}^3 (BASELINE configs[2])", "mlups": world*N*K/(ms*1e-3)/1e6, "ms_per_step": ms/K, "steps": K, "roofline": r}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--cpu-size", type=int, default=160)
-    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--size", type=int, default=352, help="edge of the cubic block per GPU for the NS+AD forward+adjoint sweep")
+    ap.add_argument("--ns-size", type=int, default=512, help="edge of the secondary NS cavity sweep (0 = skip)")
+    ap.add_argument("--cpu-size", type=int, default=128)
+    ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

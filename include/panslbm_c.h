@@ -201,11 +201,11 @@ typedef struct pl_sens_args {
     const double *diffusivity, *dkds, *dbds;
 } pl_sens_args;
 int pl_sensitivity(pl_lattice*, const pl_sens_args*);
-/* Heat-source boundary term of AAD::SensitivityTemperatureAtHeatSource (adjointadvection_avx.h:16-185): one
- * plane per call like a closure; mask/qn baked on the host. The volume term is PL_SENS_AAD_BRINKMAN_DIFF. */
-int pl_sensitivity_heat_source_plane(pl_lattice*, int axis, int coord, int dir, const uint8_t* mask_host, const double* qn_host,
-                                     double* dfds, const double* ux, const double* uy, const double* uz,
-                                     const double* igsnap, const double* diffusivity, const double* dkds);
+/* Heat-source boundary term of AAD::SensitivityTemperatureAtHeatSource (adjointadvection_avx.h:16-185) on one plane.
+ * `plane` is a pl_bc created with type PL_BC_AD_SET_Q for that plane: mask = the _bctype predicate, v0 = the _qnbc values
+ * (baked once and reusable every optimisation iteration). The volume term is pl_sensitivity(PL_SENS_AAD_BRINKMAN_DIFF). */
+int pl_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
+                               const double* igsnap, const double* diffusivity, const double* dkds);
 
 #ifdef __cplusplus
 }

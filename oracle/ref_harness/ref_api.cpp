@@ -297,4 +297,79 @@ double ref_time_cavity3d(int lx, int ly, int lz, int steps, int warmup, double* 
 }
 #endif
 
+// production/heatsink3D.cpp:148-224 (production/heatsink.cpp:140-215 for DIM 2) forward and adjoint time loops on an
+// lx*ly*lz box with caller-supplied alpha / diffusivity fields, convergence `break` disabled; secs[0] = seconds for `steps`
+// forward steps, secs[1] = seconds for `steps` adjoint steps, each after `warmup` untimed steps.
+void ref_time_heatsink(int lx, int ly, int lz, const double* alpha, const double* diffusivity, double nu, double gx, double gy, double gz,
+                       double tem0, double qn0, double L, int steps, int warmup, double* secs) {
+#if DIM == 2
+    PT pf(lx, ly), pg(lx, ly);
+#else
+    PT pf(lx, ly, lz), pg(lx, ly, lz);
+#endif
+    const int n = pf.nxyz;
+    std::vector<double> rho(n, 1.0), ux(n, 0.0), uy(n, 0.0), uz(n, 0.0), uxp(n, 0.0), uyp(n, 0.0), uzp(n, 0.0);
+    std::vector<double> tem(n, 0.0), qx(n, 0.0), qy(n, 0.0), qz(n, 0.0), qxp(n, 0.0), qyp(n, 0.0), qzp(n, 0.0);
+    std::vector<double> irho(n, 0.0), iux(n, 0.0), iuy(n, 0.0), iuz(n, 0.0), imx(n, 0.0), imy(n, 0.0), imz(n, 0.0), iuxp(n, 0.0), iuyp(n, 0.0), iuzp(n, 0.0);
+    std::vector<double> item(n, 0.0), iqx(n, 0.0), iqy(n, 0.0), iqz(n, 0.0), iqxp(n, 0.0), iqyp(n, 0.0), iqzp(n, 0.0);
+    std::vector<double> gi((size_t)n*PT::nc), igi((size_t)n*PT::nc);
+    double *pux = ux.data(), *puy = uy.data(), *puz = uz.data(), *puxp = uxp.data(), *puyp = uyp.data(), *puzp = uzp.data();
+    double *pqx = qx.data(), *pqy = qy.data(), *pqz = qz.data(), *pqxp = qxp.data(), *pqyp = qyp.data(), *pqzp = qzp.data();
+    double *piux = iux.data(), *piuy = iuy.data(), *piuz = iuz.data(), *piuxp = iuxp.data(), *piuyp = iuyp.data(), *piuzp = iuzp.data();
+    double *piqx = iqx.data(), *piqy = iqy.data(), *piqz = iqz.data(), *piqxp = iqxp.data(), *piqyp = iqyp.data(), *piqzp = iqzp.data();
+#if DIM == 2
+#define WALLF [=](int _i, int _j) { return _i == 0 ? 2 : 1; }
+#define WALLG [=](int _i, int _j) { return _i == 0 ? 2 : 0; }
+#define SETT [=](int _i, int _j) { return _i == lx - 1 || _j == ly - 1; }
+#define SETQ [=](int _i, int _j) { return _j == 0; }
+#define SRC [=](int _i, int _j) { return _j == 0 && _i < L; }
+#define QN [=](int _i, int _j) { return (_j == 0 && _i < L) ? qn0 : 0.0; }
+#define TEM [=](int _i, int _j) { return tem0; }
+#else
+#define WALLF [=](int _i, int _j, int _k) { return (_i == 0 || _k == 0) ? 2 : 1; }
+#define WALLG [=](int _i, int _j, int _k) { return (_i == 0 || _k == 0) ? 2 : 0; }
+#define SETT [=](int _i, int _j, int _k) { return _i == lx - 1 || _j == ly - 1 || _k == lz - 1; }
+#define SETQ [=](int _i, int _j, int _k) { return _j == 0; }
+#define SRC [=](int _i, int _j, int _k) { return _j == 0 && _i < L && _k < L; }
+#define QN [=](int _i, int _j, int _k) { return (_j == 0 && _i < L && _k < L) ? qn0 : 0.0; }
+#define TEM [=](int _i, int _j, int _k) { return tem0; }
+#endif
+    NS::InitialCondition(pf, rho.data(), pux, puy ZL(puz));
+    AD::InitialCondition(pg, tem.data(), pux, puy ZL(puz));
+    auto fwd = [&]() {
+        AD::MacroBrinkmanCollideNaturalConvection(pf, rho.data(), pux, puy, Z(puz) alpha, nu, pg, tem.data(), pqx, pqy, Z(pqz) diffusivity, gx, gy, Z(gz) tem0, true, gi.data());
+        pf.Stream(); pg.Stream();
+        pf.BoundaryCondition(WALLF);
+        AD::BoundaryConditionSetT(pg, TEM, pux, puy, Z(puz) SETT);
+        AD::BoundaryConditionSetQ(pg, QN, pux, puy, Z(puz) diffusivity, SETQ);
+        pg.BoundaryCondition(WALLG);
+        pf.SmoothCorner(); pg.SmoothCorner();
+        std::swap(pux, puxp); std::swap(puy, puyp); std::swap(puz, puzp); std::swap(pqx, pqxp); std::swap(pqy, pqyp); std::swap(pqz, pqzp);
+    };
+    for (int t = 0; t < warmup; ++t) fwd();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < steps; ++t) fwd();
+    auto t1 = std::chrono::steady_clock::now();
+    secs[0] = std::chrono::duration<double>(t1 - t0).count();
+    ANS::InitialCondition(pf, pux, puy, Z(puz) irho.data(), piux, piuy ZL(piuz));
+    AAD::InitialCondition(pg, pux, puy, Z(puz) item.data(), piqx, piqy ZL(piqz));
+    auto adj = [&]() {
+        AAD::MacroBrinkmanCollideNaturalConvection(pf, rho.data(), pux, puy, Z(puz) irho.data(), piux, piuy, Z(piuz) imx.data(), imy.data(), Z(imz.data()) alpha, nu,
+                                                   pg, tem.data(), item.data(), piqx, piqy, Z(piqz) diffusivity, gx, gy, Z(gz) true, igi.data());
+        pf.iStream(); pg.iStream();
+        AAD::iBoundaryConditionSetT(pg, pux, puy, Z(puz) SETT);
+        AAD::iBoundaryConditionSetQ(pg, pux, puy, Z(puz) SETQ);
+        AAD::iBoundaryConditionSetQ(pg, pux, puy, Z(puz) SRC, 1.0);
+        pg.iBoundaryCondition(WALLG);
+        pf.iBoundaryCondition(WALLF);
+        pf.SmoothCorner(); pg.SmoothCorner();
+        std::swap(piux, piuxp); std::swap(piuy, piuyp); std::swap(piuz, piuzp); std::swap(piqx, piqxp); std::swap(piqy, piqyp); std::swap(piqz, piqzp);
+    };
+    for (int t = 0; t < warmup; ++t) adj();
+    t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < steps; ++t) adj();
+    t1 = std::chrono::steady_clock::now();
+    secs[1] = std::chrono::duration<double>(t1 - t0).count();
+}
+
 }  // extern "C"

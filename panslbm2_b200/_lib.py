@@ -75,7 +75,7 @@ _PROTOS = {
     "pl_reduce_absmax": (C.c_int, [C.c_void_p, C.c_size_t, c_double_p]),
     "pl_normalize": (C.c_int, [C.c_void_p, C.c_size_t]),
     "pl_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
-    "pl_sensitivity_heat_source_plane": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 9),
+    "pl_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
 }
 EXPORTS = tuple(_PROTOS)
 

@@ -544,15 +544,9 @@ class AAD:
         _sens(q, 3, dfds, kw)
         L = _lib.lib()
         for axis, coord, d in q._faces():
-            coords = q.plane_coords(axis, coord)
-            if coords is None:
-                continue
-            mask = np.ascontiguousarray(q._eval(bctype, coords, np.float64) != 0, dtype=np.uint8)
-            if not mask.any():
-                continue
-            qn = q._eval(qnbc, coords, np.float64)
-            check(L.pl_sensitivity_heat_source_plane(q._h, axis, coord, d, mask.ctypes.data, qn.ctypes.data, dptr(dfds), dptr(kw["ux"]), dptr(kw["uy"]),
-                                                     dptr(kw.get("uz")), dptr(kw["igsnap"]), dptr(kw["diffusivity"]), dptr(kw["dkds"])))
+            plane = q.make_bc(BC_AD_SET_Q, axis, coord, d, bctype, [qnbc])   # baked once, cached by content
+            check(L.pl_sensitivity_heat_source(q._h, plane, dptr(dfds), dptr(kw["ux"]), dptr(kw["uy"]), dptr(kw.get("uz")), dptr(kw["igsnap"]),
+                                               dptr(kw["diffusivity"]), dptr(kw["dkds"])))
 
 
 def _sens(p, kind, dfds, kw):

@@ -33,12 +33,12 @@ template <int D> struct FaceK { static constexpr int n = D == 2 ? 3 : 5; };
 template <int D> PL_HD void face_list(int axis, int sgn, int (&K)[FaceK<D>::n]) {
     int m = 0;
     for (int c = 1; c < LT<D>::nc; ++c)
-        if (cdir<D>(c, axis) == sgn && m < FaceK<D>::n) K[m++] = c;
+        if (rdir<D>(c, axis) == sgn && m < FaceK<D>::n) K[m++] = c;
 }
 // sum_i sign(c_b(K_i)) p[K_i] over the diagonals, left to right
 template <int D> PL_HD double signed_diag_sum(const double (&p)[LT<D>::nc], const int (&K)[FaceK<D>::n], int b) {
-    double s = cdir<D>(K[1], b) > 0 ? p[K[1]] : -p[K[1]];
-    for (int i = 2; i < FaceK<D>::n; ++i) s = cdir<D>(K[i], b) > 0 ? s + p[K[i]] : s - p[K[i]];
+    double s = rdir<D>(K[1], b) > 0 ? p[K[1]] : -p[K[1]];
+    for (int i = 2; i < FaceK<D>::n; ++i) s = rdir<D>(K[i], b) > 0 ? s + p[K[i]] : s - p[K[i]];
     return s;
 }
 // w*p[K0] + p[K1] + ... left to right
@@ -50,7 +50,7 @@ template <int D> PL_HD double weighted_face_sum(const double (&p)[LT<D>::nc], co
 // 1.0 + cx*3ux + cy*3uy (+ cz*3uz), left to right, zero components skipped
 template <int D> PL_HD double one_plus_3cu(int c, double ux, double uy, double uz) {
     double t = 1.0;
-    int x = LT<D>::cx(c), y = LT<D>::cy(c), z = LT<D>::cz(c);
+    int x = rdir<D>(c, 0), y = rdir<D>(c, 1), z = rdir<D>(c, 2);
     if (x) t = x > 0 ? t + 3.0*ux : t - 3.0*ux;
     if (y) t = y > 0 ? t + 3.0*uy : t - 3.0*uy;
     if (D == 3 && z) t = z > 0 ? t + 3.0*uz : t - 3.0*uz;
@@ -65,11 +65,11 @@ template <int D> PL_HD void closure_bounce(double (&p)[LT<D>::nc], int axis, int
     if (type != 1 && type != 2) return;
     const int want = inverse ? dir : -dir;
     for (int c = 1; c < LT<D>::nc; ++c) {
-        if (cdir<D>(c, axis) != want) continue;
+        if (rdir<D>(c, axis) != want) continue;
         int src;
-        if (type == 1) src = LT<D>::opp(c);
+        if (type == 1) src = ropp<D>(c);
         else {
-            int x = LT<D>::cx(c), y = LT<D>::cy(c), z = LT<D>::cz(c);
+            int x = rdir<D>(c, 0), y = rdir<D>(c, 1), z = rdir<D>(c, 2);
             if (axis == 0) x = -x; else if (axis == 1) y = -y; else z = -z;
             src = find_dir<D>(x, y, z);
         }
@@ -88,9 +88,9 @@ template <int D> PL_HD void closure_bounce(double (&p)[LT<D>::nc], int axis, int
 template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir, const SiteVals& V, bool setrho) {
     constexpr int NC = LT<D>::nc;
     double s = p[0];
-    for (int c = 1; c < NC; ++c) if (cdir<D>(c, axis) == 0) s = s + p[c];
+    for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) == 0) s = s + p[c];
     double o = 0.0; bool first = true;
-    for (int c = 1; c < NC; ++c) if (cdir<D>(c, axis) == dir) { o = first ? p[c] : o + p[c]; first = false; }
+    for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) == dir) { o = first ? p[c] : o + p[c]; first = false; }
     const double tot = s + 2.0*o;
     double u[3] = {0.0, 0.0, 0.0}, rho0;
     const int t1 = D == 2 ? 1 - axis : (axis + 1)%3, t2 = D == 2 ? -1 : (axis + 2)%3;
@@ -114,14 +114,14 @@ template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir
     double out[NC];
     for (int c = 1; c < NC; ++c) {
         out[c] = p[c];
-        if (cdir<D>(c, axis) != -dir) continue;
-        int nz = abs(LT<D>::cx(c)) + abs(LT<D>::cy(c)) + abs(LT<D>::cz(c));
+        if (rdir<D>(c, axis) != -dir) continue;
+        int nz = abs(rdir<D>(c, 0)) + abs(rdir<D>(c, 1)) + abs(rdir<D>(c, 2));
         double val;
-        if (nz == 1) val = dir == -1 ? p[LT<D>::opp(c)] + ka*m[axis] : p[LT<D>::opp(c)] - ka*m[axis];
+        if (nz == 1) val = dir == -1 ? p[ropp<D>(c)] + ka*m[axis] : p[ropp<D>(c)] - ka*m[axis];
         else {
-            val = p[LT<D>::opp(c)];
+            val = p[ropp<D>(c)];
             for (int d = 0; d < D; ++d) {
-                int sg = d == axis ? cdir<D>(c, d) : -cdir<D>(c, d);
+                int sg = d == axis ? rdir<D>(c, d) : -rdir<D>(c, d);
                 val = sg > 0 ? val + m[d] : val - m[d];
             }
         }
@@ -140,17 +140,17 @@ template <int D> PL_HD void closure_ad(double (&g)[LT<D>::nc], int axis, int dir
     double tem0;
     if (!setq) {
         double s = V.v0 - g[0];
-        for (int c = 1; c < NC; ++c) if (cdir<D>(c, axis) != -dir) s = s - g[c];
+        for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) != -dir) s = s - g[c];
         tem0 = dir == -1 ? 6.0*s/(1.0 + 3.0*ua) : 6.0*s/(1.0 - 3.0*ua);
     } else {
         double s = (1.0 + 1.0/(6.0*V.kappa))*V.v0;
-        for (int c = 1; c < NC; ++c) if (cdir<D>(c, axis) == dir) s = s + g[c];
+        for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) == dir) s = s + g[c];
         tem0 = dir == -1 ? 6.0*s/(1.0 - 3.0*ua) : 6.0*s/(1.0 + 3.0*ua);
     }
     const double wd = D == 2 ? 36.0 : 72.0;
     for (int c = 1; c < NC; ++c) {
-        if (cdir<D>(c, axis) != -dir) continue;
-        int nz = abs(LT<D>::cx(c)) + abs(LT<D>::cy(c)) + abs(LT<D>::cz(c));
+        if (rdir<D>(c, axis) != -dir) continue;
+        int nz = abs(rdir<D>(c, 0)) + abs(rdir<D>(c, 1)) + abs(rdir<D>(c, 2));
         g[c] = tem0*one_plus_3cu<D>(c, V.ux, V.uy, V.uz)/(nz == 1 ? 9.0 : wd);
     }
 }
@@ -186,7 +186,7 @@ template <int D> PL_HD void closure_ans_isetu(double (&f)[LT<D>::nc], int axis, 
     }
     double nv[FaceK<D>::n];
     for (int i = 0; i < FaceK<D>::n; ++i) nv[i] = f[K[i]] + rho0;
-    for (int i = 0; i < FaceK<D>::n; ++i) f[LT<D>::opp(K[i])] = nv[i];
+    for (int i = 0; i < FaceK<D>::n; ++i) f[ropp<D>(K[i])] = nv[i];
 }
 
 // ANS::iBoundaryConditionSetRho (adjointnavierstokes.h:258-392): rho0 = ((4|8) f_K0 + sum f_Kdiag)/(3|6), f_opp(K) = f_K - rho0
@@ -194,7 +194,7 @@ template <int D> PL_HD void closure_ans_isetrho(double (&f)[LT<D>::nc], int axis
     int K[FaceK<D>::n];
     face_list<D>(axis, -dir, K);
     const double rho0 = D == 2 ? weighted_face_sum<D>(f, K, 4.0)/3.0 : weighted_face_sum<D>(f, K, 8.0)/6.0;
-    for (int i = 0; i < FaceK<D>::n; ++i) f[LT<D>::opp(K[i])] = f[K[i]] - rho0;
+    for (int i = 0; i < FaceK<D>::n; ++i) f[ropp<D>(K[i])] = f[K[i]] - rho0;
 }
 
 // AAD::iBoundaryConditionSetT (adjointadvection.h:154-300): every unknown (opposites of K) takes the same value
@@ -217,7 +217,7 @@ template <int D> PL_HD void closure_aad_isett(double (&g)[LT<D>::nc], int axis, 
             r = r - pick(b, V.ux, V.uy, V.uz)*signed_diag_sum<D>(g, K, b)/(4.0*one3);
         }
     }
-    for (int i = 0; i < FaceK<D>::n; ++i) g[LT<D>::opp(K[i])] = r;
+    for (int i = 0; i < FaceK<D>::n; ++i) g[ropp<D>(K[i])] = r;
 }
 
 // the bracket shared by AAD::iBoundaryConditionSetQ (adjointadvection.h:304-484) and the heat-source term of
@@ -254,7 +254,7 @@ template <int D> PL_HD void closure_aad_isetq(double (&g)[LT<D>::nc], int axis, 
     acc = acc - (D == 2 ? 12.0 : 24.0)*V.eps;
     const double den = (D == 2 ? 6.0 : 12.0)*(dir == -1 ? 1.0 - 3.0*ua : 1.0 + 3.0*ua);
     const double r = acc/den;
-    for (int i = 0; i < FaceK<D>::n; ++i) g[LT<D>::opp(K[i])] = r;
+    for (int i = 0; i < FaceK<D>::n; ++i) g[ropp<D>(K[i])] = r;
 }
 
 // AAD::iBoundaryConditionSetRho for D2Q9 (adjointadvection.h:488-575): f and g lattices together; the mask value
@@ -273,7 +273,7 @@ PL_HD void closure_aad_isetrho2d(double (&f)[9], const double (&g)[9], int axis,
     const double obj0 = V.eps*2.0*V.tem/(onem*V.rho);
     double nv[3];
     for (int i = 0; i < 3; ++i) nv[i] = f[K[i]] + rho0 + flux0 + obj0;
-    for (int i = 0; i < 3; ++i) f[LT<2>::opp(K[i])] = nv[i];
+    for (int i = 0; i < 3; ++i) f[ropp<2>(K[i])] = nv[i];
 }
 
 // One closure application on a site.  p = populations of the lattice the closure acts on; q = the other lattice's

@@ -6,11 +6,6 @@
 
 namespace plb {
 
-// Shell membership = union of axis-aligned planes; byte per coordinate, non-zero = plane is in the shell.
-struct ShellMask {
-    const uint8_t *x, *y, *z;   // x == nullptr: no shell (the interior kernel takes every packed site)
-};
-
 // signed index deltas to the periodic neighbours of one site (reference Index(): d3q15.h:136-141)
 struct Nbr {
     long long m[3], p[3];   // delta to coordinate-1 / coordinate+1 along x,y,z
@@ -90,30 +85,6 @@ __global__ void __launch_bounds__(256) k_collide(Geom G, double* __restrict__ fb
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The hot kernel: one fused Stream + Macro*Collide* pass, source buffer -> destination buffer, for every
-// packed site that is not in the shell (shell = planes carrying closures / SmoothCorner, handled by the
-// boundary pass k_shell).  Each population is read once and written once.
-template <int D, int M>
-__global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
-                                               const double* __restrict__ gs, double* __restrict__ gd,
-                                               CollideParams P, ShellMask S, int inverse) {
-    constexpr unsigned FL = ModelFlags<M>::v;
-    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-    if (idx >= G.npacked) return;
-    int i, j, k;
-    decompose(G, idx, i, j, k);
-    if (S.x != nullptr && (S.x[i] | S.y[j] | S.z[k])) return;
-    Nbr n = neighbours(G, i, j, k);
-    orient(n, inverse);
-    double f[LT<D>::nc], g[LT<D>::nc];
-    pull<D>(f, fs, G.pitch, idx, n);
-    if constexpr ((FL & F_G) != 0) pull<D>(g, gs, G.pitch, idx, n);
-    collide_site<D, FL, false>(f, g, P, (size_t)idx);
-    store_site<D>(f, fd, G.pitch, idx);
-    if constexpr ((FL & F_G) != 0) store_site<D>(g, gd, G.pitch, idx);
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // Plane descriptor shared by every closure kernel.  n1 x n2 local plane sites, site index = base + a*s1 + b*s2.
 struct Plane {
     int axis, dir;          // normal axis 0/1/2, outward direction -1/+1
@@ -177,38 +148,102 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// The boundary pass of a fused step: one thread per listed site does Stream (pull from the source buffers), the plan's
-// closure program in call order on the register copy, and then either the collide of the next step (t < ndirect) or,
-// for the sites SmoothCorner reads or writes (t >= ndirect), a plain store of the streamed+closed populations; those
-// few sites are finished by k_smooth + k_collide on the destination buffer.
+// Per-coordinate plane words of a plan (one 64-bit word per local x / y / z coordinate):
+//   bits 0..61: entry e of the closure program acts on this plane
+//   bit 62    : (x only) the coordinate shares an aligned group of 8 sites with an x closure plane: the boundary pass takes
+//               the whole group so that its accesses to x planes fill 64-byte DRAM bursts instead of 8 bytes of each
+//   bit 63    : the plane is a global boundary plane or next to one and the plan has SmoothCorner; sites with two such
+//               coordinates form the edge "tubes" SmoothCorner reads and writes.
+struct ShellMask {
+    const unsigned long long *x, *y, *z;
+};
+constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT);
+constexpr int MAX_PROGRAM = 62;
+PL_D bool in_tube(unsigned long long wx, unsigned long long wy, unsigned long long wz) { return (wx >> 63) + (wy >> 63) + (wz >> 63) >= 2ull; }
+
+// A plan's closure program on one site: the recorded closures whose plane passes through the site (bits of `entries`), in
+// call order, each applied where its baked mask is set.  Deliberately NOT inlined and fed through an addressable copy of
+// the populations: the closures index p[] dynamically, which would otherwise drag the populations of the collide into
+// local memory.
+template <int D, bool HASG>
+__device__ __noinline__ void run_program(double* __restrict__ fg, const ClosureArgs* __restrict__ prog, unsigned long long entries,
+                                         int i, int j, int k, long long idx) {
+    constexpr int NC = LT<D>::nc;
+    double (&f)[NC] = *reinterpret_cast<double (*)[NC]>(fg);
+    double (&g)[NC] = *reinterpret_cast<double (*)[NC]>(fg + NC);
+    const int co[3] = {i, j, k};
+    while (entries) {
+        const int e = __ffsll((long long)entries) - 1;
+        entries &= entries - 1;
+        const ClosureArgs& A = prog[e];
+        const int axis = A.pl.axis;
+        const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+        const int pt = co[a1] + A.pl.n1*co[a2];
+        const int m = A.mask[pt];
+        if (!m) continue;
+        if (A.on_g) { if constexpr (HASG) apply_closure<D>(A.type, axis, A.pl.dir, m, g, f, site_vals(A, pt, idx)); }
+        else apply_closure<D>(A.type, axis, A.pl.dir, m, f, g, site_vals(A, pt, idx));
+    }
+}
+template <int D, bool HASG>
+PL_D void boundary_path(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const ClosureArgs* __restrict__ prog, unsigned long long entries,
+                        int i, int j, int k, long long idx) {
+    constexpr int NC = LT<D>::nc;
+    double t[2*NC];
+    sfor<0, NC>([&](auto C) { constexpr int c = decltype(C)::value; t[c] = f[c]; t[NC + c] = HASG ? g[c] : 0.0; });
+    run_program<D, HASG>(t, prog, entries, i, j, k, idx);
+    sfor<0, NC>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = t[c]; if constexpr (HASG) g[c] = t[NC + c]; });
+}
+
+// The hot kernel: one fused Stream + Macro*Collide* pass, source buffer -> destination buffer, for every packed site that
+// lies on no closure plane and in no SmoothCorner tube.  Each population is read once and written once.
+template <int D, int M>
+__global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
+                                               const double* __restrict__ gs, double* __restrict__ gd,
+                                               CollideParams P, ShellMask S, int inverse) {
+    constexpr unsigned FL = ModelFlags<M>::v;
+    constexpr bool HASG = (FL & F_G) != 0;
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.npacked) return;
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    if ((S.x[i] | S.y[j] | S.z[k]) != 0ull) {
+        const unsigned long long wx = S.x[i], wy = S.y[j], wz = S.z[k];
+        if (((wx | wy | wz) & ~TUBE_BIT) != 0ull || in_tube(wx, wy, wz)) return;
+    }
+    Nbr n = neighbours(G, i, j, k);
+    orient(n, inverse);
+    double f[LT<D>::nc], g[LT<D>::nc];
+    pull<D>(f, fs, G.pitch, idx, n);
+    if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
+    collide_site<D, FL, false>(f, g, P, (size_t)idx);
+    store_site<D>(f, fd, G.pitch, idx);
+    if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+}
+
+// The boundary pass of a fused step, one thread per listed site: Stream (pull), the closure program, and then either the
+// collide of the next step (t < ndirect: sites on closure planes, sites of the last incomplete AVX pack) or, for the
+// SmoothCorner tubes (t >= ndirect), a plain store of the streamed+closed populations; the tubes are finished by
+// k_smooth + k_collide on the destination buffer.  Runs beside k_fused on its own stream.
 template <int D, int M>
 __global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
-                                               const double* __restrict__ gs, double* __restrict__ gd, CollideParams P,
-                                               const ClosureArgs* __restrict__ prog, int nprog,
+                                               const double* __restrict__ gs, double* __restrict__ gd, CollideParams P, ShellMask S,
+                                               const ClosureArgs* __restrict__ prog,
                                                const int* __restrict__ list, int nlist, int ndirect, int inverse) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     int t = blockIdx.x*blockDim.x + threadIdx.x;
     if (t >= nlist) return;
     const long long idx = list[t];
-    int co[3];
-    decompose(G, idx, co[0], co[1], co[2]);
-    Nbr n = neighbours(G, co[0], co[1], co[2]);
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    const unsigned long long entries = (S.x[i] | S.y[j] | S.z[k]) & ENTRY_BITS;
+    Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
     double f[LT<D>::nc], g[LT<D>::nc];
     pull<D>(f, fs, G.pitch, idx, n);
     if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
-    else { for (int c = 0; c < LT<D>::nc; ++c) g[c] = 0.0; }
-    for (int e = 0; e < nprog; ++e) {
-        const ClosureArgs& A = prog[e];
-        if (co[A.pl.axis] != A.loc) continue;
-        const int a1 = A.pl.axis == 0 ? 1 : 0, a2 = A.pl.axis == 2 ? 1 : 2;
-        const int pt = co[a1] + A.pl.n1*(D == 2 ? 0 : co[a2]);
-        const int m = A.mask[pt];
-        if (!m) continue;
-        if (A.on_g) { if constexpr (HASG) apply_closure<D>(A.type, A.pl.axis, A.pl.dir, m, g, f, site_vals(A, pt, idx)); }
-        else apply_closure<D>(A.type, A.pl.axis, A.pl.dir, m, f, g, site_vals(A, pt, idx));
-    }
+    if (entries) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
     if (t < ndirect) {
         if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
         else collide_site<D, FL, true>(f, g, P, (size_t)idx);

@@ -47,10 +47,32 @@ template <> struct LT<3> {
 
 template <int D> PL_HD constexpr int cdir(int c, int axis) { return axis == 0 ? LT<D>::cx(c) : (axis == 1 ? LT<D>::cy(c) : LT<D>::cz(c)); }
 
-// index of the direction with the given integer velocity, -1 if none (runtime helper for table-driven closures)
+// Run-time lookups (c not a compile-time constant: the boundary closures).  Indexing the constexpr tables above with a
+// run-time c makes the compiler rebuild the table on the thread's stack at every call; these bit-packed words are pure ALU.
+template <int D> PL_HD constexpr unsigned pack_dirs(int axis) {
+    unsigned v = 0;
+    for (int c = 0; c < LT<D>::nc; ++c) v |= (unsigned)(cdir<D>(c, axis) + 1) << (2*c);
+    return v;
+}
+template <int D> PL_HD constexpr unsigned long long pack_opps() {
+    unsigned long long v = 0;
+    for (int c = 0; c < LT<D>::nc; ++c) v |= (unsigned long long)LT<D>::opp(c) << (4*c);
+    return v;
+}
+template <int D> PL_HD int rdir(int c, int axis) {
+    constexpr unsigned X = pack_dirs<D>(0), Y = pack_dirs<D>(1), Z = pack_dirs<D>(2);
+    const unsigned w = axis == 0 ? X : (axis == 1 ? Y : Z);
+    return (int)((w >> (2*c)) & 3u) - 1;
+}
+template <int D> PL_HD int ropp(int c) {
+    constexpr unsigned long long O = pack_opps<D>();
+    return (int)((O >> (4*c)) & 15ull);
+}
+
+// index of the direction with the given integer velocity, -1 if none (run-time helper for table-driven closures)
 template <int D> PL_HD int find_dir(int x, int y, int z) {
     for (int c = 0; c < LT<D>::nc; ++c)
-        if (LT<D>::cx(c) == x && LT<D>::cy(c) == y && LT<D>::cz(c) == z) return c;
+        if (rdir<D>(c, 0) == x && rdir<D>(c, 1) == y && rdir<D>(c, 2) == z) return c;
     return -1;
 }
 

@@ -34,14 +34,29 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
             return nullptr;                                                                             \
         }                                                                                               \
     } while (0)
-#define LAUNCH(kernel, grid, block, ...)                                                                \
+#define LAUNCH_ON(stream, kernel, grid, block, ...)                                                     \
     do {                                                                                                \
-        kernel<<<(grid), (block), 0, g_stream>>>(__VA_ARGS__);                                          \
+        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                                          \
         ++g_launches;                                                                                   \
         CU(cudaGetLastError());                                                                         \
     } while (0)
+#define LAUNCH(kernel, grid, block, ...) LAUNCH_ON(g_stream, kernel, grid, block, __VA_ARGS__)
 
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1)/bs); }
+
+// grow-only device scratch for the reductions: cudaMalloc/cudaFree per call would cost milliseconds next to tens of GB of
+// live allocations and synchronise the device
+struct Scratch {
+    void* p = nullptr; size_t cap = 0;
+    void* get(size_t bytes) {
+        if (bytes > cap) {
+            if (p) { cudaStreamSynchronize(g_stream); cudaFree(p); p = nullptr; cap = 0; }
+            if (cudaMalloc(&p, bytes) != cudaSuccess) { p = nullptr; return nullptr; }
+            cap = bytes;
+        }
+        return p;
+    }
+} g_scratch;
 }  // namespace
 
 struct pl_lattice {
@@ -548,13 +563,16 @@ struct pl_plan {
     int smooth_f = 0, smooth_g = 0;
     bool finalized = false;
     int parity = 0;
-    // boundary pass: plane masks for the interior kernel, site list (direct sites first, SmoothCorner-coupled sites last),
-    // closure program per argument-set parity
-    uint8_t *mx = nullptr, *my = nullptr, *mz = nullptr;
+    // per-coordinate plane words (see ShellMask), the site list of k_shell (closure-plane and AVX-tail sites first,
+    // SmoothCorner tube sites last), the closure program per argument-set parity
+    unsigned long long *mx = nullptr, *my = nullptr, *mz = nullptr;
     int* list = nullptr;
     int nlist = 0, ndirect = 0;
     ClosureArgs* prog[2] = {nullptr, nullptr};
     int nprog = 0;
+    // the boundary pass runs beside the interior kernel on its own (high-priority) stream
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // measurement hook
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -587,8 +605,8 @@ int plan_collide_full(pl_plan* p, int parity) {              // standalone C: ev
 }
 template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
     if (p->nlist == 0) return PL_OK;
-    LAUNCH((k_shell<D, M>), blocks_for(p->nlist, 128), 128, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
-           g ? g->other() : nullptr, P, p->prog[bc_parity], p->nprog, p->list, p->nlist, p->ndirect, p->inverse);
+    LAUNCH_ON(p->side, (k_shell<D, M>), blocks_for(p->nlist, 128), 128, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
+           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz}, p->prog[bc_parity], p->list, p->nlist, p->ndirect, p->inverse);
     return PL_OK;
 }
 int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
@@ -609,6 +627,12 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     pl_lattice* g = (flags & F_G) ? p->g : nullptr;
     if (p->g && !g) return fail(PL_ERR_ARG, "plan: a single-lattice collide cannot drive a two-lattice plan");
     ShellMask S{p->mx, p->my, p->mz};
+    // boundary pass on the side stream (closure planes, SmoothCorner tubes, AVX-tail sites): it touches only sites the
+    // interior kernel skips, so the two run concurrently
+    CU(cudaEventRecord(p->ev_fork, g_stream));
+    CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
+    CU(cudaEventRecord(p->ev_join, p->side));
     // interior: one pass, source -> destination
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (p->profile) {
@@ -621,8 +645,7 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
         p->events.emplace_back(ev0, ev1);
         p->profiled_sites += p->f->g.nxyz - p->nlist;
     }
-    // boundary pass: Stream + closure program (+ collide for the sites SmoothCorner does not touch), source -> destination
-    if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
+    CU(cudaStreamWaitEvent(g_stream, p->ev_join, 0));
     p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
     // SmoothCorner and the collide of the sites it couples, in place on the destination
     if (p->smooth_f && (r = do_smooth(p->f))) return r;
@@ -640,6 +663,15 @@ pl_plan* pl_plan_create(pl_lattice* f, pl_lattice* g) {
     if (g && !same_shape(f, g)) { fail(PL_ERR_ARG, "pl_plan_create: lattices differ in shape"); return nullptr; }
     pl_plan* p = new pl_plan();
     p->f = f; p->g = g;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        fail(PL_ERR_CUDA, std::string("pl_plan_create: ") + cudaGetErrorString(cudaGetLastError()));
+        delete p;
+        return nullptr;
+    }
     return p;
 }
 int pl_plan_destroy(pl_plan* p) {
@@ -647,6 +679,9 @@ int pl_plan_destroy(pl_plan* p) {
     cudaStreamSynchronize(g_stream);
     cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
     for (auto& e : p->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     delete p;
     return PL_OK;
 }
@@ -679,14 +714,15 @@ int pl_plan_set_smooth_corner(pl_plan* p, int on_f, int on_g) {
 int pl_plan_finalize(pl_plan* p) {
     if (!p || !p->have_collide) return fail(PL_ERR_ARG, "pl_plan_finalize: no collide set");
     const Geom& g = p->f->g;
-    std::vector<uint8_t> hx(g.nx, 0), hy(g.ny, 0), hz(g.nz, 0);
-    std::vector<uint8_t>* h[3] = {&hx, &hy, &hz};
+    std::vector<unsigned long long> hx(g.nx, 0), hy(g.ny, 0), hz(g.nz, 0);
+    std::vector<unsigned long long>* h[3] = {&hx, &hy, &hz};
     int off[3] = {g.offx, g.offy, g.offz};
     // closure program: the non-empty closures in call order, one copy per argument-set parity
     std::vector<ClosureArgs> prog[2];
     for (auto& b : p->bcs) {
         if (b.bc->empty) continue;
-        (*h[b.bc->axis])[b.bc->coord - off[b.bc->axis]] = 1;
+        if (prog[0].size() >= (size_t)MAX_PROGRAM) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: more than 62 non-empty closures in one loop body");
+        (*h[b.bc->axis])[b.bc->coord - off[b.bc->axis]] |= 1ull << prog[0].size();
         for (int par = 0; par < 2; ++par) {
             ClosureArgs A;
             pl_lattice* l = b.on_g ? p->g : p->f;
@@ -696,52 +732,64 @@ int pl_plan_finalize(pl_plan* p) {
             prog[par].push_back(A);
         }
     }
-    // sites SmoothCorner writes (edge lines, corners) or reads (their inward neighbours): collide is deferred for them
-    std::vector<long long> coupled;
+    // x closure planes: the boundary pass takes the aligned group of 8 x-coordinates around each (see ShellMask)
+    for (int i = 0; i < g.nx; ++i)
+        if (hx[i] & ENTRY_BITS) for (int v = i & ~7; v < std::min(g.nx, (i & ~7) + 8); ++v) hx[v] |= SLAB_BIT;
+    // SmoothCorner: flag the global boundary planes and their inward neighbours (bit 1); sites with two flagged coordinates
+    // form the edge tubes.  Every site SmoothCorner writes (edge lines, corners) or reads (their inward neighbours) must lie
+    // in a tube: collide is deferred there until k_smooth has run.
+    int n[3] = {g.nx, g.ny, g.nz}, ext[3] = {g.lx, g.ly, g.lz};
     if (p->smooth_f || p->smooth_g) {
-        int n[3] = {g.nx, g.ny, g.nz}, ext[3] = {g.lx, g.ly, g.lz};
         for (int a = 0; a < p->f->kind; ++a) {
             int lo = 0 - off[a], hi = ext[a] - 1 - off[a];
-            if (0 <= lo && lo < n[a]) (*h[a])[lo] = 1;
-            if (0 <= hi && hi < n[a]) (*h[a])[hi] = 1;
+            for (int v : {lo, lo + 1, hi - 1, hi}) if (0 <= v && v < n[a]) (*h[a])[v] |= TUBE_BIT;
         }
+    }
+    auto coords = [&](long long idx, int& i, int& j, int& k) {
+        k = (int)(idx/((long long)g.nx*g.ny)); int r = (int)(idx - (long long)k*g.nx*g.ny); j = r/g.nx; i = r - j*g.nx;
+    };
+    auto tube = [&](int i, int j, int k) { return (hx[i] >> 63) + (hy[j] >> 63) + (hz[k] >> 63) >= 2; };
+    if (p->smooth_f || p->smooth_g) {
         SmoothList e, c;
         smooth_lists(p->f, e, c);
         for (SmoothList* L : {&e, &c})
-            for (int n = 0; n < L->count; ++n) {
-                const SmoothItem& it = L->it[n];
+            for (int m = 0; m < L->count; ++m) {
+                const SmoothItem& it = L->it[m];
                 for (int t = 0; t < it.len; ++t) {
                     long long idx = it.base + (long long)t*it.stride;
-                    coupled.push_back(idx); coupled.push_back(idx + it.n0); coupled.push_back(idx + it.n1);
-                    if (it.n2 != 0) coupled.push_back(idx + it.n2);
+                    for (long long s : {idx, idx + it.n0, idx + it.n1, idx + it.n2}) {
+                        int i, j, k;
+                        coords(s, i, j, k);
+                        if (!tube(i, j, k)) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: SmoothCorner on a block this thin is not supported by the fused plan");
+                    }
                 }
             }
-        std::sort(coupled.begin(), coupled.end());
-        coupled.erase(std::unique(coupled.begin(), coupled.end()), coupled.end());
     }
-    auto is_coupled = [&](long long idx) { return std::binary_search(coupled.begin(), coupled.end(), idx); };
-    // the interior kernel skips whole planes: every coupled site must lie on a marked plane (they all lie on the global
-    // boundary planes marked above; the fallback keeps the two kernels disjoint in any case)
-    for (long long idx : coupled) {
-        int k = (int)(idx/((long long)g.nx*g.ny)), r = (int)(idx - (long long)k*g.nx*g.ny), j = r/g.nx, i = r - j*g.nx;
-        if (!(hx[i] || hy[j] || hz[k])) hx[i] = 1;
-    }
-    // list = [sites on marked planes and AVX-tail sites that SmoothCorner does not couple | coupled sites]
-    std::vector<int> list;
+    // list = [sites on closure planes and sites of the last incomplete AVX pack, outside the tubes | tube sites]
+    std::vector<int> list, tubes;
     for (int k = 0; k < g.nz; ++k)
-        for (int j = 0; j < g.ny; ++j)
-            for (int i = 0; i < g.nx; ++i) {
-                long long idx = i + (long long)g.nx*(j + (long long)g.ny*k);
-                if ((hx[i] || hy[j] || hz[k] || idx >= g.npacked) && !is_coupled(idx)) list.push_back((int)idx);
+        for (int j = 0; j < g.ny; ++j) {
+            const unsigned long long wyz = hy[j] | hz[k];
+            const int two = (int)((hy[j] >> 63) + (hz[k] >> 63));
+            const long long row = (long long)g.nx*(j + (long long)g.ny*k);
+            const bool tailrow = row + g.nx > g.npacked;
+            if (!(wyz & ~TUBE_BIT) && two == 0 && !tailrow) {   // only the x planes can put a site of this row on the list
+                for (int i = 0; i < g.nx; ++i) if (hx[i] & ~TUBE_BIT) list.push_back((int)(row + i));
+                continue;
             }
+            for (int i = 0; i < g.nx; ++i) {
+                if (two + (int)(hx[i] >> 63) >= 2) tubes.push_back((int)(row + i));
+                else if (((wyz | hx[i]) & ~TUBE_BIT) || row + i >= g.npacked) list.push_back((int)(row + i));
+            }
+        }
     p->ndirect = (int)list.size();
-    for (long long idx : coupled) list.push_back((int)idx);
+    list.insert(list.end(), tubes.begin(), tubes.end());
     cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
     p->mx = p->my = p->mz = nullptr; p->list = nullptr; p->prog[0] = p->prog[1] = nullptr;
-    CU(cudaMalloc(&p->mx, g.nx)); CU(cudaMalloc(&p->my, g.ny)); CU(cudaMalloc(&p->mz, g.nz));
-    CU(cudaMemcpy(p->mx, hx.data(), g.nx, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(p->my, hy.data(), g.ny, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(p->mz, hz.data(), g.nz, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&p->mx, g.nx*8)); CU(cudaMalloc(&p->my, g.ny*8)); CU(cudaMalloc(&p->mz, g.nz*8));
+    CU(cudaMemcpy(p->mx, hx.data(), g.nx*8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->my, hy.data(), g.ny*8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(p->mz, hz.data(), g.nz*8, cudaMemcpyHostToDevice));
     p->nlist = (int)list.size();
     if (p->nlist) {
         CU(cudaMalloc(&p->list, list.size()*sizeof(int)));
@@ -801,40 +849,37 @@ int pl_plan_advance(pl_plan* p, int ncollides, int end_streamed) {
 // ---- reductions ---------------------------------------------------------------------------------
 int pl_residual(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, size_t n, double* out) {
     if (!ux || !uxp || !out) return fail(PL_ERR_ARG, "pl_residual: null");
-    double* scratch = nullptr;
     const int nb = 1024;
-    CU(cudaMalloc(&scratch, 2*(nb + 1)*sizeof(double)));
+    double* scratch = (double*)g_scratch.get(2*(nb + 1)*sizeof(double));
+    if (!scratch) return fail(PL_ERR_CUDA, "pl_residual: scratch allocation failed");
     LAUNCH(k_residual_partial, nb, 256, ux, uy, uz, uxp, uyp, uzp, (long long)n, scratch);
     LAUNCH(k_sum_final, 1, 256, scratch, nb, 2, scratch + 2*nb);
     double h[2];
     CU(cudaMemcpyAsync(h, scratch + 2*nb, 2*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
-    cudaFree(scratch);
     *out = sqrt(h[0]/h[1]);
     return PL_OK;
 }
 int pl_reduce_sum(const double* v, size_t n, double* out) {
     if (!v || !out) return fail(PL_ERR_ARG, "pl_reduce_sum: null");
-    double* scratch = nullptr;
     const int nb = 1024;
-    CU(cudaMalloc(&scratch, (nb + 1)*sizeof(double)));
+    double* scratch = (double*)g_scratch.get((nb + 1)*sizeof(double));
+    if (!scratch) return fail(PL_ERR_CUDA, "pl_reduce_sum: scratch allocation failed");
     LAUNCH(k_sum_partial, nb, 256, v, (long long)n, scratch);
     LAUNCH(k_sum_final, 1, 256, scratch, nb, 1, scratch + nb);
     CU(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
-    cudaFree(scratch);
     return PL_OK;
 }
 int pl_reduce_absmax(const double* v, size_t n, double* out) {
     if (!v || !out) return fail(PL_ERR_ARG, "pl_reduce_absmax: null");
-    double* scratch = nullptr;
     const int nb = 1024;
-    CU(cudaMalloc(&scratch, (nb + 1)*sizeof(double)));
+    double* scratch = (double*)g_scratch.get((nb + 1)*sizeof(double));
+    if (!scratch) return fail(PL_ERR_CUDA, "pl_reduce_absmax: scratch allocation failed");
     LAUNCH(k_absmax_partial, nb, 256, v, (long long)n, scratch);
     LAUNCH(k_absmax_final, 1, 256, scratch, nb, scratch + nb);
     CU(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
-    cudaFree(scratch);
     return PL_OK;
 }
 int pl_normalize(double* v, size_t n) {
@@ -863,28 +908,19 @@ int pl_sensitivity(pl_lattice* l, const pl_sens_args* a) {
     else LAUNCH(k_sensitivity<2>, blocks_for(l->g.nxyz, 256), 256, l->g, A);
     return PL_OK;
 }
-int pl_sensitivity_heat_source_plane(pl_lattice* l, int axis, int coord, int dir, const uint8_t* mask_host, const double* qn_host, double* dfds,
-                                     const double* ux, const double* uy, const double* uz, const double* igsnap, const double* diffusivity,
-                                     const double* dkds) {
-    if (!l || !dfds || !ux || !uy || (l->kind == PL_D3Q15 && !uz) || !igsnap || !diffusivity || !dkds)
-        return fail(PL_ERR_ARG, "pl_sensitivity_heat_source_plane: null argument");
-    pl_bc* bc = pl_bc_create(l, PL_BC_AD_SET_Q, axis, coord, dir, mask_host, qn_host, nullptr, nullptr);
-    if (!bc) return PL_ERR_ARG;
-    int r = PL_OK;
-    if (!bc->empty) {
-        if (!bc->v0) { pl_bc_destroy(bc); return fail(PL_ERR_ARG, "pl_sensitivity_heat_source_plane: qn values are required"); }
-        ClosureArgs A{};
-        A.type = 0; A.pl = bc->pl; A.mask = bc->mask; A.v0 = bc->v0; A.ux = ux; A.uy = uy; A.uz = uz; A.kappa = diffusivity;
-        int np = bc->pl.n1*bc->pl.n2;
-        cudaError_t e;
-        if (l->kind == PL_D2Q9) k_sens_heat_source<2><<<blocks_for(np, 128), 128, 0, g_stream>>>(l->g, A, igsnap, dkds, dfds);
-        else k_sens_heat_source<3><<<blocks_for(np, 128), 128, 0, g_stream>>>(l->g, A, igsnap, dkds, dfds);
-        ++g_launches;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) r = fail(PL_ERR_CUDA, std::string("k_sens_heat_source: ") + cudaGetErrorString(e));
-    }
-    pl_bc_destroy(bc);   // synchronises the stream before freeing the baked arrays
-    return r;
+int pl_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
+                                const double* igsnap, const double* diffusivity, const double* dkds) {
+    if (!l || !plane || !dfds || !ux || !uy || (l->kind == PL_D3Q15 && !uz) || !igsnap || !diffusivity || !dkds)
+        return fail(PL_ERR_ARG, "pl_sensitivity_heat_source: null argument");
+    if (plane->empty) return PL_OK;
+    if (!same_shape(plane->lat, l)) return fail(PL_ERR_ARG, "pl_sensitivity_heat_source: plane was created for a lattice of another shape");
+    if (!plane->v0) return fail(PL_ERR_ARG, "pl_sensitivity_heat_source: the plane carries no qn values");
+    ClosureArgs A{};
+    A.type = 0; A.pl = plane->pl; A.mask = plane->mask; A.v0 = plane->v0; A.ux = ux; A.uy = uy; A.uz = uz; A.kappa = diffusivity;
+    int np = plane->pl.n1*plane->pl.n2;
+    if (l->kind == PL_D2Q9) LAUNCH(k_sens_heat_source<2>, blocks_for(np, 128), 128, l->g, A, igsnap, dkds, dfds);
+    else LAUNCH(k_sens_heat_source<3>, blocks_for(np, 128), 128, l->g, A, igsnap, dkds, dfds);
+    return PL_OK;
 }
 
 }  // extern "C"
