@@ -42,6 +42,29 @@ int pl_set_stream(void* custream);
 uint64_t pl_launch_count(void);
 void pl_launch_count_reset(void);
 
+/* ---- communicator: replaces MPI_COMM_WORLD of the reference's _USE_MPI_DEFINES build --------------------------
+ * One process per GPU; rank == PEid of every lattice created afterwards; nranks == mx*my*mz.  The 128-byte id is
+ * NCCL's unique id: rank 0 obtains it and the host program distributes it (torch.distributed, MPI, a file ...).
+ * With a communicator, Stream()/iStream() of a decomposed lattice exchange the outgoing populations with the 26
+ * neighbours of the periodic PE grid (d3q15.h:1306-1407: 5 per face site, 2 per edge site, 1 per corner; d2q9.h:590-630)
+ * by ncclSend/ncclRecv on a dedicated stream, and pl_residual / pl_normalize reduce over all ranks as the reference's MPI
+ * build does (residual.h:16, normalize.h:17). */
+int pl_comm_unique_id(char* out128);
+int pl_comm_init(const char* id128, int rank, int nranks);
+/* Process-local world for parity tests on ONE device: the blocks of all `nranks` PEs are created in this process and
+ * exchange through device memory.  The caller must advance the ranks in lockstep (same call sequence on every rank, one
+ * call at a time per rank).  The n-th lattice created with a PEid pairs with the n-th lattice of every other PEid. */
+int pl_comm_init_loopback(int nranks);
+int pl_comm_destroy(void);
+int pl_comm_info(int* mode, int* rank, int* nranks);   /* mode: 0 none, 1 NCCL, 2 loopback */
+/* MPI_Allreduce(MPI_IN_PLACE, v, n<=4, MPI_DOUBLE, op) of the drivers (heatsink3D.cpp:136, 236, 272): op 0 = SUM, 1 = MAX */
+int pl_comm_allreduce(double* inout_host, int n, int op);
+/* Pure host arithmetic (no device needed): the messages rank `peid` sends per Stream (inverse=0) / iStream (1), in issue
+ * order.  out: 16 ints per message = code, peer, region sites, npop, pop[5], base, s1, s2, n1, n2, code of the message
+ * received in the same step, 0; the count in doubles is region sites * npop.  Every rank sends message `code` to `peer`
+ * and receives the message of equal size from the peer of the opposite code. */
+int pl_halo_describe(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz, int inverse, int* out, int* count);
+
 /* ---- device arrays (caller-owned macroscopic fields: `new double[nxyz]` in the drivers,
  *      e.g. production/heatsink3D.cpp:50-59) ------------------------------------------------- */
 double* pl_array_alloc(size_t n);                 /* NULL on failure */

@@ -39,6 +39,13 @@ _PROTOS = {
     "pl_set_stream": (C.c_int, [C.c_void_p]),
     "pl_launch_count": (C.c_uint64, []),
     "pl_launch_count_reset": (None, []),
+    "pl_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "pl_comm_init": (C.c_int, [C.c_char_p, C.c_int, C.c_int]),
+    "pl_comm_init_loopback": (C.c_int, [C.c_int]),
+    "pl_comm_destroy": (C.c_int, []),
+    "pl_comm_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "pl_comm_allreduce": (C.c_int, [c_double_p, C.c_int, C.c_int]),
+    "pl_halo_describe": (C.c_int, [C.c_int] * 9 + [C.c_void_p, C.POINTER(C.c_int)]),
     "pl_array_alloc": (C.c_void_p, [C.c_size_t]),
     "pl_array_free": (C.c_int, [C.c_void_p]),
     "pl_array_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -102,6 +102,58 @@ def synchronize():
 
 
 # ----------------------------------------------------------------------------------------------------------
+# communicator (replaces MPI_COMM_WORLD of the reference's _USE_MPI_DEFINES build; include/panslbm_c.h pl_comm_*)
+def comm_init_torch():
+    """One process per GPU under torchrun: rank 0 draws NCCL's unique id, torch.distributed carries it to the other ranks,
+    every rank joins.  torch.distributed is plumbing only: the halo exchange itself is ncclSend/ncclRecv issued by
+    libpanslbm_b200.so on its own stream."""
+    import torch
+    import torch.distributed as dist
+    L = _lib.lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    buf = C.create_string_buffer(128)
+    if rank == 0:
+        check(L.pl_comm_unique_id(buf))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, 0)
+    ident = bytes(t.cpu().tolist())
+    check(L.pl_comm_init(ident, rank, world))
+    return rank, world
+
+
+def comm_init_loopback(nranks: int):
+    check(_lib.lib().pl_comm_init_loopback(int(nranks)))
+
+
+def comm_destroy():
+    check(_lib.lib().pl_comm_destroy())
+
+
+def comm_allreduce(values, op="sum"):
+    """MPI_Allreduce of up to 4 doubles over the communicator (identity without one)"""
+    v = (C.c_double*len(values))(*[float(x) for x in values])
+    check(_lib.lib().pl_comm_allreduce(v, len(values), 0 if op == "sum" else 1))
+    return list(v)
+
+
+def halo_describe(kind, lx, ly, lz, peid, mx, my, mz, inverse=False):
+    """messages of rank `peid` per Stream/iStream in issue order: list of dicts (host arithmetic only, no device)"""
+    out = np.zeros(26*16, dtype=np.int32)
+    cnt = C.c_int(0)
+    check(_lib.lib().pl_halo_describe(kind, lx, ly, lz, peid, mx, my, mz, int(bool(inverse)), out.ctypes.data, C.byref(cnt)))
+    keys = ("code", "peer", "rsize", "npop")
+    res = []
+    for r in out.reshape(26, 16)[:cnt.value]:
+        d = dict(zip(keys, (int(x) for x in r[:4])))
+        d["pops"] = [int(x) for x in r[4:4 + d["npop"]]]
+        d["base"], d["s1"], d["s2"], d["n1"], d["n2"], d["recv_code"] = (int(x) for x in r[9:15])
+        d["o"] = (d["code"] % 3 - 1, (d["code"]//3) % 3 - 1, d["code"]//9 - 1)
+        res.append(d)
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------------
 class _Lattice:
     kind = 0
     nc = 0

@@ -3,6 +3,7 @@
 // base[c*pitch + idx], idx = i + nx*(j + ny*k)  (same site order as the reference, d3q15.h:136-141).
 #pragma once
 #include "lbm_sens.cuh"
+#include "lbm_halo.cuh"
 
 namespace plb {
 
@@ -44,6 +45,14 @@ template <int D> PL_D void pull(double (&f)[LT<D>::nc], const double* __restrict
         f[c] = __ldg(src + (size_t)c*pitch + (size_t)(idx + pull_offset<D, c>(n)));
     });
 }
+// the same for a block-decomposed lattice: sources beyond a decomposed block face come from the receive buffers
+template <int D> PL_D void pull_h(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx, int i, int j, int k,
+                                  const Geom& G, const Nbr& n, const HaloView& H, int inverse) {
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        f[c] = pull_halo<D, c>(src, pitch, idx, i, j, k, G, n, pull_offset<D, c>(n), H, inverse);
+    });
+}
 template <int D> PL_D void load_site(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx) {
     sfor<0, LT<D>::nc>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = src[(size_t)c*pitch + (size_t)idx]; });
 }
@@ -53,8 +62,8 @@ template <int D> PL_D void store_site(const double (&f)[LT<D>::nc], double* __re
 
 // ---------------------------------------------------------------------------------------------------------
 // Stream()/iStream(): dst(x,c) = src(x -/+ c, c) for every site (d3q15.h:601-616, 964-979)
-template <int D>
-__global__ void __launch_bounds__(256) k_stream(Geom G, const double* __restrict__ src, double* __restrict__ dst, int inverse) {
+template <int D, bool HALO>
+__global__ void __launch_bounds__(256) k_stream(Geom G, const double* __restrict__ src, double* __restrict__ dst, int inverse, HaloView H) {
     long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
     if (idx >= G.nxyz) return;
     int i, j, k;
@@ -62,7 +71,8 @@ __global__ void __launch_bounds__(256) k_stream(Geom G, const double* __restrict
     Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
     double f[LT<D>::nc];
-    pull<D>(f, src, G.pitch, idx, n);
+    if constexpr (HALO) pull_h<D>(f, src, G.pitch, idx, i, j, k, G, n, H, inverse);
+    else pull<D>(f, src, G.pitch, idx, n);
     store_site<D>(f, dst, G.pitch, idx);
 }
 // ---------------------------------------------------------------------------------------------------------
@@ -149,7 +159,9 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 
 // ---------------------------------------------------------------------------------------------------------
 // Per-coordinate plane words of a plan (one 64-bit word per local x / y / z coordinate):
-//   bits 0..61: entry e of the closure program acts on this plane
+//   bits 0..60: entry e of the closure program acts on this plane
+//   bit 61    : the plane is a face of this rank's block along a decomposed axis: its sites pull from the halo receive
+//               buffers and are the first to finish, so that the next exchange overlaps the interior kernel
 //   bit 62    : (x only) the coordinate shares an aligned group of 8 sites with an x closure plane: the boundary pass takes
 //               the whole group so that its accesses to x planes fill 64-byte DRAM bursts instead of 8 bytes of each
 //   bit 63    : the plane is a global boundary plane or next to one and the plan has SmoothCorner; sites with two such
@@ -157,8 +169,8 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 struct ShellMask {
     const unsigned long long *x, *y, *z;
 };
-constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT);
-constexpr int MAX_PROGRAM = 62;
+constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, HALO_BIT = 1ull << 61, ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT | HALO_BIT);
+constexpr int MAX_PROGRAM = 61;
 PL_D bool in_tube(unsigned long long wx, unsigned long long wy, unsigned long long wz) { return (wx >> 63) + (wy >> 63) + (wz >> 63) >= 2ull; }
 
 // A plan's closure program on one site: the recorded closures whose plane passes through the site (bits of `entries`), in
@@ -229,7 +241,7 @@ template <int D, int M>
 __global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
                                                const double* __restrict__ gs, double* __restrict__ gd, CollideParams P, ShellMask S,
                                                const ClosureArgs* __restrict__ prog,
-                                               const int* __restrict__ list, int nlist, int ndirect, int inverse) {
+                                               const int* __restrict__ list, int nlist, int ndirect, int inverse, HaloView HF, HaloView HG) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     int t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -241,8 +253,13 @@ __global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict_
     Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
     double f[LT<D>::nc], g[LT<D>::nc];
-    pull<D>(f, fs, G.pitch, idx, n);
-    if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
+    if (HF.on) {
+        pull_h<D>(f, fs, G.pitch, idx, i, j, k, G, n, HF, inverse);
+        if constexpr (HASG) pull_h<D>(g, gs, G.pitch, idx, i, j, k, G, n, HG, inverse);
+    } else {
+        pull<D>(f, fs, G.pitch, idx, n);
+        if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
+    }
     if (entries) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
     if (t < ndirect) {
         if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);

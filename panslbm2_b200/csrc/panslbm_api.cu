@@ -5,6 +5,7 @@
 #include "lbm_reduce.cuh"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -69,6 +70,24 @@ struct pl_lattice {
     int streamed = 1;              // phase: 1 = populations are "pre-collision" (after init / Stream+closures), 0 = just collided
     double* current() const { return buf[cur]; }
     double* other() const { return buf[cur ^ 1]; }
+    // ---- halo of a block-decomposed lattice (lbm_halo.cuh) ----
+    struct Halo {
+        bool on = false;
+        int e[3] = {0, 0, 0};
+        int nmsg = 0;
+        HaloMsgDesc msg[2][26];              // [inverse][message]: same codes, peers and sizes, different population sets
+        size_t off[26];                      // offset (doubles) of message m inside a send / receive buffer
+        int index_of_code[27];               // message index of a direction code, -1 if none
+        size_t total = 0;                    // doubles per buffer
+        double* send[2] = {nullptr, nullptr};// double-buffered by epoch parity (loopback peers read the previous one late)
+        double* recv = nullptr;
+        long long epoch = 0;                 // number of packs so far
+        bool packed = false;                 // send[epoch&1] holds the outgoing populations of the current state
+        int packed_dir = 0;                  // ... for Stream (0) / iStream (1)
+        bool exchanged = false;              // the exchange of this epoch has been posted
+        cudaEvent_t ev_ready = nullptr;      // NCCL mode: completes when the receive buffers hold this epoch's messages
+        int seq = -1;                        // loopback mode: n-th lattice created with this PEid (pairs f with f, g with g)
+    } halo;
 };
 
 struct pl_bc {
@@ -79,6 +98,223 @@ struct pl_bc {
     uint8_t* mask = nullptr;
     double *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;
 };
+
+
+// -------------------------------------------------------------------------------------------------
+// Communicator: NCCL over NVLink/NVSwitch (one process per GPU), or a process-local "loopback" world in which the
+// blocks of every rank live on one device (parity tests of the decomposed path on a single GPU).
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+} g_nccl;
+constexpr int NCCL_F64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;
+
+enum { COMM_NONE = 0, COMM_NCCL = 1, COMM_LOOPBACK = 2 };
+struct Comm {
+    int mode = COMM_NONE;
+    int rank = 0, nranks = 1;
+    void* nccl = nullptr;
+    cudaStream_t stream = nullptr;           // exchanges run here, beside the interior kernel
+    cudaEvent_t ev_post = nullptr;
+    std::vector<std::vector<pl_lattice*>> loop;   // loopback: lattices by PEid in creation order
+    double* red = nullptr;                   // 4 doubles of device scratch for the global reductions
+} g_comm;
+
+int load_nccl() {
+    if (g_nccl.h) return PL_OK;
+    const char* cands[] = {getenv("PANSLBM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* c : cands) {
+        if (!c) continue;
+        g_nccl.h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.h) break;
+    }
+    if (!g_nccl.h) return fail(PL_ERR_UNSUPPORTED, std::string("NCCL library not found (set PANSLBM_NCCL_LIB): ") + dlerror());
+    auto sym = [&](const char* n) { return dlsym(g_nccl.h, n); };
+    g_nccl.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.GetErrorString || !g_nccl.GroupStart || !g_nccl.GroupEnd ||
+        !g_nccl.Send || !g_nccl.Recv || !g_nccl.AllReduce) {
+        g_nccl.h = nullptr;
+        return fail(PL_ERR_UNSUPPORTED, "NCCL library lacks a required symbol");
+    }
+    return PL_OK;
+}
+#define NC(call)                                                                                        \
+    do {                                                                                                \
+        int e__ = (call);                                                                               \
+        if (e__ != 0) return fail(PL_ERR_CUDA, std::string(#call) + ": " + g_nccl.GetErrorString(e__)); \
+    } while (0)
+
+int comm_streams() {
+    if (!g_comm.stream) {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&g_comm.stream, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&g_comm.ev_post, cudaEventDisableTiming));
+        CU(cudaMalloc(&g_comm.red, 4*sizeof(double)));
+    }
+    return PL_OK;
+}
+
+template <int D> void describe_t(const pl_lattice* l, int inverse, HaloMsgDesc* out, int& cnt) {
+    const int n[3] = {l->g.nx, l->g.ny, l->g.nz}, m[3] = {l->mx, l->my, l->mz}, pe[3] = {l->pex, l->pey, l->pez};
+    cnt = halo_describe<D>(n, m, pe, inverse, out);
+}
+
+int halo_setup(pl_lattice* l) {
+    pl_lattice::Halo& h = l->halo;
+    for (int a = 0; a < 3; ++a) h.e[a] = 0;
+    h.e[0] = l->mx > 1; h.e[1] = l->my > 1; h.e[2] = l->kind == PL_D3Q15 && l->mz > 1;
+    h.on = h.e[0] || h.e[1] || h.e[2];
+    if (!h.on) return PL_OK;
+    for (int inv = 0; inv < 2; ++inv) {
+        if (l->kind == PL_D2Q9) describe_t<2>(l, inv, h.msg[inv], h.nmsg); else describe_t<3>(l, inv, h.msg[inv], h.nmsg);
+    }
+    for (int c = 0; c < 27; ++c) h.index_of_code[c] = -1;
+    h.total = 0;
+    for (int m = 0; m < h.nmsg; ++m) {
+        h.index_of_code[h.msg[0][m].code] = m;
+        h.off[m] = h.total;
+        h.total += (size_t)((h.msg[0][m].rsize*h.msg[0][m].npop + 15)/16*16);
+    }
+    for (int b = 0; b < 2; ++b) CU(cudaMalloc(&h.send[b], h.total*sizeof(double)));
+    CU(cudaMalloc(&h.recv, h.total*sizeof(double)));
+    CU(cudaMemsetAsync(h.recv, 0, h.total*sizeof(double), g_stream));
+    CU(cudaEventCreateWithFlags(&h.ev_ready, cudaEventDisableTiming));
+    if (g_comm.mode == COMM_LOOPBACK) {
+        if (l->mx*l->my*l->mz != g_comm.nranks) return fail(PL_ERR_ARG, "pl_lattice_create: PE grid does not match the loopback world size");
+        auto& v = g_comm.loop[l->peid];
+        h.seq = (int)v.size();
+        v.push_back(l);
+    } else if (g_comm.mode == COMM_NCCL) {
+        if (l->mx*l->my*l->mz != g_comm.nranks || l->peid != g_comm.rank)
+            return fail(PL_ERR_ARG, "pl_lattice_create: PEid / PE grid do not match the communicator (rank must equal PEid)");
+    }
+    return PL_OK;
+}
+void halo_release(pl_lattice* l) {
+    pl_lattice::Halo& h = l->halo;
+    if (!h.on) return;
+    if (g_comm.stream) cudaStreamSynchronize(g_comm.stream);
+    cudaFree(h.send[0]); cudaFree(h.send[1]); cudaFree(h.recv);
+    if (h.ev_ready) cudaEventDestroy(h.ev_ready);
+    if (g_comm.mode == COMM_LOOPBACK && h.seq >= 0 && l->peid < (int)g_comm.loop.size() && h.seq < (int)g_comm.loop[l->peid].size())
+        g_comm.loop[l->peid][h.seq] = nullptr;
+}
+inline void halo_touch(pl_lattice* l) { l->halo.packed = false; }
+
+int halo_pack(pl_lattice* l, int inverse) {
+    pl_lattice::Halo& h = l->halo;
+    ++h.epoch;
+    PackList L;
+    L.count = h.nmsg;
+    long long maxr = 1;
+    for (int m = 0; m < h.nmsg; ++m) {
+        const HaloMsgDesc& d = h.msg[inverse][m];
+        PackMsg& M = L.m[m];
+        M.dst = h.send[h.epoch & 1] + h.off[m];
+        M.base = d.base; M.s1 = d.s1; M.s2 = d.s2; M.n1 = d.n1; M.n2 = d.n2; M.npop = d.npop;
+        for (int s = 0; s < 5; ++s) M.pop[s] = s < d.npop ? d.pop[s] : 0;
+        maxr = std::max(maxr, d.rsize);
+    }
+    dim3 grid((unsigned)std::min<long long>((maxr + 127)/128, 1024), (unsigned)h.nmsg);
+    LAUNCH(k_halo_pack, grid, 128, l->current(), l->g.pitch, L);
+    h.packed = true; h.packed_dir = inverse; h.exchanged = false;
+    return PL_OK;
+}
+pl_lattice* loop_peer(const pl_lattice* l, int peer) {
+    if (peer < 0 || peer >= (int)g_comm.loop.size()) return nullptr;
+    auto& v = g_comm.loop[peer];
+    return l->halo.seq < (int)v.size() ? v[l->halo.seq] : nullptr;
+}
+// post the exchange of the current epoch (NCCL) / bring lagging peers to this epoch (loopback)
+int halo_exchange(pl_lattice* l) {
+    pl_lattice::Halo& h = l->halo;
+    if (g_comm.mode == COMM_NCCL) {
+        int r = comm_streams();
+        if (r) return r;
+        CU(cudaEventRecord(g_comm.ev_post, g_stream));
+        CU(cudaStreamWaitEvent(g_comm.stream, g_comm.ev_post, 0));
+        NC(g_nccl.GroupStart());
+        for (int m = 0; m < h.nmsg; ++m) {
+            const HaloMsgDesc& d = h.msg[h.packed_dir][m];
+            const size_t count = (size_t)(d.rsize*d.npop);
+            NC(g_nccl.Send(h.send[h.epoch & 1] + h.off[m], count, NCCL_F64, d.peer, g_comm.nccl, g_comm.stream));
+            // the neighbour on the opposite side sends its message `code`; it arrives from direction opposite(code)
+            const int from = h.index_of_code[halo_opposite(d.code)];
+            NC(g_nccl.Recv(h.recv + h.off[from], count, NCCL_F64, h.msg[h.packed_dir][from].peer, g_comm.nccl, g_comm.stream));
+        }
+        NC(g_nccl.GroupEnd());
+        ++g_launches;
+        CU(cudaEventRecord(h.ev_ready, g_comm.stream));
+    } else if (g_comm.mode == COMM_LOOPBACK) {
+        for (int m = 0; m < h.nmsg; ++m) {
+            pl_lattice* p = loop_peer(l, h.msg[0][m].peer);
+            if (!p) return fail(PL_ERR_ARG, "halo exchange: the block of a neighbouring PE has not been created in this loopback world");
+            if (p == l) continue;
+            if (p->halo.epoch < h.epoch) { int r = halo_pack(p, h.packed_dir); if (r) return r; p->halo.exchanged = false; }
+            if (p->halo.epoch > h.epoch + 1) return fail(PL_ERR_ARG, "halo exchange: loopback ranks must advance in lockstep (a neighbour is more than one exchange ahead)");
+        }
+    } else {
+        return fail(PL_ERR_ARG, "this lattice is block-decomposed (mx*my*mz > 1): call pl_comm_init / pl_comm_init_loopback before streaming it");
+    }
+    h.exchanged = true;
+    return PL_OK;
+}
+// make the receive side of `l` valid for a Stream (inverse = 0) / iStream (1) of its current populations
+// eager = called right after a collide, ahead of the Stream that will need it: in loopback mode only this block is packed
+// then (the neighbours pack themselves when their own collide is done; a Stream call catches up the ones that have not)
+int halo_prepare(pl_lattice* l, int inverse, bool eager = false) {
+    pl_lattice::Halo& h = l->halo;
+    if (!h.on) return PL_OK;
+    int r;
+    if (!h.packed || h.packed_dir != inverse) { if ((r = halo_pack(l, inverse))) return r; }
+    if (eager && g_comm.mode != COMM_NCCL) return PL_OK;
+    if (!h.exchanged && (r = halo_exchange(l))) return r;
+    return PL_OK;
+}
+int halo_view(const pl_lattice* l, HaloView& V) {
+    const pl_lattice::Halo& h = l->halo;
+    memset(&V, 0, sizeof(V));
+    if (!h.on) return PL_OK;
+    V.on = 1; V.e[0] = h.e[0]; V.e[1] = h.e[1]; V.e[2] = h.e[2];
+    for (int m = 0; m < h.nmsg; ++m) {
+        const int code = h.msg[0][m].code;          // data arriving from the neighbour in this direction ...
+        const int theirs = h.index_of_code[halo_opposite(code)];   // ... is its message towards the opposite direction
+        if (g_comm.mode == COMM_LOOPBACK) {
+            const pl_lattice* p = loop_peer(l, h.msg[0][m].peer);
+            if (!p) return fail(PL_ERR_ARG, "halo view: missing loopback neighbour");
+            if (p->halo.epoch < h.epoch || p->halo.epoch > h.epoch + 1) return fail(PL_ERR_ARG, "halo view: loopback ranks out of lockstep");
+            V.r[code] = p->halo.send[h.epoch & 1] + p->halo.off[theirs];
+        } else {
+            V.r[code] = h.recv + h.off[m];
+        }
+    }
+    return PL_OK;
+}
+// order `stream` after the arrival of the current epoch's messages
+int halo_wait(const pl_lattice* l, cudaStream_t stream) {
+    if (l->halo.on && g_comm.mode == COMM_NCCL) CU(cudaStreamWaitEvent(stream, l->halo.ev_ready, 0));
+    return PL_OK;
+}
+}  // namespace
 
 // -------------------------------------------------------------------------------------------------
 extern "C" {
@@ -155,11 +391,21 @@ pl_lattice* pl_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx
     }
     cudaMemsetAsync(l->buf[0], 0, g.pitch*l->nc*sizeof(double), g_stream);
     cudaMemsetAsync(l->buf[1], 0, g.pitch*l->nc*sizeof(double), g_stream);
+    if (halo_setup(l) != PL_OK) {
+        std::string keep = g_err;
+        l->halo.on = true;   // release whatever halo_setup allocated
+        halo_release(l);
+        cudaFree(l->buf[0]); cudaFree(l->buf[1]);
+        delete l;
+        g_err = keep;
+        return nullptr;
+    }
     return l;
 }
 int pl_lattice_destroy(pl_lattice* l) {
     if (!l) return PL_OK;
     cudaStreamSynchronize(g_stream);
+    halo_release(l);
     cudaFree(l->buf[0]); cudaFree(l->buf[1]);
     delete l;
     return PL_OK;
@@ -183,6 +429,7 @@ int pl_lattice_set_host(pl_lattice* l, const double* f0, const double* f) {
     else LAUNCH(k_from_aos<3>, blocks_for(l->g.nxyz, 256), 256, l->g, d0, d1, l->current());
     CU(cudaStreamSynchronize(g_stream));
     cudaFree(d0); cudaFree(d1);
+    halo_touch(l);
     return PL_OK;
 }
 int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
@@ -213,9 +460,18 @@ int pl_lattice_device_view(pl_lattice* l, double** base, size_t* pitch) {
 namespace {
 
 int do_stream_all(pl_lattice* l, int inverse) {
-    if (l->kind == PL_D2Q9) LAUNCH(k_stream<2>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse);
-    else LAUNCH(k_stream<3>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse);
+    HaloView H;
+    int r;
+    if ((r = halo_prepare(l, inverse)) || (r = halo_wait(l, g_stream)) || (r = halo_view(l, H))) return r;
+    if (l->halo.on) {
+        if (l->kind == PL_D2Q9) LAUNCH((k_stream<2, true>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
+        else LAUNCH((k_stream<3, true>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
+    } else {
+        if (l->kind == PL_D2Q9) LAUNCH((k_stream<2, false>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
+        else LAUNCH((k_stream<3, false>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
+    }
     l->cur ^= 1;
+    halo_touch(l);
     return PL_OK;
 }
 // the local sites of the global plane axis=coord
@@ -293,6 +549,7 @@ int smooth_lists(const pl_lattice* l, SmoothList& edges, SmoothList& corners) {
 int do_smooth(pl_lattice* l) {
     SmoothList e, c;
     smooth_lists(l, e, c);
+    halo_touch(l);
     double* fb = l->current();
     if (e.count > 0) {
         dim3 grid(blocks_for(e.maxlen, 128), e.count);
@@ -353,6 +610,7 @@ int do_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* au
     int r = make_closure_args(l, other, bc, aux, A);
     if (r) return r;
     int np = bc->pl.n1*bc->pl.n2;
+    halo_touch(l);
     const double* qb = (other && bc->type == PL_BC_AAD_ISET_RHO) ? other->current() : nullptr;
     if (l->kind == PL_D2Q9) LAUNCH(k_closure<2>, blocks_for(np, 128), 128, l->g, l->current(), qb, A);
     else LAUNCH(k_closure<3>, blocks_for(np, 128), 128, l->g, l->current(), qb, A);
@@ -515,6 +773,7 @@ int pl_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* a) {
     r = dispatch_collide(a->model, f, g, P, nullptr, f->g.nxyz);
     if (r) return r;
     f->streamed = 0; if (g) g->streamed = 0;
+    halo_touch(f); if (g) halo_touch(g);
     return PL_OK;
 }
 
@@ -546,6 +805,7 @@ int pl_initial_condition(pl_lattice* l, int family, const double* const* a, int 
     if (d3) LAUNCH(k_init<3>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), family, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
     else LAUNCH(k_init<2>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), family, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
     l->streamed = 1;
+    halo_touch(l);
     return PL_OK;
 }
 
@@ -601,12 +861,20 @@ int plan_collide_full(pl_plan* p, int parity) {              // standalone C: ev
     pl_lattice* g = (flags & F_G) ? p->g : nullptr;
     if ((r = dispatch_collide(p->args[parity].model, p->f, g, P, nullptr, p->f->g.nxyz))) return r;
     p->f->streamed = 0; if (p->g) p->g->streamed = 0;
+    // post the exchange the Stream of this step needs right away: it overlaps whatever is queued next
+    halo_touch(p->f); if (p->g) halo_touch(p->g);
+    if ((r = halo_prepare(p->f, p->inverse, true))) return r;
+    if (p->g && (r = halo_prepare(p->g, p->inverse, true))) return r;
     return PL_OK;
 }
 template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
     if (p->nlist == 0) return PL_OK;
+    HaloView HF, HG;
+    int r;
+    if ((r = halo_view(p->f, HF))) return r;
+    if (g) { if ((r = halo_view(g, HG))) return r; } else memset(&HG, 0, sizeof(HG));
     LAUNCH_ON(p->side, (k_shell<D, M>), blocks_for(p->nlist, 128), 128, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
-           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz}, p->prog[bc_parity], p->list, p->nlist, p->ndirect, p->inverse);
+           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz}, p->prog[bc_parity], p->list, p->nlist, p->ndirect, p->inverse, HF, HG);
     return PL_OK;
 }
 int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
@@ -627,10 +895,15 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     pl_lattice* g = (flags & F_G) ? p->g : nullptr;
     if (p->g && !g) return fail(PL_ERR_ARG, "plan: a single-lattice collide cannot drive a two-lattice plan");
     ShellMask S{p->mx, p->my, p->mz};
-    // boundary pass on the side stream (closure planes, SmoothCorner tubes, AVX-tail sites): it touches only sites the
-    // interior kernel skips, so the two run concurrently
+    // halo of a decomposed block: normally posted already by the collide that produced these populations
+    if ((r = halo_prepare(p->f, p->inverse))) return r;
+    if (p->g && (r = halo_prepare(p->g, p->inverse))) return r;
+    // boundary pass on the side stream (closure planes, block faces, SmoothCorner tubes, AVX-tail sites): it touches only
+    // sites the interior kernel skips, so the two run concurrently
     CU(cudaEventRecord(p->ev_fork, g_stream));
     CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    if ((r = halo_wait(p->f, p->side))) return r;
+    if (p->g && (r = halo_wait(p->g, p->side))) return r;
     if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
     CU(cudaEventRecord(p->ev_join, p->side));
     // interior: one pass, source -> destination
@@ -652,6 +925,10 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
     if ((r = dispatch_collide(model, p->f, g, P, p->list + p->ndirect, p->nlist - p->ndirect))) return r;
     p->f->streamed = 0; if (p->g) p->g->streamed = 0;
+    // every block-face site is final: pack and post the next exchange now, it overlaps the next interior kernel
+    halo_touch(p->f); if (p->g) halo_touch(p->g);
+    if ((r = halo_prepare(p->f, p->inverse, true))) return r;
+    if (p->g && (r = halo_prepare(p->g, p->inverse, true))) return r;
     return PL_OK;
 }
 }  // namespace
@@ -721,7 +998,7 @@ int pl_plan_finalize(pl_plan* p) {
     std::vector<ClosureArgs> prog[2];
     for (auto& b : p->bcs) {
         if (b.bc->empty) continue;
-        if (prog[0].size() >= (size_t)MAX_PROGRAM) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: more than 62 non-empty closures in one loop body");
+        if (prog[0].size() >= (size_t)MAX_PROGRAM) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: more than 61 non-empty closures in one loop body");
         (*h[b.bc->axis])[b.bc->coord - off[b.bc->axis]] |= 1ull << prog[0].size();
         for (int par = 0; par < 2; ++par) {
             ClosureArgs A;
@@ -732,9 +1009,15 @@ int pl_plan_finalize(pl_plan* p) {
             prog[par].push_back(A);
         }
     }
+    // faces of a decomposed block: their sites pull from the halo receive buffers
+    {
+        int nn[3] = {g.nx, g.ny, g.nz};
+        for (int a = 0; a < p->f->kind; ++a)
+            if (p->f->halo.on && p->f->halo.e[a]) { (*h[a])[0] |= HALO_BIT; (*h[a])[nn[a] - 1] |= HALO_BIT; }
+    }
     // x closure planes: the boundary pass takes the aligned group of 8 x-coordinates around each (see ShellMask)
     for (int i = 0; i < g.nx; ++i)
-        if (hx[i] & ENTRY_BITS) for (int v = i & ~7; v < std::min(g.nx, (i & ~7) + 8); ++v) hx[v] |= SLAB_BIT;
+        if (hx[i] & (ENTRY_BITS | HALO_BIT)) for (int v = i & ~7; v < std::min(g.nx, (i & ~7) + 8); ++v) hx[v] |= SLAB_BIT;
     // SmoothCorner: flag the global boundary planes and their inward neighbours (bit 1); sites with two flagged coordinates
     // form the edge tubes.  Every site SmoothCorner writes (edge lines, corners) or reads (their inward neighbours) must lie
     // in a tube: collide is deferred there until k_smooth has run.
@@ -846,6 +1129,82 @@ int pl_plan_advance(pl_plan* p, int ncollides, int end_streamed) {
     return PL_OK;
 }
 
+// ---- communicator ---------------------------------------------------------------------------------
+int pl_comm_unique_id(char* out128) {
+    if (!out128) return fail(PL_ERR_ARG, "pl_comm_unique_id: null");
+    int r = load_nccl();
+    if (r) return r;
+    NcclId id;
+    NC(g_nccl.GetUniqueId(&id));
+    memcpy(out128, id.internal, 128);
+    return PL_OK;
+}
+int pl_comm_init(const char* id128, int rank, int nranks) {
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(PL_ERR_ARG, "pl_comm_init: bad arguments");
+    if (g_comm.mode != COMM_NONE) return fail(PL_ERR_ARG, "pl_comm_init: a communicator already exists");
+    int r = load_nccl();
+    if (r || (r = comm_streams())) return r;
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    NC(g_nccl.CommInitRank(&g_comm.nccl, nranks, id, rank));
+    g_comm.mode = COMM_NCCL; g_comm.rank = rank; g_comm.nranks = nranks;
+    return PL_OK;
+}
+int pl_comm_init_loopback(int nranks) {
+    if (nranks < 1) return fail(PL_ERR_ARG, "pl_comm_init_loopback: bad world size");
+    if (g_comm.mode != COMM_NONE) return fail(PL_ERR_ARG, "pl_comm_init_loopback: a communicator already exists");
+    g_comm.mode = COMM_LOOPBACK; g_comm.rank = 0; g_comm.nranks = nranks;
+    g_comm.loop.assign(nranks, std::vector<pl_lattice*>());
+    return PL_OK;
+}
+int pl_comm_destroy(void) {
+    if (g_comm.mode == COMM_NCCL) {
+        cudaStreamSynchronize(g_comm.stream);
+        cudaStreamSynchronize(g_stream);
+        if (g_comm.nccl) g_nccl.CommDestroy(g_comm.nccl);
+        g_comm.nccl = nullptr;
+    }
+    g_comm.loop.clear();
+    g_comm.mode = COMM_NONE; g_comm.rank = 0; g_comm.nranks = 1;
+    return PL_OK;
+}
+int pl_comm_info(int* mode, int* rank, int* nranks) {
+    if (mode) *mode = g_comm.mode;
+    if (rank) *rank = g_comm.rank;
+    if (nranks) *nranks = g_comm.nranks;
+    return PL_OK;
+}
+int pl_comm_allreduce(double* inout_host, int n, int op) {
+    if (!inout_host || n < 1 || n > 4 || (op != 0 && op != 1)) return fail(PL_ERR_ARG, "pl_comm_allreduce: 1..4 values, op 0 (sum) / 1 (max)");
+    if (g_comm.mode != COMM_NCCL) return PL_OK;   // a world of one
+    CU(cudaMemcpyAsync(g_comm.red, inout_host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    NC(g_nccl.AllReduce(g_comm.red, g_comm.red, (size_t)n, NCCL_F64, op == 0 ? NCCL_SUM : NCCL_MAX, g_comm.nccl, g_stream));
+    ++g_launches;
+    CU(cudaMemcpyAsync(inout_host, g_comm.red, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return PL_OK;
+}
+int pl_halo_describe(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz, int inverse, int* out, int* count) {
+    if ((kind != PL_D2Q9 && kind != PL_D3Q15) || !out || !count || lx <= 0 || ly <= 0 || lz <= 0 || mx <= 0 || my <= 0 || mz <= 0 || peid < 0)
+        return fail(PL_ERR_ARG, "pl_halo_describe: bad arguments");
+    if (kind == PL_D2Q9) { lz = 1; mz = 1; }
+    if (peid >= mx*my*mz) return fail(PL_ERR_ARG, "pl_halo_describe: PEid outside the PE grid");
+    const int pe[3] = {peid%mx, kind == PL_D2Q9 ? peid/mx : (peid/mx)%my, kind == PL_D2Q9 ? 0 : peid/(mx*my)};
+    const int m[3] = {mx, my, mz};
+    const int n[3] = {(lx + pe[0])/mx, (ly + pe[1])/my, kind == PL_D2Q9 ? 1 : (lz + pe[2])/mz};
+    HaloMsgDesc d[26];
+    const int cnt = kind == PL_D2Q9 ? halo_describe<2>(n, m, pe, inverse, d) : halo_describe<3>(n, m, pe, inverse, d);
+    for (int k = 0; k < cnt; ++k) {
+        int* o = out + 16*k;
+        o[0] = d[k].code; o[1] = d[k].peer; o[2] = (int)d[k].rsize; o[3] = d[k].npop;
+        for (int q = 0; q < 5; ++q) o[4 + q] = q < d[k].npop ? d[k].pop[q] : -1;
+        o[9] = (int)d[k].base; o[10] = (int)d[k].s1; o[11] = (int)d[k].s2; o[12] = d[k].n1; o[13] = d[k].n2;
+        o[14] = halo_opposite(d[k].code); o[15] = 0;
+    }
+    *count = cnt;
+    return PL_OK;
+}
+
 // ---- reductions ---------------------------------------------------------------------------------
 int pl_residual(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, size_t n, double* out) {
     if (!ux || !uxp || !out) return fail(PL_ERR_ARG, "pl_residual: null");
@@ -855,6 +1214,8 @@ int pl_residual(const double* ux, const double* uy, const double* uz, const doub
     LAUNCH(k_residual_partial, nb, 256, ux, uy, uz, uxp, uyp, uzp, (long long)n, scratch);
     LAUNCH(k_sum_final, 1, 256, scratch, nb, 2, scratch + 2*nb);
     double h[2];
+    // MPI build of the reference: MPI_Allreduce(SUM) of the two partial sums (residual.h:16, 31, 46)
+    if (g_comm.mode == COMM_NCCL) { NC(g_nccl.AllReduce(scratch + 2*nb, scratch + 2*nb, 2, NCCL_F64, NCCL_SUM, g_comm.nccl, g_stream)); ++g_launches; }
     CU(cudaMemcpyAsync(h, scratch + 2*nb, 2*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     *out = sqrt(h[0]/h[1]);
@@ -871,20 +1232,24 @@ int pl_reduce_sum(const double* v, size_t n, double* out) {
     CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
 }
-int pl_reduce_absmax(const double* v, size_t n, double* out) {
+static int absmax_impl(const double* v, size_t n, double* out, bool global);
+int pl_reduce_absmax(const double* v, size_t n, double* out) { return absmax_impl(v, n, out, false); }
+static int absmax_impl(const double* v, size_t n, double* out, bool global) {
     if (!v || !out) return fail(PL_ERR_ARG, "pl_reduce_absmax: null");
     const int nb = 1024;
     double* scratch = (double*)g_scratch.get((nb + 1)*sizeof(double));
     if (!scratch) return fail(PL_ERR_CUDA, "pl_reduce_absmax: scratch allocation failed");
     LAUNCH(k_absmax_partial, nb, 256, v, (long long)n, scratch);
     LAUNCH(k_absmax_final, 1, 256, scratch, nb, scratch + nb);
+    // normalize.h:17 — MPI_Allreduce(MAX) in the reference's MPI build
+    if (global && g_comm.mode == COMM_NCCL) { NC(g_nccl.AllReduce(scratch + nb, scratch + nb, 1, NCCL_F64, NCCL_MAX, g_comm.nccl, g_stream)); ++g_launches; }
     CU(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
 }
 int pl_normalize(double* v, size_t n) {
     double m = 0.0;
-    int r = pl_reduce_absmax(v, n, &m);
+    int r = absmax_impl(v, n, &m, true);
     if (r) return r;
     LAUNCH(k_divide, blocks_for((long long)n, 256), 256, v, m, (long long)n);
     return PL_OK;
