@@ -85,6 +85,8 @@ int pl_lattice_info(const pl_lattice*, int* out18);
  * Device storage is fp64 SoA [c][nxyz]; these two convert (test/d2q9.cpp, test/d3q15.cpp touch f0/f directly). */
 int pl_lattice_set_host(pl_lattice*, const double* f0_host, const double* f_host);
 int pl_lattice_get_host(pl_lattice*, double* f0_host, double* f_host);
+/* Phase of the populations: 1 = pre-collision (after InitialCondition / Stream and its closures), 0 = just collided. */
+int pl_lattice_streamed(const pl_lattice*);
 /* Device SoA view of the current populations: c-th plane at base + c*pitch (pitch in doubles). */
 int pl_lattice_device_view(pl_lattice*, double** base, size_t* pitch);
 
@@ -92,6 +94,13 @@ int pl_lattice_device_view(pl_lattice*, double** base, size_t* pitch);
 int pl_stream(pl_lattice*, int inverse);
 /* SmoothCorner() (d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587) */
 int pl_smooth_corner(pl_lattice*);
+
+/* One SmoothCornerAlong{YZ,ZX,XY} / SmoothCornerAt call (d3q15.h:1242-1303, d2q9.h:578-587) at GLOBAL coordinates, as
+ * production/ncpump.cpp:159-170 issues them on interior corners.  A zero direction marks the axis the edge line runs
+ * along (its coordinate is ignored): (0,dy,dz) = AlongYZ(j,k), (dx,0,dz) = AlongZX(k,i), (dx,dy,0) = AlongXY(i,j) and, for
+ * D2Q9, the corner (i,j); three non-zero directions = the 3-D corner.  The whole line is processed, end sites included,
+ * exactly as the reference helper does; a site outside this rank's block is a no-op. */
+int pl_smooth_corner_at(pl_lattice*, int i, int j, int k, int dirx, int diry, int dirz);
 
 /* ---- boundary conditions ------------------------------------------------------------------------
  * One pl_bc = one call of a reference "...AlongXFace/YFace/ZFace (XEdge/YEdge)" helper: the plane
@@ -198,6 +207,7 @@ int pl_plan_finalize(pl_plan*);
 int pl_plan_advance(pl_plan*, int ncollides, int end_streamed);
 /* 0/1: the argument set of the last collide if the lattices are in the just-collided phase, else of the next one */
 int pl_plan_parity(const pl_plan*);
+int pl_plan_set_parity(pl_plan*, int parity);
 /* Measurement hook (bench.py "roofline"): when enabled, every launch of the fused interior kernel is bracketed by CUDA
  * events on the launching stream.  pl_plan_profile_read synchronises, returns the accumulated kernel milliseconds, the
  * number of launches and the total number of lattice sites those launches updated, and clears the accumulators. */
@@ -229,6 +239,38 @@ int pl_sensitivity(pl_lattice*, const pl_sens_args*);
  * (baked once and reusable every optimisation iteration). The volume term is pl_sensitivity(PL_SENS_AAD_BRINKMAN_DIFF). */
 int pl_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
                                const double* igsnap, const double* diffusivity, const double* dkds);
+
+/* ==== host-pointer surface (csrc/panslbm_host.cpp) ====================================================================
+ * What the drop-in C++ headers (panslbm2_b200/src/particle, src/equation, src/utility) bind.  Same operations as above, but
+ * every array argument is a HOST pointer owned by the caller exactly as in the reference (`new double[nxyz]`,
+ * production/heatsink3D.cpp:50-59): the runtime keeps a device mirror per array, moves data only when the other side
+ * actually touched it (page protection on the host copy), and fuses the per-call sequence of a time loop
+ * (collide; Stream; closures; SmoothCorner) into one pass per step once it has seen the loop body twice.
+ * Results are identical to the device-pointer calls issued one by one. */
+const char* plh_last_error(void);
+/* Host memory with a device mirror; the headers route `operator new[]` / `delete[]` of large blocks here. */
+void* plh_alloc(size_t bytes);
+void plh_free(void* p);
+int plh_owns(const void* p);
+/* The public `T *f0, *f` members of D2Q9/D3Q15 (d3q15.h:225): host views in the reference layout, kept coherent with
+ * the device populations on demand (test/d2q9.cpp, test/d3q15.cpp read and write them directly). */
+int plh_lattice_attach_views(pl_lattice*, double** f0, double** f);
+int plh_lattice_detach(pl_lattice*);    /* before pl_lattice_destroy */
+int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* host_args);
+int plh_stream(pl_lattice*, int inverse);
+int plh_smooth_corner(pl_lattice*);
+int plh_smooth_corner_at(pl_lattice*, int i, int j, int k, int dirx, int diry, int dirz);
+int plh_bc(pl_lattice*, pl_lattice* other, const pl_bc*, const pl_bc_aux* host_aux);
+int plh_initial_condition(pl_lattice*, int family, const double* const* host_arrays, int na);
+int plh_residual(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, size_t n, double* out);
+int plh_normalize(double* v, size_t n);
+int plh_sensitivity(pl_lattice*, const pl_sens_args* host_args);
+int plh_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
+                                const double* igsnap, const double* diffusivity, const double* dkds);
+/* Execute whatever is still checked off and wait for the device. */
+int plh_sync(void);
+/* out[0..7] = fused steps, calls executed one by one, uploads, downloads, page faults served, plans built, settles, stagings */
+int plh_stats(uint64_t* out8);
 
 #ifdef __cplusplus
 }

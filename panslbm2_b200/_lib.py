@@ -57,8 +57,10 @@ _PROTOS = {
     "pl_lattice_set_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_lattice_get_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_lattice_device_view": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "pl_lattice_streamed": (C.c_int, [C.c_void_p]),
     "pl_stream": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_smooth_corner": (C.c_int, [C.c_void_p]),
+    "pl_smooth_corner_at": (C.c_int, [C.c_void_p] + [C.c_int] * 6),
     "pl_bc_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_bc_destroy": (C.c_int, [C.c_void_p]),
     "pl_bc_is_empty": (C.c_int, [C.c_void_p]),
@@ -75,6 +77,7 @@ _PROTOS = {
     "pl_plan_finalize": (C.c_int, [C.c_void_p]),
     "pl_plan_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pl_plan_parity": (C.c_int, [C.c_void_p]),
+    "pl_plan_set_parity": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_plan_profile_read": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "pl_residual": (C.c_int, [C.c_void_p] * 6 + [C.c_size_t, c_double_p]),
@@ -83,6 +86,25 @@ _PROTOS = {
     "pl_normalize": (C.c_int, [C.c_void_p, C.c_size_t]),
     "pl_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
     "pl_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
+    # host-pointer surface (bound by the C++ drop-in headers; declared here so that the export test covers it)
+    "plh_last_error": (C.c_char_p, []),
+    "plh_alloc": (C.c_void_p, [C.c_size_t]),
+    "plh_free": (None, [C.c_void_p]),
+    "plh_owns": (C.c_int, [C.c_void_p]),
+    "plh_lattice_attach_views": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "plh_lattice_detach": (C.c_int, [C.c_void_p]),
+    "plh_collide": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(CollideArgs)]),
+    "plh_stream": (C.c_int, [C.c_void_p, C.c_int]),
+    "plh_smooth_corner": (C.c_int, [C.c_void_p]),
+    "plh_smooth_corner_at": (C.c_int, [C.c_void_p] + [C.c_int] * 6),
+    "plh_bc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BcAux)]),
+    "plh_initial_condition": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
+    "plh_residual": (C.c_int, [C.c_void_p] * 6 + [C.c_size_t, c_double_p]),
+    "plh_normalize": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "plh_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
+    "plh_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
+    "plh_sync": (C.c_int, []),
+    "plh_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
 }
 EXPORTS = tuple(_PROTOS)
 

@@ -446,6 +446,7 @@ int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
     cudaFree(d0); cudaFree(d1);
     return PL_OK;
 }
+int pl_lattice_streamed(const pl_lattice* l) { return l ? l->streamed : 0; }
 int pl_lattice_device_view(pl_lattice* l, double** base, size_t* pitch) {
     if (!l) return fail(PL_ERR_ARG, "pl_lattice_device_view: null");
     if (base) *base = l->current();
@@ -726,6 +727,39 @@ int pl_stream(pl_lattice* l, int inverse) {
 int pl_smooth_corner(pl_lattice* l) {
     if (!l) return fail(PL_ERR_ARG, "pl_smooth_corner: null");
     return do_smooth(l);
+}
+
+int pl_smooth_corner_at(pl_lattice* l, int gi, int gj, int gk, int dx, int dy, int dz) {
+    if (!l) return fail(PL_ERR_ARG, "pl_smooth_corner_at: null");
+    const Geom& g = l->g;
+    const int D = l->kind;
+    int d[3] = {dx, dy, D == 3 ? dz : 0}, v[3] = {gi - g.offx, gj - g.offy, D == 3 ? gk - g.offz : 0}, n[3] = {g.nx, g.ny, g.nz};
+    long long st[3] = {1, g.nx, (long long)g.nx*g.ny};
+    int nzero = 0, line = -1;
+    for (int a = 0; a < 3; ++a) {
+        if (d[a] != 0 && d[a] != 1 && d[a] != -1) return fail(PL_ERR_ARG, "pl_smooth_corner_at: directions are -1, 0 or +1");
+        if (d[a] == 0) { ++nzero; if (a < D) line = a; }
+    }
+    if ((D == 3 && nzero > 1) || (D == 2 && nzero != 1)) return fail(PL_ERR_ARG, "pl_smooth_corner_at: need two (edge line / 2-D corner) or three (3-D corner) directions");
+    for (int a = 0; a < D; ++a) if (d[a] != 0 && (v[a] < 0 || v[a] >= n[a])) return PL_OK;   // not on this rank's block (d3q15.h:1244-1245)
+    auto inward = [&](int a) -> long long {
+        int w = v[a] - d[a];
+        if (w == -1) w = n[a] - 1; else if (w == n[a]) w = 0;
+        return (long long)(w - v[a])*st[a];
+    };
+    SmoothList L; L.count = 1;
+    SmoothItem& it = L.it[0];
+    it = SmoothItem{};
+    it.base = 0; it.stride = 0; it.len = 1;
+    long long nb[3]; int k = 0;
+    for (int a = 0; a < D; ++a) if (d[a] != 0) { it.base += v[a]*st[a]; nb[k++] = inward(a); }
+    if (D == 3 && line >= 0) { it.stride = st[line]; it.len = n[line]; }
+    it.n0 = nb[0]; it.n1 = nb[1]; it.n2 = k == 3 ? nb[2] : 0;
+    L.maxlen = it.len;
+    halo_touch(l);
+    dim3 grid(blocks_for(it.len, 128), 1);
+    if (D == 2) LAUNCH(k_smooth<2>, grid, 128, l->g, l->current(), L); else LAUNCH(k_smooth<3>, grid, 128, l->g, l->current(), L);
+    return PL_OK;
 }
 
 pl_bc* pl_bc_create(pl_lattice* l, int type, int axis, int coord, int dir, const uint8_t* mask, const double* v0, const double* v1, const double* v2) {
@@ -1087,6 +1121,7 @@ int pl_plan_finalize(pl_plan* p) {
     return PL_OK;
 }
 int pl_plan_parity(const pl_plan* p) { return p ? p->parity : 0; }
+int pl_plan_set_parity(pl_plan* p, int parity) { if (!p) return fail(PL_ERR_ARG, "null plan"); p->parity = parity ? 1 : 0; return PL_OK; }
 int pl_plan_profile(pl_plan* p, int enable) { if (!p) return fail(PL_ERR_ARG, "null plan"); p->profile = enable != 0; return PL_OK; }
 int pl_plan_profile_read(pl_plan* p, double* total_ms, int* launches, long long* total_sites) {
     if (!p) return fail(PL_ERR_ARG, "null plan");

@@ -1,0 +1,611 @@
+// Host-pointer surface of libpanslbm_b200.so (plh_*, see include/panslbm_c.h): what the drop-in C++ headers in
+// panslbm2_b200/src/ call.  The reference's drivers own plain host arrays (`new double[nxyz]`, production/heatsink3D.cpp:50-59),
+// pass them to every call, std::swap them between steps (:178-183) and read them directly whenever they like (:231).
+// This file keeps that contract on top of the device-pointer C-ABI (pl_*):
+//
+//   1. coherence  every array handed out by plh_alloc (the headers route operator new[] here) has a lazily created
+//      device mirror and one of three states, enforced with page protection on the host copy:
+//        HOST   host copy current, device stale      host pages read/write
+//        SHARED both current                         host pages read-only  (first host write faults -> HOST)
+//        DEVICE device copy current, host stale      host pages no access  (first host touch faults -> sync, copy back -> SHARED)
+//      A kernel reading an array needs SHARED/DEVICE (upload if HOST); a kernel writing it moves it to DEVICE.  In the
+//      steady state of a time loop no array changes state, so no copy and no mprotect happens per step.
+//      Pointers that were not allocated here (std::vector storage, stack arrays) are staged through a transient device
+//      buffer around the call (synchronous; correct but slow — never on the time-loop arrays of the reference drivers).
+//   2. fusion     collide / Stream / closures / SmoothCorner arrive as separate calls per lattice.  The engine executes them
+//      one by one while it LEARNs two consecutive loop iterations, builds a pl_plan from them (the two argument sets the
+//      driver alternates between), and then REPLAYs: Stream/closure/SmoothCorner calls that match the recorded iteration are
+//      only checked off, and the next collide call executes "stream + closures + SmoothCorner + collide" as ONE fused pass
+//      (pl_plan_advance).  Anything unexpected — a different call, an observation of the populations, the end of the
+//      loop — settles the checked-off calls first (one standalone pass, or call by call) and falls back to LEARN.
+//      Results are identical to call-by-call execution.
+//
+// Single-threaded callers, as everywhere in this library.  TEST NOTE: no CPU arithmetic lives here; every number is
+// produced by the CUDA kernels behind pl_*.
+#include "../../include/panslbm_c.h"
+
+#include <signal.h>
+#include <sys/mman.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+enum { ST_HOST = 0, ST_SHARED = 1, ST_DEVICE = 2 };
+enum { BK_ARRAY = 0, BK_POP0 = 1, BK_POPF = 2 };
+
+struct Block {
+    char* base = nullptr;
+    size_t bytes = 0, map_bytes = 0;
+    double* dev = nullptr;
+    int state = ST_HOST;
+    int kind = BK_ARRAY;
+    pl_lattice* lat = nullptr;      // population views only
+};
+std::map<uintptr_t, Block> g_blocks;              // by base address
+struct Views { Block *f0 = nullptr, *f = nullptr; };
+std::map<pl_lattice*, Views> g_views;
+uint64_t g_stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // fused steps, unfused ops, uploads, downloads, faults, plans, settles, transient stagings
+size_t g_page = 4096;
+bool g_handler = false;
+struct sigaction g_prev;
+std::string g_herr;
+
+int hfail(const char* what) {
+    g_herr = std::string(what) + ": " + pl_last_error();
+    return PL_ERR_CUDA;
+}
+
+Block* find_block(const void* p) {
+    if (g_blocks.empty()) return nullptr;
+    auto it = g_blocks.upper_bound((uintptr_t)p);
+    if (it == g_blocks.begin()) return nullptr;
+    --it;
+    Block& b = it->second;
+    return ((const char*)p < b.base + b.map_bytes) ? &b : nullptr;
+}
+void protect(Block* b, int prot) { mprotect(b->base, b->map_bytes, prot); }
+
+void settle_all();
+
+// bring the host copy of a block up to date (it is in state DEVICE) and make it readable
+void fetch(Block* b) {
+    pl_synchronize();
+    if (b->kind == BK_ARRAY) {
+        protect(b, PROT_READ | PROT_WRITE);
+        pl_array_download((double*)b->base, b->dev, b->bytes/sizeof(double));
+        protect(b, PROT_READ);
+        b->state = ST_SHARED;
+    } else {
+        settle_all();     // checked-off Stream/closure calls change what the populations are
+        Views& v = g_views[b->lat];
+        protect(v.f0, PROT_READ | PROT_WRITE); protect(v.f, PROT_READ | PROT_WRITE);
+        pl_lattice_get_host(b->lat, (double*)v.f0->base, (double*)v.f->base);
+        protect(v.f0, PROT_READ); protect(v.f, PROT_READ);
+        v.f0->state = v.f->state = ST_SHARED;
+    }
+    ++g_stat[3];
+}
+
+std::atomic_flag g_fault_lock = ATOMIC_FLAG_INIT;     // host threads of the caller (OpenMP loops over its arrays) may fault together
+void on_fault(int sig, siginfo_t* si, void* uc) {
+    while (g_fault_lock.test_and_set(std::memory_order_acquire)) {}
+    Block* b = find_block(si->si_addr);
+    if (b && b->state == ST_DEVICE) { ++g_stat[4]; fetch(b); g_fault_lock.clear(std::memory_order_release); return; }
+    if (b && b->state == ST_SHARED) {
+        ++g_stat[4]; protect(b, PROT_READ | PROT_WRITE); b->state = ST_HOST;
+        g_fault_lock.clear(std::memory_order_release);
+        return;
+    }
+    g_fault_lock.clear(std::memory_order_release);
+    // not ours: hand over to whoever was there before (default action: re-raise and die as usual)
+    if (g_prev.sa_flags & SA_SIGINFO) { if (g_prev.sa_sigaction) { g_prev.sa_sigaction(sig, si, uc); return; } }
+    else if (g_prev.sa_handler != SIG_DFL && g_prev.sa_handler != SIG_IGN) { g_prev.sa_handler(sig); return; }
+    signal(SIGSEGV, SIG_DFL);
+}
+void install_handler() {
+    if (g_handler) return;
+    g_page = (size_t)sysconf(_SC_PAGESIZE);
+    struct sigaction sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.sa_sigaction = on_fault;
+    sa.sa_flags = SA_SIGINFO | SA_NODEFER;
+    sigemptyset(&sa.sa_mask);
+    sigaction(SIGSEGV, &sa, &g_prev);
+    g_handler = true;
+}
+
+Block* new_block(size_t bytes, int kind, pl_lattice* lat, int state, int prot) {
+    install_handler();
+    size_t mb = (bytes + g_page - 1)/g_page*g_page;
+    if (mb == 0) mb = g_page;
+    void* p = mmap(nullptr, mb, prot, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (p == MAP_FAILED) return nullptr;
+    Block b;
+    b.base = (char*)p; b.bytes = bytes; b.map_bytes = mb; b.kind = kind; b.lat = lat; b.state = state;
+    auto r = g_blocks.emplace((uintptr_t)p, b);
+    return &r.first->second;
+}
+void drop_block(Block* b) {
+    if (b->dev) { pl_synchronize(); pl_array_free(b->dev); }
+    char* base = b->base; size_t mb = b->map_bytes;
+    g_blocks.erase((uintptr_t)base);
+    munmap(base, mb);
+}
+
+// ---- translation of one array argument ----------------------------------------------------------------------
+struct Staged { double* dev; double* host; size_t n; bool write; };
+std::vector<Staged> g_staged;      // transient mirrors of the call being translated
+
+// device address of host pointer `h` (n doubles) for a kernel that reads it (rd) and/or writes it (wr)
+int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
+    *out = nullptr;
+    if (!h) return PL_OK;
+    Block* b = find_block(h);
+    if (b && b->kind == BK_ARRAY) {
+        if (!b->dev) {
+            b->dev = pl_array_alloc(b->map_bytes/sizeof(double));
+            if (!b->dev) return hfail("device mirror");
+        }
+        if (b->state == ST_HOST) {      // also before a write: a kernel may update part of an array only
+            if (pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
+            ++g_stat[2];
+            b->state = ST_SHARED;
+            if (!wr) protect(b, PROT_READ);
+        }
+        if (wr && b->state != ST_DEVICE) { protect(b, PROT_NONE); b->state = ST_DEVICE; }
+        *out = b->dev + ((const char*)h - b->base)/sizeof(double);
+        return PL_OK;
+    }
+    // foreign memory: stage through a transient device buffer
+    Staged s;
+    s.host = const_cast<double*>(h); s.n = n; s.write = wr;
+    s.dev = pl_array_alloc(n);
+    if (!s.dev) return hfail("staging buffer");
+    if (pl_array_upload(s.dev, h, n)) return hfail("staging upload");
+    (void)rd;
+    ++g_stat[7];
+    g_staged.push_back(s);
+    *out = s.dev;
+    return PL_OK;
+}
+int unstage() {
+    int rc = PL_OK;
+    for (auto& s : g_staged) {
+        if (s.write && pl_array_download(s.host, s.dev, s.n)) rc = hfail("staging download");
+        else if (!s.write) pl_synchronize();
+        pl_array_free(s.dev);
+    }
+    g_staged.clear();
+    return rc;
+}
+
+// the populations of `l` are about to change on the device: its host views (public f0/f) go stale
+void pops_written(pl_lattice* l) {
+    auto it = g_views.find(l);
+    if (it == g_views.end()) return;
+    for (Block* b : {it->second.f0, it->second.f})
+        if (b->state != ST_DEVICE) { protect(b, PROT_NONE); b->state = ST_DEVICE; }
+}
+// the host wrote into f0/f since the last device operation: import them
+int pops_sync_in(pl_lattice* l) {
+    auto it = g_views.find(l);
+    if (it == g_views.end()) return PL_OK;
+    Views& v = it->second;
+    if (v.f0->state == ST_HOST || v.f->state == ST_HOST) {
+        if (pl_lattice_set_host(l, (const double*)v.f0->base, (const double*)v.f->base)) return hfail("pl_lattice_set_host");
+        for (Block* b : {v.f0, v.f}) { protect(b, PROT_READ); b->state = ST_SHARED; }
+        ++g_stat[2];
+    }
+    return PL_OK;
+}
+
+// ---- the fusion engine -------------------------------------------------------------------------------------------
+enum { OP_STREAM = 0, OP_BC = 1, OP_SMOOTH = 2 };
+struct Op {
+    int kind = 0;
+    pl_lattice* l = nullptr;
+    pl_lattice* other = nullptr;
+    const pl_bc* bc = nullptr;
+    pl_bc_aux aux;
+    bool has_aux = false;
+    int inverse = 0;
+};
+bool same_aux(const Op& a, const Op& b) { return a.has_aux == b.has_aux && (!a.has_aux || memcmp(&a.aux, &b.aux, sizeof(pl_bc_aux)) == 0); }
+bool same_shape(const Op& a, const Op& b) { return a.kind == b.kind && a.l == b.l && a.other == b.other && a.bc == b.bc && a.inverse == b.inverse; }
+bool same_args(const pl_collide_args& a, const pl_collide_args& b) { return memcmp(&a, &b, sizeof(pl_collide_args)) == 0; }
+
+struct Iter {
+    bool have_c = false;
+    pl_lattice *f = nullptr, *g = nullptr;
+    pl_collide_args c;
+    std::vector<Op> ops;
+};
+struct Plan {
+    pl_plan* p = nullptr;
+    pl_lattice *f = nullptr, *g = nullptr;
+    pl_collide_args c[2];
+    std::vector<Op> ops[2];
+};
+struct Engine {
+    Iter hist[2];
+    int nhist = 0;
+    Iter cur;
+    Plan* active = nullptr;
+    int par = 0;          // REPLAY: argument set of the last collide executed
+    int pos = 0;          // REPLAY: Stream/closure/SmoothCorner calls of the current iteration checked off so far
+    std::vector<Plan*> plans;
+} E;
+
+int exec_op(const Op& o) {
+    ++g_stat[1];
+    pops_written(o.l);
+    switch (o.kind) {
+        case OP_STREAM: return pl_stream(o.l, o.inverse);
+        case OP_BC: return pl_bc_apply(o.l, o.other, o.bc, o.has_aux ? &o.aux : nullptr);
+        default: return pl_smooth_corner(o.l);
+    }
+}
+int settle() {
+    if (!E.active) return PL_OK;
+    Plan* pl = E.active;
+    int rc = PL_OK;
+    const int nops = (int)pl->ops[0].size();
+    if (E.pos == nops && nops > 0) rc = pl_plan_advance(pl->p, 0, 1);
+    else for (int k = 0; k < E.pos && !rc; ++k) rc = exec_op(pl->ops[E.par][k]);
+    ++g_stat[6];
+    E.active = nullptr; E.pos = 0; E.nhist = 0; E.cur = Iter();
+    return rc ? hfail("settle") : PL_OK;
+}
+void settle_all() { settle(); }
+
+// can [collide, ops] be expressed as a pl_plan?  streams of every lattice first (one direction), then closures, then SmoothCorner
+bool fusable(const Iter& a, const Iter& b) {
+    if (!a.have_c || !b.have_c || a.f != b.f || a.g != b.g || a.c.model != b.c.model || a.ops.size() != b.ops.size() || a.ops.empty()) return false;
+    const size_t nlat = a.g ? 2 : 1;
+    if (a.ops.size() < nlat) return false;
+    for (size_t k = 0; k < a.ops.size(); ++k) {
+        if (!same_shape(a.ops[k], b.ops[k])) return false;
+        const Op& o = a.ops[k];
+        if (o.l != a.f && o.l != a.g) return false;
+        if (k < nlat) { if (o.kind != OP_STREAM || o.inverse != a.ops[0].inverse) return false; }
+        else if (o.kind == OP_STREAM) return false;
+    }
+    if (nlat == 2 && a.ops[0].l == a.ops[1].l) return false;
+    bool smooth_seen = false, sf = false, sg = false;
+    for (size_t k = nlat; k < a.ops.size(); ++k) {
+        const Op& o = a.ops[k];
+        if (o.kind == OP_SMOOTH) {
+            smooth_seen = true;
+            bool& s = o.l == a.f ? sf : sg;
+            if (s) return false;
+            s = true;
+        } else if (smooth_seen) return false;
+    }
+    return true;
+}
+Plan* build_plan(const Iter& a, const Iter& b) {
+    Plan* pl = new Plan();
+    pl->f = a.f; pl->g = a.g; pl->c[0] = a.c; pl->c[1] = b.c; pl->ops[0] = a.ops; pl->ops[1] = b.ops;
+    pl->p = pl_plan_create(a.f, a.g);
+    bool ok = pl->p != nullptr;
+    ok = ok && pl_plan_set_collide(pl->p, &a.c, &b.c) == PL_OK && pl_plan_set_stream(pl->p, a.ops[0].inverse) == PL_OK;
+    int sf = 0, sg = 0;
+    for (size_t k = 0; ok && k < a.ops.size(); ++k) {
+        const Op &o = a.ops[k], &o2 = b.ops[k];
+        if (o.kind == OP_BC) ok = pl_plan_add_bc(pl->p, o.l == a.g && a.g ? 1 : 0, o.bc, o.has_aux ? &o.aux : nullptr, o2.has_aux ? &o2.aux : nullptr) == PL_OK;
+        else if (o.kind == OP_SMOOTH) { if (o.l == a.f) sf = 1; else sg = 1; }
+    }
+    ok = ok && pl_plan_set_smooth_corner(pl->p, sf, sg) == PL_OK && pl_plan_finalize(pl->p) == PL_OK;
+    if (!ok) { if (pl->p) pl_plan_destroy(pl->p); pl->p = nullptr; }     // kept as a tombstone: do not try this shape again
+    E.plans.push_back(pl);
+    ++g_stat[5];
+    return pl->p ? pl : nullptr;
+}
+bool same_plan_shape(const Plan* pl, const Iter& a, const Iter& b) {
+    if (pl->f != a.f || pl->g != a.g || pl->ops[0].size() != a.ops.size()) return false;
+    for (int par = 0; par < 2; ++par) {
+        const Iter& it = par ? b : a;
+        if (!same_args(pl->c[par], it.c)) return false;
+        for (size_t k = 0; k < a.ops.size(); ++k) if (!same_shape(pl->ops[par][k], it.ops[k]) || !same_aux(pl->ops[par][k], it.ops[k])) return false;
+    }
+    return true;
+}
+void drop_plans_of(pl_lattice* l) {
+    for (size_t k = 0; k < E.plans.size();) {
+        if (E.plans[k]->f == l || E.plans[k]->g == l) {
+            if (E.plans[k]->p) pl_plan_destroy(E.plans[k]->p);
+            delete E.plans[k];
+            E.plans.erase(E.plans.begin() + k);
+        } else ++k;
+    }
+}
+
+int enter_replay(Plan* pl, int par) {
+    if (pl_plan_set_parity(pl->p, par)) return hfail("pl_plan_set_parity");
+    if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
+    ++g_stat[0];
+    E.active = pl; E.par = par; E.pos = 0; E.nhist = 0; E.cur = Iter();
+    return PL_OK;
+}
+
+int do_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args& d, bool staged) {
+    pops_written(f); if (g) pops_written(g);
+    if (E.active) {
+        Plan* pl = E.active;
+        const int nops = (int)pl->ops[0].size();
+        const int next = E.par ^ 1;
+        if (!staged && pl->f == f && pl->g == g && E.pos == nops && same_args(d, pl->c[next])) {
+            if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
+            ++g_stat[0];
+            E.par = next; E.pos = 0;
+            return PL_OK;
+        }
+        int rc = settle();
+        if (rc) return rc;
+    }
+    // LEARN: the previous iteration (collide + what followed) is complete now
+    if (E.cur.have_c) {
+        if (E.nhist == 2) E.hist[0] = E.hist[1], E.nhist = 1;
+        E.hist[E.nhist++] = E.cur;
+        E.cur = Iter();
+    }
+    if (!staged) {
+        for (Plan* pl : E.plans) {
+            // speculative re-entry: a known plan whose collide arguments match; every following call is still verified
+            if (pl->p && pl->f == f && pl->g == g && E.nhist == 0 && pl_lattice_streamed(f) && (!g || pl_lattice_streamed(g))) {
+                for (int par = 0; par < 2; ++par) if (same_args(d, pl->c[par])) return enter_replay(pl, par);
+            }
+        }
+        if (E.nhist == 2 && fusable(E.hist[0], E.hist[1]) && E.hist[0].f == f && E.hist[0].g == g && same_args(d, E.hist[0].c) &&
+            pl_lattice_streamed(f) && (!g || pl_lattice_streamed(g))) {
+            Plan* found = nullptr;
+            bool tomb = false;
+            for (Plan* pl : E.plans) if (same_plan_shape(pl, E.hist[0], E.hist[1])) { found = pl->p ? pl : nullptr; tomb = !pl->p; break; }
+            if (!found && !tomb) found = build_plan(E.hist[0], E.hist[1]);
+            if (found) return enter_replay(found, 0);
+        }
+    }
+    ++g_stat[1];
+    if (pl_collide(f, g, &d)) return hfail("pl_collide");
+    E.cur.have_c = !staged; E.cur.f = f; E.cur.g = g; E.cur.c = d; E.cur.ops.clear();
+    return PL_OK;
+}
+
+int do_op(const Op& o, bool staged) {
+    if (E.active) {
+        Plan* pl = E.active;
+        const int nops = (int)pl->ops[0].size();
+        if (!staged && E.pos < nops && same_shape(o, pl->ops[E.par][E.pos]) && same_aux(o, pl->ops[E.par][E.pos])) {
+            ++E.pos;
+            pops_written(o.l);
+            return PL_OK;
+        }
+        int rc = settle();
+        if (rc) return rc;
+    }
+    if (exec_op(o)) return hfail("boundary/stream call");
+    if (E.cur.have_c) { if (staged) E.cur = Iter(); else E.cur.ops.push_back(o); }
+    return PL_OK;
+}
+
+// settle if `l` takes part in the loop being replayed / learned (its populations are about to be observed or replaced)
+int quiesce(pl_lattice* l) {
+    if (E.active && (E.active->f == l || E.active->g == l)) { int rc = settle(); if (rc) return rc; }
+    if (E.cur.have_c && (E.cur.f == l || E.cur.g == l)) { E.cur = Iter(); E.nhist = 0; }
+    return PL_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* plh_last_error(void) { return g_herr.c_str(); }
+
+void* plh_alloc(size_t bytes) {
+    Block* b = new_block(bytes, BK_ARRAY, nullptr, ST_HOST, PROT_READ | PROT_WRITE);
+    return b ? b->base : nullptr;
+}
+int plh_owns(const void* p) {
+    auto it = g_blocks.find((uintptr_t)p);
+    return it != g_blocks.end() && it->second.kind == BK_ARRAY;
+}
+void plh_free(void* p) {
+    auto it = g_blocks.find((uintptr_t)p);
+    if (it != g_blocks.end()) drop_block(&it->second);
+}
+
+int plh_lattice_attach_views(pl_lattice* l, double** f0, double** f) {
+    if (!l || !f0 || !f) { g_herr = "plh_lattice_attach_views: null"; return PL_ERR_ARG; }
+    int info[18];
+    if (pl_lattice_info(l, info)) return hfail("pl_lattice_info");
+    const size_t n = (size_t)info[13], nc = (size_t)info[17];
+    Views v;
+    // no access until somebody looks: the device populations (all zero after creation) are the truth
+    v.f0 = new_block(n*sizeof(double), BK_POP0, l, ST_DEVICE, PROT_NONE);
+    v.f = new_block(n*(nc - 1)*sizeof(double), BK_POPF, l, ST_DEVICE, PROT_NONE);
+    if (!v.f0 || !v.f) { g_herr = "plh_lattice_attach_views: mmap failed"; return PL_ERR_CUDA; }
+    g_views[l] = v;
+    *f0 = (double*)v.f0->base; *f = (double*)v.f->base;
+    return PL_OK;
+}
+int plh_lattice_detach(pl_lattice* l) {
+    int rc = quiesce(l);
+    drop_plans_of(l);
+    auto it = g_views.find(l);
+    if (it != g_views.end()) {
+        drop_block(it->second.f0); drop_block(it->second.f);
+        g_views.erase(it);
+    }
+    return rc;
+}
+
+// collide: every pointer of `h` is a HOST pointer; which arrays the model reads / writes follows the reference signatures
+int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* h) {
+    if (!f || !h) { g_herr = "plh_collide: null"; return PL_ERR_ARG; }
+    int info[18];
+    pl_lattice_info(f, info);
+    const size_t n = (size_t)info[13], nc = (size_t)info[17];
+    int rc;
+    if ((rc = pops_sync_in(f)) || (g && (rc = pops_sync_in(g)))) return rc;
+    pl_collide_args d;
+    memset(&d, 0, sizeof(d));
+    d.model = h->model; d.issave = h->issave; d.viscosity = h->viscosity; d.diffusivity_const = h->diffusivity_const;
+    d.gx = h->gx; d.gy = h->gy; d.gz = h->gz; d.tem0 = h->tem0;
+    const bool adj = h->model >= PL_ANS_BRINKMAN, save = h->issave != 0;
+    g_staged.clear();
+#define RD(field) if ((rc = xlate(h->field, n, true, false, (double**)&d.field))) return rc
+#define WR(field) if ((rc = xlate(h->field, n, false, save, (double**)&d.field))) return rc
+    RD(alpha); RD(diffusivity); RD(beta); RD(dirx); RD(diry); RD(dirz);
+    if (adj) { RD(rho); RD(ux); RD(uy); RD(uz); RD(tem); } else { WR(rho); WR(ux); WR(uy); WR(uz); WR(tem); }
+    WR(qx); WR(qy); WR(qz);
+    WR(ip); WR(iux); WR(iuy); WR(iuz); WR(imx); WR(imy); WR(imz); WR(item); WR(iqx); WR(iqy); WR(iqz);
+#undef RD
+#undef WR
+    if ((rc = xlate(h->snapshot, n*nc, false, save, &d.snapshot))) return rc;
+    const bool staged = !g_staged.empty();
+    rc = do_collide(f, g, d, staged);
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+
+int plh_stream(pl_lattice* l, int inverse) {
+    if (!l) { g_herr = "plh_stream: null"; return PL_ERR_ARG; }
+    int rc = pops_sync_in(l);
+    if (rc) return rc;
+    Op o; o.kind = OP_STREAM; o.l = l; o.inverse = inverse ? 1 : 0;
+    return do_op(o, false);
+}
+int plh_smooth_corner(pl_lattice* l) {
+    if (!l) { g_herr = "plh_smooth_corner: null"; return PL_ERR_ARG; }
+    int rc = pops_sync_in(l);
+    if (rc) return rc;
+    Op o; o.kind = OP_SMOOTH; o.l = l;
+    return do_op(o, false);
+}
+int plh_smooth_corner_at(pl_lattice* l, int i, int j, int k, int dx, int dy, int dz) {
+    if (!l) { g_herr = "plh_smooth_corner_at: null"; return PL_ERR_ARG; }
+    int rc;
+    if ((rc = pops_sync_in(l)) || (rc = quiesce(l))) return rc;
+    pops_written(l);
+    ++g_stat[1];
+    return pl_smooth_corner_at(l, i, j, k, dx, dy, dz) ? hfail("pl_smooth_corner_at") : PL_OK;
+}
+int plh_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* h) {
+    if (!l || !bc) { g_herr = "plh_bc: null"; return PL_ERR_ARG; }
+    if (pl_bc_is_empty(bc)) return PL_OK;      // the reference's `if (0 <= i && i < nx)` guard: nothing to do on this rank
+    int info[18];
+    pl_lattice_info(l, info);
+    const size_t n = (size_t)info[13];
+    int rc;
+    if ((rc = pops_sync_in(l)) || (other && (rc = pops_sync_in(other)))) return rc;
+    Op o; o.kind = OP_BC; o.l = l; o.other = other; o.bc = bc; o.has_aux = h != nullptr;
+    memset(&o.aux, 0, sizeof(o.aux));
+    g_staged.clear();
+    if (h) {
+        o.aux.diffusivity_const = h->diffusivity_const; o.aux.eps = h->eps;
+        if ((rc = xlate(h->rho, n, true, false, (double**)&o.aux.rho)) || (rc = xlate(h->ux, n, true, false, (double**)&o.aux.ux)) ||
+            (rc = xlate(h->uy, n, true, false, (double**)&o.aux.uy)) || (rc = xlate(h->uz, n, true, false, (double**)&o.aux.uz)) ||
+            (rc = xlate(h->tem, n, true, false, (double**)&o.aux.tem)) || (rc = xlate(h->diffusivity, n, true, false, (double**)&o.aux.diffusivity)))
+            return rc;
+    }
+    const bool staged = !g_staged.empty();
+    rc = do_op(o, staged);
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+
+int plh_initial_condition(pl_lattice* l, int family, const double* const* h, int na) {
+    if (!l || !h) { g_herr = "plh_initial_condition: null"; return PL_ERR_ARG; }
+    int info[18];
+    pl_lattice_info(l, info);
+    const size_t n = (size_t)info[13];
+    int rc = quiesce(l);
+    if (rc) return rc;
+    const double* d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    g_staged.clear();
+    for (int k = 0; k < na && k < 8; ++k) if ((rc = xlate(h[k], n, true, false, (double**)&d[k]))) return rc;
+    pops_written(l);
+    ++g_stat[1];
+    rc = pl_initial_condition(l, family, d, na) ? hfail("pl_initial_condition") : PL_OK;
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+
+int plh_residual(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, size_t n, double* out) {
+    const double* h[6] = {ux, uy, uz, uxp, uyp, uzp};
+    double* d[6];
+    int rc;
+    g_staged.clear();
+    for (int k = 0; k < 6; ++k) if ((rc = xlate(h[k], n, true, false, &d[k]))) return rc;
+    rc = pl_residual(d[0], d[1], d[2], d[3], d[4], d[5], n, out) ? hfail("pl_residual") : PL_OK;
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+int plh_normalize(double* v, size_t n) {
+    double* d;
+    int rc;
+    g_staged.clear();
+    if ((rc = xlate(v, n, true, true, &d))) return rc;
+    rc = pl_normalize(d, n) ? hfail("pl_normalize") : PL_OK;
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+int plh_sensitivity(pl_lattice* l, const pl_sens_args* h) {
+    if (!l || !h) { g_herr = "plh_sensitivity: null"; return PL_ERR_ARG; }
+    int info[18];
+    pl_lattice_info(l, info);
+    const size_t n = (size_t)info[13], nc = (size_t)info[17];
+    pl_sens_args d;
+    memset(&d, 0, sizeof(d));
+    d.kind = h->kind;
+    int rc;
+    g_staged.clear();
+    if ((rc = xlate(h->dfds, n, true, true, &d.dfds))) return rc;
+#define RD(field, len) if ((rc = xlate(h->field, len, true, false, (double**)&d.field))) return rc
+    RD(ux, n); RD(uy, n); RD(uz, n); RD(imx, n); RD(imy, n); RD(imz, n); RD(dads, n); RD(tem, n); RD(item, n); RD(iqx, n); RD(iqy, n); RD(iqz, n);
+    RD(gsnap, n*nc); RD(igsnap, n*nc); RD(diffusivity, n); RD(dkds, n); RD(dbds, n);
+#undef RD
+    rc = pl_sensitivity(l, &d) ? hfail("pl_sensitivity") : PL_OK;
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+int plh_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
+                                const double* igsnap, const double* diffusivity, const double* dkds) {
+    if (!l || !plane) { g_herr = "plh_sensitivity_heat_source: null"; return PL_ERR_ARG; }
+    if (pl_bc_is_empty(plane)) return PL_OK;
+    int info[18];
+    pl_lattice_info(l, info);
+    const size_t n = (size_t)info[13], nc = (size_t)info[17];
+    double *d_dfds, *d_ux, *d_uy, *d_uz, *d_ig, *d_k, *d_dk;
+    int rc;
+    g_staged.clear();
+    if ((rc = xlate(dfds, n, true, true, &d_dfds)) || (rc = xlate(ux, n, true, false, &d_ux)) || (rc = xlate(uy, n, true, false, &d_uy)) ||
+        (rc = xlate(uz, n, true, false, &d_uz)) || (rc = xlate(igsnap, n*nc, true, false, &d_ig)) || (rc = xlate(diffusivity, n, true, false, &d_k)) ||
+        (rc = xlate(dkds, n, true, false, &d_dk)))
+        return rc;
+    rc = pl_sensitivity_heat_source(l, plane, d_dfds, d_ux, d_uy, d_uz, d_ig, d_k, d_dk) ? hfail("pl_sensitivity_heat_source") : PL_OK;
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+
+int plh_sync(void) {
+    int rc = settle();
+    pl_synchronize();
+    return rc;
+}
+int plh_stats(uint64_t* out8) {
+    if (!out8) return PL_ERR_ARG;
+    memcpy(out8, g_stat, sizeof(g_stat));
+    return PL_OK;
+}
+
+}  // extern "C"

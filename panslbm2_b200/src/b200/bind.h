@@ -1,0 +1,196 @@
+// Glue between the drop-in PANSLBM2 headers (src/particle, src/equation, src/utility of this tree) and the C-ABI of
+// libpanslbm_b200.so (include/panslbm_c.h).  Nothing numerical happens on the host: lambdas are evaluated on the boundary
+// planes once and baked into device arrays (pl_bc), everything else is forwarded to the host-pointer surface (plh_*),
+// which mirrors the caller's arrays on the device and fuses the calls of a time loop into one pass per step.
+//
+// Build line of a reference program against this tree (the reference's own is README.md:23-25):
+//     g++ -O2 production/heatsink3D.cpp -I<repo>/include -L<repo>/panslbm2_b200 -lpanslbm_b200 -Wl,-rpath,<repo>/panslbm2_b200
+#pragma once
+#if __has_include("../../../include/panslbm_c.h")
+#include "../../../include/panslbm_c.h"
+#else
+#include <panslbm_c.h>
+#endif
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+// ---- allocation hook -------------------------------------------------------------------------------------------------
+// The drivers allocate their fields with `new double[nxyz]` (production/heatsink3D.cpp:50-59) and std::vector, hand the raw
+// pointers to every call and read them directly in between.  Large blocks therefore come from plh_alloc: ordinary host
+// memory the runtime can mirror on the device and keep coherent lazily.  Define PANSLBM_B200_NO_ALLOC_HOOK in all but one
+// translation unit of a multi-file program (replacement functions must be defined once), or everywhere to opt out
+// (arrays are then staged through the device around every call: correct, slow).
+#ifndef PANSLBM_B200_ALLOC_THRESHOLD
+#define PANSLBM_B200_ALLOC_THRESHOLD 4096
+#endif
+#ifndef PANSLBM_B200_NO_ALLOC_HOOK
+namespace PANSLBM2 { namespace b200 {
+    inline void* hooked_new(std::size_t n) {
+        void* p = n >= PANSLBM_B200_ALLOC_THRESHOLD ? plh_alloc(n) : std::malloc(n ? n : 1);
+        if (!p) throw std::bad_alloc();
+        return p;
+    }
+    inline void hooked_delete(void* p) noexcept {
+        if (!p) return;
+        if (plh_owns(p)) plh_free(p); else std::free(p);
+    }
+} }
+void* operator new(std::size_t n) { return PANSLBM2::b200::hooked_new(n); }
+void* operator new[](std::size_t n) { return PANSLBM2::b200::hooked_new(n); }
+void operator delete(void* p) noexcept { PANSLBM2::b200::hooked_delete(p); }
+void operator delete[](void* p) noexcept { PANSLBM2::b200::hooked_delete(p); }
+void operator delete(void* p, std::size_t) noexcept { PANSLBM2::b200::hooked_delete(p); }
+void operator delete[](void* p, std::size_t) noexcept { PANSLBM2::b200::hooked_delete(p); }
+#endif
+
+namespace PANSLBM2 {
+    namespace {     // bounce-back plane types (d3q15.h:19-22, d2q9.h:19-22); defined once here so that both lattices fit in one program
+        const int BARRIER = 1;
+        const int MIRROR = 2;
+    }
+namespace b200 {
+    // The reference reports nothing (assert only, d3q15.h:37); a failing device call cannot be ignored, so it is fatal and loud.
+    inline void check(int rc, const char* where) {
+        if (rc == 0) return;
+        const char* a = plh_last_error();
+        std::fprintf(stderr, "panslbm_b200: %s failed: %s%s%s\n", where, a ? a : "", (a && *a) ? " | " : "", pl_last_error());
+        std::abort();
+    }
+
+    struct none_t {};     // absent value callable
+
+    // State every lattice object carries besides the reference's public members.
+    struct Core {
+        pl_lattice* h = nullptr;
+        unsigned long long gen = 0;                 // unique per constructed lattice: keys the baked-plane caches
+        std::vector<pl_bc*> planes;                 // baked planes owned by this lattice
+        std::vector<std::string> contents;          // their content keys (dedupe: equal planes share one pl_bc)
+        static unsigned long long next_gen() { static unsigned long long g = 0; return ++g; }
+        void create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz, double** f0, double** f) {
+            h = pl_lattice_create(kind, lx, ly, lz, peid, mx, my, mz);
+            if (!h) check(1, "pl_lattice_create");
+            gen = next_gen();
+            check(plh_lattice_attach_views(h, f0, f), "plh_lattice_attach_views");
+        }
+        void destroy() {
+            if (!h) return;
+            plh_lattice_detach(h);
+            for (pl_bc* b : planes) pl_bc_destroy(b);
+            pl_lattice_destroy(h);
+            h = nullptr;
+        }
+    };
+
+    template<class F> inline void append_bytes(std::string& s, const F& f) {
+        if constexpr (!std::is_empty<F>::value) s.append(reinterpret_cast<const char*>(&f), sizeof(F));
+        s.push_back('|');
+    }
+    template<int ND, class F> inline double call_value(F& f, int i, int j, int k) {
+        if constexpr (std::is_same<F, none_t>::value) { (void)f; (void)i; (void)j; (void)k; return 0.0; }
+        else if constexpr (ND == 2) { (void)k; return (double)f(i, j); }
+        else return (double)f(i, j, k);
+    }
+    template<int ND, class F> inline int call_mask(F& f, int i, int j, int k) {
+        if constexpr (ND == 2) { (void)k; return (int)f(i, j); }
+        else return (int)f(i, j, k);
+    }
+
+    // One plane closure of lattice `p` (plane axis = GLOBAL coord, outward dir): the callables evaluated on the local plane
+    // sites with global coordinates, as the reference does (navierstokes.h:155-157), baked into a pl_bc.  Cached per call
+    // site (= per instantiation) by the bytes of the closure objects, and per lattice by content.
+    template<class P, class Fm, class F0, class F1, class F2>
+    const pl_bc* baked(P& p, int type, int axis, int coord, int dir, Fm mask, F0 v0, F1 v1, F2 v2) {
+        struct Entry { unsigned long long gen; int type, axis, coord, dir; std::string bytes; const pl_bc* bc; };
+        static std::vector<Entry> cache;
+        constexpr bool cacheable = std::is_trivially_copyable<Fm>::value && std::is_trivially_copyable<F0>::value &&
+                                   std::is_trivially_copyable<F1>::value && std::is_trivially_copyable<F2>::value;
+        Core& core = p.b200_core();
+        std::string bytes;
+        if constexpr (cacheable) {
+            append_bytes(bytes, mask); append_bytes(bytes, v0); append_bytes(bytes, v1); append_bytes(bytes, v2);
+            for (const Entry& e : cache)
+                if (e.gen == core.gen && e.type == type && e.axis == axis && e.coord == coord && e.dir == dir && e.bytes == bytes) return e.bc;
+        }
+        constexpr int ND = P::nd;
+        const int off[3] = {p.offsetx, p.offsety, p.offsetz}, n[3] = {p.nx, p.ny, p.nz};
+        const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+        const int loc = coord - off[axis];
+        const bool local = 0 <= loc && loc < n[axis];
+        const size_t np = local ? (size_t)n[a1]*n[a2] : 0;
+        std::vector<uint8_t> m(np);
+        constexpr bool h0 = !std::is_same<F0, none_t>::value, h1 = !std::is_same<F1, none_t>::value, h2 = !std::is_same<F2, none_t>::value;
+        std::vector<double> a(h0 ? np : 0), b(h1 ? np : 0), c(h2 ? np : 0);
+        const bool raw = type == PL_BC_BOUNCE || type == PL_BC_IBOUNCE || type == PL_BC_AAD_ISET_RHO;
+        for (int s2 = 0; s2 < (local ? n[a2] : 0); ++s2) {
+            for (int s1 = 0; s1 < n[a1]; ++s1) {
+                int g[3];
+                g[axis] = coord; g[a1] = s1 + off[a1]; g[a2] = s2 + off[a2];
+                const size_t t = (size_t)s1 + (size_t)n[a1]*s2;
+                const int mv = call_mask<ND>(mask, g[0], g[1], g[2]);
+                m[t] = raw ? (uint8_t)((mv == 1 || mv == 2) ? mv : 0) : (uint8_t)(mv != 0);
+                if constexpr (h0) a[t] = call_value<ND>(v0, g[0], g[1], g[2]);
+                if constexpr (h1) b[t] = call_value<ND>(v1, g[0], g[1], g[2]);
+                if constexpr (h2) c[t] = call_value<ND>(v2, g[0], g[1], g[2]);
+            }
+        }
+        // content key: equal planes of one lattice share one pl_bc (keeps handles stable for the fusion engine)
+        std::string key;
+        key.append(reinterpret_cast<const char*>(&type), sizeof(int)); key.append(reinterpret_cast<const char*>(&axis), sizeof(int));
+        key.append(reinterpret_cast<const char*>(&coord), sizeof(int)); key.append(reinterpret_cast<const char*>(&dir), sizeof(int));
+        key.append(reinterpret_cast<const char*>(m.data()), m.size());
+        key.append(reinterpret_cast<const char*>(a.data()), a.size()*sizeof(double)); key.push_back('|');
+        key.append(reinterpret_cast<const char*>(b.data()), b.size()*sizeof(double)); key.push_back('|');
+        key.append(reinterpret_cast<const char*>(c.data()), c.size()*sizeof(double));
+        const pl_bc* bc = nullptr;
+        for (size_t k = 0; k < core.contents.size(); ++k) if (core.contents[k] == key) { bc = core.planes[k]; break; }
+        if (!bc) {
+            pl_bc* nb = pl_bc_create(core.h, type, axis, coord, dir, local ? m.data() : nullptr, h0 && local ? a.data() : nullptr,
+                                     h1 && local ? b.data() : nullptr, h2 && local ? c.data() : nullptr);
+            if (!nb) check(1, "pl_bc_create");
+            core.planes.push_back(nb); core.contents.push_back(key);
+            bc = nb;
+        }
+        if constexpr (cacheable) {
+            if (cache.size() >= 256) cache.erase(cache.begin(), cache.begin() + 128);
+            cache.push_back(Entry{core.gen, type, axis, coord, dir, bytes, bc});
+        }
+        return bc;
+    }
+
+    inline pl_bc_aux aux(const double* rho, const double* ux, const double* uy, const double* uz, const double* tem, const double* kfield, double kconst, double eps) {
+        pl_bc_aux a;
+        std::memset(&a, 0, sizeof(a));
+        a.rho = rho; a.ux = ux; a.uy = uy; a.uz = uz; a.tem = tem; a.diffusivity = kfield; a.diffusivity_const = kconst; a.eps = eps;
+        return a;
+    }
+    // apply one closure type on one plane
+    template<class P, class Fm, class F0, class F1, class F2>
+    inline void plane(P& p, int type, int axis, int coord, int dir, Fm mask, F0 v0, F1 v1, F2 v2, const pl_bc_aux* a, pl_lattice* other = nullptr) {
+        const pl_bc* bc = baked(p, type, axis, coord, dir, mask, v0, v1, v2);
+        check(plh_bc(p.b200_core().h, other, bc, a), "plh_bc");
+    }
+    // ... and on the 2*nd faces of the global domain in the reference's order xmin,xmax,ymin,ymax[,zmin,zmax] (d3q15.h:182-189)
+    template<class P, class Fm, class F0, class F1, class F2>
+    inline void faces(P& p, int type, Fm mask, F0 v0, F1 v1, F2 v2, const pl_bc_aux* a, pl_lattice* other = nullptr) {
+        const int ext[3] = {p.lx, p.ly, p.lz};
+        for (int axis = 0; axis < P::nd; ++axis) {
+            plane(p, type, axis, 0, -1, mask, v0, v1, v2, a, other);
+            plane(p, type, axis, ext[axis] - 1, 1, mask, v0, v1, v2, a, other);
+        }
+    }
+
+    inline pl_collide_args collide_args(int model, bool issave, double viscosity) {
+        pl_collide_args a;
+        std::memset(&a, 0, sizeof(a));
+        a.model = model; a.issave = issave ? 1 : 0; a.viscosity = viscosity;
+        return a;
+    }
+    template<class T> inline void only_double() { static_assert(std::is_same<T, double>::value, "panslbm_b200 computes in fp64: instantiate with T = double"); }
+}  // namespace b200
+}  // namespace PANSLBM2
