@@ -13,7 +13,7 @@ LIB = os.path.join(ROOT, "panslbm2_b200", "libpanslbm_b200.so")
 def declared_symbols():
     src = open(HDR).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(pl_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(plh?_[a-z0-9_]+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")
