@@ -162,8 +162,9 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 //   bits 0..60: entry e of the closure program acts on this plane
 //   bit 61    : the plane is a face of this rank's block along a decomposed axis: its sites pull from the halo receive
 //               buffers and are the first to finish, so that the next exchange overlaps the interior kernel
-//   bit 62    : (x only) the coordinate shares an aligned group of 8 sites with an x closure plane: the boundary pass takes
-//               the whole group so that its accesses to x planes fill 64-byte DRAM bursts instead of 8 bytes of each
+//   bit 62    : (x only) the coordinate shares an aligned group of 4 sites (one 32-byte sector; PANSLBM_XSLAB) with an x closure
+//               plane: the boundary pass takes the whole group.  Splitting a sector between the two kernels, or between
+//               warps of one, costs far more than the extra sites do (measured: profiles/r01_tuning.md)
 //   bit 63    : the plane is a global boundary plane or next to one and the plan has SmoothCorner; sites with two such
 //               coordinates form the edge "tubes" SmoothCorner reads and writes.
 struct ShellMask {
@@ -271,13 +272,14 @@ __global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict_
 
 // SmoothCorner (d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587).  A line/point list is built on the host.
 struct SmoothItem {
+    double* fb;               // populations of the lattice the item belongs to (one launch serves the flow and the thermal lattice)
     long long base, stride;   // first site of the line and stride along it (corner: a single site)
     int len;                  // number of sites on the line (1 for a corner)
     long long n0, n1, n2;     // index deltas to the 2 (edge / 2-D corner) or 3 (3-D corner) inward neighbours; n2 == 0: two neighbours
 };
-struct SmoothList { SmoothItem it[12]; int count; int maxlen; };
+struct SmoothList { SmoothItem it[24]; int count; int maxlen; };
 template <int D>
-__global__ void __launch_bounds__(128) k_smooth(Geom G, double* __restrict__ fb, SmoothList L) {
+__global__ void __launch_bounds__(128) k_smooth(Geom G, SmoothList L) {
     int t = blockIdx.x*blockDim.x + threadIdx.x;
     int which = blockIdx.y;
     if (which >= L.count) return;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(128) k_smooth(Geom G, double* __restrict__ fb,
     long long idx = it.base + (long long)t*it.stride;
     #pragma unroll
     for (int c = 0; c < LT<D>::nc; ++c) {
-        double* p = fb + (size_t)c*G.pitch;
+        double* p = it.fb + (size_t)c*G.pitch;
         if (it.n2 == 0) p[idx] = 0.5*(p[idx + it.n0] + p[idx + it.n1]);
         else p[idx] = (p[idx + it.n0] + p[idx + it.n1] + p[idx + it.n2])/3.0;
     }

@@ -45,6 +45,12 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1)/bs); }
 
+// tuning knobs (environment, read once): width of the aligned x group the boundary pass takes around an x closure plane,
+// and the queueing order of interior kernel / boundary pass on a single block
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
+int opt_xslab() { static int w = std::max(1, std::min(32, env_int("PANSLBM_XSLAB", 4))); return w; }
+bool opt_fused_first() { static int v = env_int("PANSLBM_FUSED_FIRST", 0); return v != 0; }
+
 // grow-only device scratch for the reductions: cudaMalloc/cudaFree per call would cost milliseconds next to tens of GB of
 // live allocations and synchronise the device
 struct Scratch {
@@ -547,18 +553,25 @@ int smooth_lists(const pl_lattice* l, SmoothList& edges, SmoothList& corners) {
     return PL_OK;
 }
 
-int do_smooth(pl_lattice* l) {
+// SmoothCorner of one lattice, or of the two lattices of a plan together (same shape): all edge lines in one launch, then all corners
+int do_smooth(pl_lattice* l, pl_lattice* l2 = nullptr) {
     SmoothList e, c;
     smooth_lists(l, e, c);
-    halo_touch(l);
-    double* fb = l->current();
+    const int ne = e.count, ncn = c.count;
+    for (pl_lattice* q : {l, l2}) {
+        if (!q) continue;
+        halo_touch(q);
+        for (int k = 0; k < ne; ++k) { SmoothItem& it = e.it[q == l ? k : ne + k]; it = e.it[k]; it.fb = q->current(); }
+        for (int k = 0; k < ncn; ++k) { SmoothItem& it = c.it[q == l ? k : ncn + k]; it = c.it[k]; it.fb = q->current(); }
+    }
+    if (l2) { e.count = 2*ne; c.count = 2*ncn; }
     if (e.count > 0) {
         dim3 grid(blocks_for(e.maxlen, 128), e.count);
-        if (l->kind == PL_D2Q9) LAUNCH(k_smooth<2>, grid, 128, l->g, fb, e); else LAUNCH(k_smooth<3>, grid, 128, l->g, fb, e);
+        if (l->kind == PL_D2Q9) LAUNCH(k_smooth<2>, grid, 128, l->g, e); else LAUNCH(k_smooth<3>, grid, 128, l->g, e);
     }
     if (c.count > 0) {
         dim3 grid(1, c.count);
-        if (l->kind == PL_D2Q9) LAUNCH(k_smooth<2>, grid, 128, l->g, fb, c); else LAUNCH(k_smooth<3>, grid, 128, l->g, fb, c);
+        if (l->kind == PL_D2Q9) LAUNCH(k_smooth<2>, grid, 128, l->g, c); else LAUNCH(k_smooth<3>, grid, 128, l->g, c);
     }
     return PL_OK;
 }
@@ -757,8 +770,9 @@ int pl_smooth_corner_at(pl_lattice* l, int gi, int gj, int gk, int dx, int dy, i
     it.n0 = nb[0]; it.n1 = nb[1]; it.n2 = k == 3 ? nb[2] : 0;
     L.maxlen = it.len;
     halo_touch(l);
+    it.fb = l->current();
     dim3 grid(blocks_for(it.len, 128), 1);
-    if (D == 2) LAUNCH(k_smooth<2>, grid, 128, l->g, l->current(), L); else LAUNCH(k_smooth<3>, grid, 128, l->g, l->current(), L);
+    if (D == 2) LAUNCH(k_smooth<2>, grid, 128, l->g, L); else LAUNCH(k_smooth<3>, grid, 128, l->g, L);
     return PL_OK;
 }
 
@@ -938,8 +952,13 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
     if ((r = halo_wait(p->f, p->side))) return r;
     if (p->g && (r = halo_wait(p->g, p->side))) return r;
-    if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
-    CU(cudaEventRecord(p->ev_join, p->side));
+    // a decomposed block wants its faces first (the next exchange hangs on them); a single block queues the interior first
+    // so that the boundary CTAs interleave with it instead of running alone at their lower memory efficiency
+    const bool shell_first = p->f->halo.on || !opt_fused_first();
+    if (shell_first) {
+        if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
+        CU(cudaEventRecord(p->ev_join, p->side));
+    }
     // interior: one pass, source -> destination
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (p->profile) {
@@ -952,11 +971,18 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
         p->events.emplace_back(ev0, ev1);
         p->profiled_sites += p->f->g.nxyz - p->nlist;
     }
+    if (!shell_first) {
+        if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
+        CU(cudaEventRecord(p->ev_join, p->side));
+    }
     CU(cudaStreamWaitEvent(g_stream, p->ev_join, 0));
     p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
     // SmoothCorner and the collide of the sites it couples, in place on the destination
-    if (p->smooth_f && (r = do_smooth(p->f))) return r;
-    if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
+    if (p->smooth_f && p->g && p->smooth_g) { if ((r = do_smooth(p->f, p->g))) return r; }
+    else {
+        if (p->smooth_f && (r = do_smooth(p->f))) return r;
+        if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
+    }
     if ((r = dispatch_collide(model, p->f, g, P, p->list + p->ndirect, p->nlist - p->ndirect))) return r;
     p->f->streamed = 0; if (p->g) p->g->streamed = 0;
     // every block-face site is final: pack and post the next exchange now, it overlaps the next interior kernel
@@ -1049,9 +1075,12 @@ int pl_plan_finalize(pl_plan* p) {
         for (int a = 0; a < p->f->kind; ++a)
             if (p->f->halo.on && p->f->halo.e[a]) { (*h[a])[0] |= HALO_BIT; (*h[a])[nn[a] - 1] |= HALO_BIT; }
     }
-    // x closure planes: the boundary pass takes the aligned group of 8 x-coordinates around each (see ShellMask)
+    // x closure planes: the boundary pass takes the aligned group of x-coordinates around each (see ShellMask)
     for (int i = 0; i < g.nx; ++i)
-        if (hx[i] & (ENTRY_BITS | HALO_BIT)) for (int v = i & ~7; v < std::min(g.nx, (i & ~7) + 8); ++v) hx[v] |= SLAB_BIT;
+        if (hx[i] & (ENTRY_BITS | HALO_BIT)) {
+            const int w = opt_xslab(), lo = i/w*w;
+            for (int v = lo; v < std::min(g.nx, lo + w); ++v) hx[v] |= SLAB_BIT;
+        }
     // SmoothCorner: flag the global boundary planes and their inward neighbours (bit 1); sites with two flagged coordinates
     // form the edge tubes.  Every site SmoothCorner writes (edge lines, corners) or reads (their inward neighbours) must lie
     // in a tube: collide is deferred there until k_smooth has run.

@@ -5,6 +5,7 @@
 // tests/test_gpu_dropin.py can compare them bit for bit with the fixtures generated from the reference build (tests/golden).
 //   heatsink_dump <dim> <lx> <ly> <lz> <nt> <dir>      reads <dir>/{alpha,kappa,dads,dkds}.bin, <dir>/params.bin; writes <dir>/*.out
 #define _USE_AVX_DEFINES
+#include <chrono>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -23,6 +24,7 @@ static void rd(const char* name, double* p, size_t n) {
     fclose(f);
 }
 static void wr(const char* name, const double* p, size_t n) {
+    if (getenv("HEATSINK_DUMP_NO_OUTPUT") && std::string(name) != "stats") return;
     // read one element in user space first: a host copy that is stale (device newer) is refreshed by the page-fault path, which
     // a system call reading the buffer (fwrite -> write(2)) cannot trigger — it would just see EFAULT
     volatile double first = n ? p[0] : 0.0;
@@ -41,6 +43,8 @@ int main(int argc, char** argv) {
     rd("params.bin", prm, 7);
     const double nu = prm[0], gx = prm[1], gy = prm[2], gz = prm[3], tem0 = prm[4], qn0 = prm[5], L = prm[6];
     double residual = 0.0;
+    typedef std::chrono::steady_clock clk;
+    clk::time_point t0, t1, t2, t3;
 
     if (dim == 3) {
         D3Q15<double> pf(lx, ly, lz), pg(lx, ly, lz);
@@ -55,6 +59,7 @@ int main(int argc, char** argv) {
 
         NS::InitialCondition(pf, rho, ux, uy, uz);
         AD::InitialCondition(pg, tem, ux, uy, uz);
+        plh_sync(); t0 = clk::now();
         for (int t = 1; t <= nt; t++) {
             AD::MacroBrinkmanCollideNaturalConvection(pf, rho, ux, uy, uz, alpha, nu, pg, tem, qx, qy, qz, diffusivity, gx, gy, gz, tem0, true, gi);
             if (t%5 == 0) residual = Residual(ux, uy, uz, uxp, uyp, uzp, pf.nxyz);      // an observation in the middle of the loop body
@@ -70,8 +75,10 @@ int main(int argc, char** argv) {
             pg.SmoothCorner();
             std::swap(ux, uxp); std::swap(uy, uyp); std::swap(uz, uzp); std::swap(qx, qxp); std::swap(qy, qyp); std::swap(qz, qzp);
         }
+        plh_sync(); t1 = clk::now();
         ANS::InitialCondition(pf, ux, uy, uz, irho, iux, iuy, iuz);
         AAD::InitialCondition(pg, ux, uy, uz, item, iqx, iqy, iqz);
+        plh_sync(); t2 = clk::now();
         for (int t = 1; t <= nt; t++) {
             AAD::MacroBrinkmanCollideNaturalConvection(pf, rho, ux, uy, uz, irho, iux, iuy, iuz, imx, imy, imz, alpha, nu,
                                                        pg, tem, item, iqx, iqy, iqz, diffusivity, gx, gy, gz, true, igi);
@@ -86,6 +93,7 @@ int main(int argc, char** argv) {
             pg.SmoothCorner();
             std::swap(iux, iuxp); std::swap(iuy, iuyp); std::swap(iuz, iuzp); std::swap(iqx, iqxp); std::swap(iqy, iqyp); std::swap(iqz, iqzp);
         }
+        plh_sync(); t3 = clk::now();
         // objective read straight from the array, as production/heatsink3D.cpp:227-235 does
         double f_buffer = 0.0;
         for (int k = 0; k < pf.nz; ++k) for (int i = 0; i < pf.nx; ++i) if (i < L && k < L) f_buffer += tem[pf.Index(i, 0, k)];
@@ -113,6 +121,7 @@ int main(int argc, char** argv) {
 
         NS::InitialCondition(pf, rho, ux, uy);
         AD::InitialCondition(pg, tem, ux, uy);
+        plh_sync(); t0 = clk::now();
         for (int t = 1; t <= nt; t++) {
             AD::MacroBrinkmanCollideNaturalConvection(pf, rho, ux, uy, alpha, nu, pg, tem, qx, qy, diffusivity, gx, gy, tem0, true, gi);
             if (t%5 == 0) residual = Residual(ux, uy, uxp, uyp, pf.nxyz);
@@ -126,8 +135,10 @@ int main(int argc, char** argv) {
             pg.SmoothCorner();
             std::swap(ux, uxp); std::swap(uy, uyp); std::swap(qx, qxp); std::swap(qy, qyp);
         }
+        plh_sync(); t1 = clk::now();
         ANS::InitialCondition(pf, ux, uy, irho, iux, iuy);
         AAD::InitialCondition(pg, ux, uy, item, iqx, iqy);
+        plh_sync(); t2 = clk::now();
         for (int t = 1; t <= nt; t++) {
             AAD::MacroBrinkmanCollideNaturalConvection(pf, rho, ux, uy, irho, iux, iuy, imx, imy, alpha, nu, pg, tem, item, iqx, iqy, diffusivity, gx, gy, true, igi);
             pf.iStream();
@@ -141,6 +152,7 @@ int main(int argc, char** argv) {
             pg.SmoothCorner();
             std::swap(iux, iuxp); std::swap(iuy, iuyp); std::swap(iqx, iqxp); std::swap(iqy, iqyp);
         }
+        plh_sync(); t3 = clk::now();
         double f_buffer = 0.0;
         for (int i = 0; i < pf.nx; ++i) if (i < L) f_buffer += tem[pf.Index(i, 0)];
         std::vector<double> dfdss(n, 0.0);
@@ -153,6 +165,11 @@ int main(int argc, char** argv) {
         wr("f.f0", pf.f0, n); wr("f.f", pf.f, (size_t)n*(pf.nc - 1)); wr("g.f0", pg.f0, n); wr("g.f", pg.f, (size_t)n*(pg.nc - 1));
         double extra[2] = {f_buffer, residual};
         wr("extra", extra, 2);
+    }
+    {
+        const double fs = std::chrono::duration<double>(t1 - t0).count(), as = std::chrono::duration<double>(t3 - t2).count();
+        const double sites = (double)lx*ly*lz;
+        printf("forward %d steps %.3f ms/step %.1f MLUPS | adjoint %.3f ms/step %.1f MLUPS\n", nt, 1e3*fs/nt, sites*nt/fs/1e6, 1e3*as/nt, sites*nt/as/1e6);
     }
     uint64_t st[8];
     plh_stats(st);
