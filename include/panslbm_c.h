@@ -240,6 +240,17 @@ int pl_sensitivity(pl_lattice*, const pl_sens_args*);
 int pl_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
                                const double* igsnap, const double* diffusivity, const double* dkds);
 
+/* ---- filters (src/utility/densityfilter.h:389-497, heavisidefilter.h:459-563, 641-857) ---------------------------------
+ * The weight callable of the reference (`_weight(i1,j1,k1,i2,j2,k2)`, global coordinates) is baked once by the caller:
+ * weights_host[o*nxyz + idx] for the site idx and its neighbour at offset o = ((di+nR)*(2nR+1) + (dj+nR))*(2nR+1) + (dk+nR)
+ * (the reference's loop order: i2 outermost, k2 innermost), 0 for neighbours farther than R or outside the domain.
+ * mode 0: DensityFilter::GetFilteredValue(v); 1: HeavisideFilter::GetFilteredVariable(s = v, beta);
+ * 2: HeavisideFilter::GetFilteredSensitivity(s = v, dfdrho, beta).  Device pointers, nxyz doubles each. */
+typedef struct pl_filter pl_filter;
+pl_filter* pl_filter_create(pl_lattice*, int nR, const double* weights_host);
+int pl_filter_destroy(pl_filter*);
+int pl_filter_apply(pl_filter*, int mode, double beta, const double* v, const double* dfdrho, double* out);
+
 /* ==== host-pointer surface (csrc/panslbm_host.cpp) ====================================================================
  * What the drop-in C++ headers (panslbm2_b200/src/particle, src/equation, src/utility) bind.  Same operations as above, but
  * every array argument is a HOST pointer owned by the caller exactly as in the reference (`new double[nxyz]`,
@@ -267,6 +278,7 @@ int plh_normalize(double* v, size_t n);
 int plh_sensitivity(pl_lattice*, const pl_sens_args* host_args);
 int plh_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
                                 const double* igsnap, const double* diffusivity, const double* dkds);
+int plh_filter_apply(pl_filter*, int mode, double beta, const double* v_host, const double* dfdrho_host, double* out_host, size_t n);
 /* Execute whatever is still checked off and wait for the device. */
 int plh_sync(void);
 /* out[0..7] = fused steps, calls executed one by one, uploads, downloads, page faults served, plans built, settles, stagings */

@@ -45,6 +45,8 @@ typedef PANSLBM2::D3Q15<double> PT;
 #include "src/equation/adjointadvection.h"
 #include "src/utility/residual.h"
 #include "src/utility/normalize.h"
+#include "src/utility/densityfilter.h"
+#include "src/utility/heavisidefilter.h"
 
 using namespace PANSLBM2;
 
@@ -264,6 +266,32 @@ double ref_residual1(const double* ux, const double* uxp, int n) { return Residu
 void ref_normalize(double* v, int n) { Normalize(v, n); }
 
 //---------------------------------------------------------------- timed loops (CPU baseline, bench.py --impl reference)
+// Filters of the reference (src/utility/densityfilter.h, heavisidefilter.h; single-rank path).  mode 0: DensityFilter::GetFilteredValue,
+// 1: HeavisideFilter::GetFilteredVariable, 2: HeavisideFilter::GetFilteredSensitivity.  bx > 0 selects the heatsink drivers'
+// design-box weight (production/heatsink3D.cpp:87-93, heatsink.cpp:83-89), else the default cone weight of the headers.
+void ref_filter(void* h, int mode, double R, double beta, const double* v, const double* dfdrho, double* out, int bx, int by, int bz) {
+    PT& p = *L(h)->p;
+    std::vector<double> s(v, v + p.nxyz), d, res;
+    if (dfdrho) d.assign(dfdrho, dfdrho + p.nxyz);
+    auto boxw = [=](int _i1, int _j1, int _k1, int _i2, int _j2, int _k2) {
+        if (_i1 < bx && _j1 < by && _k1 < bz && _i2 < bx && _j2 < by && _k2 < bz) {
+            return (R - sqrt(pow(_i1 - _i2, 2.0) + pow(_j1 - _j2, 2.0) + pow(_k1 - _k2, 2.0)))/R;
+        } else {
+            return (_i1 == _i2 && _j1 == _j2 && _k1 == _k2) ? 1.0 : 0.0;
+        }
+    };
+    if (bx > 0) {
+        if (mode == 0) res = DensityFilter::GetFilteredValue(p, R, s, boxw);
+        else if (mode == 1) res = HeavisideFilter::GetFilteredVariable(p, R, beta, s, boxw);
+        else res = HeavisideFilter::GetFilteredSensitivity(p, R, beta, s, d, boxw);
+    } else {
+        if (mode == 0) res = DensityFilter::GetFilteredValue(p, R, s);
+        else if (mode == 1) res = HeavisideFilter::GetFilteredVariable(p, R, beta, s);
+        else res = HeavisideFilter::GetFilteredSensitivity(p, R, beta, s, d);
+    }
+    memcpy(out, res.data(), sizeof(double)*p.nxyz);
+}
+
 int ref_max_threads() { return omp_get_max_threads(); }
 void ref_set_threads(int n) { omp_set_num_threads(n); }
 

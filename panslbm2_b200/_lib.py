@@ -86,6 +86,9 @@ _PROTOS = {
     "pl_normalize": (C.c_int, [C.c_void_p, C.c_size_t]),
     "pl_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
     "pl_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
+    "pl_filter_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pl_filter_destroy": (C.c_int, [C.c_void_p]),
+    "pl_filter_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     # host-pointer surface (bound by the C++ drop-in headers; declared here so that the export test covers it)
     "plh_last_error": (C.c_char_p, []),
     "plh_alloc": (C.c_void_p, [C.c_size_t]),
@@ -103,6 +106,7 @@ _PROTOS = {
     "plh_normalize": (C.c_int, [C.c_void_p, C.c_size_t]),
     "plh_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
     "plh_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
+    "plh_filter_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "plh_sync": (C.c_int, []),
     "plh_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
 }

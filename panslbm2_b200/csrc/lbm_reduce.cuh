@@ -95,4 +95,41 @@ __global__ void __launch_bounds__(256) k_absmax_final(const double* __restrict__
     if (threadIdx.x == 0) out[0] = m;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cone density filter / Heaviside projection (src/utility/densityfilter.h:389-497, heavisidefilter.h:459-563, 641-857).
+// w[o*nxyz + idx] is the baked weight of the pair (site idx, neighbour idx + offset o), o running over the (2nR+1)^3 cube in
+// the reference's loop order (i2 outermost, k2 innermost); pairs beyond R or outside the domain carry weight 0 and are
+// skipped, which leaves both running sums bit-identical to the reference's.
+struct FilterGeom { int nx, ny, nz, nR; long long nxyz; };
+// mode 0: out = sum(w v)/sum(w)                                   DensityFilter::GetFilteredValue
+// mode 1: out = 0.5 (tanh(b/2) + tanh(b (sum(w v)/sum(w) - 1/2)))/tanh(b/2)     HeavisideFilter::GetFilteredVariable
+// mode 2: out = aux * 0.5 b (1 - tanh(b (sum(w v)/sum(w) - 1/2))^2)/tanh(b/2)   first pass of GetFilteredSensitivity (aux = dfdrho)
+// mode 3: out = sum(w v)/sum(w) with out accumulated from 0 and divided last    second pass of GetFilteredSensitivity
+__global__ void __launch_bounds__(256) k_filter(FilterGeom F, const double* __restrict__ w, const double* __restrict__ v, const double* __restrict__ aux,
+                                                double beta, int mode, double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= F.nxyz) return;
+    const int nxy = F.nx*F.ny;
+    const int k1 = (int)(idx/nxy), r = (int)(idx - (long long)k1*nxy), j1 = r/F.nx, i1 = r - j1*F.nx;
+    const int side = 2*F.nR + 1;
+    double wv = 0.0, ws = 0.0;
+    int o = 0;
+    for (int di = -F.nR; di <= F.nR; ++di)
+        for (int dj = -F.nR; dj <= F.nR; ++dj)
+            for (int dk = -F.nR; dk <= F.nR; ++dk, ++o) {
+                const int i2 = i1 + di, j2 = j1 + dj, k2 = k1 + dk;
+                if (i2 < 0 || i2 >= F.nx || j2 < 0 || j2 >= F.ny || k2 < 0 || k2 >= F.nz) continue;
+                const double wt = w[(size_t)o*(size_t)F.nxyz + (size_t)idx];
+                if (wt == 0.0) continue;
+                wv = wv + wt*v[idx + di + (long long)dj*F.nx + (long long)dk*nxy];
+                ws = ws + wt;
+            }
+    (void)side;
+    double res;
+    if (mode == 0 || mode == 3) res = wv/ws;
+    else if (mode == 1) res = 0.5*(tanh(0.5*beta) + tanh(beta*(wv/ws - 0.5)))/tanh(0.5*beta);
+    else { const double th = tanh(beta*(wv/ws - 0.5)); res = aux[idx]*(0.5*beta*(1.0 - th*th)/tanh(0.5*beta)); }
+    out[idx] = res;
+}
+
 }  // namespace plb

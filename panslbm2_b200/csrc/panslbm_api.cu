@@ -1319,6 +1319,50 @@ int pl_normalize(double* v, size_t n) {
     return PL_OK;
 }
 
+// ---- filters ----------------------------------------------------------------------------------------
+struct pl_filter {
+    FilterGeom F;
+    double* w = nullptr;
+    double* tmp = nullptr;
+};
+pl_filter* pl_filter_create(pl_lattice* l, int nR, const double* weights_host) {
+    if (!l || nR < 0 || nR > 8 || !weights_host) { fail(PL_ERR_ARG, "pl_filter_create: bad arguments"); return nullptr; }
+    if (l->halo.on) { fail(PL_ERR_UNSUPPORTED, "pl_filter_create: filters on a block-decomposed lattice need the nR-wide scalar halo (not built yet)"); return nullptr; }
+    pl_filter* f = new pl_filter();
+    f->F.nx = l->g.nx; f->F.ny = l->g.ny; f->F.nz = l->g.nz; f->F.nR = nR; f->F.nxyz = l->g.nxyz;
+    const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz;
+    if (cudaMalloc(&f->w, K*n*sizeof(double)) != cudaSuccess || cudaMalloc(&f->tmp, n*sizeof(double)) != cudaSuccess) {
+        fail(PL_ERR_CUDA, std::string("pl_filter_create: cudaMalloc: ") + cudaGetErrorString(cudaGetLastError()));
+        cudaFree(f->w); cudaFree(f->tmp); delete f;
+        return nullptr;
+    }
+    if (cudaMemcpy(f->w, weights_host, K*n*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(PL_ERR_CUDA, "pl_filter_create: upload failed");
+        cudaFree(f->w); cudaFree(f->tmp); delete f;
+        return nullptr;
+    }
+    return f;
+}
+int pl_filter_destroy(pl_filter* f) {
+    if (!f) return PL_OK;
+    cudaStreamSynchronize(g_stream);
+    cudaFree(f->w); cudaFree(f->tmp);
+    delete f;
+    return PL_OK;
+}
+int pl_filter_apply(pl_filter* f, int mode, double beta, const double* v, const double* dfdrho, double* out) {
+    if (!f || !v || !out) return fail(PL_ERR_ARG, "pl_filter_apply: null");
+    if (mode < 0 || mode > 2) return fail(PL_ERR_ARG, "pl_filter_apply: mode 0 (density), 1 (Heaviside variable), 2 (Heaviside sensitivity)");
+    if (mode == 2 && !dfdrho) return fail(PL_ERR_ARG, "pl_filter_apply: the sensitivity filter needs dfdrho");
+    const unsigned nb = blocks_for(f->F.nxyz, 256);
+    if (mode < 2) LAUNCH(k_filter, nb, 256, f->F, f->w, v, nullptr, beta, mode, out);
+    else {
+        LAUNCH(k_filter, nb, 256, f->F, f->w, v, dfdrho, beta, 2, f->tmp);
+        LAUNCH(k_filter, nb, 256, f->F, f->w, f->tmp, nullptr, beta, 3, out);
+    }
+    return PL_OK;
+}
+
 int pl_sensitivity(pl_lattice* l, const pl_sens_args* a) {
     if (!l || !a) return fail(PL_ERR_ARG, "pl_sensitivity: null");
     const bool d3 = l->kind == PL_D3Q15;

@@ -597,6 +597,17 @@ int plh_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds,
     return rc ? rc : rc2;
 }
 
+int plh_filter_apply(pl_filter* f, int mode, double beta, const double* v, const double* dfdrho, double* out, size_t n) {
+    if (!f) { g_herr = "plh_filter_apply: null"; return PL_ERR_ARG; }
+    double *dv, *dd, *dout;
+    int rc;
+    g_staged.clear();
+    if ((rc = xlate(v, n, true, false, &dv)) || (rc = xlate(dfdrho, n, true, false, &dd)) || (rc = xlate(out, n, false, true, &dout))) return rc;
+    rc = pl_filter_apply(f, mode, beta, dv, dd, dout) ? hfail("pl_filter_apply") : PL_OK;
+    int rc2 = unstage();
+    return rc ? rc : rc2;
+}
+
 int plh_sync(void) {
     int rc = settle();
     pl_synchronize();

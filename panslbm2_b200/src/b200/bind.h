@@ -12,6 +12,7 @@
 #include <panslbm_c.h>
 #endif
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,6 +72,7 @@ namespace b200 {
         unsigned long long gen = 0;                 // unique per constructed lattice: keys the baked-plane caches
         std::vector<pl_bc*> planes;                 // baked planes owned by this lattice
         std::vector<std::string> contents;          // their content keys (dedupe: equal planes share one pl_bc)
+        std::vector<pl_filter*> filters;            // baked filter weight tables owned by this lattice
         static unsigned long long next_gen() { static unsigned long long g = 0; return ++g; }
         void create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz, double** f0, double** f) {
             h = pl_lattice_create(kind, lx, ly, lz, peid, mx, my, mz);
@@ -82,6 +84,7 @@ namespace b200 {
             if (!h) return;
             plh_lattice_detach(h);
             for (pl_bc* b : planes) pl_bc_destroy(b);
+            for (pl_filter* f : filters) pl_filter_destroy(f);
             pl_lattice_destroy(h);
             h = nullptr;
         }
@@ -161,6 +164,45 @@ namespace b200 {
             cache.push_back(Entry{core.gen, type, axis, coord, dir, bytes, bc});
         }
         return bc;
+    }
+
+    // The weight table of a cone filter of radius _R on lattice `p` (densityfilter.h:389-497): the reference evaluates
+    // `_weight(i1,j1,k1,i2,j2,k2)` for every pair within _R on EVERY call; here it is evaluated once per (lattice, _R, callable)
+    // and kept on the device.  Pairs beyond _R or outside the domain get weight 0 (they do not enter the reference's sums).
+    template<class P, class F>
+    pl_filter* filter(P& p, double _R, F _weight) {
+        struct Entry { unsigned long long gen; double R; std::string bytes; pl_filter* f; };
+        static std::vector<Entry> cache;
+        Core& core = p.b200_core();
+        std::string bytes;
+        constexpr bool cacheable = std::is_trivially_copyable<F>::value;
+        if constexpr (cacheable) {
+            append_bytes(bytes, _weight);
+            for (const Entry& e : cache) if (e.gen == core.gen && e.R == _R && e.bytes == bytes) return e.f;
+        }
+        const int nR = (int)_R, side = 2*nR + 1;
+        const size_t n = (size_t)p.nxyz, K = (size_t)side*side*side;
+        std::vector<double> w(K*n, 0.0);
+        #pragma omp parallel for
+        for (int k1 = 0; k1 < p.nz; ++k1)
+            for (int j1 = 0; j1 < p.ny; ++j1)
+                for (int i1 = 0; i1 < p.nx; ++i1) {
+                    const size_t idx = (size_t)p.Index(i1, j1, k1);
+                    size_t o = 0;
+                    for (int i2 = i1 - nR; i2 <= i1 + nR; ++i2)
+                        for (int j2 = j1 - nR; j2 <= j1 + nR; ++j2)
+                            for (int k2 = k1 - nR; k2 <= k1 + nR; ++k2, ++o) {
+                                if (i2 < 0 || i2 >= p.nx || j2 < 0 || j2 >= p.ny || k2 < 0 || k2 >= p.nz) continue;
+                                const double distance = std::sqrt(std::pow(i1 - i2, 2.0) + std::pow(j1 - j2, 2.0) + std::pow(k1 - k2, 2.0));
+                                if (distance <= _R)
+                                    w[o*n + idx] = (double)_weight(i1 + p.offsetx, j1 + p.offsety, k1 + p.offsetz, i2 + p.offsetx, j2 + p.offsety, k2 + p.offsetz);
+                            }
+                }
+        pl_filter* f = pl_filter_create(core.h, nR, w.data());
+        if (!f) check(1, "pl_filter_create");
+        core.filters.push_back(f);
+        if constexpr (cacheable) cache.push_back(Entry{core.gen, _R, bytes, f});
+        return f;
     }
 
     inline pl_bc_aux aux(const double* rho, const double* ux, const double* uy, const double* uz, const double* tem, const double* kfield, double kconst, double eps) {

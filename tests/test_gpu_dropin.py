@@ -124,3 +124,32 @@ def test_unmodified_reference_cavityflow3d(tmp_path):
         want = z["cavity3D." + m.group(1)]
         # ostream's 6 significant digits: identical doubles print identically; allow nothing else
         assert np.array_equal(got, want), (m.group(1), float(np.max(np.abs(got - want))))
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="session")
+def filter_exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("dropin_f") / "filter_dump")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    lib = os.path.join(ROOT, "panslbm2_b200")
+    subprocess.check_call(["g++", "-O2", "-mavx", "-ffp-contract=off", "-w", "-I" + os.path.join(ROOT, "include"), os.path.join(HERE, "dropin", "filter_dump.cpp"),
+                           "-o", out, "-L" + lib, "-lpanslbm_b200", "-Wl,-rpath," + lib], env=env)
+    return out
+
+
+@pytest.mark.parametrize("tag", ["hs3d_box", "hs2d_box", "cone3d", "cone2d_r3"])
+def test_gpu_filters_match_reference_filters(filter_exe, tmp_path, tag):
+    """DensityFilter / HeavisideFilter through the drop-in headers (GPU kernels) vs the reference's serial host loops.
+    The weighted sums are bit-identical (same order, no FMA); the tanh projection differs by the libm/CUDA rounding of tanh."""
+    import filter_case as FC
+    dim, size, R, beta, box = FC.CASES[tag]
+    v, d = FC.inputs(tag)
+    v.tofile(tmp_path / "v.bin"); d.tofile(tmp_path / "d.bin")
+    b = box or (0, 0, 0)
+    r = subprocess.run([filter_exe, str(dim), *[str(s) for s in size], repr(R), repr(beta), *[str(x) for x in b], str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    z = np.load(os.path.join(G, "filters.npz"))
+    fv, rho, dfds = [np.fromfile(tmp_path / (n + ".out")) for n in ("fv", "rho", "dfds")]
+    assert np.array_equal(fv, z[f"{tag}/fv"])                                  # no transcendental: bit-exact
+    assert np.max(np.abs(rho - z[f"{tag}/rho"])) <= 1e-14
+    assert np.max(np.abs(dfds - z[f"{tag}/dfds"])) <= 1e-13*np.max(np.abs(z[f"{tag}/dfds"]))
