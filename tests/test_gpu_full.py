@@ -96,3 +96,21 @@ def test_heatsink_fused_equals_stepwise_equals_reference(dim, size, nt):
     H.compare(b, a, "fused vs stepwise")
     if O.have_ref(dim):
         H.compare(a, H.run_oplevel(O.Backend("ref", dim), dim, size, nt), "cuda vs reference")
+
+
+def check_fullsize(res):
+    z = np.load(os.path.join(G, "heatsink_fullsize.npz"))
+    keys = sorted(k[:-4] for k in z.files if k.endswith("/sha"))
+    for k in keys:
+        a = res[k] + 0.0
+        assert np.array_equal(a[::997], z[f"{k}/s997"]), f"full size: {k} differs from the reference fixture (max abs {np.max(np.abs(a[::997] - z[f'{k}/s997'])):.3e})"
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() == bytes(z[f"{k}/sha"]), f"full size: {k} digest"
+    return len(keys)
+
+
+def test_heatsink3d_production_size_matches_reference_fixture():
+    """81 x 161 x 81 (production/heatsink3D.cpp:42), 300 forward + 300 adjoint fused steps + sensitivity: every field bit-identical
+    to the reference build's (tests/golden/make_fullsize_golden.py)."""
+    z = np.load(os.path.join(G, "heatsink_fullsize.npz"))
+    lx, ly, lz, nt = [int(v) for v in z["shape"]]
+    assert check_fullsize(H.run_cuda(3, (lx, ly, lz), nt, fused=True, chunks=(100, 100))) >= 24
