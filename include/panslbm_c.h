@@ -59,6 +59,13 @@ int pl_comm_destroy(void);
 int pl_comm_info(int* mode, int* rank, int* nranks);   /* mode: 0 none, 1 NCCL, 2 loopback */
 /* MPI_Allreduce(MPI_IN_PLACE, v, n<=4, MPI_DOUBLE, op) of the drivers (heatsink3D.cpp:136, 236, 272): op 0 = SUM, 1 = MAX */
 int pl_comm_allreduce(double* inout_host, int n, int op);
+/* The general form (any count; MMA's distributed sums in src/utility/mma.h:256-585 reduce m and (m+1)^2 doubles, the drivers also
+ * reduce ints: heatsink3D.cpp:302-305): dtype 0 = double, 1 = int32; op 0 = SUM, 1 = MAX, 2 = MIN.  In place, host memory. */
+int pl_comm_allreduce_v(void* inout_host, size_t n, int dtype, int op);
+/* A batch of point-to-point messages between HOST buffers, matched per pair of ranks in issue order (what MPI_Isend /
+ * MPI_Irecv / MPI_Waitall of the reference's VTK writer, src/utility/vtkxmlexport.h:172-214, amount to).  Blocking. */
+typedef struct pl_p2p_op { void* host; size_t bytes; int peer; int is_send; } pl_p2p_op;
+int pl_comm_p2p(const pl_p2p_op* ops, int n);
 /* Pure host arithmetic (no device needed): the messages rank `peid` sends per Stream (inverse=0) / iStream (1), in issue
  * order.  out: 16 ints per message = code, peer, region sites, npop, pop[5], base, s1, s2, n1, n2, code of the message
  * received in the same step, 0; the count in doubles is region sites * npop.  Every rank sends message `code` to `peer`
@@ -245,7 +252,10 @@ int pl_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, co
  * weights_host[o*nxyz + idx] for the site idx and its neighbour at offset o = ((di+nR)*(2nR+1) + (dj+nR))*(2nR+1) + (dk+nR)
  * (the reference's loop order: i2 outermost, k2 innermost), 0 for neighbours farther than R or outside the domain.
  * mode 0: DensityFilter::GetFilteredValue(v); 1: HeavisideFilter::GetFilteredVariable(s = v, beta);
- * 2: HeavisideFilter::GetFilteredSensitivity(s = v, dfdrho, beta).  Device pointers, nxyz doubles each. */
+ * 2: HeavisideFilter::GetFilteredSensitivity(s = v, dfdrho, beta).  Device pointers, nxyz doubles each.
+ * On a block-decomposed lattice (NCCL communicator) the neighbours may lie in other ranks' blocks: the field is assembled
+ * over the ranks first (one all-reduce of lx*ly*lz doubles per pass, instead of the reference's 26-neighbour nR-wide halo,
+ * heavisidefilter.h:291-400); the weights then cover neighbours anywhere in the GLOBAL domain. */
 typedef struct pl_filter pl_filter;
 pl_filter* pl_filter_create(pl_lattice*, int nR, const double* weights_host);
 int pl_filter_destroy(pl_filter*);

@@ -45,6 +45,8 @@ _PROTOS = {
     "pl_comm_destroy": (C.c_int, []),
     "pl_comm_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "pl_comm_allreduce": (C.c_int, [c_double_p, C.c_int, C.c_int]),
+    "pl_comm_allreduce_v": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int]),
+    "pl_comm_p2p": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_halo_describe": (C.c_int, [C.c_int] * 9 + [C.c_void_p, C.POINTER(C.c_int)]),
     "pl_array_alloc": (C.c_void_p, [C.c_size_t]),
     "pl_array_free": (C.c_int, [C.c_void_p]),

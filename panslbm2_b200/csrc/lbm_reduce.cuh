@@ -99,8 +99,21 @@ __global__ void __launch_bounds__(256) k_absmax_final(const double* __restrict__
 // Cone density filter / Heaviside projection (src/utility/densityfilter.h:389-497, heavisidefilter.h:459-563, 641-857).
 // w[o*nxyz + idx] is the baked weight of the pair (site idx, neighbour idx + offset o), o running over the (2nR+1)^3 cube in
 // the reference's loop order (i2 outermost, k2 innermost); pairs beyond R or outside the domain carry weight 0 and are
-// skipped, which leaves both running sums bit-identical to the reference's.
-struct FilterGeom { int nx, ny, nz, nR; long long nxyz; };
+// skipped, which leaves both running sums bit-identical to the reference's.  `v` is a field of the GLOBAL domain.
+struct FilterGeom {
+    int nx, ny, nz, nR;          // this rank's block
+    long long nxyz;
+    int gx, gy, gz;              // global domain: neighbours are looked up in a field of the whole domain (the block itself when undecomposed)
+    int ox, oy, oz;              // offset of the block in it
+};
+// block -> its place in a zeroed field of the global domain (summed over the ranks afterwards: x + 0.0 == x)
+__global__ void __launch_bounds__(256) k_filter_scatter(FilterGeom F, const double* __restrict__ v, double* __restrict__ gv) {
+    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= F.nxyz) return;
+    const int nxy = F.nx*F.ny;
+    const int k1 = (int)(idx/nxy), r = (int)(idx - (long long)k1*nxy), j1 = r/F.nx, i1 = r - j1*F.nx;
+    gv[(size_t)(i1 + F.ox) + (size_t)F.gx*((size_t)(j1 + F.oy) + (size_t)F.gy*(size_t)(k1 + F.oz))] = v[idx];
+}
 // mode 0: out = sum(w v)/sum(w)                                   DensityFilter::GetFilteredValue
 // mode 1: out = 0.5 (tanh(b/2) + tanh(b (sum(w v)/sum(w) - 1/2)))/tanh(b/2)     HeavisideFilter::GetFilteredVariable
 // mode 2: out = aux * 0.5 b (1 - tanh(b (sum(w v)/sum(w) - 1/2))^2)/tanh(b/2)   first pass of GetFilteredSensitivity (aux = dfdrho)
@@ -117,11 +130,11 @@ __global__ void __launch_bounds__(256) k_filter(FilterGeom F, const double* __re
     for (int di = -F.nR; di <= F.nR; ++di)
         for (int dj = -F.nR; dj <= F.nR; ++dj)
             for (int dk = -F.nR; dk <= F.nR; ++dk, ++o) {
-                const int i2 = i1 + di, j2 = j1 + dj, k2 = k1 + dk;
-                if (i2 < 0 || i2 >= F.nx || j2 < 0 || j2 >= F.ny || k2 < 0 || k2 >= F.nz) continue;
+                const int i2 = i1 + F.ox + di, j2 = j1 + F.oy + dj, k2 = k1 + F.oz + dk;     // global coordinates of the neighbour
+                if (i2 < 0 || i2 >= F.gx || j2 < 0 || j2 >= F.gy || k2 < 0 || k2 >= F.gz) continue;
                 const double wt = w[(size_t)o*(size_t)F.nxyz + (size_t)idx];
                 if (wt == 0.0) continue;
-                wv = wv + wt*v[idx + di + (long long)dj*F.nx + (long long)dk*nxy];
+                wv = wv + wt*v[(size_t)i2 + (size_t)F.gx*((size_t)j2 + (size_t)F.gy*(size_t)k2)];
                 ws = ws + wt;
             }
     (void)side;

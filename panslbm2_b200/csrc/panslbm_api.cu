@@ -1238,6 +1238,43 @@ int pl_comm_info(int* mode, int* rank, int* nranks) {
     if (nranks) *nranks = g_comm.nranks;
     return PL_OK;
 }
+int pl_comm_allreduce_v(void* inout_host, size_t n, int dtype, int op) {
+    if (!inout_host || (dtype != 0 && dtype != 1) || op < 0 || op > 2) return fail(PL_ERR_ARG, "pl_comm_allreduce_v: dtype 0 (f64) / 1 (i32), op 0 (sum) / 1 (max) / 2 (min)");
+    if (g_comm.mode != COMM_NCCL || n == 0) return PL_OK;   // a world of one
+    const size_t bytes = n*(dtype == 0 ? sizeof(double) : sizeof(int));
+    void* d = g_scratch.get(bytes);
+    if (!d) return fail(PL_ERR_CUDA, "pl_comm_allreduce_v: scratch allocation failed");
+    CU(cudaMemcpyAsync(d, inout_host, bytes, cudaMemcpyHostToDevice, g_stream));
+    NC(g_nccl.AllReduce(d, d, n, dtype == 0 ? NCCL_F64 : 2 /* ncclInt32 */, op == 0 ? NCCL_SUM : (op == 1 ? NCCL_MAX : 3 /* ncclMin */), g_comm.nccl, g_stream));
+    ++g_launches;
+    CU(cudaMemcpyAsync(inout_host, d, bytes, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return PL_OK;
+}
+int pl_comm_p2p(const pl_p2p_op* ops, int n) {
+    if (n < 0 || (n > 0 && !ops)) return fail(PL_ERR_ARG, "pl_comm_p2p: bad arguments");
+    if (n == 0) return PL_OK;
+    if (g_comm.mode != COMM_NCCL) return fail(PL_ERR_ARG, "pl_comm_p2p: no NCCL communicator");
+    size_t total = 0;
+    std::vector<size_t> off(n);
+    for (int k = 0; k < n; ++k) { off[k] = total; total += (ops[k].bytes + 255)/256*256; }
+    char* d = (char*)g_scratch.get(std::max<size_t>(total, 256));
+    if (!d) return fail(PL_ERR_CUDA, "pl_comm_p2p: scratch allocation failed");
+    for (int k = 0; k < n; ++k)
+        if (ops[k].is_send && ops[k].bytes) CU(cudaMemcpyAsync(d + off[k], ops[k].host, ops[k].bytes, cudaMemcpyHostToDevice, g_stream));
+    NC(g_nccl.GroupStart());
+    for (int k = 0; k < n; ++k) {
+        if (ops[k].peer < 0 || ops[k].peer >= g_comm.nranks) { g_nccl.GroupEnd(); return fail(PL_ERR_ARG, "pl_comm_p2p: peer out of range"); }
+        if (ops[k].is_send) NC(g_nccl.Send(d + off[k], ops[k].bytes, 0 /* ncclInt8 */, ops[k].peer, g_comm.nccl, g_stream));
+        else NC(g_nccl.Recv(d + off[k], ops[k].bytes, 0, ops[k].peer, g_comm.nccl, g_stream));
+    }
+    NC(g_nccl.GroupEnd());
+    ++g_launches;
+    for (int k = 0; k < n; ++k)
+        if (!ops[k].is_send && ops[k].bytes) CU(cudaMemcpyAsync(ops[k].host, d + off[k], ops[k].bytes, cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return PL_OK;
+}
 int pl_comm_allreduce(double* inout_host, int n, int op) {
     if (!inout_host || n < 1 || n > 4 || (op != 0 && op != 1)) return fail(PL_ERR_ARG, "pl_comm_allreduce: 1..4 values, op 0 (sum) / 1 (max)");
     if (g_comm.mode != COMM_NCCL) return PL_OK;   // a world of one
@@ -1322,23 +1359,33 @@ int pl_normalize(double* v, size_t n) {
 // ---- filters ----------------------------------------------------------------------------------------
 struct pl_filter {
     FilterGeom F;
+    bool global = false;           // decomposed block: fields are assembled over all ranks first
     double* w = nullptr;
-    double* tmp = nullptr;
+    double* tmp = nullptr;         // first pass of the sensitivity filter (block)
+    double* gv = nullptr;          // field of the global domain
 };
 pl_filter* pl_filter_create(pl_lattice* l, int nR, const double* weights_host) {
     if (!l || nR < 0 || nR > 8 || !weights_host) { fail(PL_ERR_ARG, "pl_filter_create: bad arguments"); return nullptr; }
-    if (l->halo.on) { fail(PL_ERR_UNSUPPORTED, "pl_filter_create: filters on a block-decomposed lattice need the nR-wide scalar halo (not built yet)"); return nullptr; }
+    if (l->halo.on && g_comm.mode != COMM_NCCL) {
+        fail(PL_ERR_UNSUPPORTED, "pl_filter_create: filters on a block-decomposed lattice need the NCCL communicator (pl_comm_init)");
+        return nullptr;
+    }
     pl_filter* f = new pl_filter();
-    f->F.nx = l->g.nx; f->F.ny = l->g.ny; f->F.nz = l->g.nz; f->F.nR = nR; f->F.nxyz = l->g.nxyz;
-    const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz;
-    if (cudaMalloc(&f->w, K*n*sizeof(double)) != cudaSuccess || cudaMalloc(&f->tmp, n*sizeof(double)) != cudaSuccess) {
+    FilterGeom& F = f->F;
+    F.nx = l->g.nx; F.ny = l->g.ny; F.nz = l->g.nz; F.nR = nR; F.nxyz = l->g.nxyz;
+    F.gx = l->g.lx; F.gy = l->g.ly; F.gz = l->g.lz; F.ox = l->g.offx; F.oy = l->g.offy; F.oz = l->g.offz;
+    f->global = l->halo.on;
+    const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz, gn = (size_t)F.gx*F.gy*F.gz;
+    bool ok = cudaMalloc(&f->w, K*n*sizeof(double)) == cudaSuccess && cudaMalloc(&f->tmp, n*sizeof(double)) == cudaSuccess;
+    if (ok && f->global) ok = cudaMalloc(&f->gv, gn*sizeof(double)) == cudaSuccess;
+    if (!ok) {
         fail(PL_ERR_CUDA, std::string("pl_filter_create: cudaMalloc: ") + cudaGetErrorString(cudaGetLastError()));
-        cudaFree(f->w); cudaFree(f->tmp); delete f;
+        cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv); delete f;
         return nullptr;
     }
     if (cudaMemcpy(f->w, weights_host, K*n*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
         fail(PL_ERR_CUDA, "pl_filter_create: upload failed");
-        cudaFree(f->w); cudaFree(f->tmp); delete f;
+        cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv); delete f;
         return nullptr;
     }
     return f;
@@ -1346,8 +1393,20 @@ pl_filter* pl_filter_create(pl_lattice* l, int nR, const double* weights_host) {
 int pl_filter_destroy(pl_filter* f) {
     if (!f) return PL_OK;
     cudaStreamSynchronize(g_stream);
-    cudaFree(f->w); cudaFree(f->tmp);
+    cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv);
     delete f;
+    return PL_OK;
+}
+// the field the filter kernel reads: the block itself, or (decomposed) the global field assembled over the ranks — what
+// replaces the 26-neighbour nR-wide halo exchange of heavisidefilter.h:291-400 (three calls per optimisation iteration)
+static int filter_field(pl_filter* f, const double* v, const double** out) {
+    if (!f->global) { *out = v; return PL_OK; }
+    const size_t gn = (size_t)f->F.gx*f->F.gy*f->F.gz;
+    CU(cudaMemsetAsync(f->gv, 0, gn*sizeof(double), g_stream));
+    LAUNCH(k_filter_scatter, blocks_for(f->F.nxyz, 256), 256, f->F, v, f->gv);
+    NC(g_nccl.AllReduce(f->gv, f->gv, gn, NCCL_F64, NCCL_SUM, g_comm.nccl, g_stream));
+    ++g_launches;
+    *out = f->gv;
     return PL_OK;
 }
 int pl_filter_apply(pl_filter* f, int mode, double beta, const double* v, const double* dfdrho, double* out) {
@@ -1355,10 +1414,14 @@ int pl_filter_apply(pl_filter* f, int mode, double beta, const double* v, const 
     if (mode < 0 || mode > 2) return fail(PL_ERR_ARG, "pl_filter_apply: mode 0 (density), 1 (Heaviside variable), 2 (Heaviside sensitivity)");
     if (mode == 2 && !dfdrho) return fail(PL_ERR_ARG, "pl_filter_apply: the sensitivity filter needs dfdrho");
     const unsigned nb = blocks_for(f->F.nxyz, 256);
-    if (mode < 2) LAUNCH(k_filter, nb, 256, f->F, f->w, v, nullptr, beta, mode, out);
+    const double* field;
+    int r = filter_field(f, v, &field);
+    if (r) return r;
+    if (mode < 2) LAUNCH(k_filter, nb, 256, f->F, f->w, field, nullptr, beta, mode, out);
     else {
-        LAUNCH(k_filter, nb, 256, f->F, f->w, v, dfdrho, beta, 2, f->tmp);
-        LAUNCH(k_filter, nb, 256, f->F, f->w, f->tmp, nullptr, beta, 3, out);
+        LAUNCH(k_filter, nb, 256, f->F, f->w, field, dfdrho, beta, 2, f->tmp);
+        if ((r = filter_field(f, f->tmp, &field))) return r;
+        LAUNCH(k_filter, nb, 256, f->F, f->w, field, nullptr, beta, 3, out);
     }
     return PL_OK;
 }

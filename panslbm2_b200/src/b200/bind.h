@@ -192,7 +192,9 @@ namespace b200 {
                     for (int i2 = i1 - nR; i2 <= i1 + nR; ++i2)
                         for (int j2 = j1 - nR; j2 <= j1 + nR; ++j2)
                             for (int k2 = k1 - nR; k2 <= k1 + nR; ++k2, ++o) {
-                                if (i2 < 0 || i2 >= p.nx || j2 < 0 || j2 >= p.ny || k2 < 0 || k2 >= p.nz) continue;
+                                // neighbours anywhere in the GLOBAL domain count (own block or another rank's: heavisidefilter.h:470-556)
+                                if (i2 + p.offsetx < 0 || i2 + p.offsetx >= p.lx || j2 + p.offsety < 0 || j2 + p.offsety >= p.ly ||
+                                    k2 + p.offsetz < 0 || k2 + p.offsetz >= p.lz) continue;
                                 const double distance = std::sqrt(std::pow(i1 - i2, 2.0) + std::pow(j1 - j2, 2.0) + std::pow(k1 - k2, 2.0));
                                 if (distance <= _R)
                                     w[o*n + idx] = (double)_weight(i1 + p.offsetx, j1 + p.offsety, k1 + p.offsetz, i2 + p.offsetx, j2 + p.offsety, k2 + p.offsetz);

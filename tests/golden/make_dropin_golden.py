@@ -2,7 +2,9 @@
 flags (README.md:23-25: g++ -mavx -fopenmp; plus -O2 -ffp-contract=off) and run on the CPU in this container.
     python tests/golden/make_dropin_golden.py          (needs /root/reference; writes tests/golden/dropin.npz)
 test/d2q9.cpp, test/d3q15.cpp: stdout (the reference's only known-answer tests: LoadF/StoreF layout round trip).
-test/cavityflow3D.cpp: the point data of result/cavity3D_0.vts (rho, u; 6 significant digits as the reference writes them)."""
+test/cavityflow3D.cpp: the point data of result/cavity3D_0.vts (rho, u; 6 significant digits as the reference writes them).
+test/heavisidefilter.cpp (hard-wired _USE_MPI_DEFINES): built with the reference headers and, standing in for an MPI library, the
+world-of-one path of panslbm2_b200/src/mpi/mpi.h (no device involved); run as `heavisidefilter 1 1 1`; point data v, fv."""
 import os
 import re
 import subprocess
@@ -36,6 +38,14 @@ def main():
                 res[prog + ".stdout"] = np.frombuffer(out.encode(), dtype=np.uint8)
         for k, v in vts_arrays(os.path.join(d, "result", "cavity3D_0.vts")).items():
             res["cavity3D." + k] = v
+        root = os.path.dirname(os.path.dirname(HERE))
+        lib = os.path.join(root, "panslbm2_b200")
+        exe = os.path.join(d, "heavisidefilter")
+        subprocess.check_call(["g++", "-O2", "-mavx", "-fopenmp", "-ffp-contract=off", "-w", "-I" + os.path.join(root, "include"), "-I" + os.path.join(lib, "src", "mpi"),
+                               os.path.join(REF, "test", "heavisidefilter.cpp"), "-o", exe, "-L" + lib, "-lpanslbm_b200", "-Wl,-rpath," + lib], env=env)
+        subprocess.run([exe, "1", "1", "1"], cwd=d, capture_output=True, text=True, check=True)
+        for k, v in vts_arrays(os.path.join(d, "result", "heavisidefilter_0.vts")).items():
+            res["heavisidefilter." + k] = v
     np.savez_compressed(os.path.join(HERE, "dropin.npz"), **res)
     print({k: v.shape for k, v in res.items()})
 

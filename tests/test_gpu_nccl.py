@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _ngpu():
-    import torch
-    return torch.cuda.device_count()
+    from panslbm2_b200 import _lib
+    return _lib.lib().pl_device_count()
 
 
 def _port():
