@@ -3,6 +3,8 @@ flags (README.md:23-25: g++ -mavx -fopenmp; plus -O2 -ffp-contract=off) and run 
     python tests/golden/make_dropin_golden.py          (needs /root/reference; writes tests/golden/dropin.npz)
 test/d2q9.cpp, test/d3q15.cpp: stdout (the reference's only known-answer tests: LoadF/StoreF layout round trip).
 test/cavityflow3D.cpp: the point data of result/cavity3D_0.vts (rho, u; 6 significant digits as the reference writes them).
+test/nsadncsens.cpp: heatsink physics on 71 x 81 with a fixed design, 100 000 forward + 100 000 adjoint steps, sensitivity, Normalize:
+every point-data array of result/nsadncsens_0.vts (the best deterministic end-to-end fixture of the reference).
 test/heavisidefilter.cpp (hard-wired _USE_MPI_DEFINES): built with the reference headers and, standing in for an MPI library, the
 world-of-one path of panslbm2_b200/src/mpi/mpi.h (no device involved); run as `heavisidefilter 1 1 1`; point data v, fv."""
 import os
@@ -30,14 +32,16 @@ def main():
     res = {}
     with tempfile.TemporaryDirectory() as d:
         os.makedirs(os.path.join(d, "result"))
-        for prog in ("d2q9", "d3q15", "cavityflow3D"):
+        for prog in ("d2q9", "d3q15", "cavityflow3D", "nsadncsens"):
             exe = os.path.join(d, prog)
             subprocess.check_call(["g++", "-O2", "-mavx", "-fopenmp", "-ffp-contract=off", "-w", os.path.join(REF, "test", prog + ".cpp"), "-o", exe], env=env)
             out = subprocess.run([exe], cwd=d, capture_output=True, text=True, check=True).stdout
-            if prog != "cavityflow3D":
+            if prog in ("d2q9", "d3q15"):
                 res[prog + ".stdout"] = np.frombuffer(out.encode(), dtype=np.uint8)
         for k, v in vts_arrays(os.path.join(d, "result", "cavity3D_0.vts")).items():
             res["cavity3D." + k] = v
+        for k, v in vts_arrays(os.path.join(d, "result", "nsadncsens_0.vts")).items():
+            res["nsadncsens." + k] = v
         root = os.path.dirname(os.path.dirname(HERE))
         lib = os.path.join(root, "panslbm2_b200")
         exe = os.path.join(d, "heavisidefilter")

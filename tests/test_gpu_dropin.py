@@ -167,6 +167,25 @@ def test_gpu_filters_match_reference_filters(filter_exe, tmp_path, tag):
     assert np.max(np.abs(dfds - z[f"{tag}/dfds"])) <= 1e-13*np.max(np.abs(z[f"{tag}/dfds"]))
 
 
+def test_unmodified_reference_nsadncsens(tmp_path):
+    """test/nsadncsens.cpp unmodified (D2Q9 71 x 81, fixed two-block design, 100 000 forward + 100 000 adjoint steps through the
+    learned/fused replay, SensitivityTemperatureAtHeatSource, Normalize, the reference's VTK writer): every array it writes equals
+    the reference build's output to the 6 digits written."""
+    import re
+    os.makedirs(tmp_path / "result")
+    r = subprocess.run([need("nsadncsens")], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    txt = open(tmp_path / "result" / "nsadncsens_0.vts").read()
+    z = np.load(os.path.join(G, "dropin.npz"))
+    seen = 0
+    for m in re.finditer(r'<DataArray type="Float64" Name="(\w+)" NumberOfComponents="(\d)" format="ascii">(.*?)</DataArray>', txt, re.S):
+        got = np.array(m.group(3).split(), dtype=np.float64).reshape(-1, int(m.group(2)))
+        want = z["nsadncsens." + m.group(1)]
+        assert np.array_equal(got, want), (m.group(1), float(np.max(np.abs(got - want))), float(np.max(np.abs(want))))
+        seen += 1
+    assert seen == len([k for k in z.files if k.startswith("nsadncsens.")]) and seen >= 10
+
+
 # ---------------------------------------------------------------------------------------------------------
 def vts_pieces(result_dir, stem, names):
     """assemble the per-rank .vts pieces of a VTKXMLExport run into global arrays (pieces overlap by one layer)"""
