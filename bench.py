@@ -265,7 +265,8 @@ def run_ours(args):
     m = PE_GRIDS.get(world)
     if m is None:
         raise SystemExit(f"bench.py: no PE grid defined for {world} GPUs (1, 2, 4, 8)")
-    gsize = (S*m[0], S*m[1], S*m[2])
+    dims = [int(v) for v in args.dims.split(",")] if args.dims else [S, S, S]
+    gsize = (dims[0]*m[0], dims[1]*m[1], dims[2]*m[2])
     sw = HeatsinkSweep(pl, api, gsize, rank, m)
     N = sw.n
     sw.upload_design()
@@ -346,7 +347,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms/K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"production/heatsink3D.cpp forward+adjoint time loops (D3Q15 NS+AD, BASELINE configs[3] physics) on a synthetic {S}^3 block per GPU "
+        "config": {"workload": f"production/heatsink3D.cpp forward+adjoint time loops (D3Q15 NS+AD, BASELINE configs[3] physics) on a synthetic {dims[0]}x{dims[1]}x{dims[2]} block per GPU "
                                f"(configs[2] synthetic-domain scaling; global domain {gsize[0]}x{gsize[1]}x{gsize[2]}); 1 step = 1 forward + 1 adjoint lattice update",
                    "global_sites": world*N, "sites_per_gpu": N, "lattice_updates_per_step": 2,
                    "parallelism": "1 GPU" if world == 1 else f"block decomposition {m[0]}x{m[1]}x{m[2]} (PE grid of the reference, d3q15.h:29-35), halo exchange "
@@ -407,6 +408,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=352, help="edge of the cubic block per GPU for the NS+AD forward+adjoint sweep")
+    ap.add_argument("--dims", default="", help="lx,ly,lz of the block per GPU instead of --size^3 (e.g. 81,161,81 = production/heatsink3D.cpp:42)")
     ap.add_argument("--ns-size", type=int, default=512, help="edge of the secondary NS cavity sweep (0 = skip)")
     ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--cpu-steps", type=int, default=8)

@@ -32,18 +32,21 @@ template <int D> struct FaceK { static constexpr int n = D == 2 ? 3 : 5; };
 // K list: c with c_axis == sgn, ascending
 template <int D> PL_HD void face_list(int axis, int sgn, int (&K)[FaceK<D>::n]) {
     int m = 0;
+    PL_UNROLL
     for (int c = 1; c < LT<D>::nc; ++c)
         if (rdir<D>(c, axis) == sgn && m < FaceK<D>::n) K[m++] = c;
 }
 // sum_i sign(c_b(K_i)) p[K_i] over the diagonals, left to right
 template <int D> PL_HD double signed_diag_sum(const double (&p)[LT<D>::nc], const int (&K)[FaceK<D>::n], int b) {
     double s = rdir<D>(K[1], b) > 0 ? p[K[1]] : -p[K[1]];
+    PL_UNROLL
     for (int i = 2; i < FaceK<D>::n; ++i) s = rdir<D>(K[i], b) > 0 ? s + p[K[i]] : s - p[K[i]];
     return s;
 }
 // w*p[K0] + p[K1] + ... left to right
 template <int D> PL_HD double weighted_face_sum(const double (&p)[LT<D>::nc], const int (&K)[FaceK<D>::n], double w) {
     double s = w*p[K[0]];
+    PL_UNROLL
     for (int i = 1; i < FaceK<D>::n; ++i) s = s + p[K[i]];
     return s;
 }
@@ -64,6 +67,7 @@ PL_HD double pick(int axis, double x, double y, double z) { return axis == 0 ? x
 template <int D> PL_HD void closure_bounce(double (&p)[LT<D>::nc], int axis, int dir, int type, bool inverse) {
     if (type != 1 && type != 2) return;
     const int want = inverse ? dir : -dir;
+    PL_UNROLL
     for (int c = 1; c < LT<D>::nc; ++c) {
         if (rdir<D>(c, axis) != want) continue;
         int src;
@@ -88,8 +92,10 @@ template <int D> PL_HD void closure_bounce(double (&p)[LT<D>::nc], int axis, int
 template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir, const SiteVals& V, bool setrho) {
     constexpr int NC = LT<D>::nc;
     double s = p[0];
+    PL_UNROLL
     for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) == 0) s = s + p[c];
     double o = 0.0; bool first = true;
+    PL_UNROLL
     for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) == dir) { o = first ? p[c] : o + p[c]; first = false; }
     const double tot = s + 2.0*o;
     double u[3] = {0.0, 0.0, 0.0}, rho0;
@@ -107,11 +113,13 @@ template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir
     const double kn = D == 2 ? 6.0 : 12.0, kt = D == 2 ? 0.5 : 0.25, ka = D == 2 ? 4.0 : 8.0;
     double m[3] = {0.0, 0.0, 0.0};
     m[axis] = rho0*u[axis]/kn;
+    PL_UNROLL
     for (int d = 0; d < D; ++d) if (d != axis) {
         int cp = find_dir<D>(d == 0, d == 1, d == 2), cm = find_dir<D>(-(d == 0), -(d == 1), -(d == 2));
         m[d] = kt*(p[cp] - p[cm] - rho0*u[d]);
     }
     double out[NC];
+    PL_UNROLL
     for (int c = 1; c < NC; ++c) {
         out[c] = p[c];
         if (rdir<D>(c, axis) != -dir) continue;
@@ -120,6 +128,7 @@ template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir
         if (nz == 1) val = dir == -1 ? p[ropp<D>(c)] + ka*m[axis] : p[ropp<D>(c)] - ka*m[axis];
         else {
             val = p[ropp<D>(c)];
+            PL_UNROLL
             for (int d = 0; d < D; ++d) {
                 int sg = d == axis ? rdir<D>(c, d) : -rdir<D>(c, d);
                 val = sg > 0 ? val + m[d] : val - m[d];
@@ -127,6 +136,7 @@ template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir
         }
         out[c] = val;
     }
+    PL_UNROLL
     for (int c = 1; c < NC; ++c) p[c] = out[c];
 }
 
@@ -140,14 +150,17 @@ template <int D> PL_HD void closure_ad(double (&g)[LT<D>::nc], int axis, int dir
     double tem0;
     if (!setq) {
         double s = V.v0 - g[0];
+        PL_UNROLL
         for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) != -dir) s = s - g[c];
         tem0 = dir == -1 ? 6.0*s/(1.0 + 3.0*ua) : 6.0*s/(1.0 - 3.0*ua);
     } else {
         double s = (1.0 + 1.0/(6.0*V.kappa))*V.v0;
+        PL_UNROLL
         for (int c = 1; c < NC; ++c) if (rdir<D>(c, axis) == dir) s = s + g[c];
         tem0 = dir == -1 ? 6.0*s/(1.0 - 3.0*ua) : 6.0*s/(1.0 + 3.0*ua);
     }
     const double wd = D == 2 ? 36.0 : 72.0;
+    PL_UNROLL
     for (int c = 1; c < NC; ++c) {
         if (rdir<D>(c, axis) != -dir) continue;
         int nz = abs(rdir<D>(c, 0)) + abs(rdir<D>(c, 1)) + abs(rdir<D>(c, 2));
@@ -176,6 +189,7 @@ template <int D> PL_HD void closure_ans_isetu(double (&f)[LT<D>::nc], int axis, 
         rho0 = dir == -1 ? acc/(3.0*(1.0 - ua)) : acc/(3.0*(1.0 + ua));
     } else {
         acc = -4.0*V.eps;
+        PL_UNROLL
         for (int b = 0; b < 3; ++b) {
             if (b == axis) {
                 double tn = ua*weighted_face_sum<D>(f, K, 8.0);
@@ -185,7 +199,9 @@ template <int D> PL_HD void closure_ans_isetu(double (&f)[LT<D>::nc], int axis, 
         rho0 = dir == -1 ? acc/(6.0*(1.0 - ua)) : acc/(6.0*(1.0 + ua));
     }
     double nv[FaceK<D>::n];
+    PL_UNROLL
     for (int i = 0; i < FaceK<D>::n; ++i) nv[i] = f[K[i]] + rho0;
+    PL_UNROLL
     for (int i = 0; i < FaceK<D>::n; ++i) f[ropp<D>(K[i])] = nv[i];
 }
 
@@ -194,6 +210,7 @@ template <int D> PL_HD void closure_ans_isetrho(double (&f)[LT<D>::nc], int axis
     int K[FaceK<D>::n];
     face_list<D>(axis, -dir, K);
     const double rho0 = D == 2 ? weighted_face_sum<D>(f, K, 4.0)/3.0 : weighted_face_sum<D>(f, K, 8.0)/6.0;
+    PL_UNROLL
     for (int i = 0; i < FaceK<D>::n; ++i) f[ropp<D>(K[i])] = f[K[i]] - rho0;
 }
 
@@ -208,15 +225,18 @@ template <int D> PL_HD void closure_aad_isett(double (&g)[LT<D>::nc], int axis, 
     double r;
     if (D == 2) {
         double a = 4.0*one3*g[K[0]];
+        PL_UNROLL
         for (int i = 1; i < 3; ++i) a = a + one_plus_3cu<D>(K[i], V.ux, V.uy, V.uz)*g[K[i]];
         r = -a/(6.0*one3);
     } else {
         r = -weighted_face_sum<D>(g, K, 8.0)/12.0;
+        PL_UNROLL
         for (int t = 1; t <= 2; ++t) {
             int b = (axis + t)%3;
             r = r - pick(b, V.ux, V.uy, V.uz)*signed_diag_sum<D>(g, K, b)/(4.0*one3);
         }
     }
+    PL_UNROLL
     for (int i = 0; i < FaceK<D>::n; ++i) g[ropp<D>(K[i])] = r;
 }
 
@@ -230,7 +250,11 @@ template <int D> PL_HD double aad_q_bracket(const double (&g)[LT<D>::nc], const 
     const double ua = pick(axis, V.ux, V.uy, V.uz);
     const double one3 = dir == -1 ? 1.0 + 3.0*ua : 1.0 - 3.0*ua;
     double s;
-    if (with_lead) { s = lead + (D == 2 ? 4.0 : 8.0)*g[K[0]]; for (int i = 1; i < FaceK<D>::n; ++i) s = s + g[K[i]]; }
+    if (with_lead) {
+        s = lead + (D == 2 ? 4.0 : 8.0)*g[K[0]];
+        PL_UNROLL
+        for (int i = 1; i < FaceK<D>::n; ++i) s = s + g[K[i]];
+    }
     else s = weighted_face_sum<D>(g, K, D == 2 ? 4.0 : 8.0);
     double acc = one3*s;
     if (D == 2) {
@@ -238,6 +262,7 @@ template <int D> PL_HD double aad_q_bracket(const double (&g)[LT<D>::nc], const 
         acc = acc + 3.0*pick(b, V.ux, V.uy, V.uz)*signed_diag_sum<D>(g, K, b);
     } else {
         const bool three = axis == 0 || (axis == 1 && dir == -1);
+        PL_UNROLL
         for (int t = 1; t <= 2; ++t) {
             int b = (axis + t)%3;
             double ub = pick(b, V.ux, V.uy, V.uz);
@@ -254,6 +279,7 @@ template <int D> PL_HD void closure_aad_isetq(double (&g)[LT<D>::nc], int axis, 
     acc = acc - (D == 2 ? 12.0 : 24.0)*V.eps;
     const double den = (D == 2 ? 6.0 : 12.0)*(dir == -1 ? 1.0 - 3.0*ua : 1.0 + 3.0*ua);
     const double r = acc/den;
+    PL_UNROLL
     for (int i = 0; i < FaceK<D>::n; ++i) g[ropp<D>(K[i])] = r;
 }
 
@@ -272,14 +298,19 @@ PL_HD void closure_aad_isetrho2d(double (&f)[9], const double (&g)[9], int axis,
     else if (kind == 2) flux0 = -V.tem*(weighted_face_sum<2>(g, K, 4.0)/3.0 + ut*sd/2.0)/(onem*V.rho);
     const double obj0 = V.eps*2.0*V.tem/(onem*V.rho);
     double nv[3];
+    PL_UNROLL
     for (int i = 0; i < 3; ++i) nv[i] = f[K[i]] + rho0 + flux0 + obj0;
+    PL_UNROLL
     for (int i = 0; i < 3; ++i) f[ropp<2>(K[i])] = nv[i];
 }
 
 // One closure application on a site.  p = populations of the lattice the closure acts on; q = the other lattice's
 // populations at the same site (only BC_AAD_ISET_RHO reads it).  maskval = baked mask byte (non-zero).
+// The closure bodies above are written over run-time (axis, dir) with table lookups per direction; on the device they are
+// instantiated once per face with literal arguments, so that after inlining and unrolling every population index is a
+// constant and each closure is a few dozen straight-line fp64 instructions in the order the generic loops define.
 template <int D>
-PL_HD void apply_closure(int type, int axis, int dir, int maskval, double (&p)[LT<D>::nc], const double (&q)[LT<D>::nc], const SiteVals& V) {
+PL_HD void apply_closure_on(int type, int axis, int dir, int maskval, double (&p)[LT<D>::nc], const double (&q)[LT<D>::nc], const SiteVals& V) {
     switch (type) {
         case BC_BOUNCE: closure_bounce<D>(p, axis, dir, maskval, false); break;
         case BC_IBOUNCE: closure_bounce<D>(p, axis, dir, maskval, true); break;
@@ -294,6 +325,22 @@ PL_HD void apply_closure(int type, int axis, int dir, int maskval, double (&p)[L
         case BC_AAD_ISET_RHO: if constexpr (D == 2) closure_aad_isetrho2d(p, q, axis, dir, maskval, V); break;
         default: break;
     }
+}
+template <int D>
+PL_HD void apply_closure(int type, int axis, int dir, int maskval, double (&p)[LT<D>::nc], const double (&q)[LT<D>::nc], const SiteVals& V) {
+#ifdef __CUDA_ARCH__
+    switch (2*axis + (dir > 0 ? 1 : 0)) {
+        case 0: apply_closure_on<D>(type, 0, -1, maskval, p, q, V); break;
+        case 1: apply_closure_on<D>(type, 0, 1, maskval, p, q, V); break;
+        case 2: apply_closure_on<D>(type, 1, -1, maskval, p, q, V); break;
+        case 3: apply_closure_on<D>(type, 1, 1, maskval, p, q, V); break;
+        case 4: if constexpr (D == 3) apply_closure_on<D>(type, 2, -1, maskval, p, q, V); break;
+        case 5: if constexpr (D == 3) apply_closure_on<D>(type, 2, 1, maskval, p, q, V); break;
+        default: break;
+    }
+#else
+    apply_closure_on<D>(type, axis, dir, maskval, p, q, V);
+#endif
 }
 
 // heat-source boundary term of AAD::SensitivityTemperatureAtHeatSource on one plane site

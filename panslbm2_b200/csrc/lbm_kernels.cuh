@@ -162,17 +162,57 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 //   bits 0..60: entry e of the closure program acts on this plane
 //   bit 61    : the plane is a face of this rank's block along a decomposed axis: its sites pull from the halo receive
 //               buffers and are the first to finish, so that the next exchange overlaps the interior kernel
-//   bit 62    : (x only) the coordinate shares an aligned group of 4 sites (one 32-byte sector; PANSLBM_XSLAB) with an x closure
-//               plane: the boundary pass takes the whole group.  Splitting a sector between the two kernels, or between
+//   bit 62    : (x only) the coordinate shares an aligned group of 4 sites (one 32-byte sector; PANSLBM_XSLAB) with an x plane
+//               the boundary pass owns (a decomposed block face; any x closure plane with PANSLBM_XINLINE=0): the boundary
+//               pass takes the whole group.  Splitting a sector between the two kernels, or between
 //               warps of one, costs far more than the extra sites do (measured: profiles/r01_tuning.md)
 //   bit 63    : the plane is a global boundary plane or next to one and the plan has SmoothCorner; sites with two such
 //               coordinates form the edge "tubes" SmoothCorner reads and writes.
 struct ShellMask {
     const unsigned long long *x, *y, *z;
+    int prefetch;      // 0 = off, 1 = prefetch.global.L2, 2 = prefetch.global.L1 of the closure inputs (PANSLBM_PREFETCH)
 };
 constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, HALO_BIT = 1ull << 61, ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT | HALO_BIT);
 constexpr int MAX_PROGRAM = 61;
 PL_D bool in_tube(unsigned long long wx, unsigned long long wy, unsigned long long wz) { return (wx >> 63) + (wy >> 63) + (wz >> 63) >= 2ull; }
+
+// The closure program is a chain of dependent loads (program entry -> mask -> plane values / saved fields of the site), one
+// DRAM round trip each, behind the pull.  Issuing prefetches for all of them before the pull turns the chain into cache hits.
+PL_D void touch(const void* p, int level) {
+    if (level == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+template <unsigned FL> PL_D void prefetch_collide(const CollideParams& P, long long idx, int level) {
+    if constexpr ((FL & F_KFIELD) != 0) touch(P.kappa + idx, level);
+    if constexpr ((FL & F_BRINK) != 0 || ((FL & F_ADJ) != 0 && (FL & F_G) != 0)) touch(P.alpha + idx, level);
+    if constexpr ((FL & F_HEATEX) != 0) touch(P.beta + idx, level);
+    if constexpr ((FL & F_ADJ) != 0) {
+        touch(P.rho + idx, level); touch(P.ux + idx, level); touch(P.uy + idx, level);
+        if (P.uz) touch(P.uz + idx, level);
+        if constexpr ((FL & F_G) != 0) touch(P.tem + idx, level);
+    }
+}
+PL_D void prefetch_program(const ClosureArgs* __restrict__ prog, unsigned long long entries, int i, int j, int k, long long idx, int level) {
+    const int co[3] = {i, j, k};
+    while (entries) {
+        const int e = __ffsll((long long)entries) - 1;
+        entries &= entries - 1;
+        const ClosureArgs& A = prog[e];
+        const int axis = A.pl.axis;
+        const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+        const int pt = co[a1] + A.pl.n1*co[a2];
+        touch(A.mask + pt, level);
+        if (A.v0) touch(A.v0 + pt, level);
+        if (A.v1) touch(A.v1 + pt, level);
+        if (A.v2) touch(A.v2 + pt, level);
+        if (A.rho) touch(A.rho + idx, level);
+        if (A.ux) touch(A.ux + idx, level);
+        if (A.uy) touch(A.uy + idx, level);
+        if (A.uz) touch(A.uz + idx, level);
+        if (A.tem) touch(A.tem + idx, level);
+        if (A.kappa) touch(A.kappa + idx, level);
+    }
+}
 
 // A plan's closure program on one site: the recorded closures whose plane passes through the site (bits of `entries`), in
 // call order, each applied where its baked mask is set.  Deliberately NOT inlined and fed through an addressable copy of
@@ -182,8 +222,6 @@ template <int D, bool HASG>
 __device__ __noinline__ void run_program(double* __restrict__ fg, const ClosureArgs* __restrict__ prog, unsigned long long entries,
                                          int i, int j, int k, long long idx) {
     constexpr int NC = LT<D>::nc;
-    double (&f)[NC] = *reinterpret_cast<double (*)[NC]>(fg);
-    double (&g)[NC] = *reinterpret_cast<double (*)[NC]>(fg + NC);
     const int co[3] = {i, j, k};
     while (entries) {
         const int e = __ffsll((long long)entries) - 1;
@@ -194,8 +232,11 @@ __device__ __noinline__ void run_program(double* __restrict__ fg, const ClosureA
         const int pt = co[a1] + A.pl.n1*co[a2];
         const int m = A.mask[pt];
         if (!m) continue;
-        if (A.on_g) { if constexpr (HASG) apply_closure<D>(A.type, axis, A.pl.dir, m, g, f, site_vals(A, pt, idx)); }
-        else apply_closure<D>(A.type, axis, A.pl.dir, m, f, g, site_vals(A, pt, idx));
+        // one call site (the specialised closure bodies are instantiated once per face inside it): select the lattice by pointer
+        const bool og = HASG && A.on_g;
+        double (&p)[NC] = *reinterpret_cast<double (*)[NC]>(og ? fg + NC : fg);
+        const double (&q)[NC] = *reinterpret_cast<const double (*)[NC]>(og ? fg : fg + NC);
+        apply_closure<D>(A.type, axis, A.pl.dir, m, p, q, site_vals(A, pt, idx));
     }
 }
 template <int D, bool HASG>
@@ -209,26 +250,33 @@ PL_D void boundary_path(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Cl
 }
 
 // The hot kernel: one fused Stream + Macro*Collide* pass, source buffer -> destination buffer, for every packed site that
-// lies on no closure plane and in no SmoothCorner tube.  Each population is read once and written once.
+// lies on no y/z closure plane, in no x group of the boundary pass and in no SmoothCorner tube.  Each population is read once
+// and written once.  Sites of an x closure plane that the plan left to this kernel (no SLAB bit: PANSLBM_XINLINE) run the
+// closure program between pull and collide: one lane of the warp diverges, but no 32-byte sector is split between kernels
+// and the strided x groups disappear from the boundary pass.
 template <int D, int M>
 __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
                                                const double* __restrict__ gs, double* __restrict__ gd,
-                                               CollideParams P, ShellMask S, int inverse) {
+                                               CollideParams P, ShellMask S, const ClosureArgs* __restrict__ prog, int inverse) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
     if (idx >= G.npacked) return;
     int i, j, k;
     decompose(G, idx, i, j, k);
+    unsigned long long entries = 0ull;
     if ((S.x[i] | S.y[j] | S.z[k]) != 0ull) {
         const unsigned long long wx = S.x[i], wy = S.y[j], wz = S.z[k];
-        if (((wx | wy | wz) & ~TUBE_BIT) != 0ull || in_tube(wx, wy, wz)) return;
+        if (((wy | wz) & ~TUBE_BIT) != 0ull || (wx & (SLAB_BIT | HALO_BIT)) != 0ull || in_tube(wx, wy, wz)) return;
+        entries = wx & ENTRY_BITS;
+        if (entries && S.prefetch) { prefetch_program(prog, entries, i, j, k, idx, S.prefetch); prefetch_collide<FL>(P, idx, S.prefetch); }
     }
     Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
     double f[LT<D>::nc], g[LT<D>::nc];
     pull<D>(f, fs, G.pitch, idx, n);
     if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
+    if (entries) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
     collide_site<D, FL, false>(f, g, P, (size_t)idx);
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
@@ -251,6 +299,7 @@ __global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict_
     int i, j, k;
     decompose(G, idx, i, j, k);
     const unsigned long long entries = (S.x[i] | S.y[j] | S.z[k]) & ENTRY_BITS;
+    if (entries && S.prefetch) { prefetch_program(prog, entries, i, j, k, idx, S.prefetch); prefetch_collide<FL>(P, idx, S.prefetch); }
     Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
     double f[LT<D>::nc], g[LT<D>::nc];

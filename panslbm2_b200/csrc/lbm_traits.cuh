@@ -11,9 +11,11 @@
 #ifdef __CUDACC__
 #define PL_HD __host__ __device__ __forceinline__
 #define PL_D __device__ __forceinline__
+#define PL_UNROLL _Pragma("unroll")
 #else
 #define PL_HD inline
 #define PL_D inline
+#define PL_UNROLL
 #endif
 
 namespace plb {
@@ -71,9 +73,11 @@ template <int D> PL_HD int ropp(int c) {
 
 // index of the direction with the given integer velocity, -1 if none (run-time helper for table-driven closures)
 template <int D> PL_HD int find_dir(int x, int y, int z) {
-    for (int c = 0; c < LT<D>::nc; ++c)
-        if (rdir<D>(c, 0) == x && rdir<D>(c, 1) == y && rdir<D>(c, 2) == z) return c;
-    return -1;
+    int r = -1;
+    PL_UNROLL
+    for (int c = LT<D>::nc - 1; c >= 0; --c)
+        if (rdir<D>(c, 0) == x && rdir<D>(c, 1) == y && rdir<D>(c, 2) == z) r = c;
+    return r;
 }
 
 // compile-time loop: f(std::integral_constant<int, c>) for c in [B, E)

@@ -50,6 +50,13 @@ inline unsigned blocks_for(long long n, int bs) { return (unsigned)((n + bs - 1)
 int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
 int opt_xslab() { static int w = std::max(1, std::min(32, env_int("PANSLBM_XSLAB", 4))); return w; }
 bool opt_fused_first() { static int v = env_int("PANSLBM_FUSED_FIRST", 0); return v != 0; }
+// x closure planes of an undecomposed axis: 1 = the interior kernel runs their closures inline, 0 = the boundary pass takes
+// the aligned x group around them
+int opt_prefetch() { static int v = std::max(0, std::min(2, env_int("PANSLBM_PREFETCH", 0))); return v; }
+// single block only: 1 = the boundary pass is queued behind the interior kernel on the same stream instead of beside it
+bool opt_shell_serial() { static int v = env_int("PANSLBM_SHELL_SERIAL", 0); return v != 0; }
+int opt_shell_block() { static int v = std::max(32, std::min(128, env_int("PANSLBM_SHELL_BLOCK", 128))); return v; }
+bool opt_xinline() { static int v = env_int("PANSLBM_XINLINE", 0); return v != 0; }
 
 // grow-only device scratch for the reductions: cudaMalloc/cudaFree per call would cost milliseconds next to tens of GB of
 // live allocations and synchronise the device
@@ -687,9 +694,9 @@ template <int D, int M> int launch_collide(pl_lattice* f, pl_lattice* g, const C
     LAUNCH((k_collide<D, M>), blocks_for(count, 256), 256, f->g, f->current(), g ? g->current() : nullptr, P, list, count);
     return PL_OK;
 }
-template <int D, int M> int launch_fused(pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, int inverse) {
+template <int D, int M> int launch_fused(pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse) {
     if (f->g.npacked == 0) return PL_OK;
-    LAUNCH((k_fused<D, M>), blocks_for(f->g.npacked, 256), 256, f->g, f->current(), f->other(), g ? g->current() : nullptr, g ? g->other() : nullptr, P, S, inverse);
+    LAUNCH((k_fused<D, M>), blocks_for(f->g.npacked, 256), 256, f->g, f->current(), f->other(), g ? g->current() : nullptr, g ? g->other() : nullptr, P, S, prog, inverse);
     return PL_OK;
 }
 #define MODEL_SWITCH(D, FN, ...)                                                     \
@@ -716,12 +723,12 @@ int dispatch_collide(int model, pl_lattice* f, pl_lattice* g, const CollideParam
     }
     return fail(PL_ERR_UNSUPPORTED, "collide: model not available for this lattice");
 }
-int dispatch_fused(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, int inverse) {
+int dispatch_fused(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse) {
     if (f->kind == PL_D2Q9) {
-        MODEL_SWITCH(2, launch_fused, f, g, P, S, inverse)
-        if (model == 12) return launch_fused<2, 12>(f, g, P, S, inverse);
+        MODEL_SWITCH(2, launch_fused, f, g, P, S, prog, inverse)
+        if (model == 12) return launch_fused<2, 12>(f, g, P, S, prog, inverse);
     } else {
-        MODEL_SWITCH(3, launch_fused, f, g, P, S, inverse)
+        MODEL_SWITCH(3, launch_fused, f, g, P, S, prog, inverse)
     }
     return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
 }
@@ -915,22 +922,22 @@ int plan_collide_full(pl_plan* p, int parity) {              // standalone C: ev
     if (p->g && (r = halo_prepare(p->g, p->inverse, true))) return r;
     return PL_OK;
 }
-template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
+template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
     if (p->nlist == 0) return PL_OK;
     HaloView HF, HG;
     int r;
     if ((r = halo_view(p->f, HF))) return r;
     if (g) { if ((r = halo_view(g, HG))) return r; } else memset(&HG, 0, sizeof(HG));
-    LAUNCH_ON(p->side, (k_shell<D, M>), blocks_for(p->nlist, 128), 128, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
-           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz}, p->prog[bc_parity], p->list, p->nlist, p->ndirect, p->inverse, HF, HG);
+    LAUNCH_ON(st, (k_shell<D, M>), blocks_for(p->nlist, opt_shell_block()), opt_shell_block(), p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
+           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->nlist, p->ndirect, p->inverse, HF, HG);
     return PL_OK;
 }
-int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity) {
+int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
     if (p->f->kind == PL_D2Q9) {
-        MODEL_SWITCH(2, launch_shell, p, g, P, bc_parity)
-        if (model == 12) return launch_shell<2, 12>(p, g, P, bc_parity);
+        MODEL_SWITCH(2, launch_shell, p, g, P, bc_parity, st)
+        if (model == 12) return launch_shell<2, 12>(p, g, P, bc_parity, st);
     } else {
-        MODEL_SWITCH(3, launch_shell, p, g, P, bc_parity)
+        MODEL_SWITCH(3, launch_shell, p, g, P, bc_parity, st)
     }
     return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
 }
@@ -942,21 +949,24 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     const int model = p->args[col_parity].model;
     pl_lattice* g = (flags & F_G) ? p->g : nullptr;
     if (p->g && !g) return fail(PL_ERR_ARG, "plan: a single-lattice collide cannot drive a two-lattice plan");
-    ShellMask S{p->mx, p->my, p->mz};
+    ShellMask S{p->mx, p->my, p->mz, opt_prefetch()};
     // halo of a decomposed block: normally posted already by the collide that produced these populations
     if ((r = halo_prepare(p->f, p->inverse))) return r;
     if (p->g && (r = halo_prepare(p->g, p->inverse))) return r;
     // boundary pass on the side stream (closure planes, block faces, SmoothCorner tubes, AVX-tail sites): it touches only
     // sites the interior kernel skips, so the two run concurrently
-    CU(cudaEventRecord(p->ev_fork, g_stream));
-    CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-    if ((r = halo_wait(p->f, p->side))) return r;
-    if (p->g && (r = halo_wait(p->g, p->side))) return r;
+    const bool serial = !p->f->halo.on && opt_shell_serial();
+    if (!serial) {
+        CU(cudaEventRecord(p->ev_fork, g_stream));
+        CU(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+        if ((r = halo_wait(p->f, p->side))) return r;
+        if (p->g && (r = halo_wait(p->g, p->side))) return r;
+    }
     // a decomposed block wants its faces first (the next exchange hangs on them); a single block queues the interior first
     // so that the boundary CTAs interleave with it instead of running alone at their lower memory efficiency
-    const bool shell_first = p->f->halo.on || !opt_fused_first();
+    const bool shell_first = !serial && (p->f->halo.on || !opt_fused_first());
     if (shell_first) {
-        if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
+        if ((r = dispatch_shell(model, p, g, P, bc_parity, p->side))) return r;
         CU(cudaEventRecord(p->ev_join, p->side));
     }
     // interior: one pass, source -> destination
@@ -965,17 +975,21 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
         CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, g_stream));
     }
-    if ((r = dispatch_fused(model, p->f, g, P, S, p->inverse))) return r;
+    if ((r = dispatch_fused(model, p->f, g, P, S, p->prog[bc_parity], p->inverse))) return r;
     if (p->profile) {
         CU(cudaEventRecord(ev1, g_stream));
         p->events.emplace_back(ev0, ev1);
         p->profiled_sites += p->f->g.nxyz - p->nlist;
     }
-    if (!shell_first) {
-        if ((r = dispatch_shell(model, p, g, P, bc_parity))) return r;
-        CU(cudaEventRecord(p->ev_join, p->side));
+    if (serial) {
+        if ((r = dispatch_shell(model, p, g, P, bc_parity, g_stream))) return r;
+    } else {
+        if (!shell_first) {
+            if ((r = dispatch_shell(model, p, g, P, bc_parity, p->side))) return r;
+            CU(cudaEventRecord(p->ev_join, p->side));
+        }
+        CU(cudaStreamWaitEvent(g_stream, p->ev_join, 0));
     }
-    CU(cudaStreamWaitEvent(g_stream, p->ev_join, 0));
     p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
     // SmoothCorner and the collide of the sites it couples, in place on the destination
     if (p->smooth_f && p->g && p->smooth_g) { if ((r = do_smooth(p->f, p->g))) return r; }
@@ -1075,9 +1089,10 @@ int pl_plan_finalize(pl_plan* p) {
         for (int a = 0; a < p->f->kind; ++a)
             if (p->f->halo.on && p->f->halo.e[a]) { (*h[a])[0] |= HALO_BIT; (*h[a])[nn[a] - 1] |= HALO_BIT; }
     }
-    // x closure planes: the boundary pass takes the aligned group of x-coordinates around each (see ShellMask)
+    // x planes the boundary pass owns (block faces; closure planes unless the interior kernel takes them inline): it takes the
+    // aligned group of x-coordinates around each (see ShellMask)
     for (int i = 0; i < g.nx; ++i)
-        if (hx[i] & (ENTRY_BITS | HALO_BIT)) {
+        if ((hx[i] & HALO_BIT) || ((hx[i] & ENTRY_BITS) && !opt_xinline())) {
             const int w = opt_xslab(), lo = i/w*w;
             for (int v = lo; v < std::min(g.nx, lo + w); ++v) hx[v] |= SLAB_BIT;
         }
@@ -1120,12 +1135,12 @@ int pl_plan_finalize(pl_plan* p) {
             const long long row = (long long)g.nx*(j + (long long)g.ny*k);
             const bool tailrow = row + g.nx > g.npacked;
             if (!(wyz & ~TUBE_BIT) && two == 0 && !tailrow) {   // only the x planes can put a site of this row on the list
-                for (int i = 0; i < g.nx; ++i) if (hx[i] & ~TUBE_BIT) list.push_back((int)(row + i));
+                for (int i = 0; i < g.nx; ++i) if (hx[i] & SLAB_BIT) list.push_back((int)(row + i));
                 continue;
             }
             for (int i = 0; i < g.nx; ++i) {
                 if (two + (int)(hx[i] >> 63) >= 2) tubes.push_back((int)(row + i));
-                else if (((wyz | hx[i]) & ~TUBE_BIT) || row + i >= g.npacked) list.push_back((int)(row + i));
+                else if ((wyz & ~TUBE_BIT) || (hx[i] & SLAB_BIT) || row + i >= g.npacked) list.push_back((int)(row + i));
             }
         }
     p->ndirect = (int)list.size();
