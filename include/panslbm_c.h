@@ -212,6 +212,13 @@ int pl_plan_finalize(pl_plan*);
  * end_streamed != 0 appends the trailing Stream+closures+SmoothCorner (loop ran to nt);
  * end_streamed == 0 stops right after the last collide (the drivers' convergence `break`). */
 int pl_plan_advance(pl_plan*, int ncollides, int end_streamed);
+/* Re-bind the ARRAY arguments of one argument set of a finalized plan; the loop body, its closures, masks and scalars stay.
+ * For loops whose arrays change every step instead of alternating: the transient drivers keep one set of macroscopic arrays
+ * and one snapshot per time step (production/heatsink3D_transient.cpp:50-57, 156-160, 196-200: rho[t], ux[t], ..., gi[t]).
+ * `collide` (may be null = keep) replaces the collide arguments of set `parity` (same model and scalars as before);
+ * `aux[k]` (k < naux, in pl_plan_add_bc order; aux == null = keep) replaces the field arrays of the k-th closure that was added
+ * with fields.  Stream-ordered: takes effect for the passes queued after the call. */
+int pl_plan_rebind(pl_plan*, int parity, const pl_collide_args* collide, const pl_bc_aux* aux, int naux);
 /* 0/1: the argument set of the last collide if the lattices are in the just-collided phase, else of the next one */
 int pl_plan_parity(const pl_plan*);
 int pl_plan_set_parity(pl_plan*, int parity);
@@ -293,6 +300,11 @@ int plh_filter_apply(pl_filter*, int mode, double beta, const double* v_host, co
 int plh_sync(void);
 /* out[0..7] = fused steps, calls executed one by one, uploads, downloads, page faults served, plans built, settles, stagings */
 int plh_stats(uint64_t* out8);
+/* The device mirrors of the caller's arrays double as the HBM-resident store of the per-step states the transient drivers keep
+ * (production/heatsink3D_transient.cpp:50-57: rho[t] ... gi[t], nt of each).  Under the budget PANSLBM_B200_DEVICE_BUDGET_MB
+ * (unset: when device memory runs out) mirrors not used in the current or previous loop iteration are spilled to their host
+ * copies and restored on demand.  out[0..3] = mirrors spilled, mirrors restored, device bytes held now, peak device bytes. */
+int plh_store_stats(uint64_t* out4);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,7 @@ _PROTOS = {
     "pl_plan_set_smooth_corner": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pl_plan_finalize": (C.c_int, [C.c_void_p]),
     "pl_plan_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "pl_plan_rebind": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(CollideArgs), C.POINTER(BcAux), C.c_int]),
     "pl_plan_parity": (C.c_int, [C.c_void_p]),
     "pl_plan_set_parity": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),
@@ -111,6 +112,7 @@ _PROTOS = {
     "plh_filter_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "plh_sync": (C.c_int, []),
     "plh_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
+    "plh_store_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
 }
 EXPORTS = tuple(_PROTOS)
 

@@ -685,6 +685,13 @@ class StepPlan:
         check(_lib.lib().pl_plan_advance(self._h, int(ncollides), int(bool(end_streamed))))
 
     @property
+    def rebind(self, parity, collide: CollideArgs | None = None, aux=()):
+        """re-bind the array arguments of argument set `parity` (transient loops: one set of arrays per time step,
+        production/heatsink3D_transient.cpp:156-160); aux = one BcAux per closure that was added with fields, in order"""
+        arr = (BcAux*len(aux))(*aux) if aux else None
+        check(_lib.lib().pl_plan_rebind(self._h, int(parity), C.byref(collide) if collide is not None else None, arr, len(aux)))
+        return self
+
     def parity(self):
         return _lib.lib().pl_plan_parity(self._h)
 

@@ -885,6 +885,12 @@ struct pl_plan {
     int nlist = 0, ndirect = 0;
     ClosureArgs* prog[2] = {nullptr, nullptr};
     int nprog = 0;
+    // pl_plan_rebind: pinned staging ring for the re-built closure programs (stream-ordered copies, no host synchronisation
+    // unless the ring wraps onto a copy still in flight)
+    static constexpr int NSTAGE = 8;
+    ClosureArgs* stage = nullptr;
+    cudaEvent_t stage_ev[NSTAGE] = {};
+    int stage_next = 0;
     // the boundary pass runs beside the interior kernel on its own (high-priority) stream
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -1029,6 +1035,8 @@ int pl_plan_destroy(pl_plan* p) {
     if (!p) return PL_OK;
     cudaStreamSynchronize(g_stream);
     cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    if (p->stage) cudaFreeHost(p->stage);
+    for (auto& e : p->stage_ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -1162,6 +1170,45 @@ int pl_plan_finalize(pl_plan* p) {
         if (p->nprog) CU(cudaMemcpy(p->prog[par], prog[par].data(), prog[par].size()*sizeof(ClosureArgs), cudaMemcpyHostToDevice));
     }
     p->finalized = true;
+    return PL_OK;
+}
+int pl_plan_rebind(pl_plan* p, int parity, const pl_collide_args* collide, const pl_bc_aux* aux, int naux) {
+    if (!p || !p->finalized) return fail(PL_ERR_ARG, "pl_plan_rebind: plan not finalized");
+    if (parity != 0 && parity != 1) return fail(PL_ERR_ARG, "pl_plan_rebind: parity 0 / 1");
+    if (collide) {
+        if (collide->model != p->args[parity].model) return fail(PL_ERR_ARG, "pl_plan_rebind: the collide model of a plan cannot change");
+        p->args[parity] = *collide;
+    }
+    if (!aux || naux <= 0) return PL_OK;
+    int k = 0;
+    for (auto& b : p->bcs) {
+        if (!b.has_aux) continue;
+        if (k >= naux) break;
+        b.aux[parity] = aux[k++];
+    }
+    if (p->nprog == 0) return PL_OK;
+    // re-build the closure program of this argument set and queue its copy behind everything already queued
+    if (!p->stage) {
+        CU(cudaMallocHost(&p->stage, (size_t)pl_plan::NSTAGE*MAX_PROGRAM*sizeof(ClosureArgs)));
+        for (auto& e : p->stage_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    const int slot = p->stage_next;
+    p->stage_next = (slot + 1)%pl_plan::NSTAGE;
+    CU(cudaEventSynchronize(p->stage_ev[slot]));      // returns at once unless the ring wrapped onto a copy still queued
+    ClosureArgs* h = p->stage + (size_t)slot*MAX_PROGRAM;
+    const Geom& g = p->f->g;
+    const int off[3] = {g.offx, g.offy, g.offz};
+    int e = 0;
+    for (auto& b : p->bcs) {
+        if (b.bc->empty) continue;
+        pl_lattice* l = b.on_g ? p->g : p->f;
+        int r = make_closure_args(l, b.bc->type == PL_BC_AAD_ISET_RHO ? p->g : nullptr, b.bc, b.has_aux ? &b.aux[parity] : nullptr, h[e]);
+        if (r) return r;
+        h[e].on_g = b.on_g; h[e].loc = b.bc->coord - off[b.bc->axis];
+        ++e;
+    }
+    CU(cudaMemcpyAsync(p->prog[parity], h, (size_t)p->nprog*sizeof(ClosureArgs), cudaMemcpyHostToDevice, g_stream));
+    CU(cudaEventRecord(p->stage_ev[slot], g_stream));
     return PL_OK;
 }
 int pl_plan_parity(const pl_plan* p) { return p ? p->parity : 0; }

@@ -12,18 +12,31 @@
 //      steady state of a time loop no array changes state, so no copy and no mprotect happens per step.
 //      Pointers that were not allocated here (std::vector storage, stack arrays) are staged through a transient device
 //      buffer around the call (synchronous; correct but slow — never on the time-loop arrays of the reference drivers).
+//      A block the host has not touched since plh_alloc (no page of it present or swapped, /proc/self/pagemap) is mirrored
+//      by a zero-filled device buffer without any upload: the transient drivers allocate one set of arrays per time step
+//      that only the collide ever writes (production/heatsink3D_transient.cpp:50-57).
+//   1b. state store  the mirrors are the HBM-resident store of those per-step states.  When a device allocation would
+//      exceed the budget (PANSLBM_B200_DEVICE_BUDGET_MB, else when cudaMalloc fails), mirrors that were not used in the
+//      current or the previous loop iteration are spilled to their host copies: the ones farthest behind the direction in
+//      which the loop walks the arrays (allocation order == time order in the drivers) — the oldest states in the forward
+//      loop, the already consumed ones in the time-reversed adjoint loop (heatsink3D_transient.cpp:190-215) — and come
+//      back on demand.
 //   2. fusion     collide / Stream / closures / SmoothCorner arrive as separate calls per lattice.  The engine executes them
 //      one by one while it LEARNs two consecutive loop iterations, builds a pl_plan from them (the two argument sets the
 //      driver alternates between), and then REPLAYs: Stream/closure/SmoothCorner calls that match the recorded iteration are
 //      only checked off, and the next collide call executes "stream + closures + SmoothCorner + collide" as ONE fused pass
 //      (pl_plan_advance).  Anything unexpected — a different call, an observation of the populations, the end of the
 //      loop — settles the checked-off calls first (one standalone pass, or call by call) and falls back to LEARN.
-//      Results are identical to call-by-call execution.
+//      Results are identical to call-by-call execution.  "Match" means the same calls with the same scalars and the same
+//      arrays PRESENT; the array addresses themselves may differ from step to step (the transient drivers pass rho[t],
+//      ux[t], ..., gi[t], production/heatsink3D_transient.cpp:156-176): the plan is then re-bound (pl_plan_rebind) with the
+//      arrays of the step before the fused pass is queued.
 //
 // Single-threaded callers, as everywhere in this library.  TEST NOTE: no CPU arithmetic lives here; every number is
 // produced by the CUDA kernels behind pl_*.
 #include "../../include/panslbm_c.h"
 
+#include <fcntl.h>
 #include <signal.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -48,11 +61,21 @@ struct Block {
     int state = ST_HOST;
     int kind = BK_ARRAY;
     pl_lattice* lat = nullptr;      // population views only
+    uint64_t seq = 0;               // allocation order (the drivers allocate their per-step arrays in time order)
+    uint64_t last = 0;              // loop iteration (g_tick) of the last device use
+    bool maybe_fresh = true;        // no device use yet: the host may never have touched it (see untouched())
+    bool spilled = false;           // its mirror was given up under memory pressure
 };
 std::map<uintptr_t, Block> g_blocks;              // by base address
 struct Views { Block *f0 = nullptr, *f = nullptr; };
 std::map<pl_lattice*, Views> g_views;
 uint64_t g_stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // fused steps, unfused ops, uploads, downloads, faults, plans, settles, transient stagings
+uint64_t g_store[4] = {0, 0, 0, 0};              // mirrors spilled to the host, mirrors restored, device bytes held, peak device bytes
+uint64_t g_seq = 0, g_tick = 0;
+uint64_t g_last_new_seq = 0;                      // seq of the last block that needed a new mirror, and the direction of travel
+int g_direction = 1;
+size_t g_budget = 0;                              // bytes; 0 = unlimited (spill only when cudaMalloc fails)
+bool g_budget_read = false;
 size_t g_page = 4096;
 bool g_handler = false;
 struct sigaction g_prev;
@@ -74,6 +97,7 @@ Block* find_block(const void* p) {
 void protect(Block* b, int prot) { mprotect(b->base, b->map_bytes, prot); }
 
 void settle_all();
+int acquire_mirror(Block* b);
 
 // bring the host copy of a block up to date (it is in state DEVICE) and make it readable
 void fetch(Block* b) {
@@ -129,12 +153,12 @@ Block* new_block(size_t bytes, int kind, pl_lattice* lat, int state, int prot) {
     void* p = mmap(nullptr, mb, prot, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
     if (p == MAP_FAILED) return nullptr;
     Block b;
-    b.base = (char*)p; b.bytes = bytes; b.map_bytes = mb; b.kind = kind; b.lat = lat; b.state = state;
+    b.base = (char*)p; b.bytes = bytes; b.map_bytes = mb; b.kind = kind; b.lat = lat; b.state = state; b.seq = ++g_seq;
     auto r = g_blocks.emplace((uintptr_t)p, b);
     return &r.first->second;
 }
 void drop_block(Block* b) {
-    if (b->dev) { pl_synchronize(); pl_array_free(b->dev); }
+    if (b->dev) { pl_synchronize(); pl_array_free(b->dev); g_store[2] -= b->map_bytes; }
     char* base = b->base; size_t mb = b->map_bytes;
     g_blocks.erase((uintptr_t)base);
     munmap(base, mb);
@@ -144,16 +168,110 @@ void drop_block(Block* b) {
 struct Staged { double* dev; double* host; size_t n; bool write; };
 std::vector<Staged> g_staged;      // transient mirrors of the call being translated
 
+// true if the host never touched any page of the block since plh_alloc: every page-map entry is neither present nor swapped,
+// so the content is still the zero pages of the anonymous mapping.  Any doubt (no pagemap, short read) answers false.
+bool untouched(const Block* b) {
+    static int fd = -2;
+    if (fd == -2) fd = open("/proc/self/pagemap", O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return false;
+    const size_t npages = b->map_bytes/g_page;
+    uint64_t buf[512];
+    size_t done = 0;
+    while (done < npages) {
+        const size_t m = npages - done < 512 ? npages - done : 512;
+        const ssize_t got = pread(fd, buf, m*8, (off_t)(((uintptr_t)b->base/g_page + done)*8));
+        if (got != (ssize_t)(m*8)) return false;
+        for (size_t k = 0; k < m; ++k) if (buf[k] & (3ull << 62)) return false;      // bit 63 present, bit 62 swapped
+        done += m;
+    }
+    return true;
+}
+
+// ---- the state store: device mirrors under a budget ------------------------------------------------------------------
+// give up the mirror of `v`: bring the host copy up to date first if the device holds the only current one
+int spill(Block* v, double** keep) {
+    if (v->state == ST_DEVICE) {
+        pl_synchronize();
+        protect(v, PROT_READ | PROT_WRITE);
+        if (pl_array_download((double*)v->base, v->dev, v->bytes/sizeof(double))) return hfail("spill download");
+        ++g_stat[3];
+    } else if (v->state == ST_SHARED) {
+        pl_synchronize();
+        protect(v, PROT_READ | PROT_WRITE);
+    }
+    v->state = ST_HOST;
+    if (keep) *keep = v->dev;            // handed over to the block that needs a mirror of the same size
+    else { pl_array_free(v->dev); g_store[2] -= v->map_bytes; }
+    v->dev = nullptr;
+    v->spilled = true;
+    ++g_store[0];
+    return PL_OK;
+}
+// the mirror farthest behind the direction of travel among those not used in this or the previous iteration
+Block* pick_victim(const Block* need, bool same_size) {
+    Block* best = nullptr;
+    for (auto& kv : g_blocks) {
+        Block& c = kv.second;
+        if (c.kind != BK_ARRAY || !c.dev || &c == need || c.last + 1 >= g_tick) continue;
+        if (same_size && c.map_bytes != need->map_bytes) continue;
+        if (!best || (g_direction > 0 ? c.seq < best->seq : c.seq > best->seq)) best = &c;
+    }
+    return best;
+}
+int acquire_mirror(Block* b) {
+    if (!g_budget_read) {
+        const char* v = getenv("PANSLBM_B200_DEVICE_BUDGET_MB");
+        g_budget = v && *v ? (size_t)atoll(v) << 20 : 0;
+        g_budget_read = true;
+    }
+    if (b->seq != g_last_new_seq) { g_direction = b->seq > g_last_new_seq ? 1 : -1; g_last_new_seq = b->seq; }
+    const bool restore = b->spilled;
+    b->spilled = false;
+    if (g_budget && g_store[2] + b->map_bytes > g_budget) {
+        // over budget: take over the mirror of a victim of the same size, else free victims until the new one fits
+        if (Block* v = pick_victim(b, true)) {
+            int rc = spill(v, &b->dev);
+            if (rc) return rc;
+        } else {
+            while (g_store[2] + b->map_bytes > g_budget) {
+                Block* w = pick_victim(b, false);
+                if (!w) break;           // everything left is in use: exceed the budget rather than fail
+                int rc = spill(w, nullptr);
+                if (rc) return rc;
+            }
+        }
+    }
+    while (!b->dev) {
+        b->dev = pl_array_alloc(b->map_bytes/sizeof(double));
+        if (b->dev) { g_store[2] += b->map_bytes; break; }
+        Block* w = pick_victim(b, false);        // device memory exhausted: spill and retry
+        if (!w) return hfail("device mirror");
+        int rc = spill(w, nullptr);
+        if (rc) return rc;
+    }
+    if (g_store[2] > g_store[3]) g_store[3] = g_store[2];
+    if (restore) ++g_store[1];
+    return PL_OK;
+}
+
 // device address of host pointer `h` (n doubles) for a kernel that reads it (rd) and/or writes it (wr)
 int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
     *out = nullptr;
     if (!h) return PL_OK;
     Block* b = find_block(h);
     if (b && b->kind == BK_ARRAY) {
+        b->last = g_tick;
         if (!b->dev) {
-            b->dev = pl_array_alloc(b->map_bytes/sizeof(double));
-            if (!b->dev) return hfail("device mirror");
+            int rc = acquire_mirror(b);
+            if (rc) return rc;
         }
+        if (b->state == ST_HOST && b->maybe_fresh && untouched(b)) {
+            // never touched by the host: its content is the zero pages mmap would hand out — no upload
+            if (pl_array_fill(b->dev, 0.0, b->map_bytes/sizeof(double))) return hfail("mirror fill");
+            b->state = ST_SHARED;
+            if (!wr) protect(b, PROT_READ);
+        }
+        b->maybe_fresh = false;
         if (b->state == ST_HOST) {      // also before a write: a kernel may update part of an array only
             if (pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
             ++g_stat[2];
@@ -221,6 +339,26 @@ struct Op {
 bool same_aux(const Op& a, const Op& b) { return a.has_aux == b.has_aux && (!a.has_aux || memcmp(&a.aux, &b.aux, sizeof(pl_bc_aux)) == 0); }
 bool same_shape(const Op& a, const Op& b) { return a.kind == b.kind && a.l == b.l && a.other == b.other && a.bc == b.bc && a.inverse == b.inverse; }
 bool same_args(const pl_collide_args& a, const pl_collide_args& b) { return memcmp(&a, &b, sizeof(pl_collide_args)) == 0; }
+// equal up to the array addresses: same model, flags and scalars, and the same arrays present
+bool like_args(const pl_collide_args& a, const pl_collide_args& b) {
+    if (a.model != b.model || a.issave != b.issave || a.viscosity != b.viscosity || a.diffusivity_const != b.diffusivity_const ||
+        a.gx != b.gx || a.gy != b.gy || a.gz != b.gz || a.tem0 != b.tem0) return false;
+#define SAME_NULL(f) if ((a.f == nullptr) != (b.f == nullptr)) return false
+    SAME_NULL(alpha); SAME_NULL(diffusivity); SAME_NULL(beta); SAME_NULL(dirx); SAME_NULL(diry); SAME_NULL(dirz);
+    SAME_NULL(rho); SAME_NULL(ux); SAME_NULL(uy); SAME_NULL(uz); SAME_NULL(tem); SAME_NULL(qx); SAME_NULL(qy); SAME_NULL(qz);
+    SAME_NULL(ip); SAME_NULL(iux); SAME_NULL(iuy); SAME_NULL(iuz); SAME_NULL(imx); SAME_NULL(imy); SAME_NULL(imz);
+    SAME_NULL(item); SAME_NULL(iqx); SAME_NULL(iqy); SAME_NULL(iqz); SAME_NULL(snapshot);
+#undef SAME_NULL
+    return true;
+}
+bool like_aux(const Op& a, const Op& b) {
+    if (a.has_aux != b.has_aux) return false;
+    if (!a.has_aux) return true;
+    const pl_bc_aux &x = a.aux, &y = b.aux;
+    return x.diffusivity_const == y.diffusivity_const && x.eps == y.eps && (x.rho == nullptr) == (y.rho == nullptr) && (x.ux == nullptr) == (y.ux == nullptr) &&
+           (x.uy == nullptr) == (y.uy == nullptr) && (x.uz == nullptr) == (y.uz == nullptr) && (x.tem == nullptr) == (y.tem == nullptr) &&
+           (x.diffusivity == nullptr) == (y.diffusivity == nullptr);
+}
 
 struct Iter {
     bool have_c = false;
@@ -231,9 +369,19 @@ struct Iter {
 struct Plan {
     pl_plan* p = nullptr;
     pl_lattice *f = nullptr, *g = nullptr;
-    pl_collide_args c[2];
+    pl_collide_args c[2];         // what the caller passes now (the device plan holds the same unless flagged below)
     std::vector<Op> ops[2];
+    bool dirty_c[2] = {false, false}, dirty_aux[2] = {false, false};
 };
+// hand changed array bindings of argument set `par` to the device plan
+int flush_bindings(Plan* pl, int par) {
+    if (!pl->dirty_c[par] && !pl->dirty_aux[par]) return PL_OK;
+    std::vector<pl_bc_aux> aux;
+    if (pl->dirty_aux[par]) for (const Op& o : pl->ops[par]) if (o.kind == OP_BC && o.has_aux) aux.push_back(o.aux);
+    if (pl_plan_rebind(pl->p, par, pl->dirty_c[par] ? &pl->c[par] : nullptr, aux.empty() ? nullptr : aux.data(), (int)aux.size())) return hfail("pl_plan_rebind");
+    pl->dirty_c[par] = pl->dirty_aux[par] = false;
+    return PL_OK;
+}
 struct Engine {
     Iter hist[2];
     int nhist = 0;
@@ -258,7 +406,7 @@ int settle() {
     Plan* pl = E.active;
     int rc = PL_OK;
     const int nops = (int)pl->ops[0].size();
-    if (E.pos == nops && nops > 0) rc = pl_plan_advance(pl->p, 0, 1);
+    if (E.pos == nops && nops > 0) { rc = flush_bindings(pl, E.par); if (!rc) rc = pl_plan_advance(pl->p, 0, 1); }
     else for (int k = 0; k < E.pos && !rc; ++k) rc = exec_op(pl->ops[E.par][k]);
     ++g_stat[6];
     E.active = nullptr; E.pos = 0; E.nhist = 0; E.cur = Iter();
@@ -313,10 +461,19 @@ bool same_plan_shape(const Plan* pl, const Iter& a, const Iter& b) {
     if (pl->f != a.f || pl->g != a.g || pl->ops[0].size() != a.ops.size()) return false;
     for (int par = 0; par < 2; ++par) {
         const Iter& it = par ? b : a;
-        if (!same_args(pl->c[par], it.c)) return false;
-        for (size_t k = 0; k < a.ops.size(); ++k) if (!same_shape(pl->ops[par][k], it.ops[k]) || !same_aux(pl->ops[par][k], it.ops[k])) return false;
+        if (!like_args(pl->c[par], it.c)) return false;
+        for (size_t k = 0; k < a.ops.size(); ++k) if (!same_shape(pl->ops[par][k], it.ops[k]) || !like_aux(pl->ops[par][k], it.ops[k])) return false;
     }
     return true;
+}
+// a known plan meets the same loop body with other arrays: take the arrays of the two learned iterations
+void adopt_bindings(Plan* pl, const Iter& a, const Iter& b) {
+    for (int par = 0; par < 2; ++par) {
+        const Iter& it = par ? b : a;
+        if (!same_args(pl->c[par], it.c)) { pl->c[par] = it.c; pl->dirty_c[par] = true; }
+        for (size_t k = 0; k < it.ops.size(); ++k)
+            if (!same_aux(pl->ops[par][k], it.ops[k])) { pl->ops[par][k].aux = it.ops[k].aux; pl->dirty_aux[par] = true; }
+    }
 }
 void drop_plans_of(pl_lattice* l) {
     for (size_t k = 0; k < E.plans.size();) {
@@ -328,7 +485,10 @@ void drop_plans_of(pl_lattice* l) {
     }
 }
 
-int enter_replay(Plan* pl, int par) {
+int enter_replay(Plan* pl, int par, const pl_collide_args& d) {
+    if (!same_args(pl->c[par], d)) { pl->c[par] = d; pl->dirty_c[par] = true; }
+    int rc = flush_bindings(pl, par);
+    if (rc) return rc;
     if (pl_plan_set_parity(pl->p, par)) return hfail("pl_plan_set_parity");
     if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
     ++g_stat[0];
@@ -342,7 +502,12 @@ int do_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args& d, bool stag
         Plan* pl = E.active;
         const int nops = (int)pl->ops[0].size();
         const int next = E.par ^ 1;
-        if (!staged && pl->f == f && pl->g == g && E.pos == nops && same_args(d, pl->c[next])) {
+        if (!staged && pl->f == f && pl->g == g && E.pos == nops && like_args(d, pl->c[next])) {
+            // the fused pass runs the closures of the finished iteration (set E.par) and this collide (set next)
+            if (!same_args(d, pl->c[next])) { pl->c[next] = d; pl->dirty_c[next] = true; }
+            int rc = flush_bindings(pl, E.par);
+            if (!rc) rc = flush_bindings(pl, next);
+            if (rc) return rc;
             if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
             ++g_stat[0];
             E.par = next; E.pos = 0;
@@ -361,16 +526,22 @@ int do_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args& d, bool stag
         for (Plan* pl : E.plans) {
             // speculative re-entry: a known plan whose collide arguments match; every following call is still verified
             if (pl->p && pl->f == f && pl->g == g && E.nhist == 0 && pl_lattice_streamed(f) && (!g || pl_lattice_streamed(g))) {
-                for (int par = 0; par < 2; ++par) if (same_args(d, pl->c[par])) return enter_replay(pl, par);
+                for (int par = 0; par < 2; ++par) if (same_args(d, pl->c[par])) return enter_replay(pl, par, d);
             }
         }
-        if (E.nhist == 2 && fusable(E.hist[0], E.hist[1]) && E.hist[0].f == f && E.hist[0].g == g && same_args(d, E.hist[0].c) &&
+        for (Plan* pl : E.plans) {
+            // the same loop body met again with other arrays (per-step arrays of the transient drivers): re-bind
+            if (pl->p && pl->f == f && pl->g == g && E.nhist == 0 && pl_lattice_streamed(f) && (!g || pl_lattice_streamed(g)) && like_args(d, pl->c[0]))
+                return enter_replay(pl, 0, d);
+        }
+        if (E.nhist == 2 && fusable(E.hist[0], E.hist[1]) && E.hist[0].f == f && E.hist[0].g == g && like_args(d, E.hist[0].c) &&
             pl_lattice_streamed(f) && (!g || pl_lattice_streamed(g))) {
             Plan* found = nullptr;
             bool tomb = false;
             for (Plan* pl : E.plans) if (same_plan_shape(pl, E.hist[0], E.hist[1])) { found = pl->p ? pl : nullptr; tomb = !pl->p; break; }
+            if (found) adopt_bindings(found, E.hist[0], E.hist[1]);
             if (!found && !tomb) found = build_plan(E.hist[0], E.hist[1]);
-            if (found) return enter_replay(found, 0);
+            if (found) return enter_replay(found, 0, d);
         }
     }
     ++g_stat[1];
@@ -383,7 +554,8 @@ int do_op(const Op& o, bool staged) {
     if (E.active) {
         Plan* pl = E.active;
         const int nops = (int)pl->ops[0].size();
-        if (!staged && E.pos < nops && same_shape(o, pl->ops[E.par][E.pos]) && same_aux(o, pl->ops[E.par][E.pos])) {
+        if (!staged && E.pos < nops && same_shape(o, pl->ops[E.par][E.pos]) && like_aux(o, pl->ops[E.par][E.pos])) {
+            if (!same_aux(o, pl->ops[E.par][E.pos])) { pl->ops[E.par][E.pos].aux = o.aux; pl->dirty_aux[E.par] = true; }
             ++E.pos;
             pops_written(o.l);
             return PL_OK;
@@ -451,6 +623,7 @@ int plh_lattice_detach(pl_lattice* l) {
 // collide: every pointer of `h` is a HOST pointer; which arrays the model reads / writes follows the reference signatures
 int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* h) {
     if (!f || !h) { g_herr = "plh_collide: null"; return PL_ERR_ARG; }
+    ++g_tick;       // one loop iteration per collide: the recency window of the state store
     int info[18];
     pl_lattice_info(f, info);
     const size_t n = (size_t)info[13], nc = (size_t)info[17];
@@ -616,6 +789,11 @@ int plh_sync(void) {
 int plh_stats(uint64_t* out8) {
     if (!out8) return PL_ERR_ARG;
     memcpy(out8, g_stat, sizeof(g_stat));
+    return PL_OK;
+}
+int plh_store_stats(uint64_t* out4) {
+    if (!out4) return PL_ERR_ARG;
+    memcpy(out4, g_store, sizeof(g_store));
     return PL_OK;
 }
 
