@@ -42,6 +42,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -81,10 +82,54 @@ bool g_handler = false;
 struct sigaction g_prev;
 std::string g_herr;
 
+// PANSLBM_B200_PROFILE=1: wall time spent inside each entry point of this file, printed at exit (host-side tuning aid)
+enum { T_COLLIDE, T_STREAM, T_SMOOTH, T_BC, T_INIT, T_RESIDUAL, T_SENS, T_SENS_HS, T_FILTER, T_SYNC, T_FETCH, T_MIRROR, T_NTIMERS };
+const char* const g_tname[T_NTIMERS] = {"collide", "stream", "smooth_corner", "bc", "initial_condition", "residual", "sensitivity", "sensitivity_heat_source",
+                                        "filter", "sync", "fetch(fault)", "mirror alloc/spill"};
+double g_tms[T_NTIMERS];
+uint64_t g_tcalls[T_NTIMERS];
+bool g_profile = false;
+struct HostTimer {
+    int id; std::chrono::steady_clock::time_point t0;
+    explicit HostTimer(int i) : id(i) { if (g_profile) t0 = std::chrono::steady_clock::now(); }
+    ~HostTimer() { if (g_profile) { g_tms[id] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); ++g_tcalls[id]; } }
+};
+void profile_dump() {
+    for (int k = 0; k < T_NTIMERS; ++k) if (g_tcalls[k]) fprintf(stderr, "panslbm_b200 host profile: %-24s %10llu calls %12.3f ms\n", g_tname[k], (unsigned long long)g_tcalls[k], g_tms[k]);
+}
+struct ProfileInit { ProfileInit() { const char* v = getenv("PANSLBM_B200_PROFILE"); if (v && *v && *v != '0') { g_profile = true; atexit(profile_dump); } } } g_profile_init;
+
 int hfail(const char* what) {
     g_herr = std::string(what) + ": " + pl_last_error();
     return PL_ERR_CUDA;
 }
+
+// Device memory of the mirrors: carved from slabs and recycled by size.  cudaMalloc/cudaFree per array would cost milliseconds
+// and synchronise the device — the transient loops mirror nine new arrays per time step.  All device work is ordered on the
+// library's stream, so a recycled buffer cannot be overtaken by its previous user.
+struct DevPool {
+    std::map<size_t, std::vector<double*>> free_;
+    char* slab = nullptr;
+    size_t left = 0, next_slab = (size_t)64 << 20;
+    double* get(size_t bytes) {
+        auto it = free_.find(bytes);
+        if (it != free_.end() && !it->second.empty()) { double* p = it->second.back(); it->second.pop_back(); return p; }
+        const size_t need = (bytes + 255)/256*256;
+        if (left < need) {
+            if (left >= 4096) free_[left/256*256].push_back((double*)slab);     // the tail of the old slab stays usable
+            size_t want = need > next_slab ? need : next_slab;
+            double* p = pl_array_alloc(want/sizeof(double));
+            if (!p && want > need) { want = need; p = pl_array_alloc(want/sizeof(double)); }
+            if (!p) { left = 0; return nullptr; }
+            slab = (char*)p; left = want;
+            if (next_slab < ((size_t)1 << 30)) next_slab *= 2;
+        }
+        double* p = (double*)slab;
+        slab += need; left -= need;
+        return p;
+    }
+    void put(double* p, size_t bytes) { free_[bytes].push_back(p); }
+} g_pool;
 
 Block* find_block(const void* p) {
     if (g_blocks.empty()) return nullptr;
@@ -101,6 +146,7 @@ int acquire_mirror(Block* b);
 
 // bring the host copy of a block up to date (it is in state DEVICE) and make it readable
 void fetch(Block* b) {
+    HostTimer timer_(T_FETCH);
     pl_synchronize();
     if (b->kind == BK_ARRAY) {
         protect(b, PROT_READ | PROT_WRITE);
@@ -150,15 +196,28 @@ Block* new_block(size_t bytes, int kind, pl_lattice* lat, int state, int prot) {
     install_handler();
     size_t mb = (bytes + g_page - 1)/g_page*g_page;
     if (mb == 0) mb = g_page;
-    void* p = mmap(nullptr, mb, prot, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-    if (p == MAP_FAILED) return nullptr;
+    // large blocks: 2 MB aligned and advised for transparent huge pages, so that the first host touch of a block the device
+    // filled (a spilled state, a field read after the loops) costs one fault per 2 MB instead of one per 4 KB
+    const size_t huge = (size_t)2 << 20;
+    const bool big = mb >= 2*huge;
+    void* raw = mmap(nullptr, big ? mb + huge : mb, prot, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (raw == MAP_FAILED) return nullptr;
+    void* p = raw;
+    if (big) {
+        const uintptr_t a = ((uintptr_t)raw + huge - 1)/huge*huge;
+        if (a > (uintptr_t)raw) munmap(raw, a - (uintptr_t)raw);
+        const size_t tail = (uintptr_t)raw + mb + huge - (a + mb);
+        if (tail) munmap((void*)(a + mb), tail);
+        p = (void*)a;
+        madvise(p, mb, MADV_HUGEPAGE);
+    }
     Block b;
     b.base = (char*)p; b.bytes = bytes; b.map_bytes = mb; b.kind = kind; b.lat = lat; b.state = state; b.seq = ++g_seq;
     auto r = g_blocks.emplace((uintptr_t)p, b);
     return &r.first->second;
 }
 void drop_block(Block* b) {
-    if (b->dev) { pl_synchronize(); pl_array_free(b->dev); g_store[2] -= b->map_bytes; }
+    if (b->dev) { g_pool.put(b->dev, b->map_bytes); g_store[2] -= b->map_bytes; }
     char* base = b->base; size_t mb = b->map_bytes;
     g_blocks.erase((uintptr_t)base);
     munmap(base, mb);
@@ -175,10 +234,10 @@ bool untouched(const Block* b) {
     if (fd == -2) fd = open("/proc/self/pagemap", O_RDONLY | O_CLOEXEC);
     if (fd < 0) return false;
     const size_t npages = b->map_bytes/g_page;
-    uint64_t buf[512];
+    static uint64_t buf[8192];
     size_t done = 0;
     while (done < npages) {
-        const size_t m = npages - done < 512 ? npages - done : 512;
+        const size_t m = npages - done < 8192 ? npages - done : 8192;
         const ssize_t got = pread(fd, buf, m*8, (off_t)(((uintptr_t)b->base/g_page + done)*8));
         if (got != (ssize_t)(m*8)) return false;
         for (size_t k = 0; k < m; ++k) if (buf[k] & (3ull << 62)) return false;      // bit 63 present, bit 62 swapped
@@ -201,7 +260,7 @@ int spill(Block* v, double** keep) {
     }
     v->state = ST_HOST;
     if (keep) *keep = v->dev;            // handed over to the block that needs a mirror of the same size
-    else { pl_array_free(v->dev); g_store[2] -= v->map_bytes; }
+    else { g_pool.put(v->dev, v->map_bytes); g_store[2] -= v->map_bytes; }
     v->dev = nullptr;
     v->spilled = true;
     ++g_store[0];
@@ -219,6 +278,7 @@ Block* pick_victim(const Block* need, bool same_size) {
     return best;
 }
 int acquire_mirror(Block* b) {
+    HostTimer timer_(T_MIRROR);
     if (!g_budget_read) {
         const char* v = getenv("PANSLBM_B200_DEVICE_BUDGET_MB");
         g_budget = v && *v ? (size_t)atoll(v) << 20 : 0;
@@ -242,7 +302,7 @@ int acquire_mirror(Block* b) {
         }
     }
     while (!b->dev) {
-        b->dev = pl_array_alloc(b->map_bytes/sizeof(double));
+        b->dev = g_pool.get(b->map_bytes);
         if (b->dev) { g_store[2] += b->map_bytes; break; }
         Block* w = pick_victim(b, false);        // device memory exhausted: spill and retry
         if (!w) return hfail("device mirror");
@@ -622,6 +682,7 @@ int plh_lattice_detach(pl_lattice* l) {
 
 // collide: every pointer of `h` is a HOST pointer; which arrays the model reads / writes follows the reference signatures
 int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* h) {
+    HostTimer timer_(T_COLLIDE);
     if (!f || !h) { g_herr = "plh_collide: null"; return PL_ERR_ARG; }
     ++g_tick;       // one loop iteration per collide: the recency window of the state store
     int info[18];
@@ -651,6 +712,7 @@ int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* h) {
 }
 
 int plh_stream(pl_lattice* l, int inverse) {
+    HostTimer timer_(T_STREAM);
     if (!l) { g_herr = "plh_stream: null"; return PL_ERR_ARG; }
     int rc = pops_sync_in(l);
     if (rc) return rc;
@@ -658,6 +720,7 @@ int plh_stream(pl_lattice* l, int inverse) {
     return do_op(o, false);
 }
 int plh_smooth_corner(pl_lattice* l) {
+    HostTimer timer_(T_SMOOTH);
     if (!l) { g_herr = "plh_smooth_corner: null"; return PL_ERR_ARG; }
     int rc = pops_sync_in(l);
     if (rc) return rc;
@@ -673,6 +736,7 @@ int plh_smooth_corner_at(pl_lattice* l, int i, int j, int k, int dx, int dy, int
     return pl_smooth_corner_at(l, i, j, k, dx, dy, dz) ? hfail("pl_smooth_corner_at") : PL_OK;
 }
 int plh_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* h) {
+    HostTimer timer_(T_BC);
     if (!l || !bc) { g_herr = "plh_bc: null"; return PL_ERR_ARG; }
     if (pl_bc_is_empty(bc)) return PL_OK;      // the reference's `if (0 <= i && i < nx)` guard: nothing to do on this rank
     int info[18];
@@ -697,6 +761,7 @@ int plh_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* h
 }
 
 int plh_initial_condition(pl_lattice* l, int family, const double* const* h, int na) {
+    HostTimer timer_(T_INIT);
     if (!l || !h) { g_herr = "plh_initial_condition: null"; return PL_ERR_ARG; }
     int info[18];
     pl_lattice_info(l, info);
@@ -714,6 +779,7 @@ int plh_initial_condition(pl_lattice* l, int family, const double* const* h, int
 }
 
 int plh_residual(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, size_t n, double* out) {
+    HostTimer timer_(T_RESIDUAL);
     const double* h[6] = {ux, uy, uz, uxp, uyp, uzp};
     double* d[6];
     int rc;
@@ -733,6 +799,7 @@ int plh_normalize(double* v, size_t n) {
     return rc ? rc : rc2;
 }
 int plh_sensitivity(pl_lattice* l, const pl_sens_args* h) {
+    HostTimer timer_(T_SENS);
     if (!l || !h) { g_herr = "plh_sensitivity: null"; return PL_ERR_ARG; }
     int info[18];
     pl_lattice_info(l, info);
@@ -753,6 +820,7 @@ int plh_sensitivity(pl_lattice* l, const pl_sens_args* h) {
 }
 int plh_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
                                 const double* igsnap, const double* diffusivity, const double* dkds) {
+    HostTimer timer_(T_SENS_HS);
     if (!l || !plane) { g_herr = "plh_sensitivity_heat_source: null"; return PL_ERR_ARG; }
     if (pl_bc_is_empty(plane)) return PL_OK;
     int info[18];
@@ -771,6 +839,7 @@ int plh_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds,
 }
 
 int plh_filter_apply(pl_filter* f, int mode, double beta, const double* v, const double* dfdrho, double* out, size_t n) {
+    HostTimer timer_(T_FILTER);
     if (!f) { g_herr = "plh_filter_apply: null"; return PL_ERR_ARG; }
     double *dv, *dd, *dout;
     int rc;
@@ -782,6 +851,7 @@ int plh_filter_apply(pl_filter* f, int mode, double beta, const double* v, const
 }
 
 int plh_sync(void) {
+    HostTimer timer_(T_SYNC);
     int rc = settle();
     pl_synchronize();
     return rc;
