@@ -78,6 +78,17 @@ double* pl_array_alloc(size_t n);                 /* NULL on failure */
 int pl_array_free(double* dev);
 int pl_array_upload(double* dev, const double* host, size_t n);     /* synchronous wrt the host buffer */
 int pl_array_download(double* host, const double* dev, size_t n);   /* synchronises the stream */
+/* Copies on the library's own copy stream, beside the kernels (host buffers should be pinned, else CUDA serialises them).
+ * An optimisation iteration moves whole fields between the host optimiser and the sweep (production/heatsink3D.cpp:114-119:
+ * alpha, diffusivity, dads, dkds in; :227-246: tem, dfdss out); only alpha/diffusivity gate the first step.
+ *   upload_async    starts after everything queued so far (earlier kernels may still read `dev`); kernels queued after the
+ *                   next pl_copy_fence() see the data
+ *   download_async  starts after everything queued so far has finished (the data are final); the host buffer is valid after
+ *                   pl_copy_wait() */
+int pl_array_upload_async(double* dev, const double* host, size_t n);
+int pl_array_download_async(double* host, const double* dev, size_t n);
+int pl_copy_fence(void);     /* the compute stream waits (on the device) for the copies issued so far */
+int pl_copy_wait(void);      /* the host waits for the copies issued so far */
 int pl_array_fill(double* dev, double value, size_t n);
 
 /* ---- lattices: D2Q9<double> (src/particle/d2q9.h:24-158), D3Q15<double> (src/particle/d3q15.h:24-249) ---- */

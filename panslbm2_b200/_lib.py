@@ -52,6 +52,10 @@ _PROTOS = {
     "pl_array_free": (C.c_int, [C.c_void_p]),
     "pl_array_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "pl_array_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pl_array_upload_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pl_array_download_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pl_copy_fence": (C.c_int, []),
+    "pl_copy_wait": (C.c_int, []),
     "pl_array_fill": (C.c_int, [C.c_void_p, C.c_double, C.c_size_t]),
     "pl_lattice_create": (C.c_void_p, [C.c_int] * 8),
     "pl_lattice_destroy": (C.c_int, [C.c_void_p]),

@@ -71,6 +71,16 @@ class DeviceArray:
         check(_lib.lib().pl_array_fill(self.ptr, float(v), self.n))
         return self
 
+    def upload_async(self, host_ptr: int):
+        """start copying n doubles from a (pinned) host address on the copy stream; kernels queued after copy_fence() see them"""
+        check(_lib.lib().pl_array_upload_async(self.ptr, host_ptr, self.n))
+        return self
+
+    def download_async(self, host_ptr: int):
+        """once everything queued so far has finished, copy to a (pinned) host address beside the following kernels; valid after copy_wait()"""
+        check(_lib.lib().pl_array_download_async(host_ptr, self.ptr, self.n))
+        return self
+
     def free(self):
         if getattr(self, "ptr", None):
             _lib.lib().pl_array_free(self.ptr)
@@ -81,6 +91,49 @@ class DeviceArray:
             self.free()
         except Exception:
             pass
+
+
+def _callable_signature(f, depth=0):
+    """hashable identity of a plane callable by VALUE: (code, captured values, defaults, global scalars it names); None if it
+    captures anything whose value cannot be pinned down (arrays, objects)"""
+    import types
+    if f is None:
+        return ("none",)
+    code = getattr(f, "__code__", None)
+    if code is None or depth > 3:
+        return None
+    simple = (int, float, bool, str, type(None), np.integer, np.floating)
+
+    def value_key(v):
+        if isinstance(v, simple):
+            return (type(v).__name__, v)
+        if isinstance(v, types.FunctionType):
+            return _callable_signature(v, depth + 1)
+        if isinstance(v, dict) and all(isinstance(k, str) and isinstance(x, simple) for k, x in v.items()):
+            return ("dict", tuple(sorted((k, type(x).__name__, x) for k, x in v.items())))
+        if isinstance(v, (types.ModuleType, types.BuiltinFunctionType, type, np.ufunc)):
+            return ("code", id(v))
+        return None
+
+    cells = []
+    try:
+        captured = [c.cell_contents for c in (f.__closure__ or ())]
+    except ValueError:
+        return None
+    for v in captured + list(f.__defaults__ or ()) + [f.__globals__[n] for n in code.co_names if n in f.__globals__]:
+        k = value_key(v)
+        if k is None:
+            return None
+        cells.append(k)
+    return (code, tuple(cells))
+
+
+def copy_fence():
+    check(_lib.lib().pl_copy_fence())
+
+
+def copy_wait():
+    check(_lib.lib().pl_copy_wait())
 
 
 def dptr(x):
@@ -170,6 +223,7 @@ class _Lattice:
         (self.lx, self.ly, self.lz, self.PEid, self.mx, self.my, self.mz, self.PEx, self.PEy, self.PEz,
          self.nx, self.ny, self.nz, self.nxyz, self.offsetx, self.offsety, self.offsetz, _nc) = [int(v) for v in info]
         self._bc_cache = {}
+        self._bc_ident = {}
 
     # -- reference public helpers (d3q15.h:136-150)
     def Index(self, i, j, k=0):
@@ -232,6 +286,21 @@ class _Lattice:
     def make_bc(self, bctype_id, axis, coord, direction, maskfn, valfns=()):
         """Bake one plane closure (cached by content). Returns a pl_bc handle (int) — possibly an empty one."""
         L = _lib.lib()
+        # the same callables on the same plane again (every step of a loop written call by call, every optimisation iteration):
+        # no re-evaluation.  "Same" = same code object with the same captured scalars and defaults (the analogue of the closure
+        # bytes the C++ headers key on, src/b200/bind.h); anything else captured makes the callable uncacheable.
+        sig = tuple(_callable_signature(f) for f in (maskfn, *valfns))
+        if all(s is not None for s in sig):
+            ident = (bctype_id, axis, coord, direction, sig)
+            h = self._bc_ident.get(ident)
+            if h is None:
+                if len(self._bc_ident) >= 1024:
+                    self._bc_ident.clear()
+                h = self._bc_ident[ident] = self._make_bc(L, bctype_id, axis, coord, direction, maskfn, valfns)
+            return h
+        return self._make_bc(L, bctype_id, axis, coord, direction, maskfn, valfns)
+
+    def _make_bc(self, L, bctype_id, axis, coord, direction, maskfn, valfns):
         coords = self.plane_coords(axis, coord)
         if coords is None:
             key = (bctype_id, axis, coord, direction, None)

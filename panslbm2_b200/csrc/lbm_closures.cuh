@@ -4,6 +4,9 @@
 // order is the scalar one of src/equation/*.h and src/particle/*.h.  The host callables of the reference are
 // baked into per-plane mask/value arrays (see include/panslbm_c.h).
 //
+// The population arguments are generic (`PA`): a plain `double[nc]` (registers / the host build) or any object with
+// operator[](int) -> double& (the strided shared-memory view of the boundary pass, lbm_kernels.cuh).
+//
 // Vocabulary for a plane with normal axis a and outward direction dir:
 //   K = populations with c_a == -dir, ascending c (the axis-aligned one first, then the diagonals);
 //       for the forward closures these are the unknowns entering the domain, for the adjoint ("i") closures
@@ -37,14 +40,14 @@ template <int D> PL_HD void face_list(int axis, int sgn, int (&K)[FaceK<D>::n]) 
         if (rdir<D>(c, axis) == sgn && m < FaceK<D>::n) K[m++] = c;
 }
 // sum_i sign(c_b(K_i)) p[K_i] over the diagonals, left to right
-template <int D> PL_HD double signed_diag_sum(const double (&p)[LT<D>::nc], const int (&K)[FaceK<D>::n], int b) {
+template <int D, class PA> PL_HD double signed_diag_sum(const PA& p, const int (&K)[FaceK<D>::n], int b) {
     double s = rdir<D>(K[1], b) > 0 ? p[K[1]] : -p[K[1]];
     PL_UNROLL
     for (int i = 2; i < FaceK<D>::n; ++i) s = rdir<D>(K[i], b) > 0 ? s + p[K[i]] : s - p[K[i]];
     return s;
 }
 // w*p[K0] + p[K1] + ... left to right
-template <int D> PL_HD double weighted_face_sum(const double (&p)[LT<D>::nc], const int (&K)[FaceK<D>::n], double w) {
+template <int D, class PA> PL_HD double weighted_face_sum(const PA& p, const int (&K)[FaceK<D>::n], double w) {
     double s = w*p[K[0]];
     PL_UNROLL
     for (int i = 1; i < FaceK<D>::n; ++i) s = s + p[K[i]];
@@ -64,7 +67,7 @@ PL_HD double pick(int axis, double x, double y, double z) { return axis == 0 ? x
 // ---------------------------------------------------------------------------------------------------------
 // BARRIER / MIRROR (d3q15.h:984-1239, d2q9.h:431-575): forward rebuilds the populations entering the domain
 // (c_a == -dir) from their opposite (BARRIER=1) or mirror image (MIRROR=2); inverse the leaving ones.
-template <int D> PL_HD void closure_bounce(double (&p)[LT<D>::nc], int axis, int dir, int type, bool inverse) {
+template <int D, class PA> PL_HD void closure_bounce(PA& p, int axis, int dir, int type, bool inverse) {
     if (type != 1 && type != 2) return;
     const int want = inverse ? dir : -dir;
     PL_UNROLL
@@ -89,7 +92,7 @@ template <int D> PL_HD void closure_bounce(double (&p)[LT<D>::nc], int axis, int
 //   m_a = rho0*u_a/(6|12), m_t = (1/2|1/4)*(f_{+t} - f_{-t} - rho0*u_t)
 //   f_in(axis) = f_out -dir*(4|8)*m_a,  f_in(diagonal) = f_opp + sum_d s_d m_d with s_a = c_a, s_t = -c_t,
 // sums in ascending c and x,y,z order as written in the reference.
-template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir, const SiteVals& V, bool setrho) {
+template <int D, class PA> PL_HD void closure_ns(PA& p, int axis, int dir, const SiteVals& V, bool setrho) {
     constexpr int NC = LT<D>::nc;
     double s = p[0];
     PL_UNROLL
@@ -144,7 +147,7 @@ template <int D> PL_HD void closure_ns(double (&p)[LT<D>::nc], int axis, int dir
 //   SetT: tem0 = 6*(T - g0 - sum_{c_a != -dir} g_c)/(1 - dir*3u_a)
 //   SetQ: tem0 = 6*((1 + 1/(6 kappa))*qn + sum_{c_a == dir} g_c)/(1 + dir*3u_a)
 //   g_in = tem0*(1 + 3 c.u)/(9 | 36 | 72)
-template <int D> PL_HD void closure_ad(double (&g)[LT<D>::nc], int axis, int dir, const SiteVals& V, bool setq) {
+template <int D, class PA> PL_HD void closure_ad(PA& g, int axis, int dir, const SiteVals& V, bool setq) {
     constexpr int NC = LT<D>::nc;
     const double ua = pick(axis, V.ux, V.uy, V.uz);
     double tem0;
@@ -172,7 +175,7 @@ template <int D> PL_HD void closure_ad(double (&g)[LT<D>::nc], int axis, int dir
 //   rho0 = (-(2|4) eps -dir*u_a*((4|8) f_K0 + sum f_Kdiag) + sum_t 3 u_t sum_i c_t(K_i) f_Ki)/((3|6)(1 + dir*u_a)),  f_opp(K) = f_K + rho0
 // 3-D: terms in x,y,z order; 2-D: normal term first.  The reference's 2-D y-edge version reads ux where uy is
 // meant (adjointnavierstokes.h:134,139); reproduced.
-template <int D> PL_HD void closure_ans_isetu(double (&f)[LT<D>::nc], int axis, int dir, const SiteVals& V) {
+template <int D, class PA> PL_HD void closure_ans_isetu(PA& f, int axis, int dir, const SiteVals& V) {
     int K[FaceK<D>::n];
     face_list<D>(axis, -dir, K);
     double u[3] = {V.v0, V.v1, V.v2};
@@ -206,7 +209,7 @@ template <int D> PL_HD void closure_ans_isetu(double (&f)[LT<D>::nc], int axis, 
 }
 
 // ANS::iBoundaryConditionSetRho (adjointnavierstokes.h:258-392): rho0 = ((4|8) f_K0 + sum f_Kdiag)/(3|6), f_opp(K) = f_K - rho0
-template <int D> PL_HD void closure_ans_isetrho(double (&f)[LT<D>::nc], int axis, int dir) {
+template <int D, class PA> PL_HD void closure_ans_isetrho(PA& f, int axis, int dir) {
     int K[FaceK<D>::n];
     face_list<D>(axis, -dir, K);
     const double rho0 = D == 2 ? weighted_face_sum<D>(f, K, 4.0)/3.0 : weighted_face_sum<D>(f, K, 8.0)/6.0;
@@ -217,7 +220,7 @@ template <int D> PL_HD void closure_ans_isetrho(double (&f)[LT<D>::nc], int axis
 // AAD::iBoundaryConditionSetT (adjointadvection.h:154-300): every unknown (opposites of K) takes the same value
 //   3-D: -(8 g_K0 + sum g_Kdiag)/12 - sum_t u_t*S_t/(4(1 - dir*3u_a)), tangential axes in cyclic order (a+1, a+2)
 //   2-D: -(4(1 - dir*3u_a) g_K0 + sum (1 + 3 c.u) g_Kdiag)/(6(1 - dir*3u_a))
-template <int D> PL_HD void closure_aad_isett(double (&g)[LT<D>::nc], int axis, int dir, const SiteVals& V) {
+template <int D, class PA> PL_HD void closure_aad_isett(PA& g, int axis, int dir, const SiteVals& V) {
     int K[FaceK<D>::n];
     face_list<D>(axis, -dir, K);
     const double ua = pick(axis, V.ux, V.uy, V.uz);
@@ -245,7 +248,7 @@ template <int D> PL_HD void closure_aad_isett(double (&g)[LT<D>::nc], int axis, 
 //   (1 - dir*3u_a)*(lead + (4|8) g_K0 + sum g_Kdiag) + sum_t w_t u_t S_t,  tangential axes in cyclic order,
 //   w_t = 3 except on the 3-D ymax, zmin and zmax faces where the reference writes the bare u_t
 //   (adjointadvection.h:458-459,470-471,...; adjointadvection_avx.h:141-142,171-172,176-177); reproduced.
-template <int D> PL_HD double aad_q_bracket(const double (&g)[LT<D>::nc], const int (&K)[FaceK<D>::n], int axis, int dir,
+template <int D, class PA> PL_HD double aad_q_bracket(const PA& g, const int (&K)[FaceK<D>::n], int axis, int dir,
                                             const SiteVals& V, bool with_lead, double lead) {
     const double ua = pick(axis, V.ux, V.uy, V.uz);
     const double one3 = dir == -1 ? 1.0 + 3.0*ua : 1.0 - 3.0*ua;
@@ -271,7 +274,7 @@ template <int D> PL_HD double aad_q_bracket(const double (&g)[LT<D>::nc], const 
     }
     return acc;
 }
-template <int D> PL_HD void closure_aad_isetq(double (&g)[LT<D>::nc], int axis, int dir, const SiteVals& V) {
+template <int D, class PA> PL_HD void closure_aad_isetq(PA& g, int axis, int dir, const SiteVals& V) {
     int K[FaceK<D>::n];
     face_list<D>(axis, -dir, K);
     const double ua = pick(axis, V.ux, V.uy, V.uz);
@@ -285,7 +288,7 @@ template <int D> PL_HD void closure_aad_isetq(double (&g)[LT<D>::nc], int axis, 
 
 // AAD::iBoundaryConditionSetRho for D2Q9 (adjointadvection.h:488-575): f and g lattices together; the mask value
 // selects the thermal closure the edge carries (1 = SetT, 2 = SetQ; adjointadvection.h:16-17).
-PL_HD void closure_aad_isetrho2d(double (&f)[9], const double (&g)[9], int axis, int dir, int kind, const SiteVals& V) {
+template <class PA, class QA> PL_HD void closure_aad_isetrho2d(PA& f, const QA& g, int axis, int dir, int kind, const SiteVals& V) {
     int K[3];
     face_list<2>(axis, -dir, K);
     const double ua = axis == 0 ? V.ux : V.uy, ut = axis == 0 ? V.uy : V.ux;
@@ -309,8 +312,8 @@ PL_HD void closure_aad_isetrho2d(double (&f)[9], const double (&g)[9], int axis,
 // The closure bodies above are written over run-time (axis, dir) with table lookups per direction; on the device they are
 // instantiated once per face with literal arguments, so that after inlining and unrolling every population index is a
 // constant and each closure is a few dozen straight-line fp64 instructions in the order the generic loops define.
-template <int D>
-PL_HD void apply_closure_on(int type, int axis, int dir, int maskval, double (&p)[LT<D>::nc], const double (&q)[LT<D>::nc], const SiteVals& V) {
+template <int D, class PA, class QA>
+PL_HD void apply_closure_on(int type, int axis, int dir, int maskval, PA& p, const QA& q, const SiteVals& V) {
     switch (type) {
         case BC_BOUNCE: closure_bounce<D>(p, axis, dir, maskval, false); break;
         case BC_IBOUNCE: closure_bounce<D>(p, axis, dir, maskval, true); break;
@@ -326,8 +329,8 @@ PL_HD void apply_closure_on(int type, int axis, int dir, int maskval, double (&p
         default: break;
     }
 }
-template <int D>
-PL_HD void apply_closure(int type, int axis, int dir, int maskval, double (&p)[LT<D>::nc], const double (&q)[LT<D>::nc], const SiteVals& V) {
+template <int D, class PA, class QA>
+PL_HD void apply_closure(int type, int axis, int dir, int maskval, PA& p, const QA& q, const SiteVals& V) {
 #ifdef __CUDA_ARCH__
     switch (2*axis + (dir > 0 ? 1 : 0)) {
         case 0: apply_closure_on<D>(type, 0, -1, maskval, p, q, V); break;
@@ -345,7 +348,7 @@ PL_HD void apply_closure(int type, int axis, int dir, int maskval, double (&p)[L
 
 // heat-source boundary term of AAD::SensitivityTemperatureAtHeatSource on one plane site
 // (adjointadvection_avx.h:16-185): ig = adjoint thermal snapshot at the site, V.v0 = qn, returns the increment of dfds.
-template <int D> PL_HD double sens_heat_source_term(const double (&ig)[LT<D>::nc], int axis, int dir, const SiteVals& V, double dkds) {
+template <int D, class PA> PL_HD double sens_heat_source_term(const PA& ig, int axis, int dir, const SiteVals& V, double dkds) {
     int K[FaceK<D>::n];
     face_list<D>(axis, -dir, K);
     const double ua = pick(axis, V.ux, V.uy, V.uz);

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 //               coordinates form the edge "tubes" SmoothCorner reads and writes.
 struct ShellMask {
     const unsigned long long *x, *y, *z;
-    int prefetch;      // 0 = off, 1 = prefetch.global.L2, 2 = prefetch.global.L1 of the closure inputs (PANSLBM_PREFETCH)
+    int prefetch;      // closure inputs ahead of the pull (PANSLBM_PREFETCH): 0 = off, 1 = prefetch.global.L2, 2 = prefetch.global.L1, 3 = plain loads
 };
 constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, HALO_BIT = 1ull << 61, ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT | HALO_BIT);
 constexpr int MAX_PROGRAM = 61;
@@ -179,7 +179,10 @@ PL_D bool in_tube(unsigned long long wx, unsigned long long wy, unsigned long lo
 // The closure program is a chain of dependent loads (program entry -> mask -> plane values / saved fields of the site), one
 // DRAM round trip each, behind the pull.  Issuing prefetches for all of them before the pull turns the chain into cache hits.
 PL_D void touch(const void* p, int level) {
-    if (level == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    if (level == 3) {      // a real load whose value nobody reads: the line is in L1 when the closure asks for it
+        unsigned long long v;
+        asm volatile("ld.global.nc.L1::evict_last.b64 %0, [%1];" : "=l"(v) : "l"((unsigned long long)p & ~7ull));
+    } else if (level == 2) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
     else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
 }
 template <unsigned FL> PL_D void prefetch_collide(const CollideParams& P, long long idx, int level) {
@@ -249,6 +252,44 @@ PL_D void boundary_path(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Cl
     sfor<0, NC>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = t[c]; if constexpr (HASG) g[c] = t[NC + c]; });
 }
 
+// The boundary pass keeps the populations of a site in shared memory while the closure program runs on them: one column of
+// the CTA's [2*nc][SHELL_THREADS] tile per thread (stride = the CTA width, conflict-free for 8-byte accesses).  Thread-local
+// scratch for the same purpose lives in L1-backed local memory, which the streaming loads of the pass keep evicting (ncu:
+// half of the local loads missed L1, profiles/r01_tuning.md).
+constexpr int SHELL_THREADS = 128;
+struct SPop {
+    double* b;
+    PL_D double& operator[](int c) const { return b[c*SHELL_THREADS]; }
+};
+template <int D, bool HASG>
+__device__ __noinline__ void run_program_sh(double* __restrict__ col, const ClosureArgs* __restrict__ prog, unsigned long long entries,
+                                            int i, int j, int k, long long idx) {
+    constexpr int NC = LT<D>::nc;
+    const int co[3] = {i, j, k};
+    while (entries) {
+        const int e = __ffsll((long long)entries) - 1;
+        entries &= entries - 1;
+        const ClosureArgs& A = prog[e];
+        const int axis = A.pl.axis;
+        const int a1 = axis == 0 ? 1 : 0, a2 = axis == 2 ? 1 : 2;
+        const int pt = co[a1] + A.pl.n1*co[a2];
+        const int m = A.mask[pt];
+        if (!m) continue;
+        const bool og = HASG && A.on_g;
+        SPop p{og ? col + NC*SHELL_THREADS : col};
+        const SPop q{og ? col : col + NC*SHELL_THREADS};
+        apply_closure<D>(A.type, axis, A.pl.dir, m, p, q, site_vals(A, pt, idx));
+    }
+}
+template <int D, bool HASG>
+PL_D void boundary_path_sh(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], double* __restrict__ col, const ClosureArgs* __restrict__ prog,
+                           unsigned long long entries, int i, int j, int k, long long idx) {
+    constexpr int NC = LT<D>::nc;
+    sfor<0, NC>([&](auto C) { constexpr int c = decltype(C)::value; col[c*SHELL_THREADS] = f[c]; if constexpr (HASG) col[(NC + c)*SHELL_THREADS] = g[c]; });
+    run_program_sh<D, HASG>(col, prog, entries, i, j, k, idx);
+    sfor<0, NC>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = col[c*SHELL_THREADS]; if constexpr (HASG) g[c] = col[(NC + c)*SHELL_THREADS]; });
+}
+
 // The hot kernel: one fused Stream + Macro*Collide* pass, source buffer -> destination buffer, for every packed site that
 // lies on no y/z closure plane, in no x group of the boundary pass and in no SmoothCorner tube.  Each population is read once
 // and written once.  Sites of an x closure plane that the plan left to this kernel (no SLAB bit: PANSLBM_XINLINE) run the
@@ -287,22 +328,29 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
 // SmoothCorner tubes (t >= ndirect), a plain store of the streamed+closed populations; the tubes are finished by
 // k_smooth + k_collide on the destination buffer.  Runs beside k_fused on its own stream.
 template <int D, int M>
-__global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
-                                               const double* __restrict__ gs, double* __restrict__ gd, CollideParams P, ShellMask S,
-                                               const ClosureArgs* __restrict__ prog,
-                                               const int* __restrict__ list, int nlist, int ndirect, int inverse, HaloView HF, HaloView HG) {
+__global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
+                                                         const double* __restrict__ gs, double* __restrict__ gd, CollideParams P, ShellMask S,
+                                                         const ClosureArgs* __restrict__ prog, const int* __restrict__ list,
+                                                         const unsigned long long* __restrict__ ent, int nlist, int ndirect, int inverse,
+                                                         HaloView HF, HaloView HG) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
+    constexpr int NC = LT<D>::nc;
+    __shared__ double tile[(HASG ? 2 : 1)*NC*SHELL_THREADS];
     int t = blockIdx.x*blockDim.x + threadIdx.x;
     if (t >= nlist) return;
+    // one round trip for the site and its closure entries (baked per listed site: no dependent look-up of the plane words)
     const long long idx = list[t];
+    const unsigned long long entries = ent[t];
     int i, j, k;
     decompose(G, idx, i, j, k);
-    const unsigned long long entries = (S.x[i] | S.y[j] | S.z[k]) & ENTRY_BITS;
-    if (entries && S.prefetch) { prefetch_program(prog, entries, i, j, k, idx, S.prefetch); prefetch_collide<FL>(P, idx, S.prefetch); }
+    if (entries && S.prefetch) {
+        prefetch_program(prog, entries, i, j, k, idx, S.prefetch);
+        if (t < ndirect) prefetch_collide<FL>(P, idx, S.prefetch);
+    }
     Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
-    double f[LT<D>::nc], g[LT<D>::nc];
+    double f[NC], g[NC];
     if (HF.on) {
         pull_h<D>(f, fs, G.pitch, idx, i, j, k, G, n, HF, inverse);
         if constexpr (HASG) pull_h<D>(g, gs, G.pitch, idx, i, j, k, G, n, HG, inverse);
@@ -310,7 +358,7 @@ __global__ void __launch_bounds__(128) k_shell(Geom G, const double* __restrict_
         pull<D>(f, fs, G.pitch, idx, n);
         if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
     }
-    if (entries) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
+    if (entries) boundary_path_sh<D, HASG>(f, g, tile + threadIdx.x, prog, entries, i, j, k, idx);
     if (t < ndirect) {
         if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
         else collide_site<D, FL, true>(f, g, P, (size_t)idx);

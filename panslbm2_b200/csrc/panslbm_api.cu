@@ -52,10 +52,9 @@ int opt_xslab() { static int w = std::max(1, std::min(32, env_int("PANSLBM_XSLAB
 bool opt_fused_first() { static int v = env_int("PANSLBM_FUSED_FIRST", 0); return v != 0; }
 // x closure planes of an undecomposed axis: 1 = the interior kernel runs their closures inline, 0 = the boundary pass takes
 // the aligned x group around them
-int opt_prefetch() { static int v = std::max(0, std::min(2, env_int("PANSLBM_PREFETCH", 0))); return v; }
+int opt_prefetch() { static int v = std::max(0, std::min(3, env_int("PANSLBM_PREFETCH", 0))); return v; }
 // single block only: 1 = the boundary pass is queued behind the interior kernel on the same stream instead of beside it
 bool opt_shell_serial() { static int v = env_int("PANSLBM_SHELL_SERIAL", 0); return v != 0; }
-int opt_shell_block() { static int v = std::max(32, std::min(128, env_int("PANSLBM_SHELL_BLOCK", 128))); return v; }
 bool opt_xinline() { static int v = env_int("PANSLBM_XINLINE", 0); return v != 0; }
 
 // grow-only device scratch for the reductions: cudaMalloc/cudaFree per call would cost milliseconds next to tens of GB of
@@ -361,6 +360,51 @@ int pl_array_download(double* host, const double* dev, size_t n) {
     CU(cudaMemcpyAsync(host, dev, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
+}
+namespace {
+cudaStream_t g_copy = nullptr;
+cudaEvent_t g_copy_ev = nullptr, g_compute_ev = nullptr;
+int copy_stream() {
+    if (g_copy) return PL_OK;
+    CU(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g_copy_ev, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g_compute_ev, cudaEventDisableTiming));
+    return PL_OK;
+}
+int copy_after_compute() {
+    int r = copy_stream();
+    if (r) return r;
+    CU(cudaEventRecord(g_compute_ev, g_stream));
+    CU(cudaStreamWaitEvent(g_copy, g_compute_ev, 0));
+    return PL_OK;
+}
+}  // namespace
+extern "C" {
+int pl_array_upload_async(double* dev, const double* host, size_t n) {
+    if (!dev || !host) return fail(PL_ERR_ARG, "pl_array_upload_async: null");
+    int r = copy_after_compute();
+    if (r) return r;
+    CU(cudaMemcpyAsync(dev, host, n*sizeof(double), cudaMemcpyHostToDevice, g_copy));
+    return PL_OK;
+}
+int pl_array_download_async(double* host, const double* dev, size_t n) {
+    if (!dev || !host) return fail(PL_ERR_ARG, "pl_array_download_async: null");
+    int r = copy_after_compute();
+    if (r) return r;
+    CU(cudaMemcpyAsync(host, dev, n*sizeof(double), cudaMemcpyDeviceToHost, g_copy));
+    return PL_OK;
+}
+int pl_copy_fence(void) {
+    if (!g_copy) return PL_OK;
+    CU(cudaEventRecord(g_copy_ev, g_copy));
+    CU(cudaStreamWaitEvent(g_stream, g_copy_ev, 0));
+    return PL_OK;
+}
+int pl_copy_wait(void) {
+    if (!g_copy) return PL_OK;
+    CU(cudaStreamSynchronize(g_copy));
+    return PL_OK;
+}
 }
 int pl_array_fill(double* dev, double value, size_t n) {
     if (n == 0) return PL_OK;
@@ -882,6 +926,7 @@ struct pl_plan {
     // SmoothCorner tube sites last), the closure program per argument-set parity
     unsigned long long *mx = nullptr, *my = nullptr, *mz = nullptr;
     int* list = nullptr;
+    unsigned long long* ent = nullptr;     // closure entries of each listed site (the plane words of its coordinates, OR-ed)
     int nlist = 0, ndirect = 0;
     ClosureArgs* prog[2] = {nullptr, nullptr};
     int nprog = 0;
@@ -934,8 +979,8 @@ template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const Collid
     int r;
     if ((r = halo_view(p->f, HF))) return r;
     if (g) { if ((r = halo_view(g, HG))) return r; } else memset(&HG, 0, sizeof(HG));
-    LAUNCH_ON(st, (k_shell<D, M>), blocks_for(p->nlist, opt_shell_block()), opt_shell_block(), p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
-           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->nlist, p->ndirect, p->inverse, HF, HG);
+    LAUNCH_ON(st, (k_shell<D, M>), blocks_for(p->nlist, SHELL_THREADS), SHELL_THREADS, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
+           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->ent, p->nlist, p->ndirect, p->inverse, HF, HG);
     return PL_OK;
 }
 int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
@@ -1034,7 +1079,7 @@ pl_plan* pl_plan_create(pl_lattice* f, pl_lattice* g) {
 int pl_plan_destroy(pl_plan* p) {
     if (!p) return PL_OK;
     cudaStreamSynchronize(g_stream);
-    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
     if (p->stage) cudaFreeHost(p->stage);
     for (auto& e : p->stage_ev) if (e) cudaEventDestroy(e);
     for (auto& e : p->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -1153,8 +1198,8 @@ int pl_plan_finalize(pl_plan* p) {
         }
     p->ndirect = (int)list.size();
     list.insert(list.end(), tubes.begin(), tubes.end());
-    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
-    p->mx = p->my = p->mz = nullptr; p->list = nullptr; p->prog[0] = p->prog[1] = nullptr;
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    p->mx = p->my = p->mz = nullptr; p->list = nullptr; p->ent = nullptr; p->prog[0] = p->prog[1] = nullptr;
     CU(cudaMalloc(&p->mx, g.nx*8)); CU(cudaMalloc(&p->my, g.ny*8)); CU(cudaMalloc(&p->mz, g.nz*8));
     CU(cudaMemcpy(p->mx, hx.data(), g.nx*8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->my, hy.data(), g.ny*8, cudaMemcpyHostToDevice));
@@ -1163,6 +1208,14 @@ int pl_plan_finalize(pl_plan* p) {
     if (p->nlist) {
         CU(cudaMalloc(&p->list, list.size()*sizeof(int)));
         CU(cudaMemcpy(p->list, list.data(), list.size()*sizeof(int), cudaMemcpyHostToDevice));
+        std::vector<unsigned long long> ent(list.size());
+        for (size_t t = 0; t < list.size(); ++t) {
+            int i, j, k;
+            coords(list[t], i, j, k);
+            ent[t] = (hx[i] | hy[j] | hz[k]) & ENTRY_BITS;
+        }
+        CU(cudaMalloc(&p->ent, ent.size()*sizeof(unsigned long long)));
+        CU(cudaMemcpy(p->ent, ent.data(), ent.size()*sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
     p->nprog = (int)prog[0].size();
     for (int par = 0; par < 2; ++par) {
