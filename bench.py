@@ -409,6 +409,10 @@ def ns_cavity(pl, api, L, torch, S, K, W, barrier, maxms, world, rank=0, m=(1, 1
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner, ...) goes to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)

@@ -292,9 +292,9 @@ PL_D void boundary_path_sh(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], doubl
 
 // The hot kernel: one fused Stream + Macro*Collide* pass, source buffer -> destination buffer, for every packed site that
 // lies on no y/z closure plane, in no x group of the boundary pass and in no SmoothCorner tube.  Each population is read once
-// and written once.  Sites of an x closure plane that the plan left to this kernel (no SLAB bit: PANSLBM_XINLINE) run the
-// closure program between pull and collide: one lane of the warp diverges, but no 32-byte sector is split between kernels
-// and the strided x groups disappear from the boundary pass.
+// and written once.  Sites of an x closure plane that the plan left to this kernel (no SLAB bit) are either ordinary sites
+// here (prog == nullptr: k_xclose has already put the closure results where this kernel pulls from) or run the closure
+// program between pull and collide (PANSLBM_XINLINE: one lane of the warp diverges; measured slower, profiles/r01_tuning.md).
 template <int D, int M>
 __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
                                                const double* __restrict__ gs, double* __restrict__ gd,
@@ -310,14 +310,14 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
         const unsigned long long wx = S.x[i], wy = S.y[j], wz = S.z[k];
         if (((wy | wz) & ~TUBE_BIT) != 0ull || (wx & (SLAB_BIT | HALO_BIT)) != 0ull || in_tube(wx, wy, wz)) return;
         entries = wx & ENTRY_BITS;
-        if (entries && S.prefetch) { prefetch_program(prog, entries, i, j, k, idx, S.prefetch); prefetch_collide<FL>(P, idx, S.prefetch); }
+        if (entries && prog && S.prefetch) { prefetch_program(prog, entries, i, j, k, idx, S.prefetch); prefetch_collide<FL>(P, idx, S.prefetch); }
     }
     Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
     double f[LT<D>::nc], g[LT<D>::nc];
     pull<D>(f, fs, G.pitch, idx, n);
     if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
-    if (entries) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
+    if (entries && prog) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
     collide_site<D, FL, false>(f, g, P, (size_t)idx);
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
@@ -365,6 +365,45 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* _
     }
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+}
+
+// Closures of the x boundary planes of an undecomposed axis, ahead of the fused pass.  On such a plane the populations a
+// closure rebuilds are exactly the ones Stream() pulls through the periodic wrap (x - c beyond the wall), and the wrapped-
+// around value is dead: the closure overwrites it.  So the closure can run BEFORE the streaming pass: this kernel pulls the
+// plane site's populations from the source buffer, runs the site's closure program, and stores the rebuilt populations
+// back INTO THE WRAP SLOTS they were pulled from.  The interior kernel then treats the plane like any other site — its
+// ordinary pull picks the closure results up — with no divergence, no strided x groups in the boundary pass and no
+// 32-byte sector shared between two kernels.  One thread per plane site (sites that also lie on a y/z closure plane, in a
+// SmoothCorner tube or in the AVX tail stay with the boundary pass, which runs their whole program).
+template <int D, bool HASG>
+__global__ void __launch_bounds__(SHELL_THREADS) k_xclose(Geom G, double* fs, double* gs, const ClosureArgs* __restrict__ prog,
+                                                          const int* __restrict__ xlist, const unsigned long long* __restrict__ xent, int n, int inverse) {
+    constexpr int NC = LT<D>::nc;
+    __shared__ double tile[(HASG ? 2 : 1)*NC*SHELL_THREADS];
+    int t = blockIdx.x*blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long idx = xlist[t];
+    const unsigned long long entries = xent[t];
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    Nbr nb = neighbours(G, i, j, k);
+    orient(nb, inverse);
+    double f[NC], g[NC];
+    pull<D>(f, fs, G.pitch, idx, nb);
+    if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, nb);
+    boundary_path_sh<D, HASG>(f, g, tile + threadIdx.x, prog, entries, i, j, k, idx);
+    sfor<1, NC>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        constexpr int X = LT<D>::cx(c);
+        if constexpr (X != 0) {
+            const long long dx = X > 0 ? nb.m[0] : nb.p[0];
+            if (dx != 1 && dx != -1) {      // pulled through the wrap: the slot belongs to this site alone
+                const size_t o = (size_t)c*G.pitch + (size_t)(idx + pull_offset<D, c>(nb));
+                fs[o] = f[c];
+                if constexpr (HASG) gs[o] = g[c];
+            }
+        }
+    });
 }
 
 // SmoothCorner (d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587).  A line/point list is built on the host.

@@ -55,6 +55,12 @@ bool opt_fused_first() { static int v = env_int("PANSLBM_FUSED_FIRST", 0); retur
 int opt_prefetch() { static int v = std::max(0, std::min(3, env_int("PANSLBM_PREFETCH", 0))); return v; }
 // single block only: 1 = the boundary pass is queued behind the interior kernel on the same stream instead of beside it
 bool opt_shell_serial() { static int v = env_int("PANSLBM_SHELL_SERIAL", 0); return v != 0; }
+// replay a fused step as one captured CUDA graph (1 launch instead of 5 launches + 4 event operations); matters for the
+// launch-bound 2-D domains (production/heatsink.cpp: 141 x 161 sites)
+bool opt_graph() { static int v = env_int("PANSLBM_GRAPH", 0); return v != 0; }
+// closures of the x boundary planes run ahead of the fused pass and leave their results in the periodic wrap slots of the
+// source buffer (k_xclose); 0 = the boundary pass takes the aligned x groups around those planes
+bool opt_xghost() { static int v = env_int("PANSLBM_XGHOST", 1); return v != 0; }
 bool opt_xinline() { static int v = env_int("PANSLBM_XINLINE", 0); return v != 0; }
 
 // grow-only device scratch for the reductions: cudaMalloc/cudaFree per call would cost milliseconds next to tens of GB of
@@ -927,6 +933,9 @@ struct pl_plan {
     unsigned long long *mx = nullptr, *my = nullptr, *mz = nullptr;
     int* list = nullptr;
     unsigned long long* ent = nullptr;     // closure entries of each listed site (the plane words of its coordinates, OR-ed)
+    int* xlist = nullptr;                  // sites of the x boundary planes whose closures run ahead of the pass (k_xclose)
+    unsigned long long* xent = nullptr;
+    int nxlist = 0;
     int nlist = 0, ndirect = 0;
     ClosureArgs* prog[2] = {nullptr, nullptr};
     int nprog = 0;
@@ -939,6 +948,11 @@ struct pl_plan {
     // the boundary pass runs beside the interior kernel on its own (high-priority) stream
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // captured fused steps, by [argument set of the closures][buffer parity of f][buffer parity of g]
+    cudaGraphExec_t graphs[2][2][2] = {};
+    uint64_t graph_launches[2][2][2] = {};
+    cudaStream_t cap = nullptr;
+    int graph_cooldown = 0;        // steps to run ungraphed after the arguments were re-bound (per-step arrays: nothing to replay)
     // measurement hook
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
@@ -993,7 +1007,44 @@ int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P,
     return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
 }
 // fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1
+void drop_graphs(pl_plan* p) {
+    for (auto& a : p->graphs) for (auto& b : a) for (auto& g : b) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+}
+int plan_fused_body(pl_plan* p, int bc_parity, int col_parity);
+// fused F through a captured graph where that is possible: single block (no NCCL inside), not being profiled, arguments stable
 int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
+    if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial()) return plan_fused_body(p, bc_parity, col_parity);
+    if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity); }
+    const int fc = p->f->cur, gc = p->g ? p->g->cur : 0;
+    cudaGraphExec_t& exec = p->graphs[bc_parity][fc][gc];
+    if (exec) {
+        CU(cudaGraphLaunch(exec, g_stream));
+        g_launches += p->graph_launches[bc_parity][fc][gc];
+        // the host-side state changes of plan_fused_body
+        p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
+        p->f->streamed = 0; if (p->g) p->g->streamed = 0;
+        return PL_OK;
+    }
+    if (!p->cap) CU(cudaStreamCreateWithFlags(&p->cap, cudaStreamNonBlocking));
+    cudaStream_t user = g_stream;
+    const uint64_t before = g_launches;
+    g_stream = p->cap;
+    cudaGraph_t graph = nullptr;
+    int r = PL_OK;
+    if (cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { g_stream = user; cudaGetLastError(); return plan_fused_body(p, bc_parity, col_parity); }
+    r = plan_fused_body(p, bc_parity, col_parity);
+    cudaError_t e = cudaStreamEndCapture(p->cap, &graph);
+    g_stream = user;
+    if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (e != cudaSuccess || !graph) return fail(PL_ERR_CUDA, std::string("fused step: graph capture failed: ") + cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { exec = nullptr; return fail(PL_ERR_CUDA, std::string("fused step: cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    p->graph_launches[bc_parity][fc][gc] = g_launches - before;
+    CU(cudaGraphLaunch(exec, g_stream));      // the body ran under capture: this launch is its execution
+    return PL_OK;
+}
+int plan_fused_body(pl_plan* p, int bc_parity, int col_parity) {
     CollideParams P; unsigned flags;
     int r = make_params(p->f, p->g, &p->args[col_parity], P, flags);
     if (r) return r;
@@ -1015,6 +1066,17 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     }
     // a decomposed block wants its faces first (the next exchange hangs on them); a single block queues the interior first
     // so that the boundary CTAs interleave with it instead of running alone at their lower memory efficiency
+    // closures of the x boundary planes, into the wrap slots of the source buffers (the boundary pass may run beside this)
+    if (p->nxlist) {
+        const int nb = (int)blocks_for(p->nxlist, SHELL_THREADS);
+        if (p->f->kind == PL_D2Q9) {
+            if (g) LAUNCH((k_xclose<2, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
+            else LAUNCH((k_xclose<2, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
+        } else {
+            if (g) LAUNCH((k_xclose<3, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
+            else LAUNCH((k_xclose<3, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
+        }
+    }
     const bool shell_first = !serial && (p->f->halo.on || !opt_fused_first());
     if (shell_first) {
         if ((r = dispatch_shell(model, p, g, P, bc_parity, p->side))) return r;
@@ -1026,7 +1088,7 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
         CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, g_stream));
     }
-    if ((r = dispatch_fused(model, p->f, g, P, S, p->prog[bc_parity], p->inverse))) return r;
+    if ((r = dispatch_fused(model, p->f, g, P, S, opt_xinline() ? p->prog[bc_parity] : nullptr, p->inverse))) return r;
     if (p->profile) {
         CU(cudaEventRecord(ev1, g_stream));
         p->events.emplace_back(ev0, ev1);
@@ -1079,9 +1141,11 @@ pl_plan* pl_plan_create(pl_lattice* f, pl_lattice* g) {
 int pl_plan_destroy(pl_plan* p) {
     if (!p) return PL_OK;
     cudaStreamSynchronize(g_stream);
-    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->xlist); cudaFree(p->xent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
     if (p->stage) cudaFreeHost(p->stage);
     for (auto& e : p->stage_ev) if (e) cudaEventDestroy(e);
+    drop_graphs(p);
+    if (p->cap) cudaStreamDestroy(p->cap);
     for (auto& e : p->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
@@ -1091,6 +1155,7 @@ int pl_plan_destroy(pl_plan* p) {
 }
 int pl_plan_set_collide(pl_plan* p, const pl_collide_args* even, const pl_collide_args* odd) {
     if (!p || !even) return fail(PL_ERR_ARG, "pl_plan_set_collide: null");
+    drop_graphs(p);
     p->args[0] = *even; p->args[1] = odd ? *odd : *even;
     if (p->args[0].model != p->args[1].model) return fail(PL_ERR_ARG, "pl_plan_set_collide: the two argument sets must use the same model");
     p->have_collide = true;
@@ -1144,11 +1209,29 @@ int pl_plan_finalize(pl_plan* p) {
     }
     // x planes the boundary pass owns (block faces; closure planes unless the interior kernel takes them inline): it takes the
     // aligned group of x-coordinates around each (see ShellMask)
+    // ... except the x boundary planes whose closures can run ahead of the pass (k_xclose): a plane at the wall of an
+    // undecomposed x axis, every closure on it rebuilding exactly the populations the plan's Stream direction pulls through the
+    // periodic wrap (forward closures with Stream, the "i" closures with iStream)
+    std::vector<char> ghost(g.nx, 0);
+    if (opt_xghost() && !opt_xinline() && g.nx >= 4 && g.nx == g.lx && !(p->f->halo.on && p->f->halo.e[0])) {
+        for (int i : {0, g.nx - 1}) {
+            if (!(hx[i] & ENTRY_BITS)) continue;
+            bool ok = true;
+            for (size_t e = 0; e < prog[0].size() && ok; ++e) {
+                if (!((hx[i] >> e) & 1ull)) continue;
+                const ClosureArgs& A = prog[0][e];
+                const bool fwd = A.type == BC_BOUNCE || A.type == BC_NS_SET_U || A.type == BC_NS_SET_RHO || A.type == BC_AD_SET_T || A.type == BC_AD_SET_Q;
+                ok = A.pl.axis == 0 && A.pl.dir == (i == 0 ? -1 : 1) && fwd == (p->inverse == 0);
+            }
+            ghost[i] = ok;
+        }
+    }
     for (int i = 0; i < g.nx; ++i)
-        if ((hx[i] & HALO_BIT) || ((hx[i] & ENTRY_BITS) && !opt_xinline())) {
+        if ((hx[i] & HALO_BIT) || ((hx[i] & ENTRY_BITS) && !opt_xinline() && !ghost[i])) {
             const int w = opt_xslab(), lo = i/w*w;
             for (int v = lo; v < std::min(g.nx, lo + w); ++v) hx[v] |= SLAB_BIT;
         }
+    for (int i : {0, g.nx - 1}) if (hx[i] & SLAB_BIT) ghost[i] = 0;     // a neighbouring plane pulled it into a group
     // SmoothCorner: flag the global boundary planes and their inward neighbours (bit 1); sites with two flagged coordinates
     // form the edge tubes.  Every site SmoothCorner writes (edge lines, corners) or reads (their inward neighbours) must lie
     // in a tube: collide is deferred there until k_smooth has run.
@@ -1180,7 +1263,7 @@ int pl_plan_finalize(pl_plan* p) {
             }
     }
     // list = [sites on closure planes and sites of the last incomplete AVX pack, outside the tubes | tube sites]
-    std::vector<int> list, tubes;
+    std::vector<int> list, tubes, xlist;
     for (int k = 0; k < g.nz; ++k)
         for (int j = 0; j < g.ny; ++j) {
             const unsigned long long wyz = hy[j] | hz[k];
@@ -1189,17 +1272,21 @@ int pl_plan_finalize(pl_plan* p) {
             const bool tailrow = row + g.nx > g.npacked;
             if (!(wyz & ~TUBE_BIT) && two == 0 && !tailrow) {   // only the x planes can put a site of this row on the list
                 for (int i = 0; i < g.nx; ++i) if (hx[i] & SLAB_BIT) list.push_back((int)(row + i));
+                // the sites the interior kernel takes as ordinary ones once k_xclose has run (neither listed nor in a tube:
+                // with one flagged coordinate at most they cannot be)
+                for (int i : {0, g.nx - 1}) if (ghost[i]) xlist.push_back((int)(row + i));
                 continue;
             }
             for (int i = 0; i < g.nx; ++i) {
                 if (two + (int)(hx[i] >> 63) >= 2) tubes.push_back((int)(row + i));
                 else if ((wyz & ~TUBE_BIT) || (hx[i] & SLAB_BIT) || row + i >= g.npacked) list.push_back((int)(row + i));
+                else if (ghost[i]) xlist.push_back((int)(row + i));
             }
         }
     p->ndirect = (int)list.size();
     list.insert(list.end(), tubes.begin(), tubes.end());
-    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
-    p->mx = p->my = p->mz = nullptr; p->list = nullptr; p->ent = nullptr; p->prog[0] = p->prog[1] = nullptr;
+    cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->xlist); cudaFree(p->xent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    p->mx = p->my = p->mz = nullptr; p->list = nullptr; p->ent = nullptr; p->xlist = nullptr; p->xent = nullptr; p->nxlist = 0; p->prog[0] = p->prog[1] = nullptr;
     CU(cudaMalloc(&p->mx, g.nx*8)); CU(cudaMalloc(&p->my, g.ny*8)); CU(cudaMalloc(&p->mz, g.nz*8));
     CU(cudaMemcpy(p->mx, hx.data(), g.nx*8, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(p->my, hy.data(), g.ny*8, cudaMemcpyHostToDevice));
@@ -1217,6 +1304,19 @@ int pl_plan_finalize(pl_plan* p) {
         CU(cudaMalloc(&p->ent, ent.size()*sizeof(unsigned long long)));
         CU(cudaMemcpy(p->ent, ent.data(), ent.size()*sizeof(unsigned long long), cudaMemcpyHostToDevice));
     }
+    p->nxlist = (int)xlist.size();
+    if (p->nxlist) {
+        std::vector<unsigned long long> xent(xlist.size());
+        for (size_t t = 0; t < xlist.size(); ++t) {
+            int i, j, k;
+            coords(xlist[t], i, j, k);
+            xent[t] = hx[i] & ENTRY_BITS;
+        }
+        CU(cudaMalloc(&p->xlist, xlist.size()*sizeof(int)));
+        CU(cudaMemcpy(p->xlist, xlist.data(), xlist.size()*sizeof(int), cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&p->xent, xent.size()*sizeof(unsigned long long)));
+        CU(cudaMemcpy(p->xent, xent.data(), xent.size()*sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
     p->nprog = (int)prog[0].size();
     for (int par = 0; par < 2; ++par) {
         CU(cudaMalloc(&p->prog[par], std::max<size_t>(1, prog[par].size())*sizeof(ClosureArgs)));
@@ -1228,6 +1328,8 @@ int pl_plan_finalize(pl_plan* p) {
 int pl_plan_rebind(pl_plan* p, int parity, const pl_collide_args* collide, const pl_bc_aux* aux, int naux) {
     if (!p || !p->finalized) return fail(PL_ERR_ARG, "pl_plan_rebind: plan not finalized");
     if (parity != 0 && parity != 1) return fail(PL_ERR_ARG, "pl_plan_rebind: parity 0 / 1");
+    drop_graphs(p);               // captured steps hold the old addresses
+    p->graph_cooldown = 8;
     if (collide) {
         if (collide->model != p->args[parity].model) return fail(PL_ERR_ARG, "pl_plan_rebind: the collide model of a plan cannot change");
         p->args[parity] = *collide;
