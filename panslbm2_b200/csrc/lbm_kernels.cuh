@@ -325,14 +325,14 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
 
 // The boundary pass of a fused step, one thread per listed site: Stream (pull), the closure program, and then either the
 // collide of the next step (t < ndirect: sites on closure planes, sites of the last incomplete AVX pack) or, for the
-// SmoothCorner tubes (t >= ndirect), a plain store of the streamed+closed populations; the tubes are finished by
-// k_smooth + k_collide on the destination buffer.  Runs beside k_fused on its own stream.
+// SmoothCorner tubes (t >= ndirect), a store of the streamed+closed populations into the tube buffer, which k_tubes finishes
+// right behind this kernel.  Both run beside k_fused on their own stream.
 template <int D, int M>
 __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
                                                          const double* __restrict__ gs, double* __restrict__ gd, CollideParams P, ShellMask S,
                                                          const ClosureArgs* __restrict__ prog, const int* __restrict__ list,
                                                          const unsigned long long* __restrict__ ent, int nlist, int ndirect, int inverse,
-                                                         HaloView HF, HaloView HG) {
+                                                         double* __restrict__ tube_f, double* __restrict__ tube_g, HaloView HF, HaloView HG) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     constexpr int NC = LT<D>::nc;
@@ -362,7 +362,48 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* _
     if (t < ndirect) {
         if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
         else collide_site<D, FL, true>(f, g, P, (size_t)idx);
+        store_site<D>(f, fd, G.pitch, idx);
+        if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+    } else {
+        // SmoothCorner tube: the streamed + closed populations go to the compact tube buffer [c][ntube]; k_tubes finishes them
+        const size_t nt = (size_t)(nlist - ndirect), tt = (size_t)(t - ndirect);
+        sfor<0, NC>([&](auto C) { constexpr int c = decltype(C)::value; tube_f[c*nt + tt] = f[c]; if constexpr (HASG) tube_g[c*nt + tt] = g[c]; });
     }
+}
+
+// SmoothCorner + collide of the tube sites, one thread per site, reading the tube buffer k_shell filled and writing the
+// destination populations.  kind 0: the site's own populations; kind 1: an edge-line site (or a 2-D corner) = the mean of its
+// two inward neighbours (d3q15.h:1242-1290); kind 2: a 3-D corner = the mean of its three neighbouring edge sites
+// (d3q15.h:1291-1303), each of which is the mean of two face sites — recomputed here from the face sites with the same
+// operations, so no pass has to wait for another.  a[] holds tube indices.
+struct TubeSite { int idx; int kind; int a[6]; };
+template <int D>
+PL_D void tube_load(double (&p)[LT<D>::nc], const double* __restrict__ scr, size_t nt, size_t tt, const TubeSite& T, bool smooth) {
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        const double* s = scr + (size_t)c*nt;
+        if (!smooth || T.kind == 0) p[c] = s[tt];
+        else if (T.kind == 1) p[c] = 0.5*(s[T.a[0]] + s[T.a[1]]);
+        else {
+            const double e0 = 0.5*(s[T.a[0]] + s[T.a[1]]), e1 = 0.5*(s[T.a[2]] + s[T.a[3]]), e2 = 0.5*(s[T.a[4]] + s[T.a[5]]);
+            p[c] = (e0 + e1 + e2)/3.0;
+        }
+    });
+}
+template <int D, int M>
+__global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict__ tube_f, const double* __restrict__ tube_g, double* __restrict__ fd,
+                                               double* __restrict__ gd, CollideParams P, const TubeSite* __restrict__ info, int nt, int smooth_f, int smooth_g) {
+    constexpr unsigned FL = ModelFlags<M>::v;
+    constexpr bool HASG = (FL & F_G) != 0;
+    int tt = blockIdx.x*blockDim.x + threadIdx.x;
+    if (tt >= nt) return;
+    const TubeSite T = info[tt];
+    double f[LT<D>::nc], g[LT<D>::nc];
+    tube_load<D>(f, tube_f, (size_t)nt, (size_t)tt, T, smooth_f != 0);
+    if constexpr (HASG) tube_load<D>(g, tube_g, (size_t)nt, (size_t)tt, T, smooth_g != 0);
+    const long long idx = T.idx;
+    if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
+    else collide_site<D, FL, true>(f, g, P, (size_t)idx);
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
 }

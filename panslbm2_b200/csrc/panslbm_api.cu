@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace plb;
@@ -933,6 +934,8 @@ struct pl_plan {
     unsigned long long *mx = nullptr, *my = nullptr, *mz = nullptr;
     int* list = nullptr;
     unsigned long long* ent = nullptr;     // closure entries of each listed site (the plane words of its coordinates, OR-ed)
+    double *tube_f = nullptr, *tube_g = nullptr;   // [c][ntube] streamed+closed populations of the SmoothCorner tube sites
+    TubeSite* tube_info = nullptr;
     int* xlist = nullptr;                  // sites of the x boundary planes whose closures run ahead of the pass (k_xclose)
     unsigned long long* xent = nullptr;
     int nxlist = 0;
@@ -994,7 +997,12 @@ template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const Collid
     if ((r = halo_view(p->f, HF))) return r;
     if (g) { if ((r = halo_view(g, HG))) return r; } else memset(&HG, 0, sizeof(HG));
     LAUNCH_ON(st, (k_shell<D, M>), blocks_for(p->nlist, SHELL_THREADS), SHELL_THREADS, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
-           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->ent, p->nlist, p->ndirect, p->inverse, HF, HG);
+           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->ent, p->nlist, p->ndirect, p->inverse, p->tube_f, p->tube_g, HF, HG);
+    // SmoothCorner + collide of the tube sites, right behind the boundary pass on the same stream
+    const int ntube = p->nlist - p->ndirect;
+    if (ntube > 0)
+        LAUNCH_ON(st, (k_tubes<D, M>), blocks_for(ntube, 128), 128, p->f->g, p->tube_f, p->tube_g, p->f->other(), g ? g->other() : nullptr, P, p->tube_info, ntube,
+                  p->smooth_f, g ? p->smooth_g : 0);
     return PL_OK;
 }
 int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
@@ -1104,13 +1112,6 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity) {
         CU(cudaStreamWaitEvent(g_stream, p->ev_join, 0));
     }
     p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
-    // SmoothCorner and the collide of the sites it couples, in place on the destination
-    if (p->smooth_f && p->g && p->smooth_g) { if ((r = do_smooth(p->f, p->g))) return r; }
-    else {
-        if (p->smooth_f && (r = do_smooth(p->f))) return r;
-        if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
-    }
-    if ((r = dispatch_collide(model, p->f, g, P, p->list + p->ndirect, p->nlist - p->ndirect))) return r;
     p->f->streamed = 0; if (p->g) p->g->streamed = 0;
     // every block-face site is final: pack and post the next exchange now, it overlaps the next interior kernel
     halo_touch(p->f); if (p->g) halo_touch(p->g);
@@ -1142,6 +1143,7 @@ int pl_plan_destroy(pl_plan* p) {
     if (!p) return PL_OK;
     cudaStreamSynchronize(g_stream);
     cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->xlist); cudaFree(p->xent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    cudaFree(p->tube_f); cudaFree(p->tube_g); cudaFree(p->tube_info);
     if (p->stage) cudaFreeHost(p->stage);
     for (auto& e : p->stage_ev) if (e) cudaEventDestroy(e);
     drop_graphs(p);
@@ -1286,6 +1288,8 @@ int pl_plan_finalize(pl_plan* p) {
     p->ndirect = (int)list.size();
     list.insert(list.end(), tubes.begin(), tubes.end());
     cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->xlist); cudaFree(p->xent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
+    cudaFree(p->tube_f); cudaFree(p->tube_g); cudaFree(p->tube_info);
+    p->tube_f = p->tube_g = nullptr; p->tube_info = nullptr;
     p->mx = p->my = p->mz = nullptr; p->list = nullptr; p->ent = nullptr; p->xlist = nullptr; p->xent = nullptr; p->nxlist = 0; p->prog[0] = p->prog[1] = nullptr;
     CU(cudaMalloc(&p->mx, g.nx*8)); CU(cudaMalloc(&p->my, g.ny*8)); CU(cudaMalloc(&p->mz, g.nz*8));
     CU(cudaMemcpy(p->mx, hx.data(), g.nx*8, cudaMemcpyHostToDevice));
@@ -1303,6 +1307,55 @@ int pl_plan_finalize(pl_plan* p) {
         }
         CU(cudaMalloc(&p->ent, ent.size()*sizeof(unsigned long long)));
         CU(cudaMemcpy(p->ent, ent.data(), ent.size()*sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    }
+    if (!tubes.empty()) {
+        // per tube site: what SmoothCorner makes of it (smooth_lists: the 12 edge lines and 8 corners of the global domain, 4 corners
+        // in 2-D), with the neighbours as indices into the tube buffer
+        const int ntube = (int)tubes.size();
+        std::vector<TubeSite> info(ntube);
+        std::unordered_map<int, int> where;
+        for (int t = 0; t < ntube; ++t) { where[tubes[t]] = t; info[t].idx = tubes[t]; info[t].kind = 0; for (int& a : info[t].a) a = 0; }
+        SmoothList e, c;
+        smooth_lists(p->f, e, c);
+        std::unordered_map<long long, std::pair<long long, long long>> pair_of;      // edge-line site -> its two face neighbours
+        auto tube_of = [&](long long site) { auto it = where.find((int)site); return it == where.end() ? -1 : it->second; };
+        bool ok = true;
+        for (int m = 0; m < e.count; ++m)
+            for (int t = 0; t < e.it[m].len; ++t) {
+                const long long s0 = e.it[m].base + (long long)t*e.it[m].stride;
+                pair_of[s0] = {s0 + e.it[m].n0, s0 + e.it[m].n1};
+            }
+        for (auto& kv : pair_of) {
+            const int t = tube_of(kv.first), a = tube_of(kv.second.first), b = tube_of(kv.second.second);
+            if (t < 0 || a < 0 || b < 0) { ok = false; break; }
+            info[t].kind = 1; info[t].a[0] = a; info[t].a[1] = b;
+        }
+        for (int m = 0; m < c.count && ok; ++m) {
+            const SmoothItem& it = c.it[m];
+            const int t = tube_of(it.base);
+            if (t < 0) { ok = false; break; }
+            if (it.n2 == 0) {      // 2-D corner: the mean of two sites no SmoothCorner touches
+                const int a = tube_of(it.base + it.n0), b = tube_of(it.base + it.n1);
+                if (a < 0 || b < 0) { ok = false; break; }
+                info[t].kind = 1; info[t].a[0] = a; info[t].a[1] = b;
+            } else {
+                info[t].kind = 2;
+                const long long nb[3] = {it.base + it.n0, it.base + it.n1, it.base + it.n2};
+                for (int q = 0; q < 3 && ok; ++q) {
+                    auto pe = pair_of.find(nb[q]);
+                    if (pe == pair_of.end()) { ok = false; break; }      // the neighbour of a corner is an edge-line site
+                    const int a = tube_of(pe->second.first), b = tube_of(pe->second.second);
+                    if (a < 0 || b < 0) { ok = false; break; }
+                    info[t].a[2*q] = a; info[t].a[2*q + 1] = b;
+                }
+            }
+        }
+        if (!ok) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: SmoothCorner on a block this thin is not supported by the fused plan");
+        const size_t nb = (size_t)p->f->nc*ntube*sizeof(double);
+        CU(cudaMalloc(&p->tube_f, nb));
+        if (p->g) CU(cudaMalloc(&p->tube_g, nb));
+        CU(cudaMalloc(&p->tube_info, (size_t)ntube*sizeof(TubeSite)));
+        CU(cudaMemcpy(p->tube_info, info.data(), (size_t)ntube*sizeof(TubeSite), cudaMemcpyHostToDevice));
     }
     p->nxlist = (int)xlist.size();
     if (p->nxlist) {
