@@ -175,13 +175,24 @@ def read_profile(L, plan):
     return kms.value, kn.value, ksites.value
 
 
-def roofline(kernel, bytes_per_site, prof, peak, peak_src, step_ms_total):
+def ncu_traffic(key, grid_threads):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
+    (profiles/r01_ncu_traffic.json), if it was taken on a grid of this size; else None"""
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["kernels"][key]
+        return float(k["dram_bytes_per_launch"]) if int(k["grid_threads"]) == int(grid_threads) else None
+    except Exception:
+        return None
+
+
+def roofline(kernel, bytes_per_site, prof, peak, peak_src, step_ms_total, traffic=None):
     kms, kn, ksites = prof
     if not kn:
         return None
     avg_ms = kms/kn
     achieved = bytes_per_site*(ksites/kn)/(avg_ms*1e-3)/1e9
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": None, "kernel": kernel,
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,
+            "algorithmic_bytes_per_launch": bytes_per_site*(ksites/kn), "kernel": kernel,
             "avg_kernel_ms": avg_ms, "sites_per_launch": ksites/kn, "algorithmic_bytes_per_site": bytes_per_site, "peak_source": peak_src,
             "kernel_share_of_timed_region": kms/step_ms_total if step_ms_total else None}
 
@@ -347,8 +358,11 @@ def run_ours(args):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    rf = roofline("k_fused<3,7> (AD::MacroBrinkmanCollideNaturalConvection + Stream x2, fused)", B_FWD, fprof, peak, peak_src, fwd_ms)
-    ra = roofline("k_fused<3,11> (AAD::MacroBrinkmanCollideNaturalConvection + iStream x2, fused)", B_ADJ, aprof, peak, peak_src, adj_ms)
+    npk = N//4*4        # the grid of k_fused covers the packed sites of the block
+    rf = roofline("k_fused<3,7> (AD::MacroBrinkmanCollideNaturalConvection + Stream x2, fused)", B_FWD, fprof, peak, peak_src, fwd_ms,
+                  ncu_traffic("k_fused<3,7>", (npk + 255)//256*256))
+    ra = roofline("k_fused<3,11> (AAD::MacroBrinkmanCollideNaturalConvection + iStream x2, fused)", B_ADJ, aprof, peak, peak_src, adj_ms,
+                  ncu_traffic("k_fused<3,11>", (npk + 255)//256*256))
     line = {
         "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms/K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -404,7 +418,7 @@ def ns_cavity(pl, api, L, torch, S, K, W, barrier, maxms, world, rank=0, m=(1, 1
     ms = maxms(e0.elapsed_time(e1))
     prof = read_profile(L, plan)
     peak, src = peaks()
-    r = roofline("k_fused<3,1> (NS::MacroCollide + Stream, fused)", B_NS_SAVE, prof, peak, src, ms)
+    r = roofline("k_fused<3,1> (NS::MacroCollide + Stream, fused)", B_NS_SAVE, prof, peak, src, ms, ncu_traffic("k_fused<3,1>", (N//4*4 + 255)//256*256))
     return {"workload": f"test/cavityflow3D.cpp scaled to {S}^3 per GPU (BASELINE configs[2])", "mlups": world*N*K/(ms*1e-3)/1e6, "ms_per_step": ms/K, "steps": K, "roofline": r}
 
 
