@@ -34,7 +34,9 @@ B_NS_SAVE = 272.0     # D3Q15 NS: 15r+15w + rho,u (4w)
 B_FWD = 680.0         # D3Q15 NS+AD forward: 30r+30w + alpha,kappa (2r) + rho,u,T,q (8w) + g snapshot (15w)
 B_ADJ = 744.0         # D3Q15 NS+AD adjoint: 30r+30w + rho,u,T,alpha,kappa (7r) + ip,iu,im,iT,iq (11w) + ig snapshot (15w)
 METRIC = "MLUPS"
-PE_GRIDS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}     # mx, my, mz per GPU count
+# mx, my, mz per GPU count: pencils that keep x whole (y/z block faces are contiguous planes and the x walls stay with k_xclose);
+# --pe 2,2,2 runs the reference's own 8-rank grid (production/heatsink3D.cpp:35), measured 5 % slower
+PE_GRIDS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}
 
 
 def peaks():
@@ -272,10 +274,10 @@ def run_ours(args):
     L = _lib.lib()
     S, K, W = args.size, args.steps, args.warmup
     # weak scaling: one S^3 block per GPU, the reference's block decomposition (d3q15.h:29-35) of a (S*mx, S*my, S*mz) domain;
-    # z is split first (its faces are contiguous planes), x last
-    m = PE_GRIDS.get(world)
-    if m is None:
-        raise SystemExit(f"bench.py: no PE grid defined for {world} GPUs (1, 2, 4, 8)")
+    # z is split first (its faces are contiguous planes), x not at all up to 8 GPUs
+    m = tuple(int(v) for v in args.pe.split(",")) if args.pe else PE_GRIDS.get(world)
+    if m is None or m[0]*m[1]*m[2] != world:
+        raise SystemExit(f"bench.py: no PE grid defined for {world} GPUs (1, 2, 4, 8; or --pe mx,my,mz)")
     dims = [int(v) for v in args.dims.split(",")] if args.dims else [S, S, S]
     gsize = (dims[0]*m[0], dims[1]*m[1], dims[2]*m[2])
     sw = HeatsinkSweep(pl, api, gsize, rank, m)
@@ -434,6 +436,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=352, help="edge of the cubic block per GPU for the NS+AD forward+adjoint sweep")
     ap.add_argument("--dims", default="", help="lx,ly,lz of the block per GPU instead of --size^3 (e.g. 81,161,81 = production/heatsink3D.cpp:42)")
+    ap.add_argument("--pe", default="", help="PE grid mx,my,mz instead of the default for the GPU count (e.g. 2,2,2 = production/heatsink3D.cpp:35)")
     ap.add_argument("--ns-size", type=int, default=512, help="edge of the secondary NS cavity sweep (0 = skip)")
     ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--cpu-steps", type=int, default=8)
