@@ -328,9 +328,9 @@ def run_ours(args):
     f0.record()
     # alpha, kappa gate the first collide; dads, dkds are only read by the sensitivity: their copies run beside the loops
     sw.alpha.upload_async(hdesign[0].data_ptr()); sw.kappa.upload_async(hdesign[1].data_ptr())
+    sw.init_forward()       # InitialCondition needs neither: it runs beside the first two copies
     api.copy_fence()
     sw.dads.upload_async(hdesign[2].data_ptr()); sw.dkds.upload_async(hdesign[3].data_ptr())
-    sw.init_forward()
     sw.fplan.advance(K, end_streamed=True)
     sw.A["tem"].download_async(hout[1].data_ptr())      # final after the forward loop; the adjoint loop only reads it
     sw.init_adjoint()
