@@ -715,6 +715,7 @@ class StepPlan:
         if not self._h:
             raise _lib.PanslbmError(L.pl_last_error().decode())
         self._keep = []
+        self._aux_groups = []       # pl_plan_add_bc calls made with fields, per add_bc / add_closure call (see rebind)
 
     def set_collide(self, even: CollideArgs, odd: CollideArgs | None = None):
         self._keep += [even, odd]
@@ -727,6 +728,8 @@ class StepPlan:
 
     def add_bc(self, lattice, bc_handle, aux_even: BcAux | None = None, aux_odd: BcAux | None = None):
         self._keep += [aux_even, aux_odd]
+        if aux_even is not None:
+            self._aux_groups.append(1)
         on_g = 1 if (self.pg is not None and lattice is self.pg) else 0
         check(_lib.lib().pl_plan_add_bc(self._h, on_g, bc_handle, C.byref(aux_even) if aux_even is not None else None,
                                         C.byref(aux_odd) if aux_odd is not None else None))
@@ -738,8 +741,13 @@ class StepPlan:
         return self
 
     def add_closure(self, lattice, bctype_id, maskfn, valfns=(), aux_even=None, aux_odd=None):
+        mark = len(self._aux_groups)
         for axis, coord, d in lattice._faces():
             self.add_bc(lattice, lattice.make_bc(bctype_id, axis, coord, d, maskfn, valfns), aux_even, aux_odd)
+        if aux_even is not None:      # one rebind entry serves all the faces of this closure
+            n = sum(self._aux_groups[mark:])
+            del self._aux_groups[mark:]
+            self._aux_groups.append(n)
         return self
 
     def set_smooth_corner(self, on_f=True, on_g=False):
@@ -753,14 +761,27 @@ class StepPlan:
     def advance(self, ncollides, end_streamed=True):
         check(_lib.lib().pl_plan_advance(self._h, int(ncollides), int(bool(end_streamed))))
 
-    @property
     def rebind(self, parity, collide: CollideArgs | None = None, aux=()):
         """re-bind the array arguments of argument set `parity` (transient loops: one set of arrays per time step,
-        production/heatsink3D_transient.cpp:156-160); aux = one BcAux per closure that was added with fields, in order"""
-        arr = (BcAux*len(aux))(*aux) if aux else None
-        check(_lib.lib().pl_plan_rebind(self._h, int(parity), C.byref(collide) if collide is not None else None, arr, len(aux)))
+        production/heatsink3D_transient.cpp:156-160); aux = one BcAux per add_bc / add_closure call that was made with fields, in
+        call order (an add_closure entry serves all its faces)"""
+        flat = []
+        if aux:
+            if len(aux) != len(self._aux_groups):
+                raise ValueError(f"rebind: {len(self._aux_groups)} closures were added with fields, {len(aux)} given")
+            for a, n in zip(aux, self._aux_groups):
+                flat += [a]*n
+        arr = (BcAux*len(flat))(*flat) if flat else None
+        check(_lib.lib().pl_plan_rebind(self._h, int(parity), C.byref(collide) if collide is not None else None, arr, len(flat)))
         return self
 
+    def next_set(self):
+        """the argument set the NEXT collide of advance() uses (and the closures that follow that collide): the current set while
+        the lattices are in the streamed phase (after InitialCondition / a closing Stream), the other one after a collide"""
+        L = _lib.lib()
+        return L.pl_plan_parity(self._h) if L.pl_lattice_streamed(self.pf._h) else L.pl_plan_parity(self._h) ^ 1
+
+    @property
     def parity(self):
         return _lib.lib().pl_plan_parity(self._h)
 
