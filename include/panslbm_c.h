@@ -217,6 +217,12 @@ int pl_plan_set_collide(pl_plan*, const pl_collide_args* even, const pl_collide_
 int pl_plan_set_stream(pl_plan*, int inverse);
 int pl_plan_add_bc(pl_plan*, int on_g, const pl_bc*, const pl_bc_aux* even, const pl_bc_aux* odd);
 int pl_plan_set_smooth_corner(pl_plan*, int on_f, int on_g);
+/* SmoothCornerAt(i, j[, k], dx, dy[, dz]) of lattice f / g inside the loop body (d2q9.h:127-132, d3q15.h:212-220; the interior
+ * corners of production/ncpump.cpp:159-162, 173-176).  The body is recorded in CALL ORDER (closures, SmoothCorner, SmoothCornerAt,
+ * each numbered as it is added; pl_plan_set_smooth_corner counts where a flag is first raised); pl_plan_finalize accepts it when it
+ * is equivalent to "all closures, then SmoothCorner, then the SmoothCornerAt points" — i.e. no closure called after a smoothing
+ * touches a site that smoothing wrote or read — and answers PL_ERR_UNSUPPORTED otherwise. */
+int pl_plan_add_smooth_corner_at(pl_plan*, int on_g, int i, int j, int k, int dx, int dy, int dz);
 int pl_plan_finalize(pl_plan*);
 /* Execute `ncollides` collides starting from the lattices' current phase (streamed or just collided);
  * every stream+closures+SmoothCorner between two collides is fused with the collide that follows.

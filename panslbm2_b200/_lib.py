@@ -80,6 +80,7 @@ _PROTOS = {
     "pl_plan_set_stream": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_plan_add_bc": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(BcAux), C.POINTER(BcAux)]),
     "pl_plan_set_smooth_corner": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "pl_plan_add_smooth_corner_at": (C.c_int, [C.c_void_p] + [C.c_int]*7),
     "pl_plan_finalize": (C.c_int, [C.c_void_p]),
     "pl_plan_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "pl_plan_rebind": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(CollideArgs), C.POINTER(BcAux), C.c_int]),

@@ -754,6 +754,12 @@ class StepPlan:
         check(_lib.lib().pl_plan_set_smooth_corner(self._h, int(bool(on_f)), int(bool(on_g))))
         return self
 
+    def add_smooth_corner_at(self, lattice, i, j, k=0, dx=0, dy=0, dz=0):
+        """SmoothCornerAt inside the loop body (production/ncpump.cpp:159-162)"""
+        on_g = 1 if (self.pg is not None and lattice is self.pg) else 0
+        check(_lib.lib().pl_plan_add_smooth_corner_at(self._h, on_g, int(i), int(j), int(k), int(dx), int(dy), int(dz)))
+        return self
+
     def finalize(self):
         check(_lib.lib().pl_plan_finalize(self._h))
         return self

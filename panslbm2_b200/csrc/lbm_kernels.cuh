@@ -371,36 +371,38 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* _
     }
 }
 
-// SmoothCorner + collide of the tube sites, one thread per site, reading the tube buffer k_shell filled and writing the
-// destination populations.  kind 0: the site's own populations; kind 1: an edge-line site (or a 2-D corner) = the mean of its
-// two inward neighbours (d3q15.h:1242-1290); kind 2: a 3-D corner = the mean of its three neighbouring edge sites
-// (d3q15.h:1291-1303), each of which is the mean of two face sites — recomputed here from the face sites with the same
-// operations, so no pass has to wait for another.  a[] holds tube indices.
-struct TubeSite { int idx; int kind; int a[6]; };
+// SmoothCorner / SmoothCornerAt + collide of the tube sites, one thread per site, reading the tube buffer k_shell filled and
+// writing the destination populations.  kind 0: the site's own populations; kind 1: an edge-line site, a 2-D corner or a
+// SmoothCornerAt point/line = the mean of its two inward neighbours (d3q15.h:1242-1290, d2q9.h:578-587); kind 2: a 3-D corner of
+// SmoothCorner = the mean of its three neighbouring edge sites (d3q15.h:1291-1303), each of which is the mean of two face sites
+// — recomputed here from the face sites with the same operations, so no pass has to wait for another; kind 3: a 3-D
+// SmoothCornerAt corner = the mean of three plain sites.  a[] holds tube indices.
+struct TubeSite { int idx; int kind[2]; int a[2][6]; };     // kind / neighbours per lattice (0 = flow, 1 = thermal)
 template <int D>
-PL_D void tube_load(double (&p)[LT<D>::nc], const double* __restrict__ scr, size_t nt, size_t tt, const TubeSite& T, bool smooth) {
+PL_D void tube_load(double (&p)[LT<D>::nc], const double* __restrict__ scr, size_t nt, size_t tt, int kind, const int (&a)[6]) {
     sfor<0, LT<D>::nc>([&](auto C) {
         constexpr int c = decltype(C)::value;
         const double* s = scr + (size_t)c*nt;
-        if (!smooth || T.kind == 0) p[c] = s[tt];
-        else if (T.kind == 1) p[c] = 0.5*(s[T.a[0]] + s[T.a[1]]);
+        if (kind == 0) p[c] = s[tt];
+        else if (kind == 1) p[c] = 0.5*(s[a[0]] + s[a[1]]);
+        else if (kind == 3) p[c] = (s[a[0]] + s[a[1]] + s[a[2]])/3.0;
         else {
-            const double e0 = 0.5*(s[T.a[0]] + s[T.a[1]]), e1 = 0.5*(s[T.a[2]] + s[T.a[3]]), e2 = 0.5*(s[T.a[4]] + s[T.a[5]]);
+            const double e0 = 0.5*(s[a[0]] + s[a[1]]), e1 = 0.5*(s[a[2]] + s[a[3]]), e2 = 0.5*(s[a[4]] + s[a[5]]);
             p[c] = (e0 + e1 + e2)/3.0;
         }
     });
 }
 template <int D, int M>
 __global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict__ tube_f, const double* __restrict__ tube_g, double* __restrict__ fd,
-                                               double* __restrict__ gd, CollideParams P, const TubeSite* __restrict__ info, int nt, int smooth_f, int smooth_g) {
+                                               double* __restrict__ gd, CollideParams P, const TubeSite* __restrict__ info, int nt) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     int tt = blockIdx.x*blockDim.x + threadIdx.x;
     if (tt >= nt) return;
     const TubeSite T = info[tt];
     double f[LT<D>::nc], g[LT<D>::nc];
-    tube_load<D>(f, tube_f, (size_t)nt, (size_t)tt, T, smooth_f != 0);
-    if constexpr (HASG) tube_load<D>(g, tube_g, (size_t)nt, (size_t)tt, T, smooth_g != 0);
+    tube_load<D>(f, tube_f, (size_t)nt, (size_t)tt, T.kind[0], T.a[0]);
+    if constexpr (HASG) tube_load<D>(g, tube_g, (size_t)nt, (size_t)tt, T.kind[1], T.a[1]);
     const long long idx = T.idx;
     if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
     else collide_site<D, FL, true>(f, g, P, (size_t)idx);

@@ -116,6 +116,7 @@ struct pl_bc {
     Plane pl;
     uint8_t* mask = nullptr;
     double *v0 = nullptr, *v1 = nullptr, *v2 = nullptr;
+    std::vector<uint8_t> hmask;     // host copy of the mask (plan validation)
 };
 
 
@@ -853,6 +854,7 @@ pl_bc* pl_bc_create(pl_lattice* l, int type, int axis, int coord, int dir, const
             auto up8 = [&](const uint8_t* h) -> uint8_t* { uint8_t* d = nullptr; if (cudaMalloc(&d, np) != cudaSuccess) return nullptr; cudaMemcpy(d, h, np, cudaMemcpyHostToDevice); return d; };
             auto upd = [&](const double* h) -> double* { if (!h) return nullptr; double* d = nullptr; if (cudaMalloc(&d, np*sizeof(double)) != cudaSuccess) return nullptr; cudaMemcpy(d, h, np*sizeof(double), cudaMemcpyHostToDevice); return d; };
             bc->mask = up8(mask); bc->v0 = upd(v0); bc->v1 = upd(v1); bc->v2 = upd(v2);
+            bc->hmask.assign(mask, mask + np);
             if (!bc->mask || (v0 && !bc->v0) || (v1 && !bc->v1) || (v2 && !bc->v2)) { pl_bc_destroy(bc); fail(PL_ERR_CUDA, "pl_bc_create: device allocation failed"); return nullptr; }
         }
     }
@@ -919,7 +921,8 @@ int pl_initial_condition(pl_lattice* l, int family, const double* const* a, int 
 
 // -------------------------------------------------------------------------------------------------
 // plans
-struct PlanBC { int on_g; const pl_bc* bc; pl_bc_aux aux[2]; bool has_aux; };
+struct PlanBC { int on_g; const pl_bc* bc; pl_bc_aux aux[2]; bool has_aux; int pos; };
+struct PlanSmoothAt { int on_g, i, j, k, dx, dy, dz, pos; };      // SmoothCornerAt(i, j, k, dx, dy, dz) in global coordinates
 struct pl_plan {
     pl_lattice *f, *g;
     pl_collide_args args[2];
@@ -927,6 +930,10 @@ struct pl_plan {
     int inverse = 0;
     std::vector<PlanBC> bcs;
     int smooth_f = 0, smooth_g = 0;
+    // call order of the loop body: every closure, SmoothCorner and SmoothCornerAt gets the next sequence number
+    int seq = 0;
+    int smooth_pos[2] = {-1, -1};
+    std::vector<PlanSmoothAt> ats;
     bool finalized = false;
     int parity = 0;
     // per-coordinate plane words (see ShellMask), the site list of k_shell (closure-plane and AVX-tail sites first,
@@ -974,6 +981,8 @@ int plan_stream_bc_smooth_full(pl_plan* p, int parity) {     // standalone S: ev
     }
     if (p->smooth_f && (r = do_smooth(p->f))) return r;
     if (p->g && p->smooth_g && (r = do_smooth(p->g))) return r;
+    // pl_plan_finalize accepted the body only if this order (closures, SmoothCorner, SmoothCornerAt) equals the call order
+    for (auto& a : p->ats) if ((r = pl_smooth_corner_at(a.on_g ? p->g : p->f, a.i, a.j, a.k, a.dx, a.dy, a.dz))) return r;
     p->f->streamed = 1; if (p->g) p->g->streamed = 1;
     return PL_OK;
 }
@@ -1001,8 +1010,7 @@ template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const Collid
     // SmoothCorner + collide of the tube sites, right behind the boundary pass on the same stream
     const int ntube = p->nlist - p->ndirect;
     if (ntube > 0)
-        LAUNCH_ON(st, (k_tubes<D, M>), blocks_for(ntube, 128), 128, p->f->g, p->tube_f, p->tube_g, p->f->other(), g ? g->other() : nullptr, P, p->tube_info, ntube,
-                  p->smooth_f, g ? p->smooth_g : 0);
+        LAUNCH_ON(st, (k_tubes<D, M>), blocks_for(ntube, 128), 128, p->f->g, p->tube_f, p->tube_g, p->f->other(), g ? g->other() : nullptr, P, p->tube_info, ntube);
     return PL_OK;
 }
 int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
@@ -1171,7 +1179,7 @@ int pl_plan_add_bc(pl_plan* p, int on_g, const pl_bc* bc, const pl_bc_aux* even,
     if (bc->type == PL_BC_AAD_ISET_RHO && (on_g || !p->g)) return fail(PL_ERR_ARG, "pl_plan_add_bc: AAD iSetRho acts on the flow lattice of a two-lattice plan");
     if (!same_shape(bc->lat, p->f)) return fail(PL_ERR_ARG, "pl_plan_add_bc: closure was created for a lattice of another shape");
     PlanBC b{};
-    b.on_g = on_g ? 1 : 0; b.bc = bc; b.has_aux = even != nullptr;
+    b.on_g = on_g ? 1 : 0; b.bc = bc; b.has_aux = even != nullptr; b.pos = p->seq++;
     if (even) { b.aux[0] = *even; b.aux[1] = odd ? *odd : *even; }
     p->bcs.push_back(b);
     return PL_OK;
@@ -1179,9 +1187,54 @@ int pl_plan_add_bc(pl_plan* p, int on_g, const pl_bc* bc, const pl_bc_aux* even,
 int pl_plan_set_smooth_corner(pl_plan* p, int on_f, int on_g) {
     if (!p) return fail(PL_ERR_ARG, "null plan");
     if (p->finalized) return fail(PL_ERR_ARG, "pl_plan_set_smooth_corner: plan already finalized");
+    if (on_f && !p->smooth_f) p->smooth_pos[0] = p->seq++;       // position in the loop body = where the flag is first raised
+    if (on_g && !p->smooth_g) p->smooth_pos[1] = p->seq++;
     p->smooth_f = on_f; p->smooth_g = on_g;
     return PL_OK;
 }
+int pl_plan_add_smooth_corner_at(pl_plan* p, int on_g, int i, int j, int k, int dx, int dy, int dz) {
+    if (!p) return fail(PL_ERR_ARG, "null plan");
+    if (p->finalized) return fail(PL_ERR_ARG, "pl_plan_add_smooth_corner_at: plan already finalized");
+    if (on_g && !p->g) return fail(PL_ERR_ARG, "pl_plan_add_smooth_corner_at: plan has no thermal lattice");
+    p->ats.push_back(PlanSmoothAt{on_g ? 1 : 0, i, j, k, dx, dy, dz, p->seq++});
+    return PL_OK;
+}
+}  // extern "C"
+
+namespace {
+// geometry of one SmoothCornerAt on this rank's block (the arithmetic of pl_smooth_corner_at): the sites it writes (a point, or in
+// 3-D with one zero direction a whole line), the index deltas to the 2 or 3 inward neighbours, and per axis the two local
+// coordinates involved.  false: not on this block (d3q15.h:1244-1245) or malformed.
+struct AtGeom { std::vector<long long> sites; long long nb[3]; int nnb; int co[3][2]; bool used[3]; };
+bool smooth_at_geometry(const pl_lattice* l, const PlanSmoothAt& a, AtGeom& G) {
+    const Geom& g = l->g;
+    const int D = l->kind;
+    int d[3] = {a.dx, a.dy, D == 3 ? a.dz : 0}, v[3] = {a.i - g.offx, a.j - g.offy, D == 3 ? a.k - g.offz : 0}, n[3] = {g.nx, g.ny, g.nz};
+    long long st[3] = {1, g.nx, (long long)g.nx*g.ny};
+    int nzero = 0, line = -1;
+    for (int x = 0; x < 3; ++x) {
+        if (d[x] != 0 && d[x] != 1 && d[x] != -1) return false;
+        if (d[x] == 0) { ++nzero; if (x < D) line = x; }
+    }
+    if ((D == 3 && nzero > 1) || (D == 2 && nzero != 1)) return false;
+    for (int x = 0; x < D; ++x) if (d[x] != 0 && (v[x] < 0 || v[x] >= n[x])) return false;
+    long long base = 0;
+    G.nnb = 0;
+    for (int x = 0; x < 3; ++x) G.used[x] = false;
+    for (int x = 0; x < D; ++x) if (d[x] != 0) {
+        int w = v[x] - d[x];
+        if (w == -1) w = n[x] - 1; else if (w == n[x]) w = 0;
+        base += v[x]*st[x];
+        G.nb[G.nnb++] = (long long)(w - v[x])*st[x];
+        G.used[x] = true; G.co[x][0] = v[x]; G.co[x][1] = w;
+    }
+    G.sites.clear();
+    if (D == 3 && line >= 0) for (int t = 0; t < n[line]; ++t) G.sites.push_back(base + (long long)t*st[line]);
+    else G.sites.push_back(base);
+    return true;
+}
+}  // namespace
+extern "C" {
 int pl_plan_finalize(pl_plan* p) {
     if (!p || !p->have_collide) return fail(PL_ERR_ARG, "pl_plan_finalize: no collide set");
     const Geom& g = p->f->g;
@@ -1243,6 +1296,13 @@ int pl_plan_finalize(pl_plan* p) {
             int lo = 0 - off[a], hi = ext[a] - 1 - off[a];
             for (int v : {lo, lo + 1, hi - 1, hi}) if (0 <= v && v < n[a]) (*h[a])[v] |= TUBE_BIT;
         }
+    }
+    // SmoothCornerAt: the coordinates of each point (line) and of its inward neighbours are flagged the same way, which puts
+    // the point and its neighbours (and a few more sites, harmlessly) into the tubes
+    for (auto& a : p->ats) {
+        AtGeom ag;
+        if (!smooth_at_geometry(a.on_g ? p->g : p->f, a, ag)) continue;
+        for (int x = 0; x < p->f->kind; ++x) if (ag.used[x]) { (*h[x])[ag.co[x][0]] |= TUBE_BIT; (*h[x])[ag.co[x][1]] |= TUBE_BIT; }
     }
     auto coords = [&](long long idx, int& i, int& j, int& k) {
         k = (int)(idx/((long long)g.nx*g.ny)); int r = (int)(idx - (long long)k*g.nx*g.ny); j = r/g.nx; i = r - j*g.nx;
@@ -1314,43 +1374,104 @@ int pl_plan_finalize(pl_plan* p) {
         const int ntube = (int)tubes.size();
         std::vector<TubeSite> info(ntube);
         std::unordered_map<int, int> where;
-        for (int t = 0; t < ntube; ++t) { where[tubes[t]] = t; info[t].idx = tubes[t]; info[t].kind = 0; for (int& a : info[t].a) a = 0; }
-        SmoothList e, c;
-        smooth_lists(p->f, e, c);
-        std::unordered_map<long long, std::pair<long long, long long>> pair_of;      // edge-line site -> its two face neighbours
+        for (int t = 0; t < ntube; ++t) { where[tubes[t]] = t; memset(&info[t], 0, sizeof(TubeSite)); info[t].idx = tubes[t]; }
         auto tube_of = [&](long long site) { auto it = where.find((int)site); return it == where.end() ? -1 : it->second; };
-        bool ok = true;
-        for (int m = 0; m < e.count; ++m)
-            for (int t = 0; t < e.it[m].len; ++t) {
-                const long long s0 = e.it[m].base + (long long)t*e.it[m].stride;
-                pair_of[s0] = {s0 + e.it[m].n0, s0 + e.it[m].n1};
-            }
-        for (auto& kv : pair_of) {
-            const int t = tube_of(kv.first), a = tube_of(kv.second.first), b = tube_of(kv.second.second);
-            if (t < 0 || a < 0 || b < 0) { ok = false; break; }
-            info[t].kind = 1; info[t].a[0] = a; info[t].a[1] = b;
-        }
-        for (int m = 0; m < c.count && ok; ++m) {
-            const SmoothItem& it = c.it[m];
-            const int t = tube_of(it.base);
-            if (t < 0) { ok = false; break; }
-            if (it.n2 == 0) {      // 2-D corner: the mean of two sites no SmoothCorner touches
-                const int a = tube_of(it.base + it.n0), b = tube_of(it.base + it.n1);
-                if (a < 0 || b < 0) { ok = false; break; }
-                info[t].kind = 1; info[t].a[0] = a; info[t].a[1] = b;
-            } else {
-                info[t].kind = 2;
-                const long long nb[3] = {it.base + it.n0, it.base + it.n1, it.base + it.n2};
-                for (int q = 0; q < 3 && ok; ++q) {
-                    auto pe = pair_of.find(nb[q]);
-                    if (pe == pair_of.end()) { ok = false; break; }      // the neighbour of a corner is an edge-line site
-                    const int a = tube_of(pe->second.first), b = tube_of(pe->second.second);
-                    if (a < 0 || b < 0) { ok = false; break; }
-                    info[t].a[2*q] = a; info[t].a[2*q + 1] = b;
+        const char* thin = "pl_plan_finalize: SmoothCorner on a block this thin is not supported by the fused plan";
+        const char* order = "pl_plan_finalize: this loop body cannot be reordered into closures, SmoothCorner, SmoothCornerAt";
+        std::vector<long long> smooth_sites[2];      // per lattice: every site SmoothCorner writes or reads
+        if (p->smooth_f || p->smooth_g) {
+            SmoothList e, c;
+            smooth_lists(p->f, e, c);
+            std::unordered_map<long long, std::pair<long long, long long>> pair_of;      // edge-line site -> its two face neighbours
+            for (int m = 0; m < e.count; ++m)
+                for (int t = 0; t < e.it[m].len; ++t) {
+                    const long long s0 = e.it[m].base + (long long)t*e.it[m].stride;
+                    pair_of[s0] = {s0 + e.it[m].n0, s0 + e.it[m].n1};
+                }
+            TubeSite proto;
+            for (int l = 0; l < 2; ++l) {
+                if (!(l == 0 ? p->smooth_f : (p->g && p->smooth_g))) continue;
+                for (auto& kv : pair_of) {
+                    const int t = tube_of(kv.first), a = tube_of(kv.second.first), b = tube_of(kv.second.second);
+                    if (t < 0 || a < 0 || b < 0) return fail(PL_ERR_UNSUPPORTED, thin);
+                    info[t].kind[l] = 1; info[t].a[l][0] = a; info[t].a[l][1] = b;
+                    smooth_sites[l].insert(smooth_sites[l].end(), {kv.first, kv.second.first, kv.second.second});
+                }
+                for (int m = 0; m < c.count; ++m) {
+                    const SmoothItem& it = c.it[m];
+                    const int t = tube_of(it.base);
+                    if (t < 0) return fail(PL_ERR_UNSUPPORTED, thin);
+                    smooth_sites[l].push_back(it.base);
+                    if (it.n2 == 0) {      // 2-D corner: the mean of two sites no SmoothCorner touches
+                        const int a = tube_of(it.base + it.n0), b = tube_of(it.base + it.n1);
+                        if (a < 0 || b < 0) return fail(PL_ERR_UNSUPPORTED, thin);
+                        info[t].kind[l] = 1; info[t].a[l][0] = a; info[t].a[l][1] = b;
+                        smooth_sites[l].insert(smooth_sites[l].end(), {it.base + it.n0, it.base + it.n1});
+                    } else {
+                        info[t].kind[l] = 2;
+                        const long long nb3[3] = {it.base + it.n0, it.base + it.n1, it.base + it.n2};
+                        for (int q = 0; q < 3; ++q) {
+                            auto pe = pair_of.find(nb3[q]);
+                            if (pe == pair_of.end()) return fail(PL_ERR_UNSUPPORTED, thin);      // the neighbour of a corner is an edge-line site
+                            const int a = tube_of(pe->second.first), b = tube_of(pe->second.second);
+                            if (a < 0 || b < 0) return fail(PL_ERR_UNSUPPORTED, thin);
+                            info[t].a[l][2*q] = a; info[t].a[l][2*q + 1] = b;
+                        }
+                    }
                 }
             }
+            (void)proto;
         }
-        if (!ok) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: SmoothCorner on a block this thin is not supported by the fused plan");
+        // SmoothCornerAt: the point (line) becomes the mean of its neighbours' streamed + closed populations
+        struct AtSites { int l, pos; std::vector<long long> touched; };
+        std::vector<AtSites> at_sites;
+        for (auto& a : p->ats) {
+            AtGeom ag;
+            const int l = a.on_g;
+            if (!smooth_at_geometry(l ? p->g : p->f, a, ag)) continue;
+            if (p->smooth_pos[l] >= 0 && a.pos < p->smooth_pos[l]) return fail(PL_ERR_UNSUPPORTED, order);
+            AtSites as{l, a.pos, {}};
+            for (long long site : ag.sites) {
+                const int t = tube_of(site);
+                if (t < 0 || info[t].kind[l] != 0) return fail(PL_ERR_UNSUPPORTED, order);      // not a tube site / smoothed twice
+                info[t].kind[l] = ag.nnb == 2 ? 1 : 3;
+                as.touched.push_back(site);
+                for (int q = 0; q < ag.nnb; ++q) {
+                    const int b = tube_of(site + ag.nb[q]);
+                    if (b < 0) return fail(PL_ERR_UNSUPPORTED, order);
+                    info[t].a[l][q] = b;
+                    as.touched.push_back(site + ag.nb[q]);
+                }
+            }
+            at_sites.push_back(as);
+        }
+        // every mean is taken over sites that are not smoothed themselves (k_tubes reads the un-smoothed tube buffer)
+        for (int t = 0; t < ntube; ++t)
+            for (int l = 0; l < 2; ++l) {
+                const int kd = info[t].kind[l];
+                if (kd != 1 && kd != 3) continue;
+                for (int q = 0; q < (kd == 1 ? 2 : 3); ++q) if (info[info[t].a[l][q]].kind[l] != 0) return fail(PL_ERR_UNSUPPORTED, order);
+            }
+        // a closure called AFTER a SmoothCorner / SmoothCornerAt of its lattice must not touch a site that one wrote or read:
+        // the kernels run all closures first
+        for (auto& b : p->bcs) {
+            if (b.bc->empty) continue;
+            const int l = b.on_g;
+            auto hits = [&](const std::vector<long long>& sites) {
+                const Plane& pl = b.bc->pl;
+                const int a1 = pl.axis == 0 ? 1 : 0, a2 = pl.axis == 2 ? 1 : 2;
+                const int loc = b.bc->coord - off[pl.axis];
+                for (long long site : sites) {
+                    int c3[3];
+                    coords(site, c3[0], c3[1], c3[2]);
+                    if (c3[pl.axis] != loc) continue;
+                    if (b.bc->hmask[(size_t)c3[a1] + (size_t)pl.n1*c3[a2]]) return true;
+                }
+                return false;
+            };
+            if (p->smooth_pos[l] >= 0 && b.pos > p->smooth_pos[l] && hits(smooth_sites[l])) return fail(PL_ERR_UNSUPPORTED, order);
+            for (auto& as : at_sites) if (as.l == l && as.pos < b.pos && hits(as.touched)) return fail(PL_ERR_UNSUPPORTED, order);
+        }
         const size_t nb = (size_t)p->f->nc*ntube*sizeof(double);
         CU(cudaMalloc(&p->tube_f, nb));
         if (p->g) CU(cudaMalloc(&p->tube_g, nb));

@@ -386,7 +386,7 @@ int pops_sync_in(pl_lattice* l) {
 }
 
 // ---- the fusion engine -------------------------------------------------------------------------------------------
-enum { OP_STREAM = 0, OP_BC = 1, OP_SMOOTH = 2 };
+enum { OP_STREAM = 0, OP_BC = 1, OP_SMOOTH = 2, OP_SMOOTH_AT = 3 };
 struct Op {
     int kind = 0;
     pl_lattice* l = nullptr;
@@ -395,9 +395,12 @@ struct Op {
     pl_bc_aux aux;
     bool has_aux = false;
     int inverse = 0;
+    int at[6] = {0, 0, 0, 0, 0, 0};      // OP_SMOOTH_AT: i, j, k, dx, dy, dz
 };
 bool same_aux(const Op& a, const Op& b) { return a.has_aux == b.has_aux && (!a.has_aux || memcmp(&a.aux, &b.aux, sizeof(pl_bc_aux)) == 0); }
-bool same_shape(const Op& a, const Op& b) { return a.kind == b.kind && a.l == b.l && a.other == b.other && a.bc == b.bc && a.inverse == b.inverse; }
+bool same_shape(const Op& a, const Op& b) {
+    return a.kind == b.kind && a.l == b.l && a.other == b.other && a.bc == b.bc && a.inverse == b.inverse && memcmp(a.at, b.at, sizeof(a.at)) == 0;
+}
 bool same_args(const pl_collide_args& a, const pl_collide_args& b) { return memcmp(&a, &b, sizeof(pl_collide_args)) == 0; }
 // equal up to the array addresses: same model, flags and scalars, and the same arrays present
 bool like_args(const pl_collide_args& a, const pl_collide_args& b) {
@@ -458,6 +461,7 @@ int exec_op(const Op& o) {
     switch (o.kind) {
         case OP_STREAM: return pl_stream(o.l, o.inverse);
         case OP_BC: return pl_bc_apply(o.l, o.other, o.bc, o.has_aux ? &o.aux : nullptr);
+        case OP_SMOOTH_AT: return pl_smooth_corner_at(o.l, o.at[0], o.at[1], o.at[2], o.at[3], o.at[4], o.at[5]);
         default: return pl_smooth_corner(o.l);
     }
 }
@@ -487,15 +491,16 @@ bool fusable(const Iter& a, const Iter& b) {
         else if (o.kind == OP_STREAM) return false;
     }
     if (nlat == 2 && a.ops[0].l == a.ops[1].l) return false;
-    bool smooth_seen = false, sf = false, sg = false;
+    // closures, SmoothCorner (once per lattice) and SmoothCornerAt in any order: pl_plan_finalize decides whether the body can
+    // be run as "closures, SmoothCorner, SmoothCornerAt" and refuses otherwise (the plan is then kept as a tombstone)
+    bool sf = false, sg = false;
     for (size_t k = nlat; k < a.ops.size(); ++k) {
         const Op& o = a.ops[k];
         if (o.kind == OP_SMOOTH) {
-            smooth_seen = true;
             bool& s = o.l == a.f ? sf : sg;
             if (s) return false;
             s = true;
-        } else if (smooth_seen) return false;
+        }
     }
     return true;
 }
@@ -508,10 +513,14 @@ Plan* build_plan(const Iter& a, const Iter& b) {
     int sf = 0, sg = 0;
     for (size_t k = 0; ok && k < a.ops.size(); ++k) {
         const Op &o = a.ops[k], &o2 = b.ops[k];
-        if (o.kind == OP_BC) ok = pl_plan_add_bc(pl->p, o.l == a.g && a.g ? 1 : 0, o.bc, o.has_aux ? &o.aux : nullptr, o2.has_aux ? &o2.aux : nullptr) == PL_OK;
-        else if (o.kind == OP_SMOOTH) { if (o.l == a.f) sf = 1; else sg = 1; }
+        const int on_g = o.l == a.g && a.g ? 1 : 0;
+        if (o.kind == OP_BC) ok = pl_plan_add_bc(pl->p, on_g, o.bc, o.has_aux ? &o.aux : nullptr, o2.has_aux ? &o2.aux : nullptr) == PL_OK;
+        else if (o.kind == OP_SMOOTH) {      // raised where it is called: the plan records the call order
+            if (o.l == a.f) sf = 1; else sg = 1;
+            ok = pl_plan_set_smooth_corner(pl->p, sf, sg) == PL_OK;
+        } else if (o.kind == OP_SMOOTH_AT) ok = pl_plan_add_smooth_corner_at(pl->p, on_g, o.at[0], o.at[1], o.at[2], o.at[3], o.at[4], o.at[5]) == PL_OK;
     }
-    ok = ok && pl_plan_set_smooth_corner(pl->p, sf, sg) == PL_OK && pl_plan_finalize(pl->p) == PL_OK;
+    ok = ok && pl_plan_finalize(pl->p) == PL_OK;
     if (!ok) { if (pl->p) pl_plan_destroy(pl->p); pl->p = nullptr; }     // kept as a tombstone: do not try this shape again
     E.plans.push_back(pl);
     ++g_stat[5];
@@ -728,12 +737,13 @@ int plh_smooth_corner(pl_lattice* l) {
     return do_op(o, false);
 }
 int plh_smooth_corner_at(pl_lattice* l, int i, int j, int k, int dx, int dy, int dz) {
+    HostTimer timer_(T_SMOOTH);
     if (!l) { g_herr = "plh_smooth_corner_at: null"; return PL_ERR_ARG; }
-    int rc;
-    if ((rc = pops_sync_in(l)) || (rc = quiesce(l))) return rc;
-    pops_written(l);
-    ++g_stat[1];
-    return pl_smooth_corner_at(l, i, j, k, dx, dy, dz) ? hfail("pl_smooth_corner_at") : PL_OK;
+    int rc = pops_sync_in(l);
+    if (rc) return rc;
+    Op o; o.kind = OP_SMOOTH_AT; o.l = l;
+    o.at[0] = i; o.at[1] = j; o.at[2] = k; o.at[3] = dx; o.at[4] = dy; o.at[5] = dz;
+    return do_op(o, false);
 }
 int plh_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* h) {
     HostTimer timer_(T_BC);
