@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -12) > gpurun_out/s4y_tests.log; cat gpurun_out/s4y_tests.log
-cd /tmp && g++ -O2 -mavx -ffp-contract=off -w -DPANSLBM_B200_DROPIN -I$GRAFT_REPO_ROOT/include -I$GRAFT_REPO_ROOT/panslbm2_b200/src $GRAFT_REPO_ROOT/tests/dropin/ncpump_dump.cpp -o ncp -L$GRAFT_REPO_ROOT/panslbm2_b200 -lpanslbm_b200 -Wl,-rpath,$GRAFT_REPO_ROOT/panslbm2_b200 && mkdir -p o && ./ncp 51 101 5000 o
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 400 python bench.py > gpurun_out/r01_final_bench_n1.json 2> gpurun_out/r01_final_bench_n1.err; tail -c 400 gpurun_out/r01_final_bench_n1.json; echo
+timeout 400 python bench.py --impl reference > gpurun_out/r01_final_bench_reference.json 2> gpurun_out/r01_final_bench_reference.err; tail -c 700 gpurun_out/r01_final_bench_reference.json; echo
+timeout 300 python bench.py --no-cpu --ns-size 0 --steps 200 --dims 81,161,81 > gpurun_out/r01_final_bench_81x161x81.json 2>/dev/null
+python tools/transient_probe.py 200 0 20 > gpurun_out/r01_final_transient.json 2>/dev/null; cat gpurun_out/r01_final_transient.json
