@@ -1,6 +1,14 @@
+#!/bin/bash
+# What a round checks on a B200 box (under gpurun): the GPU suite, the smoke entry, our bench arm and the reference arm.
+#   gpurun --timeout 1500 -- 'bash tools/run_gpu_checks.sh'        outputs under gpurun_out/
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 400 python bench.py > gpurun_out/r01_final_bench_n1.json 2> gpurun_out/r01_final_bench_n1.err; tail -c 400 gpurun_out/r01_final_bench_n1.json; echo
-timeout 400 python bench.py --impl reference > gpurun_out/r01_final_bench_reference.json 2> gpurun_out/r01_final_bench_reference.err; tail -c 700 gpurun_out/r01_final_bench_reference.json; echo
-timeout 300 python bench.py --no-cpu --ns-size 0 --steps 200 --dims 81,161,81 > gpurun_out/r01_final_bench_81x161x81.json 2>/dev/null
-python tools/transient_probe.py 200 0 20 > gpurun_out/r01_final_transient.json 2>/dev/null; cat gpurun_out/r01_final_transient.json
+(timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6) | tee gpurun_out/check_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/check_smoke.log
+timeout 400 python bench.py > gpurun_out/check_bench.json 2> gpurun_out/check_bench.err
+timeout 400 python bench.py --impl reference > gpurun_out/check_bench_reference.json 2> gpurun_out/check_bench_reference.err
+python - <<'P'
+import json
+for f in ("gpurun_out/check_bench.json", "gpurun_out/check_bench_reference.json"):
+    d = json.load(open(f))
+    print(f, "value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "roofline.frac", (d.get("roofline") or {}).get("frac"))
+P
