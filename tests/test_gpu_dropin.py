@@ -110,6 +110,19 @@ def test_cpp_surface_production_size_matches_reference_fixture(dump_exe, tmp_pat
     assert res["stats"][0] >= 2*(nt - 3), log
 
 
+def test_cpp_surface_2d_production_size_matches_reference_fixture(dump_exe, tmp_path):
+    """BASELINE configs[1]: the 2-D heatsink iteration at 141 x 161 (production/heatsink.cpp:41), 2000 + 2000 steps: digests of the
+    reference build"""
+    z = np.load(os.path.join(G, "heatsink2d_fullsize.npz"))
+    lx, ly, lz, nt = [int(v) for v in z["shape"]]
+    res, log = run_dump(dump_exe, str(tmp_path), 2, (lx, ly, lz), nt)
+    for k in sorted(k[:-4] for k in z.files if k.endswith("/sha")):
+        a = res[k] + 0.0
+        assert np.array_equal(a[::997], z[f"{k}/s997"]), k
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() == bytes(z[f"{k}/sha"]), k
+    assert res["stats"][0] >= 2*(nt - 3), log
+
+
 def test_cpp_surface_without_alloc_hook_still_correct(tmp_path):
     """PANSLBM_B200_NO_ALLOC_HOOK: arrays are foreign memory, staged around every call — slow path, same numbers"""
     out = str(tmp_path / "heatsink_dump_nohook")

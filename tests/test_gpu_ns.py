@@ -250,3 +250,39 @@ def test_golden_cavity3d_reference_fixture():
     b, _ = cavity_cuda(lx, ly, lz, nt, fused=True)
     for name, x in zip(("rho", "ux", "uy", "uz"), b):
         assert same(x[::37], z[f"b_{name}_s37"]), name
+
+
+def cavity2d_host(be, lx, ly, nt, u0=0.1, nu=0.1):
+    """test/cavityflow.cpp:31-66 call by call on a CPU backend (the C oracle / the reference build)"""
+    l = be.lattice(lx, ly)
+    n = lx*ly
+    i, j, _ = gcoords(lx, ly, 1)
+    rho, ux, uy, uz = np.ones(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    wall = i32(np.where((i == 0) | (i == lx - 1) | (j == 0), 1, 0))
+    lid = i32(j == ly - 1)
+    uxg, uyg, uzg = np.full(n, u0), np.zeros(n), np.zeros(n)
+    be.ns_init(l, rho, ux, uy, uz)
+    for _ in range(nt):
+        be.ns_macro_collide(l, rho, ux, uy, uz, nu, 1)
+        be.stream(l)
+        be.bc(l, wall, 0)
+        be.ns_bc_set_u(l, uxg, uyg, uzg, lid)
+        be.smooth_corner(l)
+    pops = l.get()
+    l.free()
+    return [rho, ux, uy], pops
+
+
+def test_config0_cavityflow2d_101x101_10000_steps_equals_oracle():
+    """BASELINE configs[0] / SURVEY §8d cfg 1: test/cavityflow.cpp as committed (D2Q9 101 x 101, nu = 0.1, u0 = 0.1), 10 000 steps:
+    the fused CUDA plan against the C oracle (and the reference build where oracle/_ref travelled), bit for bit"""
+    lx = ly = 101
+    nt = 10000
+    got, pg = cavity_cuda(lx, ly, 1, nt, fused=True, dim=2)
+    checkers = [O.Backend("orc", 2)] + ([O.Backend("ref", 2)] if O.have_ref(2) else [])
+    for be in checkers:
+        want, pw = cavity2d_host(be, lx, ly, nt)
+        for name, a, b in zip(("rho", "ux", "uy"), got, want):
+            assert same(a, b), (be.kind, name, float(np.max(np.abs(a - b))))
+        assert same(pg[0], pw[0]) and same(pg[1], pw[1]), be.kind
+    assert np.max(np.abs(got[1])) > 1e-2
