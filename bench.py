@@ -193,7 +193,7 @@ def roofline(kernel, bytes_per_site, prof, peak, peak_src, step_ms_total, traffi
         return None
     avg_ms = kms/kn
     achieved = bytes_per_site*(ksites/kn)/(avg_ms*1e-3)/1e9
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": traffic,
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "frac_of_nominal_8000_GBs": achieved/8000.0, "traffic": traffic,
             "algorithmic_bytes_per_launch": bytes_per_site*(ksites/kn), "kernel": kernel,
             "avg_kernel_ms": avg_ms, "sites_per_launch": ksites/kn, "algorithmic_bytes_per_site": bytes_per_site, "peak_source": peak_src,
             "kernel_share_of_timed_region": kms/step_ms_total if step_ms_total else None}
