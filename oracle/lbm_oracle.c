@@ -357,6 +357,128 @@ void orc_ns_bc_set_rho(orc_lattice* l, const double* v0, const double* v1, const
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* AD (thermal lattice) primitives: advection.h:18-95 (scalar), advection_avx.h:25-102 (AVX)   */
+/* Macro: the same order in both (advection.h:18-51 == advection_avx.h:25-56) */
+static void ad_macro(const L* l, const double* g, double ux, double uy, double uz, double omegag, double* tem, double* qx, double* qy, double* qz) {
+    double t = g[0], x = 0.0, y = 0.0, z = 0.0;
+    for (int c = 1; c < l->nc; ++c) {
+        t = t + g[c];
+        x = x + l->cx[c]*g[c];
+        y = y + l->cy[c]*g[c];
+        if (l->nd == 3) z = z + l->cz[c]*g[c];
+    }
+    double coef = 1.0 - 0.5*omegag;
+    *tem = t;
+    *qx = coef*(x - t*ux);
+    *qy = coef*(y - t*uy);
+    *qz = l->nd == 3 ? coef*(z - t*uz) : 0.0;
+}
+/* Equilibrium, AVX order: advection_avx.h:58-74   geq = ei*(tem*(1 + 3*cu)) */
+static void ad_eq_avx(const L* l, double* geq, double tem, double ux, double uy, double uz) {
+    for (int c = 0; c < l->nc; ++c) geq[c] = l->ei[c]*(tem*(1.0 + 3.0*cdot(l, c, ux, uy, uz)));
+}
+/* Equilibrium, scalar order: advection.h:53-68    geq = (ei*tem)*(1 + 3*ciu) */
+static void ad_eq_sc(const L* l, double* geq, double tem, double ux, double uy, double uz) {
+    for (int c = 0; c < l->nc; ++c) geq[c] = l->ei[c]*tem*(1.0 + 3.0*cdot(l, c, ux, uy, uz));
+}
+/* buoyancy on the flow lattice, AVX order: advection_avx.h:76-92   f += (3*(T - T0))*(ei*(c.g)) */
+static void ad_natconv_avx(const L* l, double* p, double tem, double gx, double gy, double gz, double tem0) {
+    double coef = 3.0*(tem - tem0);
+    for (int c = 1; c < l->nc; ++c) p[c] = p[c] + coef*(l->ei[c]*cdot(l, c, gx, gy, gz));
+}
+/* ... scalar order: advection.h:70-84   f += ((3*ei)*(c.g))*(T - T0) */
+static void ad_natconv_sc(const L* l, double* p, double tem, double gx, double gy, double gz, double tem0) {
+    for (int c = 1; c < l->nc; ++c) p[c] += 3.0*l->ei[c]*cdot(l, c, gx, gy, gz)*(tem - tem0);
+}
+
+/* AD::InitialCondition: advection.h:1046-1070 (scalar Equilibrium at every site) */
+void orc_ad_init(orc_lattice* g, const double* tem, const double* ux, const double* uy, const double* uz) {
+    double geq[NCMAX];
+    for (int idx = 0; idx < g->nxyz; ++idx) {
+        ad_eq_sc(g, geq, tem[idx], ux[idx], uy[idx], g->nd == 3 ? uz[idx] : 0.0);
+        scatter(g, idx, geq);
+    }
+}
+
+/* AD::MacroBrinkmanCollideNaturalConvection: advection_avx.h:886-998 (2-D), 1001-1116 (3-D).
+ * Per site: moments of f and g -> buoyancy on f (pre-force T) -> Brinkman on f (pre-force rho, u) -> moments again (g unchanged,
+ * new u) -> save rho,u,T,q and the snapshot of g -> relax f, relax g with omega_g = 1/(3 kappa[idx] + 1/2).
+ * Snapshot layout: [pack][c][lane] for packed sites (:1047-1052), [idx][c] for the tail (:1093-1098). */
+void orc_ad_macro_brinkman_collide_natural_convection(orc_lattice* f, double* rho, double* ux, double* uy, double* uz, const double* alpha, double nu,
+        orc_lattice* g, double* tem, double* qx, double* qy, double* qz, const double* diffusivity,
+        double gx, double gy, double gz, double tem0, int issave, double* gsnap) {
+    const double omegaf = 1.0/(3.0*nu + 0.5), iomegaf = 1.0 - omegaf;
+    const int ne = npacked(f), nc = g->nc;
+    if (f->nd == 2) gz = 0.0;
+    #pragma omp parallel for
+    for (int idx = 0; idx < f->nxyz; ++idx) {
+        const int tail = idx >= ne;
+        const double omegag = 1.0/(3.0*diffusivity[idx] + 0.5), iomegag = 1.0 - omegag;
+        double p[NCMAX], q[NCMAX], feq[NCMAX], geq[NCMAX], r, x, y, z, t, hx, hy, hz;
+        gather(f, idx, p);
+        gather(g, idx, q);
+        ns_macro(f, p, &r, &x, &y, &z);
+        ad_macro(g, q, x, y, z, omegag, &t, &hx, &hy, &hz);
+        if (tail) ad_natconv_sc(f, p, t, gx, gy, gz, tem0); else ad_natconv_avx(f, p, t, gx, gy, gz, tem0);
+        ns_brinkman(f, p, r, x, y, z, alpha[idx]);
+        ns_macro(f, p, &r, &x, &y, &z);
+        ad_macro(g, q, x, y, z, omegag, &t, &hx, &hy, &hz);
+        if (issave) {
+            rho[idx] = r; ux[idx] = x; uy[idx] = y; tem[idx] = t; qx[idx] = hx; qy[idx] = hy;
+            if (f->nd == 3) { uz[idx] = z; qz[idx] = hz; }
+            if (gsnap) {
+                if (!tail) { const int base = idx - idx%4, lane = idx%4; for (int c = 0; c < nc; ++c) gsnap[(size_t)nc*base + 4*c + lane] = q[c]; }
+                else for (int c = 0; c < nc; ++c) gsnap[(size_t)nc*idx + c] = q[c];
+            }
+        }
+        if (tail) ns_eq_sc(f, feq, r, x, y, z); else ns_eq_avx(f, feq, r, x, y, z);
+        relax(f, p, feq, omegaf, iomegaf);
+        if (tail) ad_eq_sc(g, geq, t, x, y, z); else ad_eq_avx(g, geq, t, x, y, z);
+        relax(g, q, geq, omegag, iomegag);
+        scatter(f, idx, p);
+        scatter(g, idx, q);
+    }
+}
+
+/* ---- temperature / heat-flux closures on a face: advection.h:99-524 -----------------------------------
+ * Face with normal axis a and outward direction dir; "in" = populations entering the domain (c_a == -dir).
+ *   SetT: tem0 = 6*(T - g0 - g_c ... over the c with c_a != -dir, ascending)/(1 - dir*3u_a)          (e.g. :106, :159)
+ *   SetQ: tem0 = 6*((1 + 1/(6 kappa))*qn + g_c ... over the c with c_a == dir, ascending)/(1 + dir*3u_a) (e.g. :250, :301)
+ *   g_in(c) = tem0*(1 +/- 3ux +/- 3uy +/- 3uz)/(9 | 36 | 72), the velocity terms in x,y,z order, absent components skipped */
+typedef struct { const double *val, *ux, *uy, *uz, *kfield; double kconst; const int* mask; int setq; } adbc_ctx;
+static void ad_bc_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    adbc_ctx* b = (adbc_ctx*)vctx;
+    if (!b->mask[gidx]) return;
+    double g[NCMAX];
+    gather(l, idx, g);
+    const double u[3] = {b->ux[idx], b->uy[idx], l->nd == 3 ? b->uz[idx] : 0.0};
+    double tem0;
+    if (!b->setq) {
+        double s = b->val[gidx] - g[0];
+        for (int c = 1; c < l->nc; ++c) if (l->ci[c][axis] != -dir) s = s - g[c];
+        tem0 = dir == -1 ? 6.0*s/(1.0 + 3.0*u[axis]) : 6.0*s/(1.0 - 3.0*u[axis]);
+    } else {
+        const double kappa = b->kfield ? b->kfield[idx] : b->kconst;
+        double s = (1.0 + 1.0/(6.0*kappa))*b->val[gidx];
+        for (int c = 1; c < l->nc; ++c) if (l->ci[c][axis] == dir) s = s + g[c];
+        tem0 = dir == -1 ? 6.0*s/(1.0 - 3.0*u[axis]) : 6.0*s/(1.0 + 3.0*u[axis]);
+    }
+    for (int c = 1; c < l->nc; ++c) {
+        if (l->ci[c][axis] != -dir) continue;
+        double t = 1.0;
+        for (int d = 0; d < l->nd; ++d) if (l->ci[c][d]) t = l->ci[c][d] > 0 ? t + 3.0*u[d] : t - 3.0*u[d];
+        const int nz = abs(l->ci[c][0]) + abs(l->ci[c][1]) + abs(l->ci[c][2]);
+        l->f[IF(l, idx, c)] = tem0*t/(nz == 1 ? 9.0 : (l->nd == 2 ? 36.0 : 72.0));
+    }
+}
+void orc_ad_bc_set_t(orc_lattice* g, const double* temg, const double* ux, const double* uy, const double* uz, const int* mask) {
+    adbc_ctx b = {temg, ux, uy, uz, NULL, 0.0, mask, 0}; for_all_faces(g, ad_bc_site, &b);
+}
+void orc_ad_bc_set_q(orc_lattice* g, const double* qng, const double* ux, const double* uy, const double* uz, const double* kfield, double kconst, const int* mask) {
+    adbc_ctx b = {qng, ux, uy, uz, kfield, kconst, mask, 1}; for_all_faces(g, ad_bc_site, &b);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* utilities: residual.h:8-50, normalize.h:8-24 (serial loops)                                  */
 double orc_residual3(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, int n) {
     double unorm = 0.0, dunorm = 0.0;
