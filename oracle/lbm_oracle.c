@@ -479,6 +479,270 @@ void orc_ad_bc_set_q(orc_lattice* g, const double* qng, const double* ux, const 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* ANS / AAD (adjoint flow / adjoint thermal) primitives                                       */
+/* ANS::Macro, AVX order: adjointnavierstokes_avx.h:27-72 (the 2-D and 3-D versions associate the ip term differently) */
+static void ans_macro_avx(const L* l, const double* f, double ux, double uy, double uz,
+                          double* ip, double* iux, double* iuy, double* iuz, double* imx, double* imy, double* imz) {
+    double p = 0.0, ax = 0.0, ay = 0.0, az = 0.0, mx = 0.0, my = 0.0, mz = 0.0;
+    const double uu = dot3(l, ux, uy, uz, ux, uy, uz);
+    const double one_uu = 1.0 - 1.5*uu;                 /* 2-D: :35 */
+    for (int c = 0; c < l->nc; ++c) {
+        const double fei = f[c]*l->ei[c];
+        const double cu = cdot(l, c, ux, uy, uz);
+        if (l->nd == 2) p = p + fei*(one_uu + (3.0*cu + 4.5*(cu*cu)));
+        else p = p + fei*(1.0 + (3.0*cu + (4.5*(cu*cu) - 1.5*uu)));
+        ax = ax + fei*(l->cx[c] + (3.0*(cu*l->cx[c]) - ux));
+        ay = ay + fei*(l->cy[c] + (3.0*(cu*l->cy[c]) - uy));
+        if (l->nd == 3) az = az + fei*(l->cz[c] + (3.0*(cu*l->cz[c]) - uz));
+        mx = mx + fei*l->cx[c];
+        my = my + fei*l->cy[c];
+        if (l->nd == 3) mz = mz + fei*l->cz[c];
+    }
+    *ip = p; *iux = ax; *iuy = ay; *iuz = az; *imx = mx; *imy = my; *imz = mz;
+}
+/* ANS::Macro, scalar order: adjointnavierstokes.h:17-61 */
+static void ans_macro_sc(const L* l, const double* f, double ux, double uy, double uz,
+                         double* ip, double* iux, double* iuy, double* iuz, double* imx, double* imy, double* imz) {
+    const double uu = l->nd == 3 ? ux*ux + uy*uy + uz*uz : ux*ux + uy*uy;
+    double p = f[0]*l->ei[0]*(1.0 - 1.5*uu);
+    double ax = -f[0]*l->ei[0]*ux, ay = -f[0]*l->ei[0]*uy, az = l->nd == 3 ? -f[0]*l->ei[0]*uz : 0.0;
+    double mx = 0.0, my = 0.0, mz = 0.0;
+    for (int c = 1; c < l->nc; ++c) {
+        const double ciu = l->nd == 3 ? l->cx[c]*ux + l->cy[c]*uy + l->cz[c]*uz : l->cx[c]*ux + l->cy[c]*uy;
+        const double fei = f[c]*l->ei[c];
+        p += fei*(1.0 + 3.0*ciu + 4.5*ciu*ciu - 1.5*uu);
+        ax += fei*(l->cx[c] + 3.0*ciu*l->cx[c] - ux);
+        ay += fei*(l->cy[c] + 3.0*ciu*l->cy[c] - uy);
+        if (l->nd == 3) az += fei*(l->cz[c] + 3.0*ciu*l->cz[c] - uz);
+        mx += fei*l->cx[c];
+        my += fei*l->cy[c];
+        if (l->nd == 3) mz += fei*l->cz[c];
+    }
+    *ip = p; *iux = ax; *iuy = ay; *iuz = az; *imx = mx; *imy = my; *imz = mz;
+}
+/* ANS::Equilibrium: adjointnavierstokes.h:63-77 == adjointnavierstokes_avx.h:74-88 */
+static void ans_eq(const L* l, double* feq, double ux, double uy, double uz, double ip, double iux, double iuy, double iuz) {
+    for (int c = 0; c < l->nc; ++c) {
+        double s = iux*(l->cx[c] - ux) + iuy*(l->cy[c] - uy);
+        if (l->nd == 3) s = s + iuz*(l->cz[c] - uz);
+        feq[c] = ip + 3.0*s;
+    }
+}
+/* AAD::Macro: adjointadvection.h:24-50 == adjointadvection_avx.h:203-229 */
+static void aad_macro(const L* l, const double* g, double* item, double* iqx, double* iqy, double* iqz) {
+    double t = l->ei[0]*g[0], x = 0.0, y = 0.0, z = 0.0;
+    for (int c = 1; c < l->nc; ++c) {
+        const double gei = l->ei[c]*g[c];
+        t = t + gei;
+        x = x + gei*l->cx[c];
+        y = y + gei*l->cy[c];
+        if (l->nd == 3) z = z + gei*l->cz[c];
+    }
+    *item = t; *iqx = x; *iqy = y; *iqz = z;
+}
+/* AAD::Equilibrium (one value for every c): adjointadvection.h:52-68 == adjointadvection_avx.h:231-247 */
+static double aad_eq(const L* l, double item, double iqx, double iqy, double iqz, double ux, double uy, double uz) {
+    return item + 3.0*dot3(l, ux, uy, uz, iqx, iqy, iqz);
+}
+/* coupling force on the adjoint flow lattice: adjointadvection.h:70-106 / adjointadvection_avx.h:249-279 (same values) */
+static void aad_brinkman(const L* l, double* f, double rho, double ux, double uy, double uz, double imx, double imy, double imz,
+                         double tem, double iqx, double iqy, double iqz, double omegag, double alpha) {
+    const double coef = 3.0/(rho + alpha);
+    const double kx = tem*iqx*omegag - alpha*imx, ky = tem*iqy*omegag - alpha*imy, kz = l->nd == 3 ? tem*iqz*omegag - alpha*imz : 0.0;
+    f[0] = f[0] - coef*dot3(l, kx, ky, kz, ux, uy, uz);
+    for (int c = 1; c < l->nc; ++c) {
+        double s = kx*(l->cx[c] - ux) + ky*(l->cy[c] - uy);
+        if (l->nd == 3) s = s + kz*(l->cz[c] - uz);
+        f[c] = f[c] + coef*s;
+    }
+}
+/* adjoint buoyancy on the adjoint thermal lattice: adjointadvection.h:114-132 == adjointadvection_avx.h:292-306 */
+static void aad_natconv(const L* l, double* g, double imx, double imy, double imz, double gx, double gy, double gz) {
+    const double coef = 3.0*dot3(l, imx, imy, imz, gx, gy, gz);
+    for (int c = 0; c < l->nc; ++c) g[c] = g[c] + coef;
+}
+
+/* InitialCondition: adjointnavierstokes.h:474-498, adjointadvection.h:1359-1381 */
+void orc_ans_init(orc_lattice* l, const double* ux, const double* uy, const double* uz, const double* ip, const double* iux, const double* iuy, const double* iuz) {
+    double feq[NCMAX];
+    for (int idx = 0; idx < l->nxyz; ++idx) {
+        ans_eq(l, feq, ux[idx], uy[idx], l->nd == 3 ? uz[idx] : 0.0, ip[idx], iux[idx], iuy[idx], l->nd == 3 ? iuz[idx] : 0.0);
+        scatter(l, idx, feq);
+    }
+}
+void orc_aad_init(orc_lattice* g, const double* ux, const double* uy, const double* uz, const double* item, const double* iqx, const double* iqy, const double* iqz) {
+    double geq[NCMAX];
+    for (int idx = 0; idx < g->nxyz; ++idx) {
+        const double v = aad_eq(g, item[idx], iqx[idx], iqy[idx], g->nd == 3 ? iqz[idx] : 0.0, ux[idx], uy[idx], g->nd == 3 ? uz[idx] : 0.0);
+        for (int c = 0; c < g->nc; ++c) geq[c] = v;
+        scatter(g, idx, geq);
+    }
+}
+
+/* AAD::MacroBrinkmanCollideNaturalConvection: adjointadvection_avx.h:765-880 (2-D), 884-1005 (3-D).
+ * Per site: adjoint moments of f and g -> coupling force on f -> adjoint flow moments again -> adjoint buoyancy on g (new im) ->
+ * adjoint thermal moments again -> save ip,iu,im,iT,iq and the snapshot of g -> relax f (ANS equilibrium), relax g. */
+void orc_aad_macro_brinkman_collide_natural_convection(orc_lattice* f, const double* rho, const double* ux, const double* uy, const double* uz,
+        double* ip, double* iux, double* iuy, double* iuz, double* imx, double* imy, double* imz, const double* alpha, double nu,
+        orc_lattice* g, const double* tem, double* item, double* iqx, double* iqy, double* iqz, const double* diffusivity,
+        double gx, double gy, double gz, int issave, double* igsnap) {
+    const double omegaf = 1.0/(3.0*nu + 0.5), iomegaf = 1.0 - omegaf;
+    const int ne = npacked(f), nc = g->nc;
+    if (f->nd == 2) gz = 0.0;
+    #pragma omp parallel for
+    for (int idx = 0; idx < f->nxyz; ++idx) {
+        const int tail = idx >= ne;
+        const double omegag = 1.0/(3.0*diffusivity[idx] + 0.5), iomegag = 1.0 - omegag;
+        const double r = rho[idx], x = ux[idx], y = uy[idx], z = f->nd == 3 ? uz[idx] : 0.0;
+        double p[NCMAX], q[NCMAX], feq[NCMAX], geq[NCMAX], a, bx, by, bz, mx, my, mz, t, hx, hy, hz;
+        gather(f, idx, p);
+        gather(g, idx, q);
+        if (tail) ans_macro_sc(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz); else ans_macro_avx(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz);
+        aad_macro(g, q, &t, &hx, &hy, &hz);
+        aad_brinkman(f, p, r, x, y, z, mx, my, mz, tem[idx], hx, hy, hz, omegag, alpha[idx]);
+        if (tail) ans_macro_sc(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz); else ans_macro_avx(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz);
+        aad_natconv(g, q, mx, my, mz, gx, gy, gz);
+        aad_macro(g, q, &t, &hx, &hy, &hz);
+        if (issave) {
+            ip[idx] = a; iux[idx] = bx; iuy[idx] = by; imx[idx] = mx; imy[idx] = my; item[idx] = t; iqx[idx] = hx; iqy[idx] = hy;
+            if (f->nd == 3) { iuz[idx] = bz; imz[idx] = mz; iqz[idx] = hz; }
+            if (igsnap) {
+                if (!tail) { const int base = idx - idx%4, lane = idx%4; for (int c = 0; c < nc; ++c) igsnap[(size_t)nc*base + 4*c + lane] = q[c]; }
+                else for (int c = 0; c < nc; ++c) igsnap[(size_t)nc*idx + c] = q[c];
+            }
+        }
+        ans_eq(f, feq, x, y, z, a, bx, by, bz);
+        relax(f, p, feq, omegaf, iomegaf);
+        const double ge = aad_eq(g, t, hx, hy, hz, x, y, z);
+        for (int c = 0; c < nc; ++c) geq[c] = ge;
+        relax(g, q, geq, omegag, iomegag);
+        scatter(f, idx, p);
+        scatter(g, idx, q);
+    }
+}
+
+/* ---- adjoint thermal closures on a face: adjointadvection.h:154-484 ------------------------------------
+ * K = the populations with c_a == -dir, ascending (the axis-aligned one first, then the four / two diagonals): the known ones.
+ * Every unknown (the opposites of K) takes one value r.  S_t = sum over the diagonals of sign(c_t(K_i)) g_Ki.
+ *   iSetT 2-D: r = -(4 (1 - dir 3u_a) g_K0 + sum_i (1 +/- 3ux +/- 3uy) g_Ki)/(6 (1 - dir 3u_a))                       (:161, :166)
+ *   iSetT 3-D: r = -(8 g_K0 + sum g_Ki)/12 - u_t1 S_t1/(4 (1 - dir 3u_a)) - u_t2 S_t2/(4 (1 - dir 3u_a)), t1,t2 = a+1,a+2 cyclic   (:209-211)
+ *   iSetQ:     r = ((1 - dir 3u_a)((4|8) g_K0 + sum g_Ki) + w u_t1 S_t1 [+ w u_t2 S_t2] - (12|24) eps)/((6|12)(1 + dir 3u_a)),
+ *              w = 3, except that the 3-D ymax, zmin and zmax faces carry the bare u_t (:428-429, :456-457, :468-469) */
+static int face_K(const L* l, int axis, int sgn, int* K) {
+    int m = 0;
+    for (int c = 1; c < l->nc; ++c) if (l->ci[c][axis] == sgn) K[m++] = c;
+    return m;
+}
+static double signed_diag(const L* l, const double* g, const int* K, int m, int t) {
+    double s = l->ci[K[1]][t] > 0 ? g[K[1]] : -g[K[1]];
+    for (int i = 2; i < m; ++i) s = l->ci[K[i]][t] > 0 ? s + g[K[i]] : s - g[K[i]];
+    return s;
+}
+static double one_pm_3cu(const L* l, int c, const double* u) {
+    double t = 1.0;
+    for (int d = 0; d < l->nd; ++d) if (l->ci[c][d]) t = l->ci[c][d] > 0 ? t + 3.0*u[d] : t - 3.0*u[d];
+    return t;
+}
+/* (1 - dir 3u_a)(lead + (4|8) g_K0 + sum g_Ki) + w u_t S_t ...: shared by iSetQ and the heat-source sensitivity term */
+static double aad_q_bracket(const L* l, const double* g, const int* K, int m, int axis, int dir, const double* u, int with_lead, double lead) {
+    const double one3 = dir == -1 ? 1.0 + 3.0*u[axis] : 1.0 - 3.0*u[axis];
+    double s = with_lead ? lead + (l->nd == 2 ? 4.0 : 8.0)*g[K[0]] : (l->nd == 2 ? 4.0 : 8.0)*g[K[0]];
+    for (int i = 1; i < m; ++i) s = s + g[K[i]];
+    double acc = one3*s;
+    if (l->nd == 2) {
+        const int t = 1 - axis;
+        acc = acc + 3.0*u[t]*signed_diag(l, g, K, m, t);
+    } else {
+        const int three = axis == 0 || (axis == 1 && dir == -1);
+        for (int n = 1; n <= 2; ++n) {
+            const int t = (axis + n)%3;
+            acc = three ? acc + 3.0*u[t]*signed_diag(l, g, K, m, t) : acc + u[t]*signed_diag(l, g, K, m, t);
+        }
+    }
+    return acc;
+}
+typedef struct { const double *ux, *uy, *uz; const int* mask; double eps; int setq; } aadbc_ctx;
+static void aad_ibc_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    aadbc_ctx* b = (aadbc_ctx*)vctx;
+    if (!b->mask[gidx]) return;
+    double g[NCMAX];
+    int K[NCMAX];
+    gather(l, idx, g);
+    const int m = face_K(l, axis, -dir, K);
+    const double u[3] = {b->ux[idx], b->uy[idx], l->nd == 3 ? b->uz[idx] : 0.0};
+    double r;
+    if (!b->setq) {
+        const double one3 = dir == -1 ? 1.0 + 3.0*u[axis] : 1.0 - 3.0*u[axis];
+        if (l->nd == 2) {
+            double a = 4.0*one3*g[K[0]];
+            for (int i = 1; i < m; ++i) a = a + one_pm_3cu(l, K[i], u)*g[K[i]];
+            r = -a/(6.0*one3);
+        } else {
+            double a = 8.0*g[K[0]];
+            for (int i = 1; i < m; ++i) a = a + g[K[i]];
+            r = -a/12.0;
+            for (int n = 1; n <= 2; ++n) { const int t = (axis + n)%3; r = r - u[t]*signed_diag(l, g, K, m, t)/(4.0*one3); }
+        }
+    } else {
+        double acc = aad_q_bracket(l, g, K, m, axis, dir, u, 0, 0.0);
+        acc = acc - (l->nd == 2 ? 12.0 : 24.0)*b->eps;
+        r = acc/((l->nd == 2 ? 6.0 : 12.0)*(dir == -1 ? 1.0 - 3.0*u[axis] : 1.0 + 3.0*u[axis]));
+    }
+    for (int i = 0; i < m; ++i) l->f[IF(l, idx, l->opp[K[i]])] = r;
+}
+void orc_aad_ibc_set_t(orc_lattice* g, const double* ux, const double* uy, const double* uz, const int* mask) {
+    aadbc_ctx b = {ux, uy, uz, mask, 0.0, 0}; for_all_faces(g, aad_ibc_site, &b);
+}
+void orc_aad_ibc_set_q(orc_lattice* g, const double* ux, const double* uy, const double* uz, const int* mask, double eps) {
+    aadbc_ctx b = {ux, uy, uz, mask, eps, 1}; for_all_faces(g, aad_ibc_site, &b);
+}
+
+/* AAD::SensitivityTemperatureAtHeatSource: adjointadvection_avx.h:1403-1513 (volume terms, AVX order for packed sites and the
+ * scalar order with pow() for the tail), :16-185 (heat-source face terms, scalar).  gsnap / igsnap in the reference layout. */
+static size_t index_g(const L* l, int idx, int c) {
+    const int ne = npacked(l);
+    return idx < ne ? (size_t)(idx/4)*4*l->nc + 4*c + idx%4 : (size_t)l->nc*idx + c;
+}
+typedef struct { double* dfds; const double *ux, *uy, *uz, *ig, *kappa, *dkds, *qn; const int* mask; } sens_ctx;
+static void sens_face_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    sens_ctx* b = (sens_ctx*)vctx;
+    if (!b->mask[gidx]) return;
+    double ig[NCMAX];
+    int K[NCMAX];
+    for (int c = 0; c < l->nc; ++c) ig[c] = b->ig[index_g(l, idx, c)];
+    const int m = face_K(l, axis, -dir, K);
+    const double u[3] = {b->ux[idx], b->uy[idx], l->nd == 3 ? b->uz[idx] : 0.0};
+    const double e = aad_q_bracket(l, ig, K, m, axis, dir, u, 1, l->nd == 2 ? -6.0 : -12.0);
+    const double den = (l->nd == 2 ? 36.0 : 72.0)*(dir == -1 ? 1.0 - 3.0*u[axis] : 1.0 + 3.0*u[axis])*pow(b->kappa[idx], 2.0);
+    b->dfds[idx] += b->qn[gidx]*b->dkds[idx]*e/den;
+}
+void orc_aad_sensitivity_temperature_at_heat_source(orc_lattice* g, double* dfds, const double* ux, const double* uy, const double* uz,
+        const double* imx, const double* imy, const double* imz, const double* dads, const double* tem, const double* item,
+        const double* iqx, const double* iqy, const double* iqz, const double* gsnap, const double* igsnap, const double* diffusivity, const double* dkds,
+        const double* qng, const int* mask) {
+    const int ne = npacked(g), nc = g->nc, d3 = g->nd == 3;
+    for (int idx = 0; idx < g->nxyz; ++idx) {
+        double sumg = 0.0;
+        for (int c = 0; c < nc; ++c) sumg = sumg + gsnap[index_g(g, idx, c)]*igsnap[index_g(g, idx, c)];
+        if (idx < ne) {
+            const double um = d3 ? ux[idx]*imx[idx] + (uy[idx]*imy[idx] + uz[idx]*imz[idx]) : ux[idx]*imx[idx] + uy[idx]*imy[idx];
+            double v = dfds[idx] + 3.0*(dads[idx]*um);
+            const double taug = 3.0*diffusivity[idx] + 0.5;
+            const double uq = d3 ? ux[idx]*iqx[idx] + (uy[idx]*iqy[idx] + uz[idx]*iqz[idx]) : ux[idx]*iqx[idx] + uy[idx]*iqy[idx];
+            v = v - (3.0*(dkds[idx]*(sumg - tem[idx]*(item[idx] + 3.0*uq))))/(taug*taug);
+            dfds[idx] = v;
+        } else {
+            if (d3) dfds[idx] += 3.0*dads[idx]*(ux[idx]*imx[idx] + uy[idx]*imy[idx] + uz[idx]*imz[idx]);
+            else dfds[idx] += 3.0*dads[idx]*(ux[idx]*imx[idx] + uy[idx]*imy[idx]);
+            if (d3) dfds[idx] += -3.0/pow(3.0*diffusivity[idx] + 0.5, 2.0)*dkds[idx]*(sumg - tem[idx]*(item[idx] + 3.0*(ux[idx]*iqx[idx] + uy[idx]*iqy[idx] + uz[idx]*iqz[idx])));
+            else dfds[idx] += -3.0/pow(3.0*diffusivity[idx] + 0.5, 2.0)*dkds[idx]*(sumg - tem[idx]*(item[idx] + 3.0*(ux[idx]*iqx[idx] + uy[idx]*iqy[idx])));
+        }
+    }
+    sens_ctx b = {dfds, ux, uy, uz, igsnap, diffusivity, dkds, qng, mask};
+    for_all_faces(g, sens_face_site, &b);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* utilities: residual.h:8-50, normalize.h:8-24 (serial loops)                                  */
 double orc_residual3(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, int n) {
     double unorm = 0.0, dunorm = 0.0;

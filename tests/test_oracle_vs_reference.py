@@ -197,3 +197,45 @@ def test_residual_and_normalize():
     ref.normalize(a, n)
     orc.normalize(b, n)
     assert same(a, b)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the thermal / adjoint half of the path (tests/scenarios.py drives every backend the same way)
+@pytest.mark.parametrize("dim", DIMS)
+@pytest.mark.parametrize("model", ["ad_brinkman_natural_convection", "aad_natural_convection"])
+def test_thermal_collides(dim, model):
+    import scenarios as S
+    ref, orc = O.Backend("ref", dim), O.Backend("orc", dim)
+    for n, size in enumerate(SIZES[dim]):
+        S.assert_same(S.collide(ref, dim, model, size, 5 + n), S.collide(orc, dim, model, size, 5 + n), f"{model} {size}")
+
+
+@pytest.mark.parametrize("dim", DIMS)
+@pytest.mark.parametrize("kind", ["ad_set_t", "ad_set_q_const", "ad_set_q_field", "aad_iset_t", "aad_iset_q"])
+def test_thermal_closures(dim, kind):
+    import scenarios as S
+    ref, orc = O.Backend("ref", dim), O.Backend("orc", dim)
+    for n, size in enumerate(SIZES[dim]):
+        S.assert_same(S.closure(ref, dim, kind, size, 9 + n), S.closure(orc, dim, kind, size, 9 + n), f"{kind} {size}")
+
+
+@pytest.mark.parametrize("dim", DIMS)
+def test_initial_conditions_and_heat_source_sensitivity(dim):
+    import scenarios as S
+    ref, orc = O.Backend("ref", dim), O.Backend("orc", dim)
+    for n, size in enumerate(SIZES[dim]):
+        S.assert_same(S.inits(ref, dim, size, 3 + n), S.inits(orc, dim, size, 3 + n), f"inits {size}")
+        S.assert_same(S.sensitivity(ref, dim, "aad_temperature_at_heat_source", size, 11 + n),
+                      S.sensitivity(orc, dim, "aad_temperature_at_heat_source", size, 11 + n), f"sensitivity {size}")
+
+
+@pytest.mark.parametrize("dim", DIMS)
+def test_heatsink_iteration_sequence(dim):
+    """forward loop, adjoint loop and sensitivity of the heatsink drivers, op by op: every field bit-identical"""
+    import heatsink_case as H
+    size, nt = ((13, 17, 9), 25) if dim == 3 else ((23, 29, 1), 25)
+    a = H.run_oplevel(O.Backend("ref", dim), dim, size, nt)
+    b = H.run_oplevel(O.Backend("orc", dim), dim, size, nt)
+    assert sorted(a) == sorted(b)
+    for k in a:
+        assert same(a[k], b[k]), k
