@@ -743,6 +743,270 @@ void orc_aad_sensitivity_temperature_at_heat_source(orc_lattice* g, double* dfds
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* the other collide variants, from the same primitives                                        */
+/* heat exchange on the thermal lattice: advection.h:86-95 (scalar), advection_avx.h:94-102 (AVX) */
+static void ad_heatex(const L* l, double* g, double tem, double beta, int sc) {
+    const double coef = sc ? beta*(1.0 - tem)/(1.0 + beta) : beta*((1.0 - tem)/(1.0 + beta));
+    for (int c = 0; c < l->nc; ++c) g[c] = g[c] + l->ei[c]*coef;
+}
+/* forward family (advection_avx.h:106-1116): moments -> [buoyancy] -> [Brinkman] -> flow moments again if forced -> [heat exchange]
+ * -> thermal moments again if the flow was forced -> save -> relax both.  kfield / kconst: per-cell or scalar diffusivity. */
+static void ad_collide(L* f, double* rho, double* ux, double* uy, double* uz, const double* alpha, double nu,
+                       L* g, double* tem, double* qx, double* qy, double* qz, const double* kfield, double kconst, const double* beta,
+                       int natconv, double gx, double gy, double gz, double tem0, int issave, double* gsnap) {
+    const double omegaf = 1.0/(3.0*nu + 0.5), iomegaf = 1.0 - omegaf;
+    const int ne = npacked(f), nc = g->nc;
+    if (f->nd == 2) gz = 0.0;
+    #pragma omp parallel for
+    for (int idx = 0; idx < f->nxyz; ++idx) {
+        const int tail = idx >= ne;
+        const double omegag = 1.0/(3.0*(kfield ? kfield[idx] : kconst) + 0.5), iomegag = 1.0 - omegag;
+        double p[NCMAX], q[NCMAX], feq[NCMAX], geq[NCMAX], r, x, y, z, t, hx, hy, hz;
+        gather(f, idx, p);
+        gather(g, idx, q);
+        ns_macro(f, p, &r, &x, &y, &z);
+        ad_macro(g, q, x, y, z, omegag, &t, &hx, &hy, &hz);
+        if (natconv) { if (tail) ad_natconv_sc(f, p, t, gx, gy, gz, tem0); else ad_natconv_avx(f, p, t, gx, gy, gz, tem0); }
+        if (alpha) ns_brinkman(f, p, r, x, y, z, alpha[idx]);
+        if (natconv || alpha) ns_macro(f, p, &r, &x, &y, &z);
+        if (beta) ad_heatex(g, q, t, beta[idx], tail);
+        if (natconv || alpha) ad_macro(g, q, x, y, z, omegag, &t, &hx, &hy, &hz);
+        if (issave) {
+            rho[idx] = r; ux[idx] = x; uy[idx] = y; tem[idx] = t; qx[idx] = hx; qy[idx] = hy;
+            if (f->nd == 3) { uz[idx] = z; qz[idx] = hz; }
+            if (gsnap) {
+                if (!tail) { const int base = idx - idx%4, lane = idx%4; for (int c = 0; c < nc; ++c) gsnap[(size_t)nc*base + 4*c + lane] = q[c]; }
+                else for (int c = 0; c < nc; ++c) gsnap[(size_t)nc*idx + c] = q[c];
+            }
+        }
+        if (tail) ns_eq_sc(f, feq, r, x, y, z); else ns_eq_avx(f, feq, r, x, y, z);
+        relax(f, p, feq, omegaf, iomegaf);
+        if (tail) ad_eq_sc(g, geq, t, x, y, z); else ad_eq_avx(g, geq, t, x, y, z);
+        relax(g, q, geq, omegag, iomegag);
+        scatter(f, idx, p);
+        scatter(g, idx, q);
+    }
+}
+void orc_ad_macro_collide_force_convection(orc_lattice* f, double* rho, double* ux, double* uy, double* uz, double nu,
+        orc_lattice* g, double* tem, double* qx, double* qy, double* qz, double diffusivity, int issave) {
+    ad_collide(f, rho, ux, uy, uz, NULL, nu, g, tem, qx, qy, qz, NULL, diffusivity, NULL, 0, 0, 0, 0, 0, issave, NULL);
+}
+void orc_ad_macro_collide_natural_convection(orc_lattice* f, double* rho, double* ux, double* uy, double* uz, double nu,
+        orc_lattice* g, double* tem, double* qx, double* qy, double* qz, double diffusivity,
+        double gx, double gy, double gz, double tem0, int issave) {
+    ad_collide(f, rho, ux, uy, uz, NULL, nu, g, tem, qx, qy, qz, NULL, diffusivity, NULL, 1, gx, gy, gz, tem0, issave, NULL);
+}
+void orc_ad_macro_brinkman_collide_heat_exchange(orc_lattice* f, double* rho, double* ux, double* uy, double* uz, const double* alpha, double nu,
+        orc_lattice* g, double* tem, double* qx, double* qy, double* qz, const double* beta, double diffusivity, int issave) {
+    ad_collide(f, rho, ux, uy, uz, alpha, nu, g, tem, qx, qy, qz, NULL, diffusivity, beta, 0, 0, 0, 0, 0, issave, NULL);
+}
+void orc_ad_macro_brinkman_collide_force_convection(orc_lattice* f, double* rho, double* ux, double* uy, double* uz, const double* alpha, double nu,
+        orc_lattice* g, double* tem, double* qx, double* qy, double* qz, const double* diffusivity, int issave, double* gsnap) {
+    ad_collide(f, rho, ux, uy, uz, alpha, nu, g, tem, qx, qy, qz, diffusivity, 0.0, NULL, 0, 0, 0, 0, 0, issave, gsnap);
+}
+
+/* ANS::ExternalForceBrinkman: adjointnavierstokes_avx.h:90-110 (AVX), adjointnavierstokes.h:79-93 (scalar) */
+static void ans_brinkman(const L* l, double* f, double rho, double ux, double uy, double uz, double imx, double imy, double imz, double alpha, int sc) {
+    double coef;
+    if (!sc) { coef = 3.0*(alpha/(rho + alpha)); f[0] = f[0] + coef*dot3(l, ux, uy, uz, imx, imy, imz); }
+    else { coef = 3.0*alpha/(rho + alpha); f[0] -= -coef*dot3(l, ux, uy, uz, imx, imy, imz); }
+    for (int c = 1; c < l->nc; ++c) {
+        double s = (l->cx[c] - ux)*imx + (l->cy[c] - uy)*imy;
+        if (l->nd == 3) s = s + (l->cz[c] - uz)*imz;
+        f[c] = f[c] - coef*s;
+    }
+}
+/* adjoint heat exchange: adjointadvection.h:108-112 (scalar), adjointadvection_avx.h:281-290 (AVX) */
+static void aad_heatex(const L* l, double* g, double item, double beta, int sc) {
+    const double coef = sc ? beta*(1.0 + item)/(1.0 + beta) : beta*((1.0 + item)/(1.0 + beta));
+    for (int c = 0; c < l->nc; ++c) g[c] = g[c] - coef;
+}
+/* mass-flow objective force: adjointadvection.h:134-150 == adjointadvection_avx.h:308-322 (same values) */
+static void aad_massflow(const L* l, double* f, double rho, double ux, double uy, double uz, double dx, double dy, double dz) {
+    for (int c = 0; c < l->nc; ++c) {
+        double s = (l->cx[c] - ux)*dx + (l->cy[c] - uy)*dy;
+        if (l->nd == 3) s = s + (l->cz[c] - uz)*dz;
+        f[c] = f[c] - s/rho;
+    }
+}
+/* adjoint family (adjointnavierstokes_avx.h:114-259, adjointadvection_avx.h:326-1255): adjoint moments -> [mass flow] -> coupling /
+ * Brinkman force on f -> adjoint flow moments again -> [heat exchange | buoyancy on g -> adjoint thermal moments again] -> save ->
+ * relax.  g == NULL: the flow-only ANS::MacroBrinkmanCollide. */
+static void aad_collide(L* f, const double* rho, const double* ux, const double* uy, const double* uz,
+                        double* ip, double* iux, double* iuy, double* iuz, double* imx, double* imy, double* imz, const double* alpha, double nu,
+                        L* g, const double* tem, double* item, double* iqx, double* iqy, double* iqz, const double* kfield, double kconst, const double* beta,
+                        int natconv, double gx, double gy, double gz, const double* dirx, const double* diry, int issave, double* igsnap, int skip_iuz_tail) {
+    const double omegaf = 1.0/(3.0*nu + 0.5), iomegaf = 1.0 - omegaf;
+    const int ne = npacked(f), nc = f->nc;
+    if (f->nd == 2) gz = 0.0;
+    #pragma omp parallel for
+    for (int idx = 0; idx < f->nxyz; ++idx) {
+        const int tail = idx >= ne;
+        const double omegag = g ? 1.0/(3.0*(kfield ? kfield[idx] : kconst) + 0.5) : 0.0, iomegag = 1.0 - omegag;
+        const double r = rho[idx], x = ux[idx], y = uy[idx], z = f->nd == 3 ? uz[idx] : 0.0;
+        double p[NCMAX], q[NCMAX], feq[NCMAX], geq[NCMAX], a, bx, by, bz, mx, my, mz, t = 0.0, hx = 0.0, hy = 0.0, hz = 0.0;
+        gather(f, idx, p);
+        if (g) gather(g, idx, q);
+        if (tail) ans_macro_sc(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz); else ans_macro_avx(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz);
+        if (g) aad_macro(g, q, &t, &hx, &hy, &hz);
+        if (dirx) aad_massflow(f, p, r, x, y, z, dirx[idx], diry[idx], 0.0);
+        if (g) aad_brinkman(f, p, r, x, y, z, mx, my, mz, tem[idx], hx, hy, hz, omegag, alpha[idx]);
+        else ans_brinkman(f, p, r, x, y, z, mx, my, mz, alpha[idx], tail);
+        if (tail) ans_macro_sc(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz); else ans_macro_avx(f, p, x, y, z, &a, &bx, &by, &bz, &mx, &my, &mz);
+        if (beta) aad_heatex(g, q, t, beta[idx], tail);
+        if (natconv) aad_natconv(g, q, mx, my, mz, gx, gy, gz);
+        if (g && (beta || natconv)) aad_macro(g, q, &t, &hx, &hy, &hz);
+        if (issave) {
+            ip[idx] = a; iux[idx] = bx; iuy[idx] = by; imx[idx] = mx; imy[idx] = my;
+            if (f->nd == 3) { if (!(tail && skip_iuz_tail)) iuz[idx] = bz; imz[idx] = mz; }
+            if (g) {
+                item[idx] = t; iqx[idx] = hx; iqy[idx] = hy;
+                if (f->nd == 3) iqz[idx] = hz;
+                if (igsnap) {
+                    if (!tail) { const int base = idx - idx%4, lane = idx%4; for (int c = 0; c < nc; ++c) igsnap[(size_t)nc*base + 4*c + lane] = q[c]; }
+                    else for (int c = 0; c < nc; ++c) igsnap[(size_t)nc*idx + c] = q[c];
+                }
+            }
+        }
+        ans_eq(f, feq, x, y, z, a, bx, by, bz);
+        relax(f, p, feq, omegaf, iomegaf);
+        scatter(f, idx, p);
+        if (g) {
+            const double ge = aad_eq(g, t, hx, hy, hz, x, y, z);
+            for (int c = 0; c < nc; ++c) geq[c] = ge;
+            relax(g, q, geq, omegag, iomegag);
+            scatter(g, idx, q);
+        }
+    }
+}
+void orc_ans_macro_brinkman_collide(orc_lattice* l, const double* rho, const double* ux, const double* uy, const double* uz,
+        double* ip, double* iux, double* iuy, double* iuz, double* imx, double* imy, double* imz, double nu, const double* alpha, int issave) {
+    aad_collide(l, rho, ux, uy, uz, ip, iux, iuy, iuz, imx, imy, imz, alpha, nu, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0.0, NULL, 0, 0, 0, 0, NULL, NULL, issave, NULL, 0);
+}
+void orc_aad_macro_brinkman_collide_heat_exchange(orc_lattice* f, const double* rho, const double* ux, const double* uy, const double* uz,
+        double* ip, double* iux, double* iuy, double* iuz, double* imx, double* imy, double* imz, const double* alpha, double nu,
+        orc_lattice* g, const double* tem, double* item, double* iqx, double* iqy, double* iqz, const double* beta, double diffusivity, int issave) {
+    aad_collide(f, rho, ux, uy, uz, ip, iux, iuy, iuz, imx, imy, imz, alpha, nu, g, tem, item, iqx, iqy, iqz, NULL, diffusivity, beta, 0, 0, 0, 0, NULL, NULL, issave, NULL, 0);
+}
+/* quirk: the 3-D scalar tail of this one does not store _iuz (adjointadvection_avx.h:725-735) */
+void orc_aad_macro_brinkman_collide_force_convection(orc_lattice* f, const double* rho, const double* ux, const double* uy, const double* uz,
+        double* ip, double* iux, double* iuy, double* iuz, double* imx, double* imy, double* imz, const double* alpha, double nu,
+        orc_lattice* g, const double* tem, double* item, double* iqx, double* iqy, double* iqz, const double* diffusivity, int issave, double* igsnap) {
+    aad_collide(f, rho, ux, uy, uz, ip, iux, iuy, iuz, imx, imy, imz, alpha, nu, g, tem, item, iqx, iqy, iqz, diffusivity, 0.0, NULL, 0, 0, 0, 0, NULL, NULL, issave, igsnap, 1);
+}
+void orc_aad_macro_brinkman_collide_natural_convection_massflow(orc_lattice* f, const double* rho, const double* ux, const double* uy,
+        double* ip, double* iux, double* iuy, double* imx, double* imy, const double* alpha, double nu,
+        orc_lattice* g, const double* tem, double* item, double* iqx, double* iqy, const double* diffusivity,
+        double gx, double gy, const double* dirx, const double* diry, int issave, double* igsnap) {
+    aad_collide(f, rho, ux, uy, NULL, ip, iux, iuy, NULL, imx, imy, NULL, alpha, nu, g, tem, item, iqx, iqy, NULL, diffusivity, 0.0, NULL, 1, gx, gy, 0.0, dirx, diry, issave, igsnap, 0);
+}
+
+/* ---- adjoint flow closures: adjointnavierstokes.h:97-392; adjoint thermal-flow coupling closure (D2Q9): adjointadvection.h:488-575 */
+static double weighted_face_sum(const double* p, const int* K, int m, double w) {
+    double s = w*p[K[0]];
+    for (int i = 1; i < m; ++i) s = s + p[K[i]];
+    return s;
+}
+typedef struct { const double *v0, *v1, *v2; const int* mask; double eps; int setrho; } ansbc_ctx;
+static void ans_ibc_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    ansbc_ctx* b = (ansbc_ctx*)vctx;
+    if (!b->mask[gidx]) return;
+    double f[NCMAX], nv[NCMAX];
+    int K[NCMAX];
+    gather(l, idx, f);
+    const int m = face_K(l, axis, -dir, K);
+    double rho0;
+    if (b->setrho) {        /* iSetRho: rho0 = ((4|8) f_K0 + sum f_Ki)/(3|6), f_opp(K) = f_K - rho0   (:258-392) */
+        rho0 = l->nd == 2 ? weighted_face_sum(f, K, m, 4.0)/3.0 : weighted_face_sum(f, K, m, 8.0)/6.0;
+        for (int i = 0; i < m; ++i) nv[i] = f[K[i]] - rho0;
+    } else {                /* iSetU (:97-254); the 2-D y-edge version reads ux where uy is meant (:134, :139): reproduced */
+        double u[3] = {b->v0[gidx], b->v1[gidx], l->nd == 3 ? b->v2[gidx] : 0.0};
+        if (l->nd == 2 && axis == 1) u[1] = u[0];
+        const double ua = u[axis];
+        double acc;
+        if (l->nd == 2) {
+            acc = -2.0*b->eps;
+            const double tn = ua*weighted_face_sum(f, K, m, 4.0);
+            acc = dir == -1 ? acc + tn : acc - tn;
+            const int t = 1 - axis;
+            const double ut = axis == 1 ? u[0] : u[1];
+            acc = acc + 3.0*ut*signed_diag(l, f, K, m, t);
+            rho0 = dir == -1 ? acc/(3.0*(1.0 - ua)) : acc/(3.0*(1.0 + ua));
+        } else {
+            acc = -4.0*b->eps;
+            for (int t = 0; t < 3; ++t) {
+                if (t == axis) { const double tn = ua*weighted_face_sum(f, K, m, 8.0); acc = dir == -1 ? acc + tn : acc - tn; }
+                else acc = acc + 3.0*u[t]*signed_diag(l, f, K, m, t);
+            }
+            rho0 = dir == -1 ? acc/(6.0*(1.0 - ua)) : acc/(6.0*(1.0 + ua));
+        }
+        for (int i = 0; i < m; ++i) nv[i] = f[K[i]] + rho0;
+    }
+    for (int i = 0; i < m; ++i) l->f[IF(l, idx, l->opp[K[i]])] = nv[i];
+}
+void orc_ans_ibc_set_u(orc_lattice* l, const double* uxg, const double* uyg, const double* uzg, const int* mask, double eps) {
+    ansbc_ctx b = {uxg, uyg, uzg, mask, eps, 0}; for_all_faces(l, ans_ibc_site, &b);
+}
+void orc_ans_ibc_set_rho(orc_lattice* l, const int* mask) {
+    ansbc_ctx b = {NULL, NULL, NULL, mask, 0.0, 1}; for_all_faces(l, ans_ibc_site, &b);
+}
+/* AAD::iBoundaryConditionSetRho (D2Q9): the mask value selects the thermal closure the edge carries (1 = SetT, 2 = SetQ) */
+typedef struct { L* g; const double *rho, *ux, *uy, *tem; const int* mask; double eps; } aadrho_ctx;
+static void aad_isetrho_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    aadrho_ctx* b = (aadrho_ctx*)vctx;
+    const int kind = b->mask[gidx];
+    if (!kind) return;
+    double f[NCMAX], g[NCMAX], nv[3];
+    int K[NCMAX];
+    gather(l, idx, f);
+    gather(b->g, idx, g);
+    const int m = face_K(l, axis, -dir, K);
+    const double ua = axis == 0 ? b->ux[idx] : b->uy[idx], ut = axis == 0 ? b->uy[idx] : b->ux[idx];
+    const double rho0 = -weighted_face_sum(f, K, m, 4.0)/3.0;
+    const double sd = signed_diag(l, g, K, m, 1 - axis);
+    const double onep = dir == -1 ? 1.0 + 3.0*ua : 1.0 - 3.0*ua;
+    const double onem = dir == -1 ? 1.0 - 3.0*ua : 1.0 + 3.0*ua;
+    double flux0 = 0.0;
+    if (kind == 1) flux0 = b->tem[idx]*ut*sd/(2.0*onep*b->rho[idx]);
+    else if (kind == 2) flux0 = -b->tem[idx]*(weighted_face_sum(g, K, m, 4.0)/3.0 + ut*sd/2.0)/(onem*b->rho[idx]);
+    const double obj0 = b->eps*2.0*b->tem[idx]/(onem*b->rho[idx]);
+    for (int i = 0; i < m; ++i) nv[i] = f[K[i]] + rho0 + flux0 + obj0;
+    for (int i = 0; i < m; ++i) l->f[IF(l, idx, l->opp[K[i]])] = nv[i];
+}
+void orc_aad_ibc_set_rho(orc_lattice* f, orc_lattice* g, const double* rho, const double* ux, const double* uy, const double* tem, const int* mask, double eps) {
+    aadrho_ctx b = {g, rho, ux, uy, tem, mask, eps}; for_all_faces(f, aad_isetrho_site, &b);
+}
+
+/* ---- the other sensitivities: adjointnavierstokes_avx.h:262-293, adjointadvection_avx.h:1257-1401 */
+void orc_ans_sensitivity_brinkman(orc_lattice* l, double* dfds, const double* ux, const double* uy, const double* uz,
+        const double* imx, const double* imy, const double* imz, const double* dads) {
+    const int ne = npacked(l), d3 = l->nd == 3;
+    for (int idx = 0; idx < l->nxyz; ++idx) {
+        if (idx < ne) {
+            const double um = d3 ? ux[idx]*imx[idx] + (uy[idx]*imy[idx] + uz[idx]*imz[idx]) : ux[idx]*imx[idx] + uy[idx]*imy[idx];
+            dfds[idx] = dfds[idx] + 3.0*(dads[idx]*um);
+        } else if (d3) dfds[idx] += 3.0*dads[idx]*(ux[idx]*imx[idx] + uy[idx]*imy[idx] + uz[idx]*imz[idx]);
+        else dfds[idx] += 3.0*dads[idx]*(ux[idx]*imx[idx] + uy[idx]*imy[idx]);
+    }
+}
+void orc_aad_sensitivity_heat_exchange(orc_lattice* g, double* dfds, const double* ux, const double* uy, const double* uz,
+        const double* imx, const double* imy, const double* imz, const double* dads, const double* tem, const double* item, const double* dbds) {
+    for (int idx = 0; idx < g->nxyz; ++idx) {
+        double d = ux[idx]*imx[idx] + uy[idx]*imy[idx];
+        if (g->nd == 3) d = d + uz[idx]*imz[idx];
+        dfds[idx] = dfds[idx] + (3.0*dads[idx]*d - dbds[idx]*(1.0 - tem[idx])*(1.0 + item[idx]));
+    }
+}
+void orc_aad_sensitivity_brinkman_diffusivity(orc_lattice* g, double* dfds, const double* ux, const double* uy, const double* uz,
+        const double* imx, const double* imy, const double* imz, const double* dads, const double* tem, const double* item,
+        const double* iqx, const double* iqy, const double* iqz, const double* gsnap, const double* igsnap, const double* diffusivity, const double* dkds) {
+    /* the volume terms of SensitivityTemperatureAtHeatSource without the face terms (adjointadvection_avx.h:1302-1401) */
+    int* nomask = (int*)calloc((size_t)g->lx*g->ly*g->lz, sizeof(int));
+    orc_aad_sensitivity_temperature_at_heat_source(g, dfds, ux, uy, uz, imx, imy, imz, dads, tem, item, iqx, iqy, iqz, gsnap, igsnap, diffusivity, dkds, NULL, nomask);
+    free(nomask);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* utilities: residual.h:8-50, normalize.h:8-24 (serial loops)                                  */
 double orc_residual3(const double* ux, const double* uy, const double* uz, const double* uxp, const double* uyp, const double* uzp, int n) {
     double unorm = 0.0, dunorm = 0.0;
