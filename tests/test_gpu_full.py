@@ -63,6 +63,41 @@ def test_inits_vs_reference(dim):
     _vs_ref(dim, lambda be, size, n: S.inits(be, dim, size, 90 + n))
 
 
+# the same against the plain-C restatement (oracle/lbm_oracle.c), which always travels with the repository
+def _vs_oracle(dim, fn):
+    orc, cu = O.Backend("orc", dim), cuda(dim)
+    for n, size in enumerate(SIZES[dim]):
+        S.assert_same(fn(orc, size, n), fn(cu, size, n), str(size))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("model", S.FORWARD_MODELS + S.ADJOINT_MODELS)
+def test_collide_models_vs_c_oracle(dim, model):
+    if model.endswith("massflow") and dim == 3:
+        pytest.skip("the reference's D3Q15 MassFlow overload does not compile")
+    _vs_oracle(dim, lambda be, size, n: S.collide(be, dim, model, size, 130 + n))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("kind", S.CLOSURES)
+def test_closures_vs_c_oracle(dim, kind):
+    if kind == "aad_iset_rho" and dim == 3:
+        pytest.skip("the reference's D3Q15 AAD::iBoundaryConditionSetRho does not compile")
+    _vs_oracle(dim, lambda be, size, n: S.closure(be, dim, kind, size, 150 + n))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_inits_and_sensitivities_vs_c_oracle(dim):
+    _vs_oracle(dim, lambda be, size, n: S.inits(be, dim, size, 190 + n))
+    for kind in S.SENSITIVITIES:
+        _vs_oracle(dim, lambda be, size, n: S.sensitivity(be, dim, kind, size, 170 + n))
+
+
+@pytest.mark.parametrize("dim,size,nt", [(3, (11, 10, 9), 25), (2, (18, 15, 1), 31)])
+def test_heatsink_fused_equals_c_oracle(dim, size, nt):
+    H.compare(H.run_cuda(dim, size, nt, fused=True, chunks=(2, 5)), H.run_oplevel(O.Backend("orc", dim), dim, size, nt), "cuda fused vs C oracle")
+
+
 # ---------------------------------------------------------------------------------------------------------
 def check_fixture(tag, res):
     z = np.load(os.path.join(G, "heatsink.npz"))
