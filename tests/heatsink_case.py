@@ -122,6 +122,57 @@ def run_oplevel(be, dim, size, nt, peid=0, m=(1, 1, 1), only_forward=False):
     return res
 
 
+def time_oplevel(be, size, steps, warmup):
+    """seconds of `steps` forward and `steps` adjoint time-loop iterations (after `warmup` each) of the 3-D heatsink loops on a CPU
+    backend, op by op as run_oplevel does — bench.py's CPU baseline when only the C restatement is available (kind "port")"""
+    import time
+    dim = 3
+    p = params(dim, size)
+    f, g = be.lattice(*size), be.lattice(*size)
+    n = f.nxyz
+    alpha, kappa, _, _ = [np.ascontiguousarray(a) for a in design_fields(p, *local_coords(f))]
+    P = predicates(p)
+    gc = gcoords(*size)
+    D = {k: (i32(v(*gc)) if k in ("f_wall", "g_wall", "setT", "setQ", "source") else np.ascontiguousarray(v(*gc), dtype=np.float64)) for k, v in P.items()}
+    A = {k: np.zeros(n) for k in FWD + ADJ}
+    A["rho"][:] = 1.0
+    gsnap, igsnap = np.zeros(n*f.nc), np.zeros(n*f.nc)
+    G = (p["gx"], p["gy"], p["gz"])
+    be.ns_init(f, A["rho"], A["ux"], A["uy"], A["uz"])
+    be.ad_init(g, A["tem"], A["ux"], A["uy"], A["uz"])
+    secs = [0.0, 0.0]
+    for t in range(warmup + steps):
+        if t == warmup:
+            t0 = time.perf_counter()
+        be.ad_macro_brinkman_collide_natural_convection(f, A["rho"], A["ux"], A["uy"], A["uz"], alpha, p["nu"], g, A["tem"], A["qx"], A["qy"], A["qz"],
+                                                        kappa, *G, p["tem0"], 1, gsnap)
+        be.stream(f); be.stream(g)
+        be.bc(f, D["f_wall"], 0)
+        be.ad_bc_set_t(g, D["tem"], A["ux"], A["uy"], A["uz"], D["setT"])
+        be.ad_bc_set_q(g, D["qn"], A["ux"], A["uy"], A["uz"], kappa, 0.0, D["setQ"])
+        be.bc(g, D["g_wall"], 0)
+        be.smooth_corner(f); be.smooth_corner(g)
+    secs[0] = time.perf_counter() - t0
+    be.ans_init(f, A["ux"], A["uy"], A["uz"], A["ip"], A["iux"], A["iuy"], A["iuz"])
+    be.aad_init(g, A["ux"], A["uy"], A["uz"], A["item"], A["iqx"], A["iqy"], A["iqz"])
+    for t in range(warmup + steps):
+        if t == warmup:
+            t0 = time.perf_counter()
+        be.aad_macro_brinkman_collide_natural_convection(f, A["rho"], A["ux"], A["uy"], A["uz"], A["ip"], A["iux"], A["iuy"], A["iuz"],
+                                                         A["imx"], A["imy"], A["imz"], alpha, p["nu"], g, A["tem"], A["item"], A["iqx"], A["iqy"], A["iqz"],
+                                                         kappa, *G, 1, igsnap)
+        be.istream(f); be.istream(g)
+        be.aad_ibc_set_t(g, A["ux"], A["uy"], A["uz"], D["setT"])
+        be.aad_ibc_set_q(g, A["ux"], A["uy"], A["uz"], D["setQ"], 0.0)
+        be.aad_ibc_set_q(g, A["ux"], A["uy"], A["uz"], D["source"], 1.0)
+        be.bc(g, D["g_wall"], 1)
+        be.bc(f, D["f_wall"], 1)
+        be.smooth_corner(f); be.smooth_corner(g)
+    secs[1] = time.perf_counter() - t0
+    f.free(); g.free()
+    return secs
+
+
 def run_cuda(dim, size, nt, fused, peid=0, m=(1, 1, 1), only_forward=False, chunks=(1, 3)):
     """the same iteration through panslbm2_b200's Python mirror of the reference API.  fused=False issues the calls one
     by one exactly like the driver; fused=True records the loop bodies into step plans and advances them in chunks
