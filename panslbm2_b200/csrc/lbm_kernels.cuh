@@ -53,6 +53,14 @@ template <int D> PL_D void pull_h(double (&f)[LT<D>::nc], const double* __restri
         f[c] = pull_halo<D, c>(src, pitch, idx, i, j, k, G, n, pull_offset<D, c>(n), H, inverse);
     });
 }
+// the same, only the directions whose bit is set in `need` (the others read as 0.0 and must not be used)
+template <int D> PL_D void pull_some(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx, const Nbr& n, unsigned need) {
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        f[c] = 0.0;
+        if ((need >> c) & 1u) f[c] = __ldg(src + (size_t)c*pitch + (size_t)(idx + pull_offset<D, c>(n)));
+    });
+}
 template <int D> PL_D void load_site(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx) {
     sfor<0, LT<D>::nc>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = src[(size_t)c*pitch + (size_t)idx]; });
 }
@@ -418,9 +426,13 @@ __global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict_
 // ordinary pull picks the closure results up — with no divergence, no strided x groups in the boundary pass and no
 // 32-byte sector shared between two kernels.  One thread per plane site (sites that also lie on a y/z closure plane, in a
 // SmoothCorner tube or in the AVX tail stay with the boundary pass, which runs their whole program).
+// Directions the closures of the plane at x = 0 ([0]) / x = nx-1 ([1]) read, per lattice (bit c): every one of these 8-byte
+// loads costs a whole 128-byte line of DRAM traffic (ncu: 3.9 DRAM sectors per requested sector).
+struct XNeed { unsigned f[2], g[2]; };
 template <int D, bool HASG>
 __global__ void __launch_bounds__(SHELL_THREADS) k_xclose(Geom G, double* fs, double* gs, const ClosureArgs* __restrict__ prog,
-                                                          const int* __restrict__ xlist, const unsigned long long* __restrict__ xent, int n, int inverse) {
+                                                          const int* __restrict__ xlist, const unsigned long long* __restrict__ xent, int n, int inverse,
+                                                          XNeed need) {
     constexpr int NC = LT<D>::nc;
     __shared__ double tile[(HASG ? 2 : 1)*NC*SHELL_THREADS];
     int t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -432,8 +444,9 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_xclose(Geom G, double* fs, do
     Nbr nb = neighbours(G, i, j, k);
     orient(nb, inverse);
     double f[NC], g[NC];
-    pull<D>(f, fs, G.pitch, idx, nb);
-    if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, nb);
+    const int side = i == 0 ? 0 : 1;
+    pull_some<D>(f, fs, G.pitch, idx, nb, need.f[side]);
+    if constexpr (HASG) pull_some<D>(g, gs, G.pitch, idx, nb, need.g[side]);
     boundary_path_sh<D, HASG>(f, g, tile + threadIdx.x, prog, entries, i, j, k, idx);
     sfor<1, NC>([&](auto C) {
         constexpr int c = decltype(C)::value;

@@ -946,6 +946,7 @@ struct pl_plan {
     int* xlist = nullptr;                  // sites of the x boundary planes whose closures run ahead of the pass (k_xclose)
     unsigned long long* xent = nullptr;
     int nxlist = 0;
+    XNeed xneed = {};
     int nlist = 0, ndirect = 0;
     ClosureArgs* prog[2] = {nullptr, nullptr};
     int nprog = 0;
@@ -1086,11 +1087,11 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity) {
     if (p->nxlist) {
         const int nb = (int)blocks_for(p->nxlist, SHELL_THREADS);
         if (p->f->kind == PL_D2Q9) {
-            if (g) LAUNCH((k_xclose<2, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
-            else LAUNCH((k_xclose<2, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
+            if (g) LAUNCH((k_xclose<2, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
+            else LAUNCH((k_xclose<2, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
         } else {
-            if (g) LAUNCH((k_xclose<3, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
-            else LAUNCH((k_xclose<3, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse);
+            if (g) LAUNCH((k_xclose<3, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
+            else LAUNCH((k_xclose<3, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
         }
     }
     const bool shell_first = !serial && (p->f->halo.on || !opt_fused_first());
@@ -1287,6 +1288,37 @@ int pl_plan_finalize(pl_plan* p) {
             for (int v = lo; v < std::min(g.nx, lo + w); ++v) hx[v] |= SLAB_BIT;
         }
     for (int i : {0, g.nx - 1}) if (hx[i] & SLAB_BIT) ghost[i] = 0;     // a neighbouring plane pulled it into a group
+    // the directions those closures read (lbm_closures.cuh): bounce-back its sources, SetU/SetRho/SetT everything but the
+    // incoming set, SetQ the outgoing set, the adjoint closures their known set K
+    p->xneed = XNeed{};
+    for (int side = 0; side < 2; ++side) {
+        const int i = side ? g.nx - 1 : 0, dir = side ? 1 : -1;
+        if (!ghost[i]) continue;
+        auto set_of = [&](int want, bool equal) {      // directions with c_x == want (equal) or c_x != want
+            unsigned m = 0;
+            for (int c = 0; c < p->f->nc; ++c) {
+                const int cx = p->f->kind == PL_D2Q9 ? LT<2>::cx(c) : LT<3>::cx(c);
+                if ((cx == want) == equal) m |= 1u << c;
+            }
+            return m;
+        };
+        for (size_t e = 0; e < prog[0].size(); ++e) {
+            if (!((hx[i] >> e) & 1ull)) continue;
+            const ClosureArgs& A = prog[0][e];
+            unsigned own = 0, other = 0;
+            switch (A.type) {
+                case BC_BOUNCE: own = set_of(dir, true); break;
+                case BC_IBOUNCE: own = set_of(-dir, true); break;
+                case BC_NS_SET_U: case BC_NS_SET_RHO: case BC_AD_SET_T: own = set_of(-dir, false); break;
+                case BC_AD_SET_Q: own = set_of(dir, true); break;
+                case BC_AAD_ISET_RHO: own = set_of(-dir, true); other = own; break;
+                default: own = set_of(-dir, true); break;      // ANS iSetU/iSetRho, AAD iSetT/iSetQ: the known set K
+            }
+            if (A.on_g) { p->xneed.g[side] |= own; p->xneed.f[side] |= other; }
+            else { p->xneed.f[side] |= own; p->xneed.g[side] |= other; }
+        }
+    }
+    if (env_int("PANSLBM_XNEED_ALL", 0)) p->xneed = XNeed{{0x7fffu, 0x7fffu}, {0x7fffu, 0x7fffu}};
     // SmoothCorner: flag the global boundary planes and their inward neighbours (bit 1); sites with two flagged coordinates
     // form the edge tubes.  Every site SmoothCorner writes (edge lines, corners) or reads (their inward neighbours) must lie
     // in a tube: collide is deferred there until k_smooth has run.
