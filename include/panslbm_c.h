@@ -229,6 +229,15 @@ int pl_plan_finalize(pl_plan*);
  * end_streamed != 0 appends the trailing Stream+closures+SmoothCorner (loop ran to nt);
  * end_streamed == 0 stops right after the last collide (the drivers' convergence `break`). */
 int pl_plan_advance(pl_plan*, int ncollides, int end_streamed);
+/* The same for a caller that knows when it will look at the saved fields.  The reference stores rho, u, T, q (and the thermal
+ * snapshot `_g`) at every site on every step because that is free on a CPU (production/heatsink3D.cpp:151,
+ * advection_avx.h:1040-1052); nobody reads the interior values except Residual every `dt` steps (heatsink3D.cpp:152-160) and the code
+ * after the loop (:227-246).  Only the LAST `save_last` collides of this call store what `issave` asks for at every site; the
+ * earlier ones store it on the closure planes only, where the closures of the same step read the saved velocities
+ * (advection.h:1083-1090).  With the two argument sets a driver alternates between (heatsink3D.cpp:178-183) save_last = 2 leaves
+ * every array exactly as running all steps with stores would: both sets were last written by the final two collides.
+ * save_last < 0: every collide stores everywhere (= pl_plan_advance). */
+int pl_plan_advance_observed(pl_plan*, int ncollides, int end_streamed, int save_last);
 /* Re-bind the ARRAY arguments of one argument set of a finalized plan; the loop body, its closures, masks and scalars stay.
  * For loops whose arrays change every step instead of alternating: the transient drivers keep one set of macroscopic arrays
  * and one snapshot per time step (production/heatsink3D_transient.cpp:50-57, 156-160, 196-200: rho[t], ux[t], ..., gi[t]).
@@ -244,6 +253,9 @@ int pl_plan_set_parity(pl_plan*, int parity);
  * number of launches and the total number of lattice sites those launches updated, and clears the accumulators. */
 int pl_plan_profile(pl_plan*, int enable);
 int pl_plan_profile_read(pl_plan*, double* total_ms, int* launches, long long* total_sites);
+/* the same split by pass kind: [0] = passes that store on the closure planes only (pl_plan_advance_observed), [1] = passes in
+ * which every site stores its macros / snapshot */
+int pl_plan_profile_read2(pl_plan*, double* ms2, int* launches2, long long* sites2);
 
 /* ---- reductions and sensitivities ---------------------------------------------------------------- */
 /* Residual (src/utility/residual.h:8-50): sqrt(sum|u-up|^2 / sum|u|^2) over 1, 2 or 3 components. */

@@ -83,11 +83,13 @@ _PROTOS = {
     "pl_plan_add_smooth_corner_at": (C.c_int, [C.c_void_p] + [C.c_int]*7),
     "pl_plan_finalize": (C.c_int, [C.c_void_p]),
     "pl_plan_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "pl_plan_advance_observed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "pl_plan_rebind": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(CollideArgs), C.POINTER(BcAux), C.c_int]),
     "pl_plan_parity": (C.c_int, [C.c_void_p]),
     "pl_plan_set_parity": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_plan_profile_read": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "pl_plan_profile_read2": (C.c_int, [C.c_void_p, c_double_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "pl_residual": (C.c_int, [C.c_void_p] * 6 + [C.c_size_t, c_double_p]),
     "pl_reduce_sum": (C.c_int, [C.c_void_p, C.c_size_t, c_double_p]),
     "pl_reduce_absmax": (C.c_int, [C.c_void_p, C.c_size_t, c_double_p]),

@@ -764,8 +764,11 @@ class StepPlan:
         check(_lib.lib().pl_plan_finalize(self._h))
         return self
 
-    def advance(self, ncollides, end_streamed=True):
-        check(_lib.lib().pl_plan_advance(self._h, int(ncollides), int(bool(end_streamed))))
+    def advance(self, ncollides, end_streamed=True, save_last=None):
+        """save_last=None: every collide stores its macros / snapshot at every site, as the reference does.  save_last=k: only the
+        last k collides of the call do (pl_plan_advance_observed) — k = 2 leaves both alternating argument sets exactly as the
+        reference loop would at this point, which is all Residual and the code after the loop can see (heatsink3D.cpp:152-160)."""
+        check(_lib.lib().pl_plan_advance_observed(self._h, int(ncollides), int(bool(end_streamed)), -1 if save_last is None else int(save_last)))
 
     def rebind(self, parity, collide: CollideArgs | None = None, aux=()):
         """re-bind the array arguments of argument set `parity` (transient loops: one set of arrays per time step,

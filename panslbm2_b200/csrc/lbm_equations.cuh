@@ -37,7 +37,7 @@ template <> struct ModelFlags<12> { static constexpr unsigned v = F_ADJ | F_G | 
 
 // kernel-side argument block of one collide (built on the host from pl_collide_args)
 struct CollideParams {
-    int issave;
+    int issave;               // 0 = nothing is stored, 1 = every site stores its macros / snapshot, 2 = only the sites on closure planes do
     double omegaf, iomegaf;   // 1/(3 nu + 1/2), 1 - omegaf   (navierstokes_avx.h:151)
     double omegag, iomegag;   // scalar-diffusivity models
     double gx, gy, gz, tem0;
@@ -272,8 +272,10 @@ template <int D> PL_D void relax(double (&p)[LT<D>::nc], const double (&eq)[LT<D
 
 // One site of any Macro*Collide*: f (and g) hold the pre-collision populations on entry and the
 // post-collision ones on exit.  FL = ModelFlags, SC = scalar (tail) order.
+// `save`: store the macroscopic fields (and the thermal snapshot) of this site — P.issave for every site of a saving step; on a
+// step whose outputs nobody can observe (pl_plan_advance_observed) only the sites a closure of the plan reads them at.
 template <int D, unsigned FL, bool SC>
-PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const CollideParams& P, size_t idx) {
+PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const CollideParams& P, size_t idx, bool save) {
     constexpr int NC = LT<D>::nc;
     constexpr bool G = (FL & F_G) != 0;
     double omegag = P.omegag, iomegag = P.iomegag;
@@ -293,13 +295,13 @@ PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Col
         if constexpr (G) ad_macro<D>(g, ux, uy, uz, omegag, tem, qx, qy, qz);
         // quirk: the 2-D scalar tail of NS::MacroBrinkmanCollide stores the macros before the force (navierstokes_avx.h:246-254)
         constexpr bool early = SC && D == 2 && FL == F_BRINK;
-        if constexpr (early) { if (P.issave) { P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy; } }
+        if constexpr (early) { if (save) { P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy; } }
         if constexpr ((FL & F_NATCONV) != 0) ad_natconv<D, SC>(f, tem, P);
         if constexpr ((FL & F_BRINK) != 0) ns_brinkman<D>(f, rho, ux, uy, uz, P.alpha[idx]);
         if constexpr ((FL & (F_NATCONV | F_BRINK)) != 0) ns_macro<D>(f, rho, ux, uy, uz);
         if constexpr ((FL & F_HEATEX) != 0) ad_heatex<D, SC>(g, tem, P.beta[idx]);
         if constexpr (G && (FL & (F_NATCONV | F_BRINK)) != 0) ad_macro<D>(g, ux, uy, uz, omegag, tem, qx, qy, qz);
-        if (P.issave) {
+        if (save) {
             if constexpr (!early) {
                 P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy;
                 if constexpr (D == 3) P.uz[idx] = uz;
@@ -332,7 +334,7 @@ PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Col
         if constexpr ((FL & F_HEATEX) != 0) aad_heatex<D, SC>(g, item, P.beta[idx]);
         if constexpr ((FL & F_NATCONV) != 0) aad_natconv<D>(g, imx, imy, imz, P);
         if constexpr (G && (FL & (F_HEATEX | F_NATCONV)) != 0) aad_macro<D>(g, item, iqx, iqy, iqz);
-        if (P.issave) {
+        if (save) {
             P.ip[idx] = ip; P.iux[idx] = iux; P.iuy[idx] = iuy; P.imx[idx] = imx; P.imy[idx] = imy;
             if constexpr (D == 3) {
                 // quirk: the 3-D scalar tail of AAD::MacroBrinkmanCollideForceConvection does not store _iuz (adjointadvection_avx.h:725-735)

@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(256) k_collide(Geom G, double* __restrict__ fb
     double f[LT<D>::nc], g[LT<D>::nc];
     load_site<D>(f, fb, G.pitch, idx);
     if constexpr ((FL & F_G) != 0) load_site<D>(g, gb, G.pitch, idx);
-    if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
-    else collide_site<D, FL, true>(f, g, P, (size_t)idx);
+    if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave != 0);
+    else collide_site<D, FL, true>(f, g, P, (size_t)idx, P.issave != 0);
     store_site<D>(f, fb, G.pitch, idx);
     if constexpr ((FL & F_G) != 0) store_site<D>(g, gb, G.pitch, idx);
 }
@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
     pull<D>(f, fs, G.pitch, idx, n);
     if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
     if (entries && prog) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
-    collide_site<D, FL, false>(f, g, P, (size_t)idx);
+    // a step nobody observes (issave == 2) stores its macros only where the closures of the next step read them: on the x
+    // closure planes this kernel owns (the sites of every other closure plane belong to the boundary pass, which always stores)
+    collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave == 1 || (P.issave == 2 && entries != 0ull));
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
 }
@@ -368,8 +370,8 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* _
     }
     if (entries) boundary_path_sh<D, HASG>(f, g, tile + threadIdx.x, prog, entries, i, j, k, idx);
     if (t < ndirect) {
-        if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
-        else collide_site<D, FL, true>(f, g, P, (size_t)idx);
+        if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave != 0);
+        else collide_site<D, FL, true>(f, g, P, (size_t)idx, P.issave != 0);
         store_site<D>(f, fd, G.pitch, idx);
         if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
     } else {
@@ -412,8 +414,8 @@ __global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict_
     tube_load<D>(f, tube_f, (size_t)nt, (size_t)tt, T.kind[0], T.a[0]);
     if constexpr (HASG) tube_load<D>(g, tube_g, (size_t)nt, (size_t)tt, T.kind[1], T.a[1]);
     const long long idx = T.idx;
-    if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx);
-    else collide_site<D, FL, true>(f, g, P, (size_t)idx);
+    if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave != 0);
+    else collide_site<D, FL, true>(f, g, P, (size_t)idx, P.issave != 0);
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
 }

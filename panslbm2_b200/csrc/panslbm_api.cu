@@ -960,14 +960,14 @@ struct pl_plan {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // captured fused steps, by [argument set of the closures][buffer parity of f][buffer parity of g]
-    cudaGraphExec_t graphs[2][2][2] = {};
-    uint64_t graph_launches[2][2][2] = {};
+    cudaGraphExec_t graphs[2][2][2][2] = {};       // ... and [every site stores / only the closure planes store]
+    uint64_t graph_launches[2][2][2][2] = {};
     cudaStream_t cap = nullptr;
     int graph_cooldown = 0;        // steps to run ungraphed after the arguments were re-bound (per-step arrays: nothing to replay)
     // measurement hook
     bool profile = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
-    long long profiled_sites = 0;
+    struct ProfEv { cudaEvent_t a, b; int cls; long long sites; };   // cls 0 = a pass that stores only on the closure planes, 1 = every site stores
+    std::vector<ProfEv> events;
 };
 
 namespace {
@@ -1025,18 +1025,19 @@ int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P,
 }
 // fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1
 void drop_graphs(pl_plan* p) {
-    for (auto& a : p->graphs) for (auto& b : a) for (auto& g : b) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    for (auto& a : p->graphs) for (auto& b : a) for (auto& c : b) for (auto& g : c) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
 }
-int plan_fused_body(pl_plan* p, int bc_parity, int col_parity);
+int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save);
 // fused F through a captured graph where that is possible: single block (no NCCL inside), not being profiled, arguments stable
-int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
-    if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial()) return plan_fused_body(p, bc_parity, col_parity);
-    if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity); }
-    const int fc = p->f->cur, gc = p->g ? p->g->cur : 0;
-    cudaGraphExec_t& exec = p->graphs[bc_parity][fc][gc];
+// full_save: every site stores what _issave asks for; else only the sites on closure planes do (pl_plan_advance_observed)
+int plan_fused(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
+    if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial()) return plan_fused_body(p, bc_parity, col_parity, full_save);
+    if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity, full_save); }
+    const int fc = p->f->cur, gc = p->g ? p->g->cur : 0, sv = full_save ? 1 : 0;
+    cudaGraphExec_t& exec = p->graphs[bc_parity][fc][gc][sv];
     if (exec) {
         CU(cudaGraphLaunch(exec, g_stream));
-        g_launches += p->graph_launches[bc_parity][fc][gc];
+        g_launches += p->graph_launches[bc_parity][fc][gc][sv];
         // the host-side state changes of plan_fused_body
         p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
         p->f->streamed = 0; if (p->g) p->g->streamed = 0;
@@ -1048,8 +1049,8 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     g_stream = p->cap;
     cudaGraph_t graph = nullptr;
     int r = PL_OK;
-    if (cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { g_stream = user; cudaGetLastError(); return plan_fused_body(p, bc_parity, col_parity); }
-    r = plan_fused_body(p, bc_parity, col_parity);
+    if (cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { g_stream = user; cudaGetLastError(); return plan_fused_body(p, bc_parity, col_parity, full_save); }
+    r = plan_fused_body(p, bc_parity, col_parity, full_save);
     cudaError_t e = cudaStreamEndCapture(p->cap, &graph);
     g_stream = user;
     if (r) { if (graph) cudaGraphDestroy(graph); return r; }
@@ -1057,14 +1058,15 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity) {
     e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { exec = nullptr; return fail(PL_ERR_CUDA, std::string("fused step: cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-    p->graph_launches[bc_parity][fc][gc] = g_launches - before;
+    p->graph_launches[bc_parity][fc][gc][sv] = g_launches - before;
     CU(cudaGraphLaunch(exec, g_stream));      // the body ran under capture: this launch is its execution
     return PL_OK;
 }
-int plan_fused_body(pl_plan* p, int bc_parity, int col_parity) {
+int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
     CollideParams P; unsigned flags;
     int r = make_params(p->f, p->g, &p->args[col_parity], P, flags);
     if (r) return r;
+    if (P.issave && !full_save) P.issave = 2;
     const int model = p->args[col_parity].model;
     pl_lattice* g = (flags & F_G) ? p->g : nullptr;
     if (p->g && !g) return fail(PL_ERR_ARG, "plan: a single-lattice collide cannot drive a two-lattice plan");
@@ -1108,8 +1110,7 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity) {
     if ((r = dispatch_fused(model, p->f, g, P, S, opt_xinline() ? p->prog[bc_parity] : nullptr, p->inverse))) return r;
     if (p->profile) {
         CU(cudaEventRecord(ev1, g_stream));
-        p->events.emplace_back(ev0, ev1);
-        p->profiled_sites += p->f->g.nxyz - p->nlist;
+        p->events.push_back(pl_plan::ProfEv{ev0, ev1, P.issave == 2 ? 0 : 1, (long long)(p->f->g.nxyz - p->nlist)});
     }
     if (serial) {
         if ((r = dispatch_shell(model, p, g, P, bc_parity, g_stream))) return r;
@@ -1157,7 +1158,7 @@ int pl_plan_destroy(pl_plan* p) {
     for (auto& e : p->stage_ev) if (e) cudaEventDestroy(e);
     drop_graphs(p);
     if (p->cap) cudaStreamDestroy(p->cap);
-    for (auto& e : p->events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto& e : p->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (p->side) { cudaStreamSynchronize(p->side); cudaStreamDestroy(p->side); }
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
@@ -1575,24 +1576,36 @@ int pl_plan_rebind(pl_plan* p, int parity, const pl_collide_args* collide, const
 int pl_plan_parity(const pl_plan* p) { return p ? p->parity : 0; }
 int pl_plan_set_parity(pl_plan* p, int parity) { if (!p) return fail(PL_ERR_ARG, "null plan"); p->parity = parity ? 1 : 0; return PL_OK; }
 int pl_plan_profile(pl_plan* p, int enable) { if (!p) return fail(PL_ERR_ARG, "null plan"); p->profile = enable != 0; return PL_OK; }
-int pl_plan_profile_read(pl_plan* p, double* total_ms, int* launches, long long* total_sites) {
+int pl_plan_profile_read2(pl_plan* p, double* ms2, int* launches2, long long* sites2) {
     if (!p) return fail(PL_ERR_ARG, "null plan");
     CU(cudaStreamSynchronize(g_stream));
-    double ms = 0.0;
+    double ms[2] = {0.0, 0.0}; int n[2] = {0, 0}; long long sites[2] = {0, 0};
     for (auto& e : p->events) {
         float t = 0.f;
-        CU(cudaEventElapsedTime(&t, e.first, e.second));
-        ms += t;
-        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+        CU(cudaEventElapsedTime(&t, e.a, e.b));
+        ms[e.cls] += t; ++n[e.cls]; sites[e.cls] += e.sites;
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
     }
-    if (total_ms) *total_ms = ms;
-    if (launches) *launches = (int)p->events.size();
-    if (total_sites) *total_sites = p->profiled_sites;
-    p->events.clear(); p->profiled_sites = 0;
+    for (int c = 0; c < 2; ++c) {
+        if (ms2) ms2[c] = ms[c];
+        if (launches2) launches2[c] = n[c];
+        if (sites2) sites2[c] = sites[c];
+    }
+    p->events.clear();
+    return PL_OK;
+}
+int pl_plan_profile_read(pl_plan* p, double* total_ms, int* launches, long long* total_sites) {
+    double ms[2]; int n[2]; long long sites[2];
+    int r = pl_plan_profile_read2(p, ms, n, sites);
+    if (r) return r;
+    if (total_ms) *total_ms = ms[0] + ms[1];
+    if (launches) *launches = n[0] + n[1];
+    if (total_sites) *total_sites = sites[0] + sites[1];
     return PL_OK;
 }
 
-int pl_plan_advance(pl_plan* p, int ncollides, int end_streamed) {
+int pl_plan_advance(pl_plan* p, int ncollides, int end_streamed) { return pl_plan_advance_observed(p, ncollides, end_streamed, -1); }
+int pl_plan_advance_observed(pl_plan* p, int ncollides, int end_streamed, int save_last) {
     if (!p || !p->finalized) return fail(PL_ERR_ARG, "pl_plan_advance: plan not finalized");
     if (ncollides < 0) return fail(PL_ERR_ARG, "pl_plan_advance: negative count");
     int r;
@@ -1605,7 +1618,8 @@ int pl_plan_advance(pl_plan* p, int ncollides, int end_streamed) {
     }
     while (done < ncollides) {
         // state: just collided with set `parity`; fuse S(parity) with C(parity^1)
-        if ((r = plan_fused(p, p->parity, p->parity ^ 1))) return r;
+        // only the last `save_last` collides of the call leave their macroscopic fields / snapshot behind at every site
+        if ((r = plan_fused(p, p->parity, p->parity ^ 1, save_last < 0 || ncollides - done <= save_last))) return r;
         p->parity ^= 1;
         ++done;
     }

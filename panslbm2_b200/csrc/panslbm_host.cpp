@@ -142,11 +142,13 @@ Block* find_block(const void* p) {
 void protect(Block* b, int prot) { mprotect(b->base, b->map_bytes, prot); }
 
 void settle_all();
+int flush_pending();
 int acquire_mirror(Block* b);
 
 // bring the host copy of a block up to date (it is in state DEVICE) and make it readable
 void fetch(Block* b) {
     HostTimer timer_(T_FETCH);
+    flush_pending();      // fused passes the engine still holds back may write this array
     pl_synchronize();
     if (b->kind == BK_ARRAY) {
         protect(b, PROT_READ | PROT_WRITE);
@@ -170,6 +172,7 @@ void on_fault(int sig, siginfo_t* si, void* uc) {
     Block* b = find_block(si->si_addr);
     if (b && b->state == ST_DEVICE) { ++g_stat[4]; fetch(b); g_fault_lock.clear(std::memory_order_release); return; }
     if (b && b->state == ST_SHARED) {
+        flush_pending();      // ... or read it: they must see the content it had when the collide was called
         ++g_stat[4]; protect(b, PROT_READ | PROT_WRITE); b->state = ST_HOST;
         g_fault_lock.clear(std::memory_order_release);
         return;
@@ -249,6 +252,7 @@ bool untouched(const Block* b) {
 // ---- the state store: device mirrors under a budget ------------------------------------------------------------------
 // give up the mirror of `v`: bring the host copy up to date first if the device holds the only current one
 int spill(Block* v, double** keep) {
+    flush_pending();
     if (v->state == ST_DEVICE) {
         pl_synchronize();
         protect(v, PROT_READ | PROT_WRITE);
@@ -333,6 +337,7 @@ int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
         }
         b->maybe_fresh = false;
         if (b->state == ST_HOST) {      // also before a write: a kernel may update part of an array only
+            flush_pending();            // passes held back were called with the previous content of the mirror
             if (pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
             ++g_stat[2];
             b->state = ST_SHARED;
@@ -452,6 +457,14 @@ struct Engine {
     Plan* active = nullptr;
     int par = 0;          // REPLAY: argument set of the last collide executed
     int pos = 0;          // REPLAY: Stream/closure/SmoothCorner calls of the current iteration checked off so far
+    // REPLAY: fused passes accepted but not yet queued on the device (0..2, the most recent ones).  The reference stores its
+    // macroscopic fields and the thermal snapshot at every site on every step (production/heatsink3D.cpp:151); a pass is queued
+    // WITHOUT those stores (pl_plan_advance_observed, save_last = 0) once the collide call two steps later has arrived with no
+    // observation in between: by then both alternating argument sets are being overwritten by newer steps, so nothing can
+    // ever see what that pass would have stored.  Any observation — a call that reads an array (Residual, Sensitivity*,
+    // filters), a host access to a mirrored array (page fault), the end of the loop — first queues the held-back passes WITH
+    // their stores, which leaves every array exactly as step-by-step execution would.
+    int pending = 0;
     std::vector<Plan*> plans;
 } E;
 
@@ -465,10 +478,18 @@ int exec_op(const Op& o) {
         default: return pl_smooth_corner(o.l);
     }
 }
+int flush_pending() {
+    if (!E.active || E.pending == 0) return PL_OK;
+    const int n = E.pending;
+    E.pending = 0;
+    if (pl_plan_advance_observed(E.active->p, n, 0, n)) return hfail("pl_plan_advance");
+    return PL_OK;
+}
 int settle() {
     if (!E.active) return PL_OK;
     Plan* pl = E.active;
-    int rc = PL_OK;
+    int rc = flush_pending();
+    if (rc) return rc;
     const int nops = (int)pl->ops[0].size();
     if (E.pos == nops && nops > 0) { rc = flush_bindings(pl, E.par); if (!rc) rc = pl_plan_advance(pl->p, 0, 1); }
     else for (int k = 0; k < E.pos && !rc; ++k) rc = exec_op(pl->ops[E.par][k]);
@@ -573,11 +594,20 @@ int do_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args& d, bool stag
         const int next = E.par ^ 1;
         if (!staged && pl->f == f && pl->g == g && E.pos == nops && like_args(d, pl->c[next])) {
             // the fused pass runs the closures of the finished iteration (set E.par) and this collide (set next)
-            if (!same_args(d, pl->c[next])) { pl->c[next] = d; pl->dirty_c[next] = true; }
-            int rc = flush_bindings(pl, E.par);
-            if (!rc) rc = flush_bindings(pl, next);
-            if (rc) return rc;
-            if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
+            int rc = PL_OK;
+            if (!same_args(d, pl->c[next])) { rc = flush_pending(); pl->c[next] = d; pl->dirty_c[next] = true; }
+            if (pl->dirty_c[E.par] || pl->dirty_aux[E.par] || pl->dirty_c[next] || pl->dirty_aux[next]) {
+                // arrays that change from step to step (transient drivers): every step's stores are read later
+                if (!rc) rc = flush_pending();
+                if (!rc) rc = flush_bindings(pl, E.par);
+                if (!rc) rc = flush_bindings(pl, next);
+                if (rc) return rc;
+                if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
+            } else if (++E.pending > 2) {
+                // the pass accepted two collides ago: its stores can no longer be observed (see Engine::pending)
+                --E.pending;
+                if (pl_plan_advance_observed(pl->p, 1, 0, 0)) return hfail("pl_plan_advance");
+            }
             ++g_stat[0];
             E.par = next; E.pos = 0;
             return PL_OK;
@@ -624,7 +654,11 @@ int do_op(const Op& o, bool staged) {
         Plan* pl = E.active;
         const int nops = (int)pl->ops[0].size();
         if (!staged && E.pos < nops && same_shape(o, pl->ops[E.par][E.pos]) && like_aux(o, pl->ops[E.par][E.pos])) {
-            if (!same_aux(o, pl->ops[E.par][E.pos])) { pl->ops[E.par][E.pos].aux = o.aux; pl->dirty_aux[E.par] = true; }
+            if (!same_aux(o, pl->ops[E.par][E.pos])) {
+                int rc = flush_pending();
+                if (rc) return rc;
+                pl->ops[E.par][E.pos].aux = o.aux; pl->dirty_aux[E.par] = true;
+            }
             ++E.pos;
             pops_written(o.l);
             return PL_OK;
@@ -660,6 +694,7 @@ int plh_owns(const void* p) {
     return it != g_blocks.end() && it->second.kind == BK_ARRAY;
 }
 void plh_free(void* p) {
+    flush_pending();
     auto it = g_blocks.find((uintptr_t)p);
     if (it != g_blocks.end()) drop_block(&it->second);
 }
@@ -776,7 +811,8 @@ int plh_initial_condition(pl_lattice* l, int family, const double* const* h, int
     int info[18];
     pl_lattice_info(l, info);
     const size_t n = (size_t)info[13];
-    int rc = quiesce(l);
+    int rc = flush_pending();
+    if (!rc) rc = quiesce(l);
     if (rc) return rc;
     const double* d[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     g_staged.clear();
@@ -793,6 +829,7 @@ int plh_residual(const double* ux, const double* uy, const double* uz, const dou
     const double* h[6] = {ux, uy, uz, uxp, uyp, uzp};
     double* d[6];
     int rc;
+    if ((rc = flush_pending())) return rc;
     g_staged.clear();
     for (int k = 0; k < 6; ++k) if ((rc = xlate(h[k], n, true, false, &d[k]))) return rc;
     rc = pl_residual(d[0], d[1], d[2], d[3], d[4], d[5], n, out) ? hfail("pl_residual") : PL_OK;
@@ -802,6 +839,7 @@ int plh_residual(const double* ux, const double* uy, const double* uz, const dou
 int plh_normalize(double* v, size_t n) {
     double* d;
     int rc;
+    if ((rc = flush_pending())) return rc;
     g_staged.clear();
     if ((rc = xlate(v, n, true, true, &d))) return rc;
     rc = pl_normalize(d, n) ? hfail("pl_normalize") : PL_OK;
@@ -818,6 +856,7 @@ int plh_sensitivity(pl_lattice* l, const pl_sens_args* h) {
     memset(&d, 0, sizeof(d));
     d.kind = h->kind;
     int rc;
+    if ((rc = flush_pending())) return rc;
     g_staged.clear();
     if ((rc = xlate(h->dfds, n, true, true, &d.dfds))) return rc;
 #define RD(field, len) if ((rc = xlate(h->field, len, true, false, (double**)&d.field))) return rc
@@ -838,6 +877,7 @@ int plh_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds,
     const size_t n = (size_t)info[13], nc = (size_t)info[17];
     double *d_dfds, *d_ux, *d_uy, *d_uz, *d_ig, *d_k, *d_dk;
     int rc;
+    if ((rc = flush_pending())) return rc;
     g_staged.clear();
     if ((rc = xlate(dfds, n, true, true, &d_dfds)) || (rc = xlate(ux, n, true, false, &d_ux)) || (rc = xlate(uy, n, true, false, &d_uy)) ||
         (rc = xlate(uz, n, true, false, &d_uz)) || (rc = xlate(igsnap, n*nc, true, false, &d_ig)) || (rc = xlate(diffusivity, n, true, false, &d_k)) ||
@@ -853,6 +893,7 @@ int plh_filter_apply(pl_filter* f, int mode, double beta, const double* v, const
     if (!f) { g_herr = "plh_filter_apply: null"; return PL_ERR_ARG; }
     double *dv, *dd, *dout;
     int rc;
+    if ((rc = flush_pending())) return rc;
     g_staged.clear();
     if ((rc = xlate(v, n, true, false, &dv)) || (rc = xlate(dfdrho, n, true, false, &dd)) || (rc = xlate(out, n, false, true, &dout))) return rc;
     rc = pl_filter_apply(f, mode, beta, dv, dd, dout) ? hfail("pl_filter_apply") : PL_OK;

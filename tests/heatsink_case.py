@@ -173,10 +173,12 @@ def time_oplevel(be, size, steps, warmup):
     return secs
 
 
-def run_cuda(dim, size, nt, fused, peid=0, m=(1, 1, 1), only_forward=False, chunks=(1, 3)):
+def run_cuda(dim, size, nt, fused, peid=0, m=(1, 1, 1), only_forward=False, chunks=(1, 3), save_last=None, observe=None):
     """the same iteration through panslbm2_b200's Python mirror of the reference API.  fused=False issues the calls one
     by one exactly like the driver; fused=True records the loop bodies into step plans and advances them in chunks
-    (as a driver checking Residual every `dt` steps would)."""
+    (as a driver checking Residual every `dt` steps would).  save_last: only the last k collides of every chunk store their
+    macros / snapshot at every site (pl_plan_advance_observed); observe(A, gsnap, igsnap) is called after every chunk, where
+    the driver would look at its arrays (heatsink3D.cpp:152-160)."""
     import panslbm2_b200 as pl
     from panslbm2_b200 import api
     p = params(dim, size)
@@ -211,8 +213,10 @@ def run_cuda(dim, size, nt, fused, peid=0, m=(1, 1, 1), only_forward=False, chun
             c = min(sizes[len(sizes) - 1] if done else sizes[0], nt - done)
             last = done + c == nt
             par0 = plan.parity
-            plan.advance(c, end_streamed=last)
+            plan.advance(c, end_streamed=last, save_last=save_last)
             done += c
+            if observe is not None:
+                observe(A, gsnap, igsnap)
         # the driver's pointer state after nt full iterations = nt swaps
         if nt % 2:
             swap(pairs)

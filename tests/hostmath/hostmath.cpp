@@ -92,8 +92,8 @@ template <int D, int M> void collide_all(Lat* f, Lat* g, CollideParams P, double
         double p[NC], q[NC];
         load<D>(f, idx, p);
         if constexpr ((FL & F_G) != 0) load<D>(g, idx, q); else for (int c = 0; c < NC; ++c) q[c] = 0.0;
-        if (idx < f->npacked) collide_site<D, FL, false>(p, q, P, (size_t)idx);
-        else collide_site<D, FL, true>(p, q, P, (size_t)idx);
+        if (idx < f->npacked) collide_site<D, FL, false>(p, q, P, (size_t)idx, P.issave != 0);
+        else collide_site<D, FL, true>(p, q, P, (size_t)idx, P.issave != 0);
         store<D>(f, idx, p);
         if constexpr ((FL & F_G) != 0) store<D>(g, idx, q);
     }
