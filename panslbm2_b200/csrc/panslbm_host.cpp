@@ -122,7 +122,7 @@ struct DevPool {
             if (!p && want > need) { want = need; p = pl_array_alloc(want/sizeof(double)); }
             if (!p) { left = 0; return nullptr; }
             slab = (char*)p; left = want;
-            if (next_slab < ((size_t)1 << 30)) next_slab *= 2;
+            if (next_slab < ((size_t)4 << 30)) next_slab *= 2;
         }
         double* p = (double*)slab;
         slab += need; left -= need;
@@ -318,7 +318,10 @@ int acquire_mirror(Block* b) {
     return PL_OK;
 }
 
-// device address of host pointer `h` (n doubles) for a kernel that reads it (rd) and/or writes it (wr)
+// device address of host pointer `h` (n doubles) for a kernel that reads it (rd) and/or writes it (wr).  wr && !rd: the kernel
+// overwrites EVERY element (the macroscopic outputs and the snapshot of a storing collide, a filter result): whatever the array
+// held before is irrelevant, so its mirror needs neither an upload nor a zero-fill — the transient drivers hand nine such
+// arrays (194 MB at 81 x 161 x 81) to every step of the forward loop (production/heatsink3D_transient.cpp:156-160).
 int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
     *out = nullptr;
     if (!h) return PL_OK;
@@ -329,14 +332,15 @@ int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
             int rc = acquire_mirror(b);
             if (rc) return rc;
         }
-        if (b->state == ST_HOST && b->maybe_fresh && untouched(b)) {
+        const bool overwrite = wr && !rd;
+        if (!overwrite && b->state == ST_HOST && b->maybe_fresh && untouched(b)) {
             // never touched by the host: its content is the zero pages mmap would hand out — no upload
             if (pl_array_fill(b->dev, 0.0, b->map_bytes/sizeof(double))) return hfail("mirror fill");
             b->state = ST_SHARED;
             if (!wr) protect(b, PROT_READ);
         }
         b->maybe_fresh = false;
-        if (b->state == ST_HOST) {      // also before a write: a kernel may update part of an array only
+        if (!overwrite && b->state == ST_HOST) {      // also before a partial write: the rest of the array must survive
             flush_pending();            // passes held back were called with the previous content of the mirror
             if (pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
             ++g_stat[2];
@@ -745,7 +749,10 @@ int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* h) {
     RD(alpha); RD(diffusivity); RD(beta); RD(dirx); RD(diry); RD(dirz);
     if (adj) { RD(rho); RD(ux); RD(uy); RD(uz); RD(tem); } else { WR(rho); WR(ux); WR(uy); WR(uz); WR(tem); }
     WR(qx); WR(qy); WR(qz);
-    WR(ip); WR(iux); WR(iuy); WR(iuz); WR(imx); WR(imy); WR(imz); WR(item); WR(iqx); WR(iqy); WR(iqz);
+    WR(ip); WR(iux); WR(iuy);
+    // the 3-D scalar tail of AAD::MacroBrinkmanCollideForceConvection does not store _iuz (adjointadvection_avx.h:725-735): a partial write
+    if (h->model == PL_AAD_FORCE_CONV) { if ((rc = xlate(h->iuz, n, true, save, (double**)&d.iuz))) return rc; } else WR(iuz);
+    WR(imx); WR(imy); WR(imz); WR(item); WR(iqx); WR(iqy); WR(iqz);
 #undef RD
 #undef WR
     if ((rc = xlate(h->snapshot, n*nc, false, save, &d.snapshot))) return rc;

@@ -9,6 +9,7 @@ timeout 600 python bench.py --steps 20 --warmup 5 > $O/r02a_bench_n1.json 2> $O/
 timeout 300 python bench.py --steps 20 --warmup 5 --dims 81,161,81 --ns-size 0 --no-cpu > $O/r02a_bench_81x161x81.json 2> $O/r02a_bench_81.err
 timeout 300 python bench.py --steps 20 --warmup 5 --save-every-step --ns-size 0 --no-cpu > $O/r02a_bench_n1_save_every_step.json 2> $O/r02a_bench_ses.err
 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > $O/r02a_bench_reference.json 2> $O/r02a_bench_reference.err
+PANSLBM_B200_PROFILE=1 timeout 600 python tools/transient_probe.py 200 > $O/r02a_transient_81x161x81_nt200.json 2> $O/r02a_transient.err
 # launch list (cold-cache, serialised: the SHARES count)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02a_launches_bench_default.csv python bench.py --steps 4 --warmup 3 --ns-size 0 --no-cpu > $O/r02a_ncu_list.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02a_launches_bench_81x161x81.csv python bench.py --steps 4 --warmup 3 --dims 81,161,81 --ns-size 0 --no-cpu > $O/r02a_ncu_list81.log 2>&1
@@ -24,7 +25,7 @@ timeout 600 ncu --set full --clock-control none -k regex:k_xclose --launch-skip 
 ncu -i $O/r02a_ncu_full_xclose_81.ncu-rep --page raw --csv > $O/r02a_ncu_full_xclose_81_raw.csv 2>/dev/null
 rm -f $O/*.ncu-rep.tmp
 ls -la $O | tail -30
-tail -3 $O/r02a_tests.log; cat $O/r02a_smoke.log
+tail -3 $O/r02a_tests.log; cat $O/r02a_smoke.log; cat $O/r02a_transient_81x161x81_nt200.json; grep "host profile" $O/r02a_transient.err | tail -30
 python - <<'P'
 import json
 for f in ("r02a_bench_n1", "r02a_bench_81x161x81", "r02a_bench_n1_save_every_step", "r02a_bench_reference"):
