@@ -53,14 +53,6 @@ template <int D> PL_D void pull_h(double (&f)[LT<D>::nc], const double* __restri
         f[c] = pull_halo<D, c>(src, pitch, idx, i, j, k, G, n, pull_offset<D, c>(n), H, inverse);
     });
 }
-// the same, only the directions whose bit is set in `need` (the others read as 0.0 and must not be used)
-template <int D> PL_D void pull_some(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx, const Nbr& n, unsigned need) {
-    sfor<0, LT<D>::nc>([&](auto C) {
-        constexpr int c = decltype(C)::value;
-        f[c] = 0.0;
-        if ((need >> c) & 1u) f[c] = __ldg(src + (size_t)c*pitch + (size_t)(idx + pull_offset<D, c>(n)));
-    });
-}
 template <int D> PL_D void load_site(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx) {
     sfor<0, LT<D>::nc>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = src[(size_t)c*pitch + (size_t)idx]; });
 }
@@ -167,7 +159,9 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 
 // ---------------------------------------------------------------------------------------------------------
 // Per-coordinate plane words of a plan (one 64-bit word per local x / y / z coordinate):
-//   bits 0..60: entry e of the closure program acts on this plane
+//   bits 0..59: entry e of the closure program acts on this plane
+//   bit 60    : (x only) the closures of this x boundary plane run AHEAD of the pass (k_xclose) on the compact wall buffers; the
+//               interior kernel takes the plane's sites as ordinary ones and picks the rebuilt populations up from there (XWall)
 //   bit 61    : the plane is a face of this rank's block along a decomposed axis: its sites pull from the halo receive
 //               buffers and are the first to finish, so that the next exchange overlaps the interior kernel
 //   bit 62    : (x only) the coordinate shares an aligned group of 4 sites (one 32-byte sector; PANSLBM_XSLAB) with an x plane
@@ -180,8 +174,74 @@ struct ShellMask {
     const unsigned long long *x, *y, *z;
     int prefetch;      // closure inputs ahead of the pull (PANSLBM_PREFETCH): 0 = off, 1 = prefetch.global.L2, 2 = prefetch.global.L1, 3 = plain loads
 };
-constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, HALO_BIT = 1ull << 61, ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT | HALO_BIT);
-constexpr int MAX_PROGRAM = 61;
+constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, HALO_BIT = 1ull << 61, GHOST_BIT = 1ull << 60,
+                             ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT | HALO_BIT | GHOST_BIT);
+constexpr int MAX_PROGRAM = 60;
+
+// Compact staging of the x boundary planes whose closures run ahead of the pass.  x planes are the expensive ones for any
+// boundary treatment: consecutive plane sites lie nx*8 bytes apart, so every 8-byte access of a per-site kernel moves a whole
+// 32-byte sector (ncu, round 1: 3.9 DRAM sectors per requested sector in the old k_xclose).  Instead every kernel that produces
+// post-collision populations also drops the ones that Stream() will carry ONTO such a plane into a compact buffer, at the plane
+// index of the site they arrive at:
+//     out[side][c][t],  t = j + ny*k of the TARGET site, side 0: x = 0, side 1: x = nx-1
+// (written by the threads with x in {0, 1} / {nx-2, nx-1}: a handful of extra stores in the warps that hold such a lane).
+// k_xclose of the next pass reads `in` = the `out` of this one — fully coalesced, no shifts: the values already sit where
+// they arrive — runs the closure program of the plane site and leaves the rebuilt populations (the ones Stream() would have
+// pulled through the periodic wrap, whose wrapped-around value is dead) in res[side][c][t]; the interior kernel of that pass
+// overwrites what it pulled through the wrap with them.  Nothing strided is left on the critical path.
+struct XWall {
+    double *out_f, *out_g;            // [2][nc][np]: written by this pass for the next one
+    const double *res_f, *res_g;      // [2][nc][np]: rebuilt populations for this pass (k_xclose)
+    int np;                           // ny*nz
+    int on[2];                        // the plane x = 0 / x = nx-1 is handled this way
+};
+// after the collide of site (i,j,k): the populations that stream onto a compact x plane
+template <int D, bool HASG>
+PL_D void wall_scatter(const XWall& W, const double (&f)[LT<D>::nc], const double (&g)[LT<D>::nc], const Geom& G, int i, int j, int k, int inverse) {
+    constexpr int NC = LT<D>::nc;
+    if (W.out_f == nullptr || (i > 1 && i < G.nx - 2)) return;
+    PL_UNROLL
+    for (int side = 0; side < 2; ++side) {
+        if (!W.on[side]) continue;
+        // the x step that lands on the plane — also through the periodic wrap: a population no closure of the plane rebuilds keeps
+        // the wrapped-around value, exactly as after Stream() (a plane whose closure mask covers only part of it, a lattice without
+        // closures on a plane the other lattice has them on)
+        int di = (side ? G.nx - 1 : 0) - i;
+        di = di == G.nx - 1 ? -1 : (di == 1 - G.nx ? 1 : di);
+        if (di < -1 || di > 1) continue;
+        sfor<0, NC>([&](auto C) {
+            constexpr int c = decltype(C)::value;
+            constexpr int X = LT<D>::cx(c), Y = LT<D>::cy(c), Z = LT<D>::cz(c);
+            if ((inverse ? -X : X) != di) return;
+            int jt = j + (inverse ? -Y : Y), kt = k + (inverse ? -Z : Z);
+            jt = jt < 0 ? G.ny - 1 : (jt >= G.ny ? 0 : jt);
+            kt = kt < 0 ? G.nz - 1 : (kt >= G.nz ? 0 : kt);
+            const size_t o = (size_t)(side*NC + c)*W.np + (size_t)(jt + G.ny*kt);
+            W.out_f[o] = f[c];
+            if constexpr (HASG) W.out_g[o] = g[c];
+        });
+    }
+}
+// after the pull of a site on a compact x plane: the populations pulled through the periodic wrap are replaced by what the
+// closures of the plane made of them
+template <int D, bool HASG>
+PL_D void wall_patch(const XWall& W, double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Geom& G, int i, int j, int k, int inverse) {
+    constexpr int NC = LT<D>::nc;
+    const int side = i == 0 ? 0 : 1;
+    const int want = side ? -1 : 1;      // s*c_x of the populations that arrive from beyond the wall
+    const size_t t = (size_t)(j + G.ny*k);
+    sfor<1, NC>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        constexpr int X = LT<D>::cx(c);
+        if constexpr (X != 0) {
+            if ((inverse ? -X : X) == want) {
+                const size_t o = (size_t)(side*NC + c)*W.np + t;
+                f[c] = W.res_f[o];
+                if constexpr (HASG) g[c] = W.res_g[o];
+            }
+        }
+    });
+}
 PL_D bool in_tube(unsigned long long wx, unsigned long long wy, unsigned long long wz) { return (wx >> 63) + (wy >> 63) + (wz >> 63) >= 2ull; }
 
 // The closure program is a chain of dependent loads (program entry -> mask -> plane values / saved fields of the site), one
@@ -306,7 +366,7 @@ PL_D void boundary_path_sh(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], doubl
 template <int D, int M>
 __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
                                                const double* __restrict__ gs, double* __restrict__ gd,
-                                               CollideParams P, ShellMask S, const ClosureArgs* __restrict__ prog, int inverse) {
+                                               CollideParams P, ShellMask S, const ClosureArgs* __restrict__ prog, int inverse, XWall W) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
@@ -314,10 +374,12 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
     int i, j, k;
     decompose(G, idx, i, j, k);
     unsigned long long entries = 0ull;
+    bool ghost = false;
     if ((S.x[i] | S.y[j] | S.z[k]) != 0ull) {
         const unsigned long long wx = S.x[i], wy = S.y[j], wz = S.z[k];
         if (((wy | wz) & ~TUBE_BIT) != 0ull || (wx & (SLAB_BIT | HALO_BIT)) != 0ull || in_tube(wx, wy, wz)) return;
         entries = wx & ENTRY_BITS;
+        ghost = (wx & GHOST_BIT) != 0ull;
         if (entries && prog && S.prefetch) { prefetch_program(prog, entries, i, j, k, idx, S.prefetch); prefetch_collide<FL>(P, idx, S.prefetch); }
     }
     Nbr n = neighbours(G, i, j, k);
@@ -325,12 +387,14 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
     double f[LT<D>::nc], g[LT<D>::nc];
     pull<D>(f, fs, G.pitch, idx, n);
     if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
+    if (ghost) wall_patch<D, HASG>(W, f, g, G, i, j, k, inverse);
     if (entries && prog) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
     // a step nobody observes (issave == 2) stores its macros only where the closures of the next step read them: on the x
     // closure planes this kernel owns (the sites of every other closure plane belong to the boundary pass, which always stores)
     collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave == 1 || (P.issave == 2 && entries != 0ull));
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+    wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
 }
 
 // The boundary pass of a fused step, one thread per listed site: Stream (pull), the closure program, and then either the
@@ -342,7 +406,7 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* _
                                                          const double* __restrict__ gs, double* __restrict__ gd, CollideParams P, ShellMask S,
                                                          const ClosureArgs* __restrict__ prog, const int* __restrict__ list,
                                                          const unsigned long long* __restrict__ ent, int nlist, int ndirect, int inverse,
-                                                         double* __restrict__ tube_f, double* __restrict__ tube_g, HaloView HF, HaloView HG) {
+                                                         double* __restrict__ tube_f, double* __restrict__ tube_g, HaloView HF, HaloView HG, XWall W) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     constexpr int NC = LT<D>::nc;
@@ -374,6 +438,7 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* _
         else collide_site<D, FL, true>(f, g, P, (size_t)idx, P.issave != 0);
         store_site<D>(f, fd, G.pitch, idx);
         if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+        wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
     } else {
         // SmoothCorner tube: the streamed + closed populations go to the compact tube buffer [c][ntube]; k_tubes finishes them
         const size_t nt = (size_t)(nlist - ndirect), tt = (size_t)(t - ndirect);
@@ -404,7 +469,7 @@ PL_D void tube_load(double (&p)[LT<D>::nc], const double* __restrict__ scr, size
 }
 template <int D, int M>
 __global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict__ tube_f, const double* __restrict__ tube_g, double* __restrict__ fd,
-                                               double* __restrict__ gd, CollideParams P, const TubeSite* __restrict__ info, int nt) {
+                                               double* __restrict__ gd, CollideParams P, const TubeSite* __restrict__ info, int nt, XWall W, int inverse) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     int tt = blockIdx.x*blockDim.x + threadIdx.x;
@@ -418,21 +483,27 @@ __global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict_
     else collide_site<D, FL, true>(f, g, P, (size_t)idx, P.issave != 0);
     store_site<D>(f, fd, G.pitch, idx);
     if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+    if (W.out_f != nullptr) {
+        int i, j, k;
+        decompose(G, idx, i, j, k);
+        wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
+    }
 }
 
 // Closures of the x boundary planes of an undecomposed axis, ahead of the fused pass.  On such a plane the populations a
 // closure rebuilds are exactly the ones Stream() pulls through the periodic wrap (x - c beyond the wall), and the wrapped-
-// around value is dead: the closure overwrites it.  So the closure can run BEFORE the streaming pass: this kernel pulls the
-// plane site's populations from the source buffer, runs the site's closure program, and stores the rebuilt populations
-// back INTO THE WRAP SLOTS they were pulled from.  The interior kernel then treats the plane like any other site — its
-// ordinary pull picks the closure results up — with no divergence, no strided x groups in the boundary pass and no
-// 32-byte sector shared between two kernels.  One thread per plane site (sites that also lie on a y/z closure plane, in a
-// SmoothCorner tube or in the AVX tail stay with the boundary pass, which runs their whole program).
-// Directions the closures of the plane at x = 0 ([0]) / x = nx-1 ([1]) read, per lattice (bit c): every one of these 8-byte
-// loads costs a whole 128-byte line of DRAM traffic (ncu: 3.9 DRAM sectors per requested sector).
+// around value is dead: the closure overwrites it.  So the closure can run BEFORE the streaming pass, on the compact wall
+// buffers (XWall): this kernel reads the populations that arrive at the plane site from `in` (left there by the kernels of the
+// previous pass), runs the site's closure program and stores the rebuilt populations in `res`, from where the interior kernel
+// patches its pull.  The interior kernel then treats the plane like any other site — no divergent closure code, no strided x
+// groups in the boundary pass, no 32-byte sector shared between two kernels, and every access of this kernel is coalesced.
+// One thread per plane site (sites that also lie on a y/z closure plane, in a SmoothCorner tube or in the AVX tail stay with
+// the boundary pass, which runs their whole program on what it pulls itself).
+// Directions the closures of the plane at x = 0 ([0]) / x = nx-1 ([1]) read, per lattice (bit c).
 struct XNeed { unsigned f[2], g[2]; };
 template <int D, bool HASG>
-__global__ void __launch_bounds__(SHELL_THREADS) k_xclose(Geom G, double* fs, double* gs, const ClosureArgs* __restrict__ prog,
+__global__ void __launch_bounds__(SHELL_THREADS) k_xclose(Geom G, const double* __restrict__ in_f, const double* __restrict__ in_g, double* __restrict__ res_f,
+                                                          double* __restrict__ res_g, int np, const ClosureArgs* __restrict__ prog,
                                                           const int* __restrict__ xlist, const unsigned long long* __restrict__ xent, int n, int inverse,
                                                           XNeed need) {
     constexpr int NC = LT<D>::nc;
@@ -443,25 +514,48 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_xclose(Geom G, double* fs, do
     const unsigned long long entries = xent[t];
     int i, j, k;
     decompose(G, idx, i, j, k);
-    Nbr nb = neighbours(G, i, j, k);
-    orient(nb, inverse);
-    double f[NC], g[NC];
     const int side = i == 0 ? 0 : 1;
-    pull_some<D>(f, fs, G.pitch, idx, nb, need.f[side]);
-    if constexpr (HASG) pull_some<D>(g, gs, G.pitch, idx, nb, need.g[side]);
+    const size_t tp = (size_t)(j + G.ny*k);
+    double f[NC], g[NC];
+    sfor<0, NC>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        const size_t o = (size_t)(side*NC + c)*np + tp;
+        // what the closures read, and the populations that arrive through the wrap (the default of whatever they do not rebuild)
+        const bool wrapped = (inverse ? -LT<D>::cx(c) : LT<D>::cx(c)) == (side ? -1 : 1);
+        f[c] = (((need.f[side] >> c) & 1u) || wrapped) ? in_f[o] : 0.0;
+        if constexpr (HASG) g[c] = (((need.g[side] >> c) & 1u) || wrapped) ? in_g[o] : 0.0;
+    });
     boundary_path_sh<D, HASG>(f, g, tile + threadIdx.x, prog, entries, i, j, k, idx);
+    const int want = side ? -1 : 1;
     sfor<1, NC>([&](auto C) {
         constexpr int c = decltype(C)::value;
         constexpr int X = LT<D>::cx(c);
         if constexpr (X != 0) {
-            const long long dx = X > 0 ? nb.m[0] : nb.p[0];
-            if (dx != 1 && dx != -1) {      // pulled through the wrap: the slot belongs to this site alone
-                const size_t o = (size_t)c*G.pitch + (size_t)(idx + pull_offset<D, c>(nb));
-                fs[o] = f[c];
-                if constexpr (HASG) gs[o] = g[c];
+            if ((inverse ? -X : X) == want) {
+                const size_t o = (size_t)(side*NC + c)*np + tp;
+                res_f[o] = f[c];
+                if constexpr (HASG) res_g[o] = g[c];
             }
         }
     });
+}
+// fill the compact wall buffer from the (just collided) populations of the lattice: what wall_scatter of a fused pass would have
+// left — needed once, when something other than a fused pass of the plan produced the current populations
+template <int D>
+__global__ void __launch_bounds__(128) k_xfill(Geom G, const double* __restrict__ src, double* __restrict__ out, int np, int inverse, int on0, int on1) {
+    constexpr int NC = LT<D>::nc;
+    const int t = blockIdx.x*blockDim.x + threadIdx.x;
+    const int c = blockIdx.y % NC, side = blockIdx.y / NC;
+    if (t >= np || !(side ? on1 : on0)) return;
+    const int jt = t % G.ny, kt = t / G.ny;
+    const int X = rdir<D>(c, 0), Y = rdir<D>(c, 1), Z = rdir<D>(c, 2);
+    const int s = inverse ? -1 : 1;
+    int is = (side ? G.nx - 1 : 0) - s*X;
+    is = is < 0 ? G.nx - 1 : (is >= G.nx ? 0 : is);
+    int js = jt - s*Y, ks = kt - s*Z;
+    js = js < 0 ? G.ny - 1 : (js >= G.ny ? 0 : js);
+    ks = ks < 0 ? G.nz - 1 : (ks >= G.nz ? 0 : ks);
+    out[(size_t)(side*NC + c)*np + t] = src[(size_t)c*G.pitch + (size_t)(is + (long long)G.nx*(js + (long long)G.ny*ks))];
 }
 
 // SmoothCorner (d3q15.h:199-220, 1242-1303; d2q9.h:127-132, 578-587).  A line/point list is built on the host.

@@ -87,6 +87,7 @@ struct pl_lattice {
     double* buf[2] = {nullptr, nullptr};
     int cur = 0;
     int streamed = 1;              // phase: 1 = populations are "pre-collision" (after init / Stream+closures), 0 = just collided
+    uint64_t version = 0;          // bumped by everything that changes the populations (plans check whether their wall buffers still describe them)
     double* current() const { return buf[cur]; }
     double* other() const { return buf[cur ^ 1]; }
     // ---- halo of a block-decomposed lattice (lbm_halo.cuh) ----
@@ -238,7 +239,7 @@ void halo_release(pl_lattice* l) {
     if (g_comm.mode == COMM_LOOPBACK && h.seq >= 0 && l->peid < (int)g_comm.loop.size() && h.seq < (int)g_comm.loop[l->peid].size())
         g_comm.loop[l->peid][h.seq] = nullptr;
 }
-inline void halo_touch(pl_lattice* l) { l->halo.packed = false; }
+inline void halo_touch(pl_lattice* l) { l->halo.packed = false; ++l->version; }
 
 int halo_pack(pl_lattice* l, int inverse) {
     pl_lattice::Halo& h = l->halo;
@@ -746,9 +747,9 @@ template <int D, int M> int launch_collide(pl_lattice* f, pl_lattice* g, const C
     LAUNCH((k_collide<D, M>), blocks_for(count, 256), 256, f->g, f->current(), g ? g->current() : nullptr, P, list, count);
     return PL_OK;
 }
-template <int D, int M> int launch_fused(pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse) {
+template <int D, int M> int launch_fused(pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse, const XWall& W) {
     if (f->g.npacked == 0) return PL_OK;
-    LAUNCH((k_fused<D, M>), blocks_for(f->g.npacked, 256), 256, f->g, f->current(), f->other(), g ? g->current() : nullptr, g ? g->other() : nullptr, P, S, prog, inverse);
+    LAUNCH((k_fused<D, M>), blocks_for(f->g.npacked, 256), 256, f->g, f->current(), f->other(), g ? g->current() : nullptr, g ? g->other() : nullptr, P, S, prog, inverse, W);
     return PL_OK;
 }
 #define MODEL_SWITCH(D, FN, ...)                                                     \
@@ -775,12 +776,12 @@ int dispatch_collide(int model, pl_lattice* f, pl_lattice* g, const CollideParam
     }
     return fail(PL_ERR_UNSUPPORTED, "collide: model not available for this lattice");
 }
-int dispatch_fused(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse) {
+int dispatch_fused(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse, const XWall& W) {
     if (f->kind == PL_D2Q9) {
-        MODEL_SWITCH(2, launch_fused, f, g, P, S, prog, inverse)
-        if (model == 12) return launch_fused<2, 12>(f, g, P, S, prog, inverse);
+        MODEL_SWITCH(2, launch_fused, f, g, P, S, prog, inverse, W)
+        if (model == 12) return launch_fused<2, 12>(f, g, P, S, prog, inverse, W);
     } else {
-        MODEL_SWITCH(3, launch_fused, f, g, P, S, prog, inverse)
+        MODEL_SWITCH(3, launch_fused, f, g, P, S, prog, inverse, W)
     }
     return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
 }
@@ -947,6 +948,11 @@ struct pl_plan {
     unsigned long long* xent = nullptr;
     int nxlist = 0;
     XNeed xneed = {};
+    // compact wall buffers of those planes (XWall): per lattice two `out` buffers, alternating with the population buffer the pass
+    // reads (a pass writes the one the next pass reads while k_xclose of this pass may still be reading the other), one `res`
+    double *xout[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}}, *xres[2] = {nullptr, nullptr};
+    int xon[2] = {0, 0};
+    uint64_t xver[2] = {~0ull, ~0ull};     // lattice versions the buffers were left for by the plan's own last pass
     int nlist = 0, ndirect = 0;
     ClosureArgs* prog[2] = {nullptr, nullptr};
     int nprog = 0;
@@ -1000,18 +1006,29 @@ int plan_collide_full(pl_plan* p, int parity) {              // standalone C: ev
     if (p->g && (r = halo_prepare(p->g, p->inverse, true))) return r;
     return PL_OK;
 }
+XWall plan_xwall(const pl_plan* p, bool with_g) {
+    XWall W;
+    memset(&W, 0, sizeof(W));
+    if (!p->nxlist) return W;
+    const int wr = p->f->cur ^ 1;      // the buffer the NEXT pass reads (it alternates with the population buffers)
+    W.out_f = p->xout[0][wr]; W.res_f = p->xres[0];
+    if (with_g) { W.out_g = p->xout[1][wr]; W.res_g = p->xres[1]; }
+    W.np = p->f->g.ny*p->f->g.nz; W.on[0] = p->xon[0]; W.on[1] = p->xon[1];
+    return W;
+}
 template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
     if (p->nlist == 0) return PL_OK;
+    const XWall W = plan_xwall(p, g != nullptr);
     HaloView HF, HG;
     int r;
     if ((r = halo_view(p->f, HF))) return r;
     if (g) { if ((r = halo_view(g, HG))) return r; } else memset(&HG, 0, sizeof(HG));
     LAUNCH_ON(st, (k_shell<D, M>), blocks_for(p->nlist, SHELL_THREADS), SHELL_THREADS, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
-           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->ent, p->nlist, p->ndirect, p->inverse, p->tube_f, p->tube_g, HF, HG);
+           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->ent, p->nlist, p->ndirect, p->inverse, p->tube_f, p->tube_g, HF, HG, W);
     // SmoothCorner + collide of the tube sites, right behind the boundary pass on the same stream
     const int ntube = p->nlist - p->ndirect;
     if (ntube > 0)
-        LAUNCH_ON(st, (k_tubes<D, M>), blocks_for(ntube, 128), 128, p->f->g, p->tube_f, p->tube_g, p->f->other(), g ? g->other() : nullptr, P, p->tube_info, ntube);
+        LAUNCH_ON(st, (k_tubes<D, M>), blocks_for(ntube, 128), 128, p->f->g, p->tube_f, p->tube_g, p->f->other(), g ? g->other() : nullptr, P, p->tube_info, ntube, W, p->inverse);
     return PL_OK;
 }
 int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
@@ -1031,7 +1048,8 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save);
 // fused F through a captured graph where that is possible: single block (no NCCL inside), not being profiled, arguments stable
 // full_save: every site stores what _issave asks for; else only the sites on closure planes do (pl_plan_advance_observed)
 int plan_fused(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
-    if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial()) return plan_fused_body(p, bc_parity, col_parity, full_save);
+    const bool xstale = p->nxlist && (p->xver[0] != p->f->version || (p->g && p->xver[1] != p->g->version));      // the one-off refill must not be captured
+    if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial() || xstale) return plan_fused_body(p, bc_parity, col_parity, full_save);
     if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity, full_save); }
     const int fc = p->f->cur, gc = p->g ? p->g->cur : 0, sv = full_save ? 1 : 0;
     cudaGraphExec_t& exec = p->graphs[bc_parity][fc][gc][sv];
@@ -1086,14 +1104,26 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
     // a decomposed block wants its faces first (the next exchange hangs on them); a single block queues the interior first
     // so that the boundary CTAs interleave with it instead of running alone at their lower memory efficiency
     // closures of the x boundary planes, into the wrap slots of the source buffers (the boundary pass may run beside this)
+    const XWall W = plan_xwall(p, g != nullptr);
     if (p->nxlist) {
+        const int rd = p->f->cur, np = W.np, nc = p->f->nc;
+        // wall buffers left by something else than this plan's own last pass (first pass after a standalone collide): refill
+        for (int l = 0; l < (g ? 2 : 1); ++l) {
+            pl_lattice* q = l ? g : p->f;
+            if (p->xver[l] == q->version) continue;
+            dim3 grid(blocks_for(np, 128), 2*nc);
+            if (q->kind == PL_D2Q9) LAUNCH(k_xfill<2>, grid, 128, q->g, q->current(), p->xout[l][rd], np, p->inverse, p->xon[0], p->xon[1]);
+            else LAUNCH(k_xfill<3>, grid, 128, q->g, q->current(), p->xout[l][rd], np, p->inverse, p->xon[0], p->xon[1]);
+        }
         const int nb = (int)blocks_for(p->nxlist, SHELL_THREADS);
+        const double *inf = p->xout[0][rd], *ing = g ? p->xout[1][rd] : nullptr;
+        double *rf = p->xres[0], *rg = g ? p->xres[1] : nullptr;
         if (p->f->kind == PL_D2Q9) {
-            if (g) LAUNCH((k_xclose<2, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
-            else LAUNCH((k_xclose<2, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
+            if (g) LAUNCH((k_xclose<2, true>), nb, SHELL_THREADS, p->f->g, inf, ing, rf, rg, np, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
+            else LAUNCH((k_xclose<2, false>), nb, SHELL_THREADS, p->f->g, inf, ing, rf, rg, np, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
         } else {
-            if (g) LAUNCH((k_xclose<3, true>), nb, SHELL_THREADS, p->f->g, p->f->current(), g->current(), p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
-            else LAUNCH((k_xclose<3, false>), nb, SHELL_THREADS, p->f->g, p->f->current(), (double*)nullptr, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
+            if (g) LAUNCH((k_xclose<3, true>), nb, SHELL_THREADS, p->f->g, inf, ing, rf, rg, np, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
+            else LAUNCH((k_xclose<3, false>), nb, SHELL_THREADS, p->f->g, inf, ing, rf, rg, np, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
         }
     }
     const bool shell_first = !serial && (p->f->halo.on || !opt_fused_first());
@@ -1107,7 +1137,7 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
         CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, g_stream));
     }
-    if ((r = dispatch_fused(model, p->f, g, P, S, opt_xinline() ? p->prog[bc_parity] : nullptr, p->inverse))) return r;
+    if ((r = dispatch_fused(model, p->f, g, P, S, opt_xinline() ? p->prog[bc_parity] : nullptr, p->inverse, W))) return r;
     if (p->profile) {
         CU(cudaEventRecord(ev1, g_stream));
         p->events.push_back(pl_plan::ProfEv{ev0, ev1, P.issave == 2 ? 0 : 1, (long long)(p->f->g.nxyz - p->nlist)});
@@ -1125,6 +1155,7 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
     p->f->streamed = 0; if (p->g) p->g->streamed = 0;
     // every block-face site is final: pack and post the next exchange now, it overlaps the next interior kernel
     halo_touch(p->f); if (p->g) halo_touch(p->g);
+    p->xver[0] = p->f->version; if (p->g) p->xver[1] = p->g->version;      // the wall buffers describe exactly these populations
     if ((r = halo_prepare(p->f, p->inverse, true))) return r;
     if (p->g && (r = halo_prepare(p->g, p->inverse, true))) return r;
     return PL_OK;
@@ -1154,6 +1185,7 @@ int pl_plan_destroy(pl_plan* p) {
     cudaStreamSynchronize(g_stream);
     cudaFree(p->mx); cudaFree(p->my); cudaFree(p->mz); cudaFree(p->list); cudaFree(p->ent); cudaFree(p->xlist); cudaFree(p->xent); cudaFree(p->prog[0]); cudaFree(p->prog[1]);
     cudaFree(p->tube_f); cudaFree(p->tube_g); cudaFree(p->tube_info);
+    for (int l = 0; l < 2; ++l) { cudaFree(p->xout[l][0]); cudaFree(p->xout[l][1]); cudaFree(p->xres[l]); }
     if (p->stage) cudaFreeHost(p->stage);
     for (auto& e : p->stage_ev) if (e) cudaEventDestroy(e);
     drop_graphs(p);
@@ -1247,7 +1279,7 @@ int pl_plan_finalize(pl_plan* p) {
     std::vector<ClosureArgs> prog[2];
     for (auto& b : p->bcs) {
         if (b.bc->empty) continue;
-        if (prog[0].size() >= (size_t)MAX_PROGRAM) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: more than 61 non-empty closures in one loop body");
+        if (prog[0].size() >= (size_t)MAX_PROGRAM) return fail(PL_ERR_UNSUPPORTED, "pl_plan_finalize: more than 60 non-empty closures in one loop body");
         (*h[b.bc->axis])[b.bc->coord - off[b.bc->axis]] |= 1ull << prog[0].size();
         for (int par = 0; par < 2; ++par) {
             ClosureArgs A;
@@ -1289,6 +1321,7 @@ int pl_plan_finalize(pl_plan* p) {
             for (int v = lo; v < std::min(g.nx, lo + w); ++v) hx[v] |= SLAB_BIT;
         }
     for (int i : {0, g.nx - 1}) if (hx[i] & SLAB_BIT) ghost[i] = 0;     // a neighbouring plane pulled it into a group
+    for (int i : {0, g.nx - 1}) if (ghost[i]) hx[i] |= GHOST_BIT;
     // the directions those closures read (lbm_closures.cuh): bounce-back its sources, SetU/SetRho/SetT everything but the
     // incoming set, SetQ the outgoing set, the adjoint closures their known set K
     p->xneed = XNeed{};
@@ -1512,7 +1545,14 @@ int pl_plan_finalize(pl_plan* p) {
         CU(cudaMemcpy(p->tube_info, info.data(), (size_t)ntube*sizeof(TubeSite), cudaMemcpyHostToDevice));
     }
     p->nxlist = (int)xlist.size();
+    for (int l = 0; l < 2; ++l) { cudaFree(p->xout[l][0]); cudaFree(p->xout[l][1]); cudaFree(p->xres[l]); p->xout[l][0] = p->xout[l][1] = p->xres[l] = nullptr; p->xver[l] = ~0ull; }
+    p->xon[0] = ghost[0]; p->xon[1] = ghost[g.nx - 1];
     if (p->nxlist) {
+        const size_t wb = (size_t)2*p->f->nc*g.ny*g.nz*sizeof(double);
+        for (int l = 0; l < (p->g ? 2 : 1); ++l) {
+            CU(cudaMalloc(&p->xout[l][0], wb)); CU(cudaMalloc(&p->xout[l][1], wb)); CU(cudaMalloc(&p->xres[l], wb));
+            CU(cudaMemsetAsync(p->xout[l][0], 0, wb, g_stream)); CU(cudaMemsetAsync(p->xout[l][1], 0, wb, g_stream)); CU(cudaMemsetAsync(p->xres[l], 0, wb, g_stream));
+        }
         std::vector<unsigned long long> xent(xlist.size());
         for (size_t t = 0; t < xlist.size(); ++t) {
             int i, j, k;

@@ -3,7 +3,7 @@
 # launch list and ncu --set full captures of the passes that store on the closure planes only
 mkdir -p gpurun_out
 O=gpurun_out
-(timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15) > $O/r02a_tests.log
+(timeout 1200 python -m pytest tests -m gpu -q --maxfail=25 2>&1 | tail -60) > $O/r02a_tests.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 > $O/r02a_smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > $O/r02a_bench_n1.json 2> $O/r02a_bench_n1.err
 timeout 300 python bench.py --steps 20 --warmup 5 --dims 81,161,81 --ns-size 0 --no-cpu > $O/r02a_bench_81x161x81.json 2> $O/r02a_bench_81.err
