@@ -38,13 +38,15 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = LIB + ".tmp"       # replaced atomically: a snapshot of the tree (gpurun) never sees a half-written library
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)   # this image exports CC=/opt/gcc/bin/gcc; let nvcc use the system g++
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libpanslbm_b200.so")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(r.stderr)
     return LIB
