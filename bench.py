@@ -524,7 +524,9 @@ def run_ours(args):
                    "global_sites": NG, "sites_per_gpu": N, "lattice_updates_per_step": 2, "save_policy": policy,
                    "parallelism": "1 GPU" if world == 1 else f"block decomposition {m[0]}x{m[1]}x{m[2]} (PE grid of the reference, d3q15.h:29-35), halo exchange "
                                                              "by ncclSend/ncclRecv per step and lattice, overlapped with the interior kernel",
-                   "l2": f"population buffers {4*15*8*N/1e9:.1f} GB per GPU " + (">> 126 MB L2, no flush needed" if 4*15*8*N > 4*126e6 else "(L2-sized: the step is launch-bound, see DESIGN.md)")},
+                   "l2": f"population buffers {2*15*8*N/1e9:.1f} GB per GPU (ONE buffer per lattice, updated in place" + ("" if os.environ.get("PANSLBM_INPLACE", "1") != "0" else "; PANSLBM_INPLACE=0: plus two spares") + ") " +
+                         (">> 126 MB L2, no flush needed" if 2*15*8*N > 4*126e6 else "(L2-sized: the step is launch-bound, see DESIGN.md)"),
+                   "library": os.path.basename(_lib.LIB_PATH)},
         "clocks": sampler.summary(),
         "sweeps": {"forward_mlups": NG*K/(fwd_ms*1e-3)/1e6, "adjoint_mlups": NG*K/(adj_ms*1e-3)/1e6, **extra},
         "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": 4*N*8/K, "d2h_bytes_per_step": 2*N*8/K,

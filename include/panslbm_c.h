@@ -107,6 +107,14 @@ int pl_lattice_get_host(pl_lattice*, double* f0_host, double* f_host);
 int pl_lattice_streamed(const pl_lattice*);
 /* Device SoA view of the current populations: c-th plane at base + c*pitch (pitch in doubles). */
 int pl_lattice_device_view(pl_lattice*, double** base, size_t* pitch);
+/* Population memory.  A lattice owns ONE buffer of nc*pitch doubles (the reference keeps two, f and the hidden fnext, d3q15.h:41-45,
+ * 238): the fused passes of a plan update it in place.  Only the operations that cannot — a standalone Stream()/iStream(), bringing
+ * a lattice a fused pass left in its streamed layout back to the natural one — borrow a spare buffer, shared by all lattices of one
+ * shape and given back to the device once a few in-place passes have gone by without a borrow (or by pl_memory_trim).
+ * out[0] = bytes of population buffers owned by live lattices, out[1] = spare bytes held right now, out[2] = borrows so far,
+ * out[3] = layout conversions so far. */
+int pl_memory_stats(uint64_t* out4);
+int pl_memory_trim(void);
 
 /* Stream()/iStream() single-rank path (d3q15.h:601-616, 964-979; d2q9.h:284-295): pull with periodic wrap. */
 int pl_stream(pl_lattice*, int inverse);

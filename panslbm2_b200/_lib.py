@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpanslbm_b200.so")
+# PANSLBM_LIB_TAG=<tag>: an A/B build variant (build.py, PANSLBM_BUILD_TAG) instead of the library; tuning experiments only
+_TAG = os.environ.get("PANSLBM_LIB_TAG", "")
+LIB_PATH = os.path.join(HERE, "libpanslbm_b200" + ("_" + _TAG if _TAG else "") + ".so")
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -64,6 +66,8 @@ _PROTOS = {
     "pl_lattice_get_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_lattice_device_view": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "pl_lattice_streamed": (C.c_int, [C.c_void_p]),
+    "pl_memory_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
+    "pl_memory_trim": (C.c_int, []),
     "pl_stream": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_smooth_corner": (C.c_int, [C.c_void_p]),
     "pl_smooth_corner_at": (C.c_int, [C.c_void_p] + [C.c_int] * 6),

@@ -52,14 +52,14 @@ struct HaloView {
 // population c of the site (i,j,k) after Stream (inverse = 0: source x - c) / iStream (inverse = 1: source x + c);
 // `n` holds the local periodic neighbour deltas already oriented for `inverse` (see orient()).
 template <int D, int c, class NbrT>
-PL_D double pull_halo(const double* __restrict__ src, size_t pitch, long long idx, int i, int j, int k, const Geom& G, const NbrT& n,
-                      long long local_offset, const HaloView& H, int inverse) {
+PL_D double pull_halo(const double* __restrict__ src, long long idx, int i, int j, int k, const Geom& G, const NbrT& n,
+                      size_t local_loc, const HaloView& H, int inverse) {
     constexpr int X = LT<D>::cx(c), Y = LT<D>::cy(c), Z = LT<D>::cz(c);
     const int dx = inverse ? X : -X, dy = inverse ? Y : -Y, dz = inverse ? Z : -Z;   // where the source lies
     const bool bx = X != 0 && H.e[0] && (dx < 0 ? i == 0 : i == G.nx - 1);
     const bool by = Y != 0 && H.e[1] && (dy < 0 ? j == 0 : j == G.ny - 1);
     const bool bz = D == 3 && Z != 0 && H.e[2] && (dz < 0 ? k == 0 : k == G.nz - 1);
-    if (!(bx || by || bz)) return src[(size_t)c*pitch + (size_t)(idx + local_offset)];
+    if (!(bx || by || bz)) return src[local_loc];      // inside the block: wherever the layout of the pass keeps it (lbm_kernels.cuh: read_loc)
     const int code = halo_code(bx ? dx : 0, by ? dy : 0, bz ? dz : 0);
     const int mask = (bx ? 1 : 0) | (by ? 2 : 0) | (bz ? 4 : 0);
     // source coordinates along the free axes (local periodic wrap as Index(), d3q15.h:136-141)
@@ -86,14 +86,32 @@ struct PackMsg {
 };
 struct PackList { PackMsg m[26]; int count; };
 
-// gather the outgoing populations of every message from the current populations (one launch per lattice; grid.y = message)
-__global__ void __launch_bounds__(128) k_halo_pack(const double* __restrict__ cur, size_t pitch, PackList L) {
+// gather the outgoing populations of every message from the current populations (one launch per lattice; grid.y = message).
+// streamed != 0: the lattice is in the streamed layout P of the in-place passes (lbm_kernels.cuh): population c of site x sits at
+// (opp(c), x + s*c), the step taken with the LOCAL periodic wrap — for an outgoing population that is a site of the opposite face.
+template <int D>
+__global__ void __launch_bounds__(128) k_halo_pack(const double* __restrict__ cur, Geom G, PackList L, int streamed, int inverse) {
     const PackMsg& M = L.m[blockIdx.y];
     const long long rsize = (long long)M.n1*M.n2;
+    const size_t pitch = G.pitch;
     for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < rsize; t += (long long)gridDim.x*blockDim.x) {
         const long long a = t%M.n1, b = t/M.n1;
         const long long site = M.base + a*M.s1 + b*M.s2;
-        for (int s = 0; s < M.npop; ++s) M.dst[(size_t)s*rsize + t] = cur[(size_t)M.pop[s]*pitch + site];
+        if (!streamed) {
+            for (int s = 0; s < M.npop; ++s) M.dst[(size_t)s*rsize + t] = cur[(size_t)M.pop[s]*pitch + site];
+        } else {
+            const long long nxy = (long long)G.nx*G.ny;
+            const int k = (int)(site/nxy), j = (int)((site - k*nxy)/G.nx), i = (int)(site - k*nxy - (long long)j*G.nx);
+            const int sg = inverse ? -1 : 1;
+            for (int s = 0; s < M.npop; ++s) {
+                const int c = M.pop[s];
+                int ti = i + sg*rdir<D>(c, 0), tj = j + sg*rdir<D>(c, 1), tk = k + sg*rdir<D>(c, 2);
+                ti = ti < 0 ? G.nx - 1 : (ti >= G.nx ? 0 : ti);
+                tj = tj < 0 ? G.ny - 1 : (tj >= G.ny ? 0 : tj);
+                tk = tk < 0 ? G.nz - 1 : (tk >= G.nz ? 0 : tk);
+                M.dst[(size_t)s*rsize + t] = cur[(size_t)ropp<D>(c)*pitch + (size_t)(ti + (long long)G.nx*(tj + (long long)G.ny*tk))];
+            }
+        }
     }
 }
 #endif

@@ -9,7 +9,8 @@ namespace plb {
 
 // signed index deltas to the periodic neighbours of one site (reference Index(): d3q15.h:136-141)
 struct Nbr {
-    long long m[3], p[3];   // delta to coordinate-1 / coordinate+1 along x,y,z
+    int m[3], p[3];   // delta to coordinate-1 / coordinate+1 along x,y,z (a block holds fewer than 2^31 sites: 32-bit index arithmetic
+                      // keeps the thirty load / store addresses of the fused pass cheap to recompute instead of living in registers)
 };
 PL_D void decompose(const Geom& G, long long idx, int& i, int& j, int& k) {
     unsigned u = (unsigned)idx, nxy = (unsigned)(G.nx*G.ny);
@@ -18,16 +19,16 @@ PL_D void decompose(const Geom& G, long long idx, int& i, int& j, int& k) {
 }
 PL_D Nbr neighbours(const Geom& G, int i, int j, int k) {
     Nbr n;
-    long long sx = 1, sy = G.nx, sz = (long long)G.nx*G.ny;
+    const int sx = 1, sy = G.nx, sz = G.nx*G.ny;
     n.m[0] = i == 0 ? (G.nx - 1)*sx : -sx;  n.p[0] = i == G.nx - 1 ? -(G.nx - 1)*sx : sx;
     n.m[1] = j == 0 ? (G.ny - 1)*sy : -sy;  n.p[1] = j == G.ny - 1 ? -(G.ny - 1)*sy : sy;
     n.m[2] = k == 0 ? (G.nz - 1)*sz : -sz;  n.p[2] = k == G.nz - 1 ? -(G.nz - 1)*sz : sz;
     return n;
 }
 // offset of the site population c is pulled from: x - c (Stream) or x + c (iStream, n has m/p swapped by the caller)
-template <int D, int c> PL_D long long pull_offset(const Nbr& n) {
+template <int D, int c> PL_D int pull_offset(const Nbr& n) {
     constexpr int X = LT<D>::cx(c), Y = LT<D>::cy(c), Z = LT<D>::cz(c);
-    long long o = 0;
+    int o = 0;
     if constexpr (X > 0) o += n.m[0]; else if constexpr (X < 0) o += n.p[0];
     if constexpr (Y > 0) o += n.m[1]; else if constexpr (Y < 0) o += n.p[1];
     if constexpr (Z > 0) o += n.m[2]; else if constexpr (Z < 0) o += n.p[2];
@@ -35,14 +36,14 @@ template <int D, int c> PL_D long long pull_offset(const Nbr& n) {
 }
 PL_D void orient(Nbr& n, int inverse) {
     if (inverse) {
-        for (int d = 0; d < 3; ++d) { long long t = n.m[d]; n.m[d] = n.p[d]; n.p[d] = t; }
+        for (int d = 0; d < 3; ++d) { int t = n.m[d]; n.m[d] = n.p[d]; n.p[d] = t; }
     }
 }
 
 template <int D> PL_D void pull(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx, const Nbr& n) {
     sfor<0, LT<D>::nc>([&](auto C) {
         constexpr int c = decltype(C)::value;
-        f[c] = __ldg(src + (size_t)c*pitch + (size_t)(idx + pull_offset<D, c>(n)));
+        f[c] = __ldg(src + (size_t)c*pitch + (size_t)(unsigned)((int)idx + pull_offset<D, c>(n)));
     });
 }
 // the same for a block-decomposed lattice: sources beyond a decomposed block face come from the receive buffers
@@ -50,7 +51,7 @@ template <int D> PL_D void pull_h(double (&f)[LT<D>::nc], const double* __restri
                                   const Geom& G, const Nbr& n, const HaloView& H, int inverse) {
     sfor<0, LT<D>::nc>([&](auto C) {
         constexpr int c = decltype(C)::value;
-        f[c] = pull_halo<D, c>(src, pitch, idx, i, j, k, G, n, pull_offset<D, c>(n), H, inverse);
+        f[c] = pull_halo<D, c>(src, idx, i, j, k, G, n, (size_t)c*pitch + (size_t)(unsigned)((int)idx + pull_offset<D, c>(n)), H, inverse);
     });
 }
 template <int D> PL_D void load_site(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx) {
@@ -58,6 +59,49 @@ template <int D> PL_D void load_site(double (&f)[LT<D>::nc], const double* __res
 }
 template <int D> PL_D void store_site(const double (&f)[LT<D>::nc], double* __restrict__ dst, size_t pitch, long long idx) {
     sfor<0, LT<D>::nc>([&](auto C) { constexpr int c = decltype(C)::value; dst[(size_t)c*pitch + (size_t)idx] = f[c]; });
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Addressing of one fused stream+collide pass.  The reference keeps two population buffers per lattice (f and the hidden fnext,
+// d3q15.h:41-45, 238); the fused pass needs only ONE, AA-pattern style: every thread writes exactly the locations it has read.
+//   natural layout N  : location (c, x) holds the post-collision population c of site x            (= what every other
+//                       function of this library reads and writes)
+//   streamed layout P : location (opp(c), x + s*c) holds the post-collision population c of site x, s = +1 Stream / -1 iStream;
+//                       i.e. location (opp(c), y) holds the population c ARRIVING at y — Stream() has happened, slots swapped
+//   PASS_GATHER  N -> P : population c is pulled from (c, x - s*c) — the classic pull — and, after closures and collide, the new
+//                         population c goes to (opp(c), x + s*c): the very location the thread pulled population opp(c) from
+//   PASS_LOCAL   P -> N : population c is read from (opp(c), x), the new one goes to (c, x): no shifted access at all
+//   PASS_COPY    N -> N': the two-buffer pass (pull from the source buffer, store to the destination buffer; PANSLBM_INPLACE=0)
+// Each location belongs to exactly one thread per pass (x - s*c is a bijection on the periodic block), so the interior kernel,
+// the boundary pass and the tube kernel can still run side by side.
+enum { PASS_COPY = 0, PASS_GATHER = 1, PASS_LOCAL = 2 };
+template <int D, int MODE, int c> PL_D size_t read_loc(size_t pitch, long long idx, const Nbr& n) {
+    if constexpr (MODE == PASS_LOCAL) return (size_t)LT<D>::opp(c)*pitch + (size_t)(unsigned)(int)idx;
+    else return (size_t)c*pitch + (size_t)(unsigned)((int)idx + pull_offset<D, c>(n));
+}
+template <int D, int MODE, int c> PL_D size_t write_loc(size_t pitch, long long idx, const Nbr& n) {
+    if constexpr (MODE == PASS_GATHER) return (size_t)LT<D>::opp(c)*pitch + (size_t)(unsigned)((int)idx + pull_offset<D, LT<D>::opp(c)>(n));
+    else return (size_t)c*pitch + (size_t)(unsigned)(int)idx;
+}
+template <int D, int MODE> PL_D void pass_load(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx, const Nbr& n) {
+    // the in-place passes write what they read: no read-only (non-coherent) loads there
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        if constexpr (MODE == PASS_COPY) f[c] = __ldg(src + read_loc<D, MODE, c>(pitch, idx, n));
+        else f[c] = src[read_loc<D, MODE, c>(pitch, idx, n)];
+    });
+}
+template <int D, int MODE> PL_D void pass_store(const double (&f)[LT<D>::nc], double* __restrict__ dst, size_t pitch, long long idx, const Nbr& n) {
+    sfor<0, LT<D>::nc>([&](auto C) { constexpr int c = decltype(C)::value; dst[write_loc<D, MODE, c>(pitch, idx, n)] = f[c]; });
+}
+// the same load for a block-decomposed lattice: populations whose source site lies beyond a decomposed block face come from the
+// receive buffers whatever the layout (what the neighbour packed is the population itself, not a location)
+template <int D, int MODE> PL_D void pass_load_h(double (&f)[LT<D>::nc], const double* __restrict__ src, size_t pitch, long long idx, int i, int j, int k,
+                                                const Geom& G, const Nbr& n, const HaloView& H, int inverse) {
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        f[c] = pull_halo<D, c>(src, idx, i, j, k, G, n, read_loc<D, MODE, c>(pitch, idx, n), H, inverse);
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -74,6 +118,21 @@ __global__ void __launch_bounds__(256) k_stream(Geom G, const double* __restrict
     if constexpr (HALO) pull_h<D>(f, src, G.pitch, idx, i, j, k, G, n, H, inverse);
     else pull<D>(f, src, G.pitch, idx, n);
     store_site<D>(f, dst, G.pitch, idx);
+}
+// streamed layout P -> natural layout N (see the pass modes above): dst(c, x) = src(opp(c), x + s*c), the post-collision
+// populations back at their own sites.  Only when something other than the next fused pass wants to look at the lattice.
+template <int D>
+__global__ void __launch_bounds__(256) k_unstream(Geom G, const double* __restrict__ src, double* __restrict__ dst, int inverse) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    Nbr n = neighbours(G, i, j, k);
+    orient(n, inverse);
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        dst[(size_t)c*G.pitch + (size_t)idx] = src[write_loc<D, PASS_GATHER, c>(G.pitch, idx, n)];
+    });
 }
 // ---------------------------------------------------------------------------------------------------------
 // In-place Macro*Collide* over all sites (list == nullptr) or over a site list.  Tail sites
@@ -222,26 +281,30 @@ PL_D void wall_scatter(const XWall& W, const double (&f)[LT<D>::nc], const doubl
         });
     }
 }
-// after the pull of a site on a compact x plane: the populations pulled through the periodic wrap are replaced by what the
-// closures of the plane made of them
-template <int D, bool HASG>
-PL_D void wall_patch(const XWall& W, double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Geom& G, int i, int j, int k, int inverse) {
+// the load of the interior kernel: a site on a compact x plane (wside = 0: x = 0, 1: x = nx-1; -1: any other site) takes the
+// populations that would come through the periodic wrap from what the closures of the plane made of them (XWall::res) instead —
+// chosen by ADDRESS, one load per population either way (overwriting them after the pull would make the warp wait for its loads twice)
+template <int D, int MODE, bool HASG>
+PL_D void pass_load_wall(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const double* fs, const double* gs, size_t pitch, long long idx, const Nbr& n,
+                         const XWall& W, int wside, size_t wt, int inverse) {
     constexpr int NC = LT<D>::nc;
-    const int side = i == 0 ? 0 : 1;
-    const int want = side ? -1 : 1;      // s*c_x of the populations that arrive from beyond the wall
-    const size_t t = (size_t)(j + G.ny*k);
-    sfor<1, NC>([&](auto C) {
+    sfor<0, NC>([&](auto C) {
         constexpr int c = decltype(C)::value;
         constexpr int X = LT<D>::cx(c);
+        const size_t loc = read_loc<D, MODE, c>(pitch, idx, n);
+        const double *pf = fs + loc, *pg = HASG ? gs + loc : nullptr;
         if constexpr (X != 0) {
-            if ((inverse ? -X : X) == want) {
-                const size_t o = (size_t)(side*NC + c)*W.np + t;
-                f[c] = W.res_f[o];
-                if constexpr (HASG) g[c] = W.res_g[o];
+            if (wside >= 0 && (inverse ? -X : X) == (wside ? -1 : 1)) {
+                const size_t o = (size_t)(wside*NC + c)*W.np + wt;
+                pf = W.res_f + o;
+                if constexpr (HASG) pg = W.res_g + o;
             }
         }
+        if constexpr (MODE == PASS_COPY) { f[c] = __ldg(pf); if constexpr (HASG) g[c] = __ldg(pg); }
+        else { f[c] = *pf; if constexpr (HASG) g[c] = *pg; }
     });
 }
+
 PL_D bool in_tube(unsigned long long wx, unsigned long long wy, unsigned long long wz) { return (wx >> 63) + (wy >> 63) + (wz >> 63) >= 2ull; }
 
 // The closure program is a chain of dependent loads (program entry -> mask -> plane values / saved fields of the site), one
@@ -363,9 +426,15 @@ PL_D void boundary_path_sh(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], doubl
 // and written once.  Sites of an x closure plane that the plan left to this kernel (no SLAB bit) are either ordinary sites
 // here (prog == nullptr: k_xclose has already put the closure results where this kernel pulls from) or run the closure
 // program between pull and collide (PANSLBM_XINLINE: one lane of the warp diverges; measured slower, profiles/r01_tuning.md).
-template <int D, int M>
-__global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
-                                               const double* __restrict__ gs, double* __restrict__ gd,
+// CTA shape of the interior kernel: 256 threads, 124-128 registers -> 2 CTAs (16 warps) per SM.  -DPLK_FUSED_THREADS=128
+// -DPLK_FUSED_MINB=5 caps the registers at 96 for 5 CTAs (20 warps) per SM at the price of a few spilled doubles (build.py,
+// PANSLBM_BUILD_TAG: an A/B variant of the library)
+#ifndef PLK_FUSED_THREADS
+#define PLK_FUSED_THREADS 256
+#define PLK_FUSED_MINB 1
+#endif
+template <int D, int M, int MODE>
+__global__ void __launch_bounds__(PLK_FUSED_THREADS, PLK_FUSED_MINB) k_fused(Geom G, const double* fs, double* fd, const double* gs, double* gd,
                                                CollideParams P, ShellMask S, const ClosureArgs* __restrict__ prog, int inverse, XWall W) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
@@ -374,26 +443,24 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
     int i, j, k;
     decompose(G, idx, i, j, k);
     unsigned long long entries = 0ull;
-    bool ghost = false;
+    int wside = -1;
     if ((S.x[i] | S.y[j] | S.z[k]) != 0ull) {
         const unsigned long long wx = S.x[i], wy = S.y[j], wz = S.z[k];
         if (((wy | wz) & ~TUBE_BIT) != 0ull || (wx & (SLAB_BIT | HALO_BIT)) != 0ull || in_tube(wx, wy, wz)) return;
         entries = wx & ENTRY_BITS;
-        ghost = (wx & GHOST_BIT) != 0ull;
+        if ((wx & GHOST_BIT) != 0ull) wside = i == 0 ? 0 : 1;
         if (entries && prog && S.prefetch) { prefetch_program(prog, entries, i, j, k, idx, S.prefetch); prefetch_collide<FL>(P, idx, S.prefetch); }
     }
     Nbr n = neighbours(G, i, j, k);
     orient(n, inverse);
     double f[LT<D>::nc], g[LT<D>::nc];
-    pull<D>(f, fs, G.pitch, idx, n);
-    if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
-    if (ghost) wall_patch<D, HASG>(W, f, g, G, i, j, k, inverse);
+    pass_load_wall<D, MODE, HASG>(f, g, fs, gs, G.pitch, idx, n, W, wside, (size_t)(j + G.ny*k), inverse);
     if (entries && prog) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
     // a step nobody observes (issave == 2) stores its macros only where the closures of the next step read them: on the x
     // closure planes this kernel owns (the sites of every other closure plane belong to the boundary pass, which always stores)
     collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave == 1 || (P.issave == 2 && entries != 0ull));
-    store_site<D>(f, fd, G.pitch, idx);
-    if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+    pass_store<D, MODE>(f, fd, G.pitch, idx, n);
+    if constexpr (HASG) pass_store<D, MODE>(g, gd, G.pitch, idx, n);
     wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
 }
 
@@ -401,9 +468,8 @@ __global__ void __launch_bounds__(256) k_fused(Geom G, const double* __restrict_
 // collide of the next step (t < ndirect: sites on closure planes, sites of the last incomplete AVX pack) or, for the
 // SmoothCorner tubes (t >= ndirect), a store of the streamed+closed populations into the tube buffer, which k_tubes finishes
 // right behind this kernel.  Both run beside k_fused on their own stream.
-template <int D, int M>
-__global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* __restrict__ fs, double* __restrict__ fd,
-                                                         const double* __restrict__ gs, double* __restrict__ gd, CollideParams P, ShellMask S,
+template <int D, int M, int MODE>
+__global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* fs, double* fd, const double* gs, double* gd, CollideParams P, ShellMask S,
                                                          const ClosureArgs* __restrict__ prog, const int* __restrict__ list,
                                                          const unsigned long long* __restrict__ ent, int nlist, int ndirect, int inverse,
                                                          double* __restrict__ tube_f, double* __restrict__ tube_g, HaloView HF, HaloView HG, XWall W) {
@@ -426,18 +492,18 @@ __global__ void __launch_bounds__(SHELL_THREADS) k_shell(Geom G, const double* _
     orient(n, inverse);
     double f[NC], g[NC];
     if (HF.on) {
-        pull_h<D>(f, fs, G.pitch, idx, i, j, k, G, n, HF, inverse);
-        if constexpr (HASG) pull_h<D>(g, gs, G.pitch, idx, i, j, k, G, n, HG, inverse);
+        pass_load_h<D, MODE>(f, fs, G.pitch, idx, i, j, k, G, n, HF, inverse);
+        if constexpr (HASG) pass_load_h<D, MODE>(g, gs, G.pitch, idx, i, j, k, G, n, HG, inverse);
     } else {
-        pull<D>(f, fs, G.pitch, idx, n);
-        if constexpr (HASG) pull<D>(g, gs, G.pitch, idx, n);
+        pass_load<D, MODE>(f, fs, G.pitch, idx, n);
+        if constexpr (HASG) pass_load<D, MODE>(g, gs, G.pitch, idx, n);
     }
     if (entries) boundary_path_sh<D, HASG>(f, g, tile + threadIdx.x, prog, entries, i, j, k, idx);
     if (t < ndirect) {
         if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave != 0);
         else collide_site<D, FL, true>(f, g, P, (size_t)idx, P.issave != 0);
-        store_site<D>(f, fd, G.pitch, idx);
-        if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
+        pass_store<D, MODE>(f, fd, G.pitch, idx, n);
+        if constexpr (HASG) pass_store<D, MODE>(g, gd, G.pitch, idx, n);
         wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
     } else {
         // SmoothCorner tube: the streamed + closed populations go to the compact tube buffer [c][ntube]; k_tubes finishes them
@@ -467,9 +533,9 @@ PL_D void tube_load(double (&p)[LT<D>::nc], const double* __restrict__ scr, size
         }
     });
 }
-template <int D, int M>
-__global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict__ tube_f, const double* __restrict__ tube_g, double* __restrict__ fd,
-                                               double* __restrict__ gd, CollideParams P, const TubeSite* __restrict__ info, int nt, XWall W, int inverse) {
+template <int D, int M, int MODE>
+__global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict__ tube_f, const double* __restrict__ tube_g, double* fd,
+                                               double* gd, CollideParams P, const TubeSite* __restrict__ info, int nt, XWall W, int inverse) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
     int tt = blockIdx.x*blockDim.x + threadIdx.x;
@@ -481,13 +547,13 @@ __global__ void __launch_bounds__(128) k_tubes(Geom G, const double* __restrict_
     const long long idx = T.idx;
     if (idx < G.npacked) collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave != 0);
     else collide_site<D, FL, true>(f, g, P, (size_t)idx, P.issave != 0);
-    store_site<D>(f, fd, G.pitch, idx);
-    if constexpr (HASG) store_site<D>(g, gd, G.pitch, idx);
-    if (W.out_f != nullptr) {
-        int i, j, k;
-        decompose(G, idx, i, j, k);
-        wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
-    }
+    int i, j, k;
+    decompose(G, idx, i, j, k);
+    Nbr n = neighbours(G, i, j, k);
+    orient(n, inverse);
+    pass_store<D, MODE>(f, fd, G.pitch, idx, n);
+    if constexpr (HASG) pass_store<D, MODE>(g, gd, G.pitch, idx, n);
+    wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
 }
 
 // Closures of the x boundary planes of an undecomposed axis, ahead of the fused pass.  On such a plane the populations a

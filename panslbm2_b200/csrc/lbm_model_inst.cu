@@ -1,0 +1,61 @@
+// One (lattice, collide model) pair of the per-model kernels: compiled once per pair with -DPLI_DIM=<2|3> -DPLI_MODEL=<1..12>
+// (panslbm2_b200/build.py), so that the 23 pairs build in parallel.  See lbm_launch.h.
+#include "lbm_launch.h"
+
+#if !defined(PLI_DIM) || !defined(PLI_MODEL)
+#error "compile with -DPLI_DIM=<2|3> -DPLI_MODEL=<model>"
+#endif
+
+namespace plb {
+namespace {
+
+inline unsigned blocks(long long n, int bs) { return (unsigned)((n + bs - 1)/bs); }
+
+cudaError_t collide_(cudaStream_t st, const Geom& G, double* fb, double* gb, const CollideParams& P, const int* list, long long count) {
+    if (count == 0) return cudaSuccess;
+    k_collide<PLI_DIM, PLI_MODEL><<<blocks(count, 256), 256, 0, st>>>(G, fb, gb, P, list, count);
+    return cudaGetLastError();
+}
+
+template <int MODE> cudaError_t fused_m(cudaStream_t st, const FusedArgs& A) {
+    k_fused<PLI_DIM, PLI_MODEL, MODE><<<blocks(A.G.npacked, PLK_FUSED_THREADS), PLK_FUSED_THREADS, 0, st>>>(A.G, A.fs, A.fd, A.gs, A.gd, A.P, A.S, A.prog, A.inverse, A.W);
+    return cudaGetLastError();
+}
+cudaError_t fused_(cudaStream_t st, const FusedArgs& A, int mode) {
+    if (A.G.npacked == 0) return cudaSuccess;
+    switch (mode) {
+        case PASS_GATHER: return fused_m<PASS_GATHER>(st, A);
+        case PASS_LOCAL: return fused_m<PASS_LOCAL>(st, A);
+        default: return fused_m<PASS_COPY>(st, A);
+    }
+}
+
+template <int MODE> cudaError_t shell_m(cudaStream_t st, const FusedArgs& A) {
+    k_shell<PLI_DIM, PLI_MODEL, MODE><<<blocks(A.nlist, SHELL_THREADS), SHELL_THREADS, 0, st>>>(A.G, A.fs, A.fd, A.gs, A.gd, A.P, A.S, A.prog, A.list, A.ent, A.nlist, A.ndirect,
+                                                                                       A.inverse, A.tube_f, A.tube_g, A.HF, A.HG, A.W);
+    cudaError_t e = cudaGetLastError();
+    // SmoothCorner + collide of the tube sites, right behind the boundary pass on the same stream
+    const int ntube = A.nlist - A.ndirect;
+    if (e == cudaSuccess && ntube > 0) {
+        k_tubes<PLI_DIM, PLI_MODEL, MODE><<<blocks(ntube, 128), 128, 0, st>>>(A.G, A.tube_f, A.tube_g, A.fd, A.gd, A.P, A.tube_info, ntube, A.W, A.inverse);
+        e = cudaGetLastError();
+    }
+    return e;
+}
+cudaError_t shell_(cudaStream_t st, const FusedArgs& A, int mode) {
+    if (A.nlist == 0) return cudaSuccess;
+    switch (mode) {
+        case PASS_GATHER: return shell_m<PASS_GATHER>(st, A);
+        case PASS_LOCAL: return shell_m<PASS_LOCAL>(st, A);
+        default: return shell_m<PASS_COPY>(st, A);
+    }
+}
+
+}  // namespace
+
+#define PL_CAT_(a, b, c) a##b##_##c
+#define PL_CAT(a, b, c) PL_CAT_(a, b, c)
+extern const ModelLaunch PL_CAT(model_launch_, PLI_DIM, PLI_MODEL);
+const ModelLaunch PL_CAT(model_launch_, PLI_DIM, PLI_MODEL) = {collide_, fused_, shell_};
+
+}  // namespace plb

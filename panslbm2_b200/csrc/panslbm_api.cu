@@ -2,6 +2,7 @@
 // operation is a CUDA kernel from lbm_kernels.cuh / lbm_closures.cuh / lbm_reduce.cuh.  No CPU fallback.
 #include "../../include/panslbm_c.h"
 #include "lbm_kernels.cuh"
+#include "lbm_launch.h"
 #include "lbm_reduce.cuh"
 
 #include <cuda_runtime.h>
@@ -9,11 +10,27 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 using namespace plb;
+
+namespace plb {
+#define PL_ML(D, M) extern const ModelLaunch model_launch_##D##_##M;
+PL_ML(2, 1) PL_ML(2, 2) PL_ML(2, 3) PL_ML(2, 4) PL_ML(2, 5) PL_ML(2, 6) PL_ML(2, 7) PL_ML(2, 8) PL_ML(2, 9) PL_ML(2, 10) PL_ML(2, 11) PL_ML(2, 12)
+PL_ML(3, 1) PL_ML(3, 2) PL_ML(3, 3) PL_ML(3, 4) PL_ML(3, 5) PL_ML(3, 6) PL_ML(3, 7) PL_ML(3, 8) PL_ML(3, 9) PL_ML(3, 10) PL_ML(3, 11)
+#undef PL_ML
+const ModelLaunch* model_launch(int D, int M) {
+    static const ModelLaunch* const t2[13] = {nullptr, &model_launch_2_1, &model_launch_2_2, &model_launch_2_3, &model_launch_2_4, &model_launch_2_5, &model_launch_2_6,
+                                              &model_launch_2_7, &model_launch_2_8, &model_launch_2_9, &model_launch_2_10, &model_launch_2_11, &model_launch_2_12};
+    static const ModelLaunch* const t3[13] = {nullptr, &model_launch_3_1, &model_launch_3_2, &model_launch_3_3, &model_launch_3_4, &model_launch_3_5, &model_launch_3_6,
+                                              &model_launch_3_7, &model_launch_3_8, &model_launch_3_9, &model_launch_3_10, &model_launch_3_11, nullptr};
+    if (M < 1 || M > 12) return nullptr;
+    return D == 2 ? t2[M] : (D == 3 ? t3[M] : nullptr);
+}
+}  // namespace plb
 
 // -------------------------------------------------------------------------------------------------
 namespace {
@@ -63,6 +80,37 @@ bool opt_graph() { static int v = env_int("PANSLBM_GRAPH", 0); return v != 0; }
 // source buffer (k_xclose); 0 = the boundary pass takes the aligned x groups around those planes
 bool opt_xghost() { static int v = env_int("PANSLBM_XGHOST", 1); return v != 0; }
 bool opt_xinline() { static int v = env_int("PANSLBM_XINLINE", 0); return v != 0; }
+// fused passes update the ONE population buffer of a lattice in place (AA pattern: gather pass, local pass, ...);
+// 0 = every pass goes from the buffer to a second one borrowed from the spare pool (the reference's f / fnext scheme)
+bool opt_inplace() { static int v = env_int("PANSLBM_INPLACE", 1); return v != 0; }
+
+// Spare population buffers.  A lattice owns ONE buffer; the operations that cannot work in place — a standalone Stream()/iStream(),
+// the conversion of the streamed layout back to the natural one, the two-buffer passes of PANSLBM_INPLACE=0 — write into a buffer
+// borrowed here and hand their old one back.  Lattices of one shape share the spares (f and g of a driver stream one after the
+// other through the same one), and the pool is emptied once a run of in-place passes shows that nobody needs them.
+struct SparePool {
+    std::multimap<size_t, double*> free_;
+    int streak = 0;                    // fused in-place passes since the last borrow
+    uint64_t borrows = 0;
+    size_t held() const { size_t b = 0; for (auto& kv : free_) b += kv.first; return b; }
+    double* get(size_t bytes) {
+        streak = 0; ++borrows;
+        auto it = free_.find(bytes);
+        if (it != free_.end()) { double* p = it->second; free_.erase(it); return p; }
+        double* p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); trim(); if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } }
+        return p;
+    }
+    void put(double* p, size_t bytes) { free_.emplace(bytes, p); }
+    void trim() {
+        if (free_.empty()) return;
+        cudaStreamSynchronize(g_stream);
+        for (auto& kv : free_) cudaFree(kv.second);
+        free_.clear();
+    }
+    void inplace_pass() { if (!free_.empty() && ++streak >= 3) trim(); }
+} g_spares;
+uint64_t g_lattice_bytes = 0, g_conversions = 0;      // population buffers owned by live lattices; streamed -> natural conversions so far
 
 // grow-only device scratch for the reductions: cudaMalloc/cudaFree per call would cost milliseconds next to tens of GB of
 // live allocations and synchronise the device
@@ -84,12 +132,13 @@ struct pl_lattice {
     int nc;
     int lx, ly, lz, peid, mx, my, mz, pex, pey, pez;
     Geom g;
-    double* buf[2] = {nullptr, nullptr};
-    int cur = 0;
+    double* buf = nullptr;         // the populations: ONE buffer, fp64 SoA [c][pitch]
+    int rep = 0;                   // layout: 0 = natural, 1 = streamed (left by an in-place gather pass; lbm_kernels.cuh, pass modes)
+    int rep_inverse = 0;           // ... of a Stream (0) / iStream (1)
     int streamed = 1;              // phase: 1 = populations are "pre-collision" (after init / Stream+closures), 0 = just collided
     uint64_t version = 0;          // bumped by everything that changes the populations (plans check whether their wall buffers still describe them)
-    double* current() const { return buf[cur]; }
-    double* other() const { return buf[cur ^ 1]; }
+    double* current() const { return buf; }
+    size_t bytes() const { return g.pitch*(size_t)nc*sizeof(double); }
     // ---- halo of a block-decomposed lattice (lbm_halo.cuh) ----
     struct Halo {
         bool on = false;
@@ -256,7 +305,8 @@ int halo_pack(pl_lattice* l, int inverse) {
         maxr = std::max(maxr, d.rsize);
     }
     dim3 grid((unsigned)std::min<long long>((maxr + 127)/128, 1024), (unsigned)h.nmsg);
-    LAUNCH(k_halo_pack, grid, 128, l->current(), l->g.pitch, L);
+    if (l->kind == PL_D2Q9) LAUNCH(k_halo_pack<2>, grid, 128, l->current(), l->g, L, l->rep, l->rep_inverse);
+    else LAUNCH(k_halo_pack<3>, grid, 128, l->current(), l->g, L, l->rep, l->rep_inverse);
     h.packed = true; h.packed_dir = inverse; h.exchanged = false;
     return PL_OK;
 }
@@ -333,6 +383,20 @@ int halo_view(const pl_lattice* l, HaloView& V) {
 // order `stream` after the arrival of the current epoch's messages
 int halo_wait(const pl_lattice* l, cudaStream_t stream) {
     if (l->halo.on && g_comm.mode == COMM_NCCL) CU(cudaStreamWaitEvent(stream, l->halo.ev_ready, 0));
+    return PL_OK;
+}
+// bring the populations back to the natural layout (every function but the fused passes works on that one).  The content does not
+// change: neither the halo buffers nor a plan's wall buffers go stale.
+int make_natural(pl_lattice* l) {
+    if (!l || l->rep == 0) return PL_OK;
+    double* dst = g_spares.get(l->bytes());
+    if (!dst) return fail(PL_ERR_CUDA, "out of device memory for the spare population buffer (streamed -> natural layout)");
+    if (l->kind == PL_D2Q9) LAUNCH(k_unstream<2>, blocks_for(l->g.nxyz, 256), 256, l->g, l->buf, dst, l->rep_inverse);
+    else LAUNCH(k_unstream<3>, blocks_for(l->g.nxyz, 256), 256, l->g, l->buf, dst, l->rep_inverse);
+    g_spares.put(l->buf, l->bytes());
+    l->buf = dst;
+    l->rep = 0;
+    ++g_conversions;
     return PL_OK;
 }
 }  // namespace
@@ -446,22 +510,22 @@ pl_lattice* pl_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx
     if (g.nxyz <= 0 || g.nxyz >= (1LL << 31)) { delete l; fail(PL_ERR_ARG, "pl_lattice_create: block must hold 1..2^31-1 sites"); return nullptr; }
     g.npacked = 4*(g.nxyz/4);
     g.pitch = (size_t)((g.nxyz + 15)/16*16);
-    for (int b = 0; b < 2; ++b) {
-        cudaError_t e = cudaMalloc(&l->buf[b], g.pitch*l->nc*sizeof(double));
+    {
+        cudaError_t e = cudaMalloc(&l->buf, l->bytes());
         if (e != cudaSuccess) {
             fail(PL_ERR_CUDA, std::string("pl_lattice_create: cudaMalloc: ") + cudaGetErrorString(e));
-            if (l->buf[0]) cudaFree(l->buf[0]);
             delete l;
             return nullptr;
         }
     }
-    cudaMemsetAsync(l->buf[0], 0, g.pitch*l->nc*sizeof(double), g_stream);
-    cudaMemsetAsync(l->buf[1], 0, g.pitch*l->nc*sizeof(double), g_stream);
+    cudaMemsetAsync(l->buf, 0, l->bytes(), g_stream);
+    g_lattice_bytes += l->bytes();
     if (halo_setup(l) != PL_OK) {
         std::string keep = g_err;
         l->halo.on = true;   // release whatever halo_setup allocated
         halo_release(l);
-        cudaFree(l->buf[0]); cudaFree(l->buf[1]);
+        cudaFree(l->buf);
+        g_lattice_bytes -= l->bytes();
         delete l;
         g_err = keep;
         return nullptr;
@@ -472,7 +536,9 @@ int pl_lattice_destroy(pl_lattice* l) {
     if (!l) return PL_OK;
     cudaStreamSynchronize(g_stream);
     halo_release(l);
-    cudaFree(l->buf[0]); cudaFree(l->buf[1]);
+    cudaFree(l->buf);
+    g_lattice_bytes -= l->bytes();
+    g_spares.trim();
     delete l;
     return PL_OK;
 }
@@ -495,11 +561,13 @@ int pl_lattice_set_host(pl_lattice* l, const double* f0, const double* f) {
     else LAUNCH(k_from_aos<3>, blocks_for(l->g.nxyz, 256), 256, l->g, d0, d1, l->current());
     CU(cudaStreamSynchronize(g_stream));
     cudaFree(d0); cudaFree(d1);
+    l->rep = 0;
     halo_touch(l);
     return PL_OK;
 }
 int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
     if (!l || !f0 || !f) return fail(PL_ERR_ARG, "pl_lattice_get_host: null");
+    { int r = make_natural(l); if (r) return r; }
     size_t n = (size_t)l->g.nxyz, nf = n*(l->nc - 1);
     double *d0 = nullptr, *d1 = nullptr;
     CU(cudaMalloc(&d0, n*sizeof(double)));
@@ -513,8 +581,15 @@ int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
     return PL_OK;
 }
 int pl_lattice_streamed(const pl_lattice* l) { return l ? l->streamed : 0; }
+int pl_memory_stats(uint64_t* out4) {
+    if (!out4) return fail(PL_ERR_ARG, "pl_memory_stats: null");
+    out4[0] = g_lattice_bytes; out4[1] = g_spares.held(); out4[2] = g_spares.borrows; out4[3] = g_conversions;
+    return PL_OK;
+}
+int pl_memory_trim(void) { g_spares.trim(); return PL_OK; }
 int pl_lattice_device_view(pl_lattice* l, double** base, size_t* pitch) {
     if (!l) return fail(PL_ERR_ARG, "pl_lattice_device_view: null");
+    { int r = make_natural(l); if (r) return r; }
     if (base) *base = l->current();
     if (pitch) *pitch = l->g.pitch;
     return PL_OK;
@@ -529,15 +604,18 @@ namespace {
 int do_stream_all(pl_lattice* l, int inverse) {
     HaloView H;
     int r;
-    if ((r = halo_prepare(l, inverse)) || (r = halo_wait(l, g_stream)) || (r = halo_view(l, H))) return r;
+    if ((r = make_natural(l)) || (r = halo_prepare(l, inverse)) || (r = halo_wait(l, g_stream)) || (r = halo_view(l, H))) return r;
+    double* dst = g_spares.get(l->bytes());
+    if (!dst) return fail(PL_ERR_CUDA, "out of device memory for the spare population buffer (Stream)");
     if (l->halo.on) {
-        if (l->kind == PL_D2Q9) LAUNCH((k_stream<2, true>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
-        else LAUNCH((k_stream<3, true>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
+        if (l->kind == PL_D2Q9) LAUNCH((k_stream<2, true>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), dst, inverse, H);
+        else LAUNCH((k_stream<3, true>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), dst, inverse, H);
     } else {
-        if (l->kind == PL_D2Q9) LAUNCH((k_stream<2, false>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
-        else LAUNCH((k_stream<3, false>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), l->other(), inverse, H);
+        if (l->kind == PL_D2Q9) LAUNCH((k_stream<2, false>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), dst, inverse, H);
+        else LAUNCH((k_stream<3, false>), blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), dst, inverse, H);
     }
-    l->cur ^= 1;
+    g_spares.put(l->buf, l->bytes());
+    l->buf = dst;
     halo_touch(l);
     return PL_OK;
 }
@@ -620,6 +698,7 @@ int do_smooth(pl_lattice* l, pl_lattice* l2 = nullptr) {
     const int ne = e.count, ncn = c.count;
     for (pl_lattice* q : {l, l2}) {
         if (!q) continue;
+        { int r = make_natural(q); if (r) return r; }
         halo_touch(q);
         for (int k = 0; k < ne; ++k) { SmoothItem& it = e.it[q == l ? k : ne + k]; it = e.it[k]; it.fb = q->current(); }
         for (int k = 0; k < ncn; ++k) { SmoothItem& it = c.it[q == l ? k : ncn + k]; it = c.it[k]; it.fb = q->current(); }
@@ -684,6 +763,7 @@ int do_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* au
     int r = make_closure_args(l, other, bc, aux, A);
     if (r) return r;
     int np = bc->pl.n1*bc->pl.n2;
+    if ((r = make_natural(l)) || (other && (r = make_natural(other)))) return r;
     halo_touch(l);
     const double* qb = (other && bc->type == PL_BC_AAD_ISET_RHO) ? other->current() : nullptr;
     if (l->kind == PL_D2Q9) LAUNCH(k_closure<2>, blocks_for(np, 128), 128, l->g, l->current(), qb, A);
@@ -742,48 +822,21 @@ int make_params(const pl_lattice* f, const pl_lattice* g, const pl_collide_args*
     return ok ? PL_OK : PL_ERR_ARG;
 }
 
-template <int D, int M> int launch_collide(pl_lattice* f, pl_lattice* g, const CollideParams& P, const int* list, long long count) {
-    if (count == 0) return PL_OK;
-    LAUNCH((k_collide<D, M>), blocks_for(count, 256), 256, f->g, f->current(), g ? g->current() : nullptr, P, list, count);
-    return PL_OK;
+// the kernels of one (lattice, collide model) pair: lbm_model_inst.cu, one translation unit per pair
+const ModelLaunch* launcher(const pl_lattice* f, int model) {
+    const ModelLaunch* ml = model_launch(f->kind == PL_D2Q9 ? 2 : 3, model);
+    if (!ml) fail(PL_ERR_UNSUPPORTED, "collide: model not available for this lattice");
+    return ml;
 }
-template <int D, int M> int launch_fused(pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse, const XWall& W) {
-    if (f->g.npacked == 0) return PL_OK;
-    LAUNCH((k_fused<D, M>), blocks_for(f->g.npacked, 256), 256, f->g, f->current(), f->other(), g ? g->current() : nullptr, g ? g->other() : nullptr, P, S, prog, inverse, W);
-    return PL_OK;
-}
-#define MODEL_SWITCH(D, FN, ...)                                                     \
-    switch (model) {                                                                 \
-        case 1: return FN<D, 1>(__VA_ARGS__);                                        \
-        case 2: return FN<D, 2>(__VA_ARGS__);                                        \
-        case 3: return FN<D, 3>(__VA_ARGS__);                                        \
-        case 4: return FN<D, 4>(__VA_ARGS__);                                        \
-        case 5: return FN<D, 5>(__VA_ARGS__);                                        \
-        case 6: return FN<D, 6>(__VA_ARGS__);                                        \
-        case 7: return FN<D, 7>(__VA_ARGS__);                                        \
-        case 8: return FN<D, 8>(__VA_ARGS__);                                        \
-        case 9: return FN<D, 9>(__VA_ARGS__);                                        \
-        case 10: return FN<D, 10>(__VA_ARGS__);                                      \
-        case 11: return FN<D, 11>(__VA_ARGS__);                                      \
-        default: break;                                                              \
-    }
 int dispatch_collide(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, const int* list, long long count) {
-    if (f->kind == PL_D2Q9) {
-        MODEL_SWITCH(2, launch_collide, f, g, P, list, count)
-        if (model == 12) return launch_collide<2, 12>(f, g, P, list, count);
-    } else {
-        MODEL_SWITCH(3, launch_collide, f, g, P, list, count)
-    }
-    return fail(PL_ERR_UNSUPPORTED, "collide: model not available for this lattice");
-}
-int dispatch_fused(int model, pl_lattice* f, pl_lattice* g, const CollideParams& P, ShellMask S, const ClosureArgs* prog, int inverse, const XWall& W) {
-    if (f->kind == PL_D2Q9) {
-        MODEL_SWITCH(2, launch_fused, f, g, P, S, prog, inverse, W)
-        if (model == 12) return launch_fused<2, 12>(f, g, P, S, prog, inverse, W);
-    } else {
-        MODEL_SWITCH(3, launch_fused, f, g, P, S, prog, inverse, W)
-    }
-    return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
+    const ModelLaunch* ml = launcher(f, model);
+    if (!ml) return PL_ERR_UNSUPPORTED;
+    int r;
+    if ((r = make_natural(f)) || (g && (r = make_natural(g)))) return r;
+    if (count == 0) return PL_OK;
+    ++g_launches;
+    CU(ml->collide(g_stream, f->g, f->current(), g ? g->current() : nullptr, P, list, count));
+    return PL_OK;
 }
 
 }  // namespace
@@ -829,6 +882,7 @@ int pl_smooth_corner_at(pl_lattice* l, int gi, int gj, int gk, int dx, int dy, i
     if (D == 3 && line >= 0) { it.stride = st[line]; it.len = n[line]; }
     it.n0 = nb[0]; it.n1 = nb[1]; it.n2 = k == 3 ? nb[2] : 0;
     L.maxlen = it.len;
+    { int r = make_natural(l); if (r) return r; }
     halo_touch(l);
     it.fb = l->current();
     dim3 grid(blocks_for(it.len, 128), 1);
@@ -911,6 +965,7 @@ int pl_initial_condition(pl_lattice* l, int family, const double* const* a, int 
         bool zslot = family <= 2 ? n == 3 : (n == 2 || n == 6);
         if (!p[n] && !(zslot && !d3)) return fail(PL_ERR_ARG, "pl_initial_condition: null array");
     }
+    l->rep = 0;      // every population is overwritten: whatever layout the buffer was in is irrelevant
     if (d3) LAUNCH(k_init<3>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), family, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
     else LAUNCH(k_init<2>, blocks_for(l->g.nxyz, 256), 256, l->g, l->current(), family, p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
     l->streamed = 1;
@@ -965,9 +1020,10 @@ struct pl_plan {
     // the boundary pass runs beside the interior kernel on its own (high-priority) stream
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    // captured fused steps, by [argument set of the closures][buffer parity of f][buffer parity of g]
-    cudaGraphExec_t graphs[2][2][2][2] = {};       // ... and [every site stores / only the closure planes store]
-    uint64_t graph_launches[2][2][2][2] = {};
+    // captured fused steps, by [argument set of the closures][pass mode][wall-buffer phase][every site stores / only the closure planes]
+    struct Graph { cudaGraphExec_t exec = nullptr; uint64_t launches = 0; const double *fbuf = nullptr, *gbuf = nullptr; };
+    Graph graphs[2][3][2][2];
+    int xphase = 0;                // which of the two wall `out` buffers the next pass reads
     cudaStream_t cap = nullptr;
     int graph_cooldown = 0;        // steps to run ungraphed after the arguments were re-bound (per-step arrays: nothing to replay)
     // measurement hook
@@ -1006,81 +1062,70 @@ int plan_collide_full(pl_plan* p, int parity) {              // standalone C: ev
     if (p->g && (r = halo_prepare(p->g, p->inverse, true))) return r;
     return PL_OK;
 }
-XWall plan_xwall(const pl_plan* p, bool with_g) {
-    XWall W;
-    memset(&W, 0, sizeof(W));
-    if (!p->nxlist) return W;
-    const int wr = p->f->cur ^ 1;      // the buffer the NEXT pass reads (it alternates with the population buffers)
-    W.out_f = p->xout[0][wr]; W.res_f = p->xres[0];
-    if (with_g) { W.out_g = p->xout[1][wr]; W.res_g = p->xres[1]; }
-    W.np = p->f->g.ny*p->f->g.nz; W.on[0] = p->xon[0]; W.on[1] = p->xon[1];
-    return W;
+void drop_graphs(pl_plan* p) {
+    for (auto& a : p->graphs) for (auto& b : a) for (auto& c : b) for (auto& g : c) if (g.exec) { cudaGraphExecDestroy(g.exec); g = pl_plan::Graph(); }
 }
-template <int D, int M> int launch_shell(pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
-    if (p->nlist == 0) return PL_OK;
-    const XWall W = plan_xwall(p, g != nullptr);
-    HaloView HF, HG;
+// which kind of pass comes next (lbm_kernels.cuh, pass modes), bringing the two lattices to a common layout first if needed
+int plan_pass_mode(pl_plan* p, int& mode) {
     int r;
-    if ((r = halo_view(p->f, HF))) return r;
-    if (g) { if ((r = halo_view(g, HG))) return r; } else memset(&HG, 0, sizeof(HG));
-    LAUNCH_ON(st, (k_shell<D, M>), blocks_for(p->nlist, SHELL_THREADS), SHELL_THREADS, p->f->g, p->f->current(), p->f->other(), g ? g->current() : nullptr,
-           g ? g->other() : nullptr, P, ShellMask{p->mx, p->my, p->mz, opt_prefetch()}, p->prog[bc_parity], p->list, p->ent, p->nlist, p->ndirect, p->inverse, p->tube_f, p->tube_g, HF, HG, W);
-    // SmoothCorner + collide of the tube sites, right behind the boundary pass on the same stream
-    const int ntube = p->nlist - p->ndirect;
-    if (ntube > 0)
-        LAUNCH_ON(st, (k_tubes<D, M>), blocks_for(ntube, 128), 128, p->f->g, p->tube_f, p->tube_g, p->f->other(), g ? g->other() : nullptr, P, p->tube_info, ntube, W, p->inverse);
+    const bool xstale = p->nxlist && (p->xver[0] != p->f->version || (p->g && p->xver[1] != p->g->version));
+    if (!opt_inplace() || xstale) {      // the wall buffers are refilled from the natural layout
+        if ((r = make_natural(p->f)) || (p->g && (r = make_natural(p->g)))) return r;
+    }
+    if (!opt_inplace()) { mode = PASS_COPY; return PL_OK; }
+    for (pl_lattice* l : {p->f, p->g}) if (l && l->rep && l->rep_inverse != p->inverse && (r = make_natural(l))) return r;
+    if (p->g && p->f->rep != p->g->rep && ((r = make_natural(p->f)) || (r = make_natural(p->g)))) return r;
+    mode = p->f->rep ? PASS_LOCAL : PASS_GATHER;
     return PL_OK;
 }
-int dispatch_shell(int model, pl_plan* p, pl_lattice* g, const CollideParams& P, int bc_parity, cudaStream_t st) {
-    if (p->f->kind == PL_D2Q9) {
-        MODEL_SWITCH(2, launch_shell, p, g, P, bc_parity, st)
-        if (model == 12) return launch_shell<2, 12>(p, g, P, bc_parity, st);
-    } else {
-        MODEL_SWITCH(3, launch_shell, p, g, P, bc_parity, st)
+void plan_pass_done(pl_plan* p, int mode) {
+    for (pl_lattice* l : {p->f, p->g}) {
+        if (!l) continue;
+        if (mode == PASS_GATHER) { l->rep = 1; l->rep_inverse = p->inverse; }
+        else if (mode == PASS_LOCAL) l->rep = 0;
+        l->streamed = 0;
     }
-    return fail(PL_ERR_UNSUPPORTED, "fused step: model not available for this lattice");
+    p->xphase ^= 1;
+    if (mode != PASS_COPY) g_spares.inplace_pass();
 }
-// fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1
-void drop_graphs(pl_plan* p) {
-    for (auto& a : p->graphs) for (auto& b : a) for (auto& c : b) for (auto& g : c) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-}
-int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save);
-// fused F through a captured graph where that is possible: single block (no NCCL inside), not being profiled, arguments stable
+int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, int mode);
+// fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1 —
+// through a captured graph where that is possible: single block (no NCCL inside), in place, not being profiled, arguments stable.
 // full_save: every site stores what _issave asks for; else only the sites on closure planes do (pl_plan_advance_observed)
 int plan_fused(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
     const bool xstale = p->nxlist && (p->xver[0] != p->f->version || (p->g && p->xver[1] != p->g->version));      // the one-off refill must not be captured
-    if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial() || xstale) return plan_fused_body(p, bc_parity, col_parity, full_save);
-    if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity, full_save); }
-    const int fc = p->f->cur, gc = p->g ? p->g->cur : 0, sv = full_save ? 1 : 0;
-    cudaGraphExec_t& exec = p->graphs[bc_parity][fc][gc][sv];
-    if (exec) {
-        CU(cudaGraphLaunch(exec, g_stream));
-        g_launches += p->graph_launches[bc_parity][fc][gc][sv];
-        // the host-side state changes of plan_fused_body
-        p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
-        p->f->streamed = 0; if (p->g) p->g->streamed = 0;
+    int mode, r;
+    if ((r = plan_pass_mode(p, mode))) return r;
+    if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial() || xstale || mode == PASS_COPY) return plan_fused_body(p, bc_parity, col_parity, full_save, mode);
+    if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity, full_save, mode); }
+    pl_plan::Graph& G = p->graphs[bc_parity][mode][p->xphase][full_save ? 1 : 0];
+    if (G.exec && (G.fbuf != p->f->buf || G.gbuf != (p->g ? p->g->buf : nullptr))) { cudaGraphExecDestroy(G.exec); G = pl_plan::Graph(); }   // a Stream() swapped the buffers
+    if (G.exec) {
+        CU(cudaGraphLaunch(G.exec, g_stream));
+        g_launches += G.launches;
+        plan_pass_done(p, mode);      // the host-side state changes of plan_fused_body (the content version stays in step with xver)
         return PL_OK;
     }
     if (!p->cap) CU(cudaStreamCreateWithFlags(&p->cap, cudaStreamNonBlocking));
     cudaStream_t user = g_stream;
     const uint64_t before = g_launches;
+    G.fbuf = p->f->buf; G.gbuf = p->g ? p->g->buf : nullptr;
     g_stream = p->cap;
     cudaGraph_t graph = nullptr;
-    int r = PL_OK;
-    if (cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { g_stream = user; cudaGetLastError(); return plan_fused_body(p, bc_parity, col_parity, full_save); }
-    r = plan_fused_body(p, bc_parity, col_parity, full_save);
+    if (cudaStreamBeginCapture(p->cap, cudaStreamCaptureModeRelaxed) != cudaSuccess) { g_stream = user; cudaGetLastError(); return plan_fused_body(p, bc_parity, col_parity, full_save, mode); }
+    r = plan_fused_body(p, bc_parity, col_parity, full_save, mode);
     cudaError_t e = cudaStreamEndCapture(p->cap, &graph);
     g_stream = user;
     if (r) { if (graph) cudaGraphDestroy(graph); return r; }
     if (e != cudaSuccess || !graph) return fail(PL_ERR_CUDA, std::string("fused step: graph capture failed: ") + cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&exec, graph, 0);
+    e = cudaGraphInstantiate(&G.exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { exec = nullptr; return fail(PL_ERR_CUDA, std::string("fused step: cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
-    p->graph_launches[bc_parity][fc][gc][sv] = g_launches - before;
-    CU(cudaGraphLaunch(exec, g_stream));      // the body ran under capture: this launch is its execution
+    if (e != cudaSuccess) { G.exec = nullptr; return fail(PL_ERR_CUDA, std::string("fused step: cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+    G.launches = g_launches - before;
+    CU(cudaGraphLaunch(G.exec, g_stream));      // the body ran under capture: this launch is its execution
     return PL_OK;
 }
-int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
+int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, int mode) {
     CollideParams P; unsigned flags;
     int r = make_params(p->f, p->g, &p->args[col_parity], P, flags);
     if (r) return r;
@@ -1088,12 +1133,33 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
     const int model = p->args[col_parity].model;
     pl_lattice* g = (flags & F_G) ? p->g : nullptr;
     if (p->g && !g) return fail(PL_ERR_ARG, "plan: a single-lattice collide cannot drive a two-lattice plan");
-    ShellMask S{p->mx, p->my, p->mz, opt_prefetch()};
+    const ModelLaunch* ml = launcher(p->f, model);
+    if (!ml) return PL_ERR_UNSUPPORTED;
     // halo of a decomposed block: normally posted already by the collide that produced these populations
     if ((r = halo_prepare(p->f, p->inverse))) return r;
     if (p->g && (r = halo_prepare(p->g, p->inverse))) return r;
+    FusedArgs A;
+    memset(&A, 0, sizeof(A));
+    A.G = p->f->g; A.P = P; A.S = ShellMask{p->mx, p->my, p->mz, opt_prefetch()}; A.inverse = p->inverse;
+    A.fs = p->f->buf; A.gs = g ? g->buf : nullptr;
+    double *fdst = p->f->buf, *gdst = g ? g->buf : nullptr;
+    if (mode == PASS_COPY) {
+        fdst = g_spares.get(p->f->bytes());
+        gdst = g ? g_spares.get(g->bytes()) : nullptr;
+        if (!fdst || (g && !gdst)) return fail(PL_ERR_CUDA, "out of device memory for the second population buffer (PANSLBM_INPLACE=0)");
+    }
+    A.fd = fdst; A.gd = gdst;
+    A.list = p->list; A.ent = p->ent; A.nlist = p->nlist; A.ndirect = p->ndirect; A.tube_f = p->tube_f; A.tube_g = p->tube_g; A.tube_info = p->tube_info;
+    if ((r = halo_view(p->f, A.HF))) return r;
+    if (g && (r = halo_view(g, A.HG))) return r;
+    // compact wall buffers of the x boundary planes (XWall): this pass reads xout[.][xphase] and fills xout[.][xphase ^ 1]
+    if (p->nxlist) {
+        A.W.out_f = p->xout[0][p->xphase ^ 1]; A.W.res_f = p->xres[0];
+        if (g) { A.W.out_g = p->xout[1][p->xphase ^ 1]; A.W.res_g = p->xres[1]; }
+        A.W.np = p->f->g.ny*p->f->g.nz; A.W.on[0] = p->xon[0]; A.W.on[1] = p->xon[1];
+    }
     // boundary pass on the side stream (closure planes, block faces, SmoothCorner tubes, AVX-tail sites): it touches only
-    // sites the interior kernel skips, so the two run concurrently
+    // locations the interior kernel leaves alone, so the two run concurrently
     const bool serial = !p->f->halo.on && opt_shell_serial();
     if (!serial) {
         CU(cudaEventRecord(p->ev_fork, g_stream));
@@ -1101,16 +1167,21 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
         if ((r = halo_wait(p->f, p->side))) return r;
         if (p->g && (r = halo_wait(p->g, p->side))) return r;
     }
-    // a decomposed block wants its faces first (the next exchange hangs on them); a single block queues the interior first
-    // so that the boundary CTAs interleave with it instead of running alone at their lower memory efficiency
-    // closures of the x boundary planes, into the wrap slots of the source buffers (the boundary pass may run beside this)
-    const XWall W = plan_xwall(p, g != nullptr);
+    auto shell = [&](cudaStream_t st) -> int {
+        A.prog = p->prog[bc_parity];
+        if (p->nlist == 0) return PL_OK;
+        g_launches += p->nlist > p->ndirect ? 2 : 1;
+        CU(ml->shell(st, A, mode));
+        return PL_OK;
+    };
+    // closures of the x boundary planes on the compact wall buffers (the boundary pass may run beside this)
     if (p->nxlist) {
-        const int rd = p->f->cur, np = W.np, nc = p->f->nc;
+        const int rd = p->xphase, np = A.W.np, nc = p->f->nc;
         // wall buffers left by something else than this plan's own last pass (first pass after a standalone collide): refill
         for (int l = 0; l < (g ? 2 : 1); ++l) {
             pl_lattice* q = l ? g : p->f;
             if (p->xver[l] == q->version) continue;
+            if (q->rep) return fail(PL_ERR_ARG, "plan: internal error (wall buffers stale on a streamed layout)");
             dim3 grid(blocks_for(np, 128), 2*nc);
             if (q->kind == PL_D2Q9) LAUNCH(k_xfill<2>, grid, 128, q->g, q->current(), p->xout[l][rd], np, p->inverse, p->xon[0], p->xon[1]);
             else LAUNCH(k_xfill<3>, grid, 128, q->g, q->current(), p->xout[l][rd], np, p->inverse, p->xon[0], p->xon[1]);
@@ -1126,33 +1197,38 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
             else LAUNCH((k_xclose<3, false>), nb, SHELL_THREADS, p->f->g, inf, ing, rf, rg, np, p->prog[bc_parity], p->xlist, p->xent, p->nxlist, p->inverse, p->xneed);
         }
     }
+    // a decomposed block wants its faces first (the next exchange hangs on them); a single block may queue the interior first
     const bool shell_first = !serial && (p->f->halo.on || !opt_fused_first());
     if (shell_first) {
-        if ((r = dispatch_shell(model, p, g, P, bc_parity, p->side))) return r;
+        if ((r = shell(p->side))) return r;
         CU(cudaEventRecord(p->ev_join, p->side));
     }
-    // interior: one pass, source -> destination
+    // interior: one pass
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (p->profile) {
         CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
         CU(cudaEventRecord(ev0, g_stream));
     }
-    if ((r = dispatch_fused(model, p->f, g, P, S, opt_xinline() ? p->prog[bc_parity] : nullptr, p->inverse, W))) return r;
+    A.prog = opt_xinline() ? p->prog[bc_parity] : nullptr;
+    if (p->f->g.npacked > 0) { ++g_launches; CU(ml->fused(g_stream, A, mode)); }
     if (p->profile) {
         CU(cudaEventRecord(ev1, g_stream));
         p->events.push_back(pl_plan::ProfEv{ev0, ev1, P.issave == 2 ? 0 : 1, (long long)(p->f->g.nxyz - p->nlist)});
     }
     if (serial) {
-        if ((r = dispatch_shell(model, p, g, P, bc_parity, g_stream))) return r;
+        if ((r = shell(g_stream))) return r;
     } else {
         if (!shell_first) {
-            if ((r = dispatch_shell(model, p, g, P, bc_parity, p->side))) return r;
+            if ((r = shell(p->side))) return r;
             CU(cudaEventRecord(p->ev_join, p->side));
         }
         CU(cudaStreamWaitEvent(g_stream, p->ev_join, 0));
     }
-    p->f->cur ^= 1; if (p->g) p->g->cur ^= 1;
-    p->f->streamed = 0; if (p->g) p->g->streamed = 0;
+    if (mode == PASS_COPY) {
+        g_spares.put(p->f->buf, p->f->bytes()); p->f->buf = fdst;
+        if (g) { g_spares.put(g->buf, g->bytes()); g->buf = gdst; }
+    }
+    plan_pass_done(p, mode);
     // every block-face site is final: pack and post the next exchange now, it overlaps the next interior kernel
     halo_touch(p->f); if (p->g) halo_touch(p->g);
     p->xver[0] = p->f->version; if (p->g) p->xver[1] = p->g->version;      // the wall buffers describe exactly these populations

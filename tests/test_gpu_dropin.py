@@ -55,13 +55,15 @@ def run_dump(exe, d, dim, size, nt, env=None):
 
 
 @pytest.mark.parametrize("knobs", [{"PANSLBM_XGHOST": "0"}, {"PANSLBM_XGHOST": "0", "PANSLBM_XINLINE": "1"}, {"PANSLBM_GRAPH": "1"},
-                                   {"PANSLBM_XGHOST": "0", "PANSLBM_SHELL_SERIAL": "1", "PANSLBM_PREFETCH": "3"}],
-                         ids=["xslab", "xinline", "graph", "serial_prefetch"])
+                                   {"PANSLBM_XGHOST": "0", "PANSLBM_SHELL_SERIAL": "1", "PANSLBM_PREFETCH": "3"}, {"PANSLBM_INPLACE": "0"},
+                                   {"PANSLBM_INPLACE": "0", "PANSLBM_XGHOST": "0"}, {"PANSLBM_GRAPH": "1", "PANSLBM_XGHOST": "0"}],
+                         ids=["xslab", "xinline", "graph", "serial_prefetch", "two_buffers", "two_buffers_xslab", "graph_xslab"])
 @pytest.mark.parametrize("tag", ["hs3d", "hs2d"])
 def test_alternative_boundary_schedules_give_the_same_numbers(dump_exe, tmp_path, tag, knobs):
-    """the x closure planes can be served three ways (k_xclose ahead of the pass = default, aligned x groups in the boundary pass,
-    inline in the interior kernel), the step replayed as a CUDA graph, the boundary pass queued behind the interior kernel: all are
-    schedules of the same arithmetic and must reproduce the reference fixture bit for bit"""
+    """the x closure planes can be served three ways (k_xclose ahead of the pass on the compact wall buffers = default, aligned x
+    groups in the boundary pass, inline in the interior kernel), the step replayed as a CUDA graph, the boundary pass queued behind
+    the interior kernel, the passes run from one population buffer into a second one instead of in place: all are schedules of the
+    same arithmetic and must reproduce the reference fixture bit for bit"""
     dim, size, nt = heatsink_cases()[tag]
     res, log = run_dump(dump_exe, str(tmp_path), dim, size, nt, env=knobs)
     z = np.load(os.path.join(G, "heatsink.npz"))

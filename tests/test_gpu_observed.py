@@ -95,13 +95,13 @@ def test_unobserved_steps_really_skip_their_stores():
     H.compare(el, fl, "after the next storing collides")
     i, j, k = gcoords(*size)
     n = i.size
-    interior = (i > 0) & (i < size[0] - 1) & (j > 0) & (j < size[1] - 1) & (k > 0) & (k < size[2] - 1)
+    # two sites in from every wall: the sites next to two walls form the SmoothCorner tubes, which the boundary pass owns
+    interior = (i > 1) & (i < size[0] - 2) & (j > 1) & (j < size[1] - 2) & (k > 1) & (k < size[2] - 2)
     interior &= np.arange(n) < 4*(n//4)                       # the sites of the last incomplete AVX pack belong to the boundary pass
     for name in ("rho", "ux", "uy", "uz", "tem", "qx", "qy", "qz"):
         assert np.array_equal(em[name][interior], e0[name][interior]), f"{name}: an elided pass stored in the interior"
         assert not np.array_equal(fm[name][interior], f0[name][interior]), f"{name}: the storing run did not move (test too weak)"
     # the closure planes are current after every pass: the x walls belong to the interior kernel + k_xclose, the others to the boundary pass
-    face = ~interior & (np.arange(n) < 4*(n//4))
     plane = (i == 0) | (i == size[0] - 1) | (j == 0) | (j == size[1] - 1) | (k == 0) | (k == size[2] - 1)
     for name in ("ux", "uy", "uz"):
-        assert np.array_equal(em[name][plane & face], fm[name][plane & face]), f"{name} on the closure planes"
+        assert np.array_equal(em[name][plane], fm[name][plane]), f"{name} on the closure planes"
