@@ -30,6 +30,9 @@ typedef struct pl_plan pl_plan;
 
 /* ---- library ------------------------------------------------------------------------------- */
 const char* pl_last_error(void);
+/* != 0 while the calling thread is inside an entry point that passes caller host pointers to the CUDA runtime (used by the
+ * coherence layer of the host-pointer surface to refuse serving a page fault from in there) */
+int pl_in_call(void);
 const char* pl_version(void);
 int pl_device_count(void);
 int pl_set_device(int device);
@@ -154,6 +157,9 @@ pl_bc* pl_bc_create(pl_lattice*, int type, int axis, int coord, int dir,
                     const uint8_t* mask_host, const double* v0_host, const double* v1_host, const double* v2_host);
 int pl_bc_destroy(pl_bc*);
 int pl_bc_is_empty(const pl_bc*);
+/* Replace the per-site VALUES of a plane (same arrays as at creation, host pointers; the mask stays): a time-dependent inlet
+ * profile keeps its handle — and every plan that holds it — while its numbers change.  Stream-ordered behind the passes queued. */
+int pl_bc_update_values(pl_bc*, const double* v0, const double* v1, const double* v2);
 
 /* Per-site fields some closures read at the boundary site (device pointers, nxyz doubles; unused = NULL):
  * the velocities saved by the collide of the same step (advection.h:1083-1090), the per-cell diffusivity
@@ -317,6 +323,9 @@ const char* plh_last_error(void);
 void* plh_alloc(size_t bytes);
 void plh_free(void* p);
 int plh_owns(const void* p);
+int plh_owns_range(const void* p);   /* p lies anywhere inside a mirrored block (arrays and population views) */
+/* pl_bc_update_values behind the passes the fusion engine still holds back */
+int plh_bc_update_values(pl_bc*, const double* v0, const double* v1, const double* v2);
 /* The public `T *f0, *f` members of D2Q9/D3Q15 (d3q15.h:225): host views in the reference layout, kept coherent with
  * the device populations on demand (test/d2q9.cpp, test/d3q15.cpp read and write them directly). */
 int plh_lattice_attach_views(pl_lattice*, double** f0, double** f);
@@ -333,6 +342,11 @@ int plh_sensitivity(pl_lattice*, const pl_sens_args* host_args);
 int plh_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
                                 const double* igsnap, const double* diffusivity, const double* dkds);
 int plh_filter_apply(pl_filter*, int mode, double beta, const double* v_host, const double* dfdrho_host, double* out_host, size_t n);
+/* Before handing a mirrored host array to code that is not this program's own loads and stores — a system call (fwrite of a whole
+ * field), another library, a device-pointer entry point of this one (pl_comm_*, pl_array_upload): make [p, p + bytes) current and
+ * readable on the host (for_write: writable, the host copy becomes the only current one).  The page-fault path serves ordinary
+ * accesses transparently; those callers it cannot serve (EFAULT, or a fault inside the CUDA runtime, which aborts with a message). */
+int plh_host_acquire(const void* p, size_t bytes, int for_write);
 /* Execute whatever is still checked off and wait for the device. */
 int plh_sync(void);
 /* out[0..7] = fused steps, calls executed one by one, uploads, downloads, page faults served, plans built, settles, stagings */

@@ -39,6 +39,10 @@ cudaStream_t g_stream = 0;          // legacy default stream unless the caller i
 uint64_t g_launches = 0;
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+// entry points that hand CALLER host pointers to the CUDA runtime mark themselves: the coherence layer of the host-pointer surface
+// (panslbm_host.cpp) must not try to serve a page fault taken in there
+thread_local int g_in_call = 0;
+struct InCall { InCall() { ++g_in_call; } ~InCall() { --g_in_call; } };
 #define CU(call)                                                                                        \
     do {                                                                                                \
         cudaError_t e__ = (call);                                                                       \
@@ -405,6 +409,7 @@ int make_natural(pl_lattice* l) {
 extern "C" {
 
 const char* pl_last_error(void) { return g_err.c_str(); }
+int pl_in_call(void) { return g_in_call; }
 const char* pl_version(void) { return "panslbm_b200 0.1 (sm_100a, fp64, fmad=off)"; }
 int pl_device_count(void) {
     int n = 0;
@@ -425,11 +430,13 @@ double* pl_array_alloc(size_t n) {
 }
 int pl_array_free(double* dev) { CU(cudaFree(dev)); return PL_OK; }
 int pl_array_upload(double* dev, const double* host, size_t n) {
+    InCall in_call_;
     CU(cudaMemcpyAsync(dev, host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
 }
 int pl_array_download(double* host, const double* dev, size_t n) {
+    InCall in_call_;
     CU(cudaMemcpyAsync(host, dev, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
@@ -550,6 +557,7 @@ int pl_lattice_info(const pl_lattice* l, int* o) {
     return PL_OK;
 }
 int pl_lattice_set_host(pl_lattice* l, const double* f0, const double* f) {
+    InCall in_call_;
     if (!l || !f0 || !f) return fail(PL_ERR_ARG, "pl_lattice_set_host: null");
     size_t n = (size_t)l->g.nxyz, nf = n*(l->nc - 1);
     double *d0 = nullptr, *d1 = nullptr;
@@ -566,6 +574,7 @@ int pl_lattice_set_host(pl_lattice* l, const double* f0, const double* f) {
     return PL_OK;
 }
 int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
+    InCall in_call_;
     if (!l || !f0 || !f) return fail(PL_ERR_ARG, "pl_lattice_get_host: null");
     { int r = make_natural(l); if (r) return r; }
     size_t n = (size_t)l->g.nxyz, nf = n*(l->nc - 1);
@@ -923,6 +932,19 @@ int pl_bc_destroy(pl_bc* bc) {
     return PL_OK;
 }
 int pl_bc_is_empty(const pl_bc* bc) { return bc ? (bc->empty ? 1 : 0) : 1; }
+int pl_bc_update_values(pl_bc* bc, const double* v0, const double* v1, const double* v2) {
+    InCall in_call_;
+    if (!bc) return fail(PL_ERR_ARG, "pl_bc_update_values: null");
+    if (bc->empty) return PL_OK;
+    if ((v0 != nullptr) != (bc->v0 != nullptr) || (v1 != nullptr) != (bc->v1 != nullptr) || (v2 != nullptr) != (bc->v2 != nullptr))
+        return fail(PL_ERR_ARG, "pl_bc_update_values: the plane was created with other value arrays");
+    const size_t nb = (size_t)bc->pl.n1*bc->pl.n2*sizeof(double);
+    // pageable source: the runtime stages it before returning, the device copy is ordered behind every pass already queued
+    if (v0) CU(cudaMemcpyAsync(bc->v0, v0, nb, cudaMemcpyHostToDevice, g_stream));
+    if (v1) CU(cudaMemcpyAsync(bc->v1, v1, nb, cudaMemcpyHostToDevice, g_stream));
+    if (v2) CU(cudaMemcpyAsync(bc->v2, v2, nb, cudaMemcpyHostToDevice, g_stream));
+    return PL_OK;
+}
 int pl_bc_apply(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* aux) {
     if (!l || !bc) return fail(PL_ERR_ARG, "pl_bc_apply: null");
     return do_bc(l, other, bc, aux);
@@ -1792,6 +1814,7 @@ int pl_comm_info(int* mode, int* rank, int* nranks) {
     return PL_OK;
 }
 int pl_comm_allreduce_v(void* inout_host, size_t n, int dtype, int op) {
+    InCall in_call_;
     if (!inout_host || (dtype != 0 && dtype != 1) || op < 0 || op > 2) return fail(PL_ERR_ARG, "pl_comm_allreduce_v: dtype 0 (f64) / 1 (i32), op 0 (sum) / 1 (max) / 2 (min)");
     if (g_comm.mode != COMM_NCCL || n == 0) return PL_OK;   // a world of one
     const size_t bytes = n*(dtype == 0 ? sizeof(double) : sizeof(int));
@@ -1805,6 +1828,7 @@ int pl_comm_allreduce_v(void* inout_host, size_t n, int dtype, int op) {
     return PL_OK;
 }
 int pl_comm_p2p(const pl_p2p_op* ops, int n) {
+    InCall in_call_;
     if (n < 0 || (n > 0 && !ops)) return fail(PL_ERR_ARG, "pl_comm_p2p: bad arguments");
     if (n == 0) return PL_OK;
     if (g_comm.mode != COMM_NCCL) return fail(PL_ERR_ARG, "pl_comm_p2p: no NCCL communicator");
@@ -1829,6 +1853,7 @@ int pl_comm_p2p(const pl_p2p_op* ops, int n) {
     return PL_OK;
 }
 int pl_comm_allreduce(double* inout_host, int n, int op) {
+    InCall in_call_;
     if (!inout_host || n < 1 || n > 4 || (op != 0 && op != 1)) return fail(PL_ERR_ARG, "pl_comm_allreduce: 1..4 values, op 0 (sum) / 1 (max)");
     if (g_comm.mode != COMM_NCCL) return PL_OK;   // a world of one
     CU(cudaMemcpyAsync(g_comm.red, inout_host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
