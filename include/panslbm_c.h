@@ -277,6 +277,17 @@ int pl_residual(const double* ux, const double* uy, const double* uz,
                 const double* uxp, const double* uyp, const double* uzp, size_t n, double* out_host);
 int pl_reduce_sum(const double* v, size_t n, double* out_host);
 int pl_reduce_absmax(const double* v, size_t n, double* out_host);
+/* Sum of a per-site field over the box [i0,i1) x [j0,j1) x [k0,k1) of GLOBAL coordinates, clipped to this rank's block and summed
+ * over the ranks: the objective of the heatsink drivers (mean temperature of the heat patch, production/heatsink3D.cpp:227-240,
+ * with its MPI_Allreduce) without bringing the whole field to the host. */
+int pl_reduce_box_sum(const pl_lattice*, const double* v, int i0, int i1, int j0, int j1, int k0, int k1, double* out_host);
+/* The design map of the heatsink drivers on the device (production/heatsink3D.cpp:114-119): from the filtered design ss the
+ * diffusivity, the Brinkman coefficient and their derivatives, alpha0 = alphamax/(ly - 1); the reference's operation order. */
+int pl_design_map(const double* ss, size_t n, double diff_fluid, double diff_solid, double qg, double alpha0, double qf,
+                  double* diffusivity, double* alpha, double* dkds, double* dads);
+/* Every rank's block of a per-site field assembled into the field of the global domain (lx*ly*lz doubles, host) on every rank:
+ * what the reference's VTK writers gather with MPI_Isend/Irecv (src/utility/vtkxmlexport.h:172-214). */
+int pl_comm_gather_field(const pl_lattice*, const double* v_dev, double* out_host_global);
 /* Normalize (src/utility/normalize.h:8-24) */
 int pl_normalize(double* v, size_t n);
 
@@ -308,6 +319,12 @@ int pl_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, co
  * heavisidefilter.h:291-400); the weights then cover neighbours anywhere in the GLOBAL domain. */
 typedef struct pl_filter pl_filter;
 pl_filter* pl_filter_create(pl_lattice*, int nR, const double* weights_host);
+/* The same from weight PATTERNS: patterns[p*K + o] (K = (2nR+1)^3) for the sites with pattern_of_site[idx] == p.  The weights of the
+ * reference's drivers depend on the offset and on which side of the design box the two sites lie (production/heatsink3D.cpp:87-93) —
+ * a few hundred distinct patterns whatever the lattice size; the drop-in headers bake the callable straight into this form (no
+ * dense table is ever built), pl_filter_create folds its dense input into it.  pl_filter_patterns: how many patterns a filter holds. */
+pl_filter* pl_filter_create_patterns(pl_lattice*, int nR, const double* patterns, int npatterns, const int* pattern_of_site);
+int pl_filter_patterns(const pl_filter*);
 int pl_filter_destroy(pl_filter*);
 int pl_filter_apply(pl_filter*, int mode, double beta, const double* v, const double* dfdrho, double* out);
 

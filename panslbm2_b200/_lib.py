@@ -103,6 +103,11 @@ _PROTOS = {
     "pl_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
     "pl_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
     "pl_filter_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pl_filter_create_patterns": (C.c_void_p, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "pl_filter_patterns": (C.c_int, [C.c_void_p]),
+    "pl_reduce_box_sum": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int]*6 + [c_double_p]),
+    "pl_design_map": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_double]*5 + [C.c_void_p]*4),
+    "pl_comm_gather_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_filter_destroy": (C.c_int, [C.c_void_p]),
     "pl_filter_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     # host-pointer surface (bound by the C++ drop-in headers; declared here so that the export test covers it)

@@ -1938,40 +1938,68 @@ int pl_normalize(double* v, size_t n) {
 struct pl_filter {
     FilterGeom F;
     bool global = false;           // decomposed block: fields are assembled over all ranks first
-    double* w = nullptr;
+    double* wtab = nullptr;        // [npat][K] weight patterns
+    int* pid = nullptr;            // pattern of each site
+    int npat = 0;
     double* tmp = nullptr;         // first pass of the sensitivity filter (block)
     double* gv = nullptr;          // field of the global domain
 };
-pl_filter* pl_filter_create(pl_lattice* l, int nR, const double* weights_host) {
-    if (!l || nR < 0 || nR > 8 || !weights_host) { fail(PL_ERR_ARG, "pl_filter_create: bad arguments"); return nullptr; }
-    if (l->halo.on && g_comm.mode != COMM_NCCL) {
-        fail(PL_ERR_UNSUPPORTED, "pl_filter_create: filters on a block-decomposed lattice need the NCCL communicator (pl_comm_init)");
-        return nullptr;
-    }
+static pl_filter* filter_from_patterns(pl_lattice* l, int nR, const double* patterns, int npat, const int* pattern_of_site) {
     pl_filter* f = new pl_filter();
     FilterGeom& F = f->F;
     F.nx = l->g.nx; F.ny = l->g.ny; F.nz = l->g.nz; F.nR = nR; F.nxyz = l->g.nxyz;
     F.gx = l->g.lx; F.gy = l->g.ly; F.gz = l->g.lz; F.ox = l->g.offx; F.oy = l->g.offy; F.oz = l->g.offz;
     f->global = l->halo.on;
+    f->npat = npat;
     const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz, gn = (size_t)F.gx*F.gy*F.gz;
-    bool ok = cudaMalloc(&f->w, K*n*sizeof(double)) == cudaSuccess && cudaMalloc(&f->tmp, n*sizeof(double)) == cudaSuccess;
+    bool ok = cudaMalloc(&f->wtab, std::max<size_t>(1, K*npat)*sizeof(double)) == cudaSuccess && cudaMalloc(&f->pid, n*sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&f->tmp, n*sizeof(double)) == cudaSuccess;
     if (ok && f->global) ok = cudaMalloc(&f->gv, gn*sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMemcpy(f->wtab, patterns, K*npat*sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(f->pid, pattern_of_site, n*sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
-        fail(PL_ERR_CUDA, std::string("pl_filter_create: cudaMalloc: ") + cudaGetErrorString(cudaGetLastError()));
-        cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv); delete f;
-        return nullptr;
-    }
-    if (cudaMemcpy(f->w, weights_host, K*n*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
-        fail(PL_ERR_CUDA, "pl_filter_create: upload failed");
-        cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv); delete f;
+        fail(PL_ERR_CUDA, std::string("pl_filter_create: ") + cudaGetErrorString(cudaGetLastError()));
+        cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gv); delete f;
         return nullptr;
     }
     return f;
 }
+static bool filter_args_ok(pl_lattice* l, int nR, const void* a, const void* b) {
+    if (!l || nR < 0 || nR > 8 || !a || !b) { fail(PL_ERR_ARG, "pl_filter_create: bad arguments"); return false; }
+    if (l->halo.on && g_comm.mode != COMM_NCCL) {
+        fail(PL_ERR_UNSUPPORTED, "pl_filter_create: filters on a block-decomposed lattice need the NCCL communicator (pl_comm_init)");
+        return false;
+    }
+    return true;
+}
+pl_filter* pl_filter_create_patterns(pl_lattice* l, int nR, const double* patterns, int npatterns, const int* pattern_of_site) {
+    InCall in_call_;
+    if (!filter_args_ok(l, nR, patterns, pattern_of_site) || npatterns < 1) { if (npatterns < 1) fail(PL_ERR_ARG, "pl_filter_create_patterns: no pattern"); return nullptr; }
+    for (long long i = 0; i < l->g.nxyz; ++i)
+        if (pattern_of_site[i] < 0 || pattern_of_site[i] >= npatterns) { fail(PL_ERR_ARG, "pl_filter_create_patterns: pattern index out of range"); return nullptr; }
+    return filter_from_patterns(l, nR, patterns, npatterns, pattern_of_site);
+}
+// dense per-site table (weights_host[o*nxyz + idx]): sites with the same K weights share one pattern
+pl_filter* pl_filter_create(pl_lattice* l, int nR, const double* weights_host) {
+    InCall in_call_;
+    if (!filter_args_ok(l, nR, weights_host, weights_host)) return nullptr;
+    const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz;
+    std::unordered_map<std::string, int> seen;
+    std::vector<double> patterns, row(K);
+    std::vector<int> pid(n);
+    for (size_t i = 0; i < n; ++i) {
+        for (size_t o = 0; o < K; ++o) row[o] = weights_host[o*n + i];
+        auto r = seen.emplace(std::string(reinterpret_cast<const char*>(row.data()), K*sizeof(double)), (int)seen.size());
+        if (r.second) patterns.insert(patterns.end(), row.begin(), row.end());
+        pid[i] = r.first->second;
+    }
+    return filter_from_patterns(l, nR, patterns.data(), (int)seen.size(), pid.data());
+}
+int pl_filter_patterns(const pl_filter* f) { return f ? f->npat : 0; }
 int pl_filter_destroy(pl_filter* f) {
     if (!f) return PL_OK;
     cudaStreamSynchronize(g_stream);
-    cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv);
+    cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gv);
     delete f;
     return PL_OK;
 }
@@ -1995,12 +2023,61 @@ int pl_filter_apply(pl_filter* f, int mode, double beta, const double* v, const 
     const double* field;
     int r = filter_field(f, v, &field);
     if (r) return r;
-    if (mode < 2) LAUNCH(k_filter, nb, 256, f->F, f->w, field, nullptr, beta, mode, out);
+    if (mode < 2) LAUNCH(k_filter, nb, 256, f->F, f->wtab, f->pid, field, nullptr, beta, mode, out);
     else {
-        LAUNCH(k_filter, nb, 256, f->F, f->w, field, dfdrho, beta, 2, f->tmp);
+        LAUNCH(k_filter, nb, 256, f->F, f->wtab, f->pid, field, dfdrho, beta, 2, f->tmp);
         if ((r = filter_field(f, f->tmp, &field))) return r;
-        LAUNCH(k_filter, nb, 256, f->F, f->w, field, nullptr, beta, 3, out);
+        LAUNCH(k_filter, nb, 256, f->F, f->wtab, f->pid, field, nullptr, beta, 3, out);
     }
+    return PL_OK;
+}
+int pl_design_map(const double* ss, size_t n, double diff_fluid, double diff_solid, double qg, double alpha0, double qf, double* diffusivity, double* alpha,
+                  double* dkds, double* dads) {
+    if (!ss || !diffusivity || !alpha || !dkds || !dads) return fail(PL_ERR_ARG, "pl_design_map: null");
+    if (n == 0) return PL_OK;
+    LAUNCH(k_design_map, blocks_for((long long)n, 256), 256, ss, (long long)n, diff_fluid, diff_solid, qg, alpha0, qf, diffusivity, alpha, dkds, dads);
+    return PL_OK;
+}
+int pl_reduce_box_sum(const pl_lattice* l, const double* v, int i0, int i1, int j0, int j1, int k0, int k1, double* out) {
+    if (!l || !v || !out) return fail(PL_ERR_ARG, "pl_reduce_box_sum: null");
+    const Geom& g = l->g;
+    // global coordinates, clipped to this rank's block (the drivers' `(i + offsetx) < L` tests, heatsink3D.cpp:229-235)
+    i0 = std::max(i0 - g.offx, 0); i1 = std::min(i1 - g.offx, g.nx); j0 = std::max(j0 - g.offy, 0); j1 = std::min(j1 - g.offy, g.ny);
+    k0 = std::max(k0 - g.offz, 0); k1 = std::min(k1 - g.offz, g.nz);
+    const int nb = 256;
+    double* scratch = (double*)g_scratch.get((nb + 1)*sizeof(double));
+    if (!scratch) return fail(PL_ERR_CUDA, "pl_reduce_box_sum: scratch allocation failed");
+    if (i1 <= i0 || j1 <= j0 || k1 <= k0) { *out = 0.0; }
+    else {
+        LAUNCH(k_box_sum_partial, nb, 256, v, g.nx, g.ny, i0, i1, j0, j1, k0, k1, scratch);
+        LAUNCH(k_sum_final, 1, 256, scratch, nb, 1, scratch + nb);
+    }
+    if (i1 <= i0 || j1 <= j0 || k1 <= k0) CU(cudaMemsetAsync(scratch + nb, 0, sizeof(double), g_stream));
+    // the drivers' MPI_Allreduce(SUM) of the partial objective (heatsink3D.cpp:236)
+    if (g_comm.mode == COMM_NCCL) { NC(g_nccl.AllReduce(scratch + nb, scratch + nb, 1, NCCL_F64, NCCL_SUM, g_comm.nccl, g_stream)); ++g_launches; }
+    CU(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return PL_OK;
+}
+// every rank's block of a per-site field into the field of the GLOBAL domain, on every rank (what the VTK writers of the
+// reference gather block by block with MPI_Isend/Irecv, vtkxmlexport.h:172-214): device-side scatter + one all-reduce
+int pl_comm_gather_field(const pl_lattice* l, const double* v, double* out_host_global) {
+    InCall in_call_;
+    if (!l || !v || !out_host_global) return fail(PL_ERR_ARG, "pl_comm_gather_field: null");
+    const Geom& g = l->g;
+    const size_t gn = (size_t)g.lx*g.ly*g.lz;
+    if (!l->halo.on) { CU(cudaMemcpyAsync(out_host_global, v, gn*sizeof(double), cudaMemcpyDeviceToHost, g_stream)); CU(cudaStreamSynchronize(g_stream)); return PL_OK; }
+    if (g_comm.mode != COMM_NCCL) return fail(PL_ERR_UNSUPPORTED, "pl_comm_gather_field: a block-decomposed lattice needs the NCCL communicator");
+    double* gv = (double*)g_scratch.get(gn*sizeof(double));
+    if (!gv) return fail(PL_ERR_CUDA, "pl_comm_gather_field: scratch allocation failed");
+    FilterGeom F;
+    F.nx = g.nx; F.ny = g.ny; F.nz = g.nz; F.nR = 0; F.nxyz = g.nxyz; F.gx = g.lx; F.gy = g.ly; F.gz = g.lz; F.ox = g.offx; F.oy = g.offy; F.oz = g.offz;
+    CU(cudaMemsetAsync(gv, 0, gn*sizeof(double), g_stream));
+    LAUNCH(k_filter_scatter, blocks_for(g.nxyz, 256), 256, F, v, gv);
+    NC(g_nccl.AllReduce(gv, gv, gn, NCCL_F64, NCCL_SUM, g_comm.nccl, g_stream));
+    ++g_launches;
+    CU(cudaMemcpyAsync(out_host_global, gv, gn*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
 }
 

@@ -19,6 +19,7 @@
 #include <new>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 #include <unistd.h>
 
@@ -76,10 +77,12 @@ namespace b200 {
         std::vector<char> exclusive;                // plane of one volatile call site (updated in place): never shared by content
         std::vector<pl_filter*> filters;            // baked filter weight tables owned by this lattice
         static unsigned long long next_gen() { static unsigned long long g = 0; return ++g; }
+        static std::vector<unsigned long long>& live() { static std::vector<unsigned long long> v; return v; }
         void create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz, double** f0, double** f) {
             h = pl_lattice_create(kind, lx, ly, lz, peid, mx, my, mz);
             if (!h) check(1, "pl_lattice_create");
             gen = next_gen();
+            live().push_back(gen);
             check(plh_lattice_attach_views(h, f0, f), "plh_lattice_attach_views");
         }
         void destroy() {
@@ -89,6 +92,7 @@ namespace b200 {
             for (pl_filter* f : filters) pl_filter_destroy(f);
             pl_lattice_destroy(h);
             h = nullptr;
+            for (size_t k = 0; k < live().size(); ++k) if (live()[k] == gen) { live().erase(live().begin() + k); break; }
         }
     };
 
@@ -100,6 +104,7 @@ namespace b200 {
     // so a changed inlet velocity or time step is seen.  What this cannot see — state behind two indirections, a global the
     // lambda reads — is caught by re-evaluating each call site every PANSLBM_B200_REVALIDATE-th call (default 256) and comparing
     // the content; a site caught changing that way is evaluated on every call from then on.  plh_bc_invalidate() drops all keys.
+    inline bool lattice_alive(unsigned long long gen) { for (unsigned long long g : Core::live()) if (g == gen) return true; return false; }
     template<class F> inline void append_bytes(std::string& s, const F& f) {
         if constexpr (!std::is_empty<F>::value) s.append(reinterpret_cast<const char*>(&f), sizeof(F));
         s.push_back('|');
@@ -244,44 +249,54 @@ namespace b200 {
         return core.planes[site->own];
     }
 
-    // The weight table of a cone filter of radius _R on lattice `p` (densityfilter.h:389-497): the reference evaluates
-    // `_weight(i1,j1,k1,i2,j2,k2)` for every pair within _R on EVERY call; here it is evaluated once per (lattice, _R, callable)
-    // and kept on the device.  Pairs beyond _R or outside the domain get weight 0 (they do not enter the reference's sums).
+    // The weights of a cone filter of radius _R on lattice `p` (densityfilter.h:389-497): the reference evaluates
+    // `_weight(i1,j1,k1,i2,j2,k2)` for every pair within _R on EVERY call; here it is evaluated once per (lattice, _R, callable),
+    // site by site, and folded into PATTERNS on the fly: sites with the same (2nR+1)^nd weights share one entry (the drivers'
+    // weights depend on the offset and on which side of the design box the two sites lie, production/heatsink3D.cpp:87-93: a
+    // few hundred patterns), so neither the host nor the device ever holds a per-site table.  Pairs beyond _R or outside the
+    // domain get weight 0 (they do not enter the reference's sums).
     template<class P, class F>
     pl_filter* filter(P& p, double _R, F _weight) {
-        struct Entry { unsigned long long gen; double R; std::string bytes; pl_filter* f; };
+        struct Entry { unsigned long long gen, epoch; double R; std::string bytes; pl_filter* f; };
         static std::vector<Entry> cache;
         Core& core = p.b200_core();
         std::string bytes;
         constexpr bool cacheable = std::is_trivially_copyable<F>::value;
         if constexpr (cacheable) {
-            append_bytes(bytes, _weight);
-            for (const Entry& e : cache) if (e.gen == core.gen && e.R == _R && e.bytes == bytes) return e.f;
+            append_bytes(bytes, _weight); append_pointees(bytes, _weight);
+            for (const Entry& e : cache) if (e.gen == core.gen && e.epoch == bake_epoch() && e.R == _R && e.bytes == bytes) return e.f;
         }
+        // entries of lattices that are gone (their filters were destroyed with them) leave the cache
+        for (size_t k = 0; k < cache.size();) { if (cache[k].gen != core.gen && !lattice_alive(cache[k].gen)) cache.erase(cache.begin() + k); else ++k; }
         const int nR = (int)_R, side = 2*nR + 1;
         const size_t n = (size_t)p.nxyz, K = (size_t)side*side*side;
-        std::vector<double> w(K*n, 0.0);
-        #pragma omp parallel for
+        std::vector<double> patterns, row(K);
+        std::vector<int> pid(n);
+        std::unordered_map<std::string, int> seen;
         for (int k1 = 0; k1 < p.nz; ++k1)
             for (int j1 = 0; j1 < p.ny; ++j1)
                 for (int i1 = 0; i1 < p.nx; ++i1) {
-                    const size_t idx = (size_t)p.Index(i1, j1, k1);
                     size_t o = 0;
                     for (int i2 = i1 - nR; i2 <= i1 + nR; ++i2)
                         for (int j2 = j1 - nR; j2 <= j1 + nR; ++j2)
                             for (int k2 = k1 - nR; k2 <= k1 + nR; ++k2, ++o) {
+                                row[o] = 0.0;
+                                if (P::nd == 2 && k2 != k1) continue;
                                 // neighbours anywhere in the GLOBAL domain count (own block or another rank's: heavisidefilter.h:470-556)
                                 if (i2 + p.offsetx < 0 || i2 + p.offsetx >= p.lx || j2 + p.offsety < 0 || j2 + p.offsety >= p.ly ||
                                     k2 + p.offsetz < 0 || k2 + p.offsetz >= p.lz) continue;
                                 const double distance = std::sqrt(std::pow(i1 - i2, 2.0) + std::pow(j1 - j2, 2.0) + std::pow(k1 - k2, 2.0));
                                 if (distance <= _R)
-                                    w[o*n + idx] = (double)_weight(i1 + p.offsetx, j1 + p.offsety, k1 + p.offsetz, i2 + p.offsetx, j2 + p.offsety, k2 + p.offsetz);
+                                    row[o] = (double)_weight(i1 + p.offsetx, j1 + p.offsety, k1 + p.offsetz, i2 + p.offsetx, j2 + p.offsety, k2 + p.offsetz);
                             }
+                    auto r = seen.emplace(std::string(reinterpret_cast<const char*>(row.data()), K*sizeof(double)), (int)seen.size());
+                    if (r.second) patterns.insert(patterns.end(), row.begin(), row.end());
+                    pid[(size_t)p.Index(i1, j1, k1)] = r.first->second;
                 }
-        pl_filter* f = pl_filter_create(core.h, nR, w.data());
-        if (!f) check(1, "pl_filter_create");
+        pl_filter* f = pl_filter_create_patterns(core.h, nR, patterns.data(), (int)seen.size(), pid.data());
+        if (!f) check(1, "pl_filter_create_patterns");
         core.filters.push_back(f);
-        if constexpr (cacheable) cache.push_back(Entry{core.gen, _R, bytes, f});
+        if constexpr (cacheable) cache.push_back(Entry{core.gen, bake_epoch(), _R, bytes, f});
         return f;
     }
 
