@@ -87,6 +87,13 @@ bool opt_xinline() { static int v = env_int("PANSLBM_XINLINE", 0); return v != 0
 // fused passes update the ONE population buffer of a lattice in place (AA pattern: gather pass, local pass, ...);
 // 0 = every pass goes from the buffer to a second one borrowed from the spare pool (the reference's f / fnext scheme)
 bool opt_inplace() { static int v = env_int("PANSLBM_INPLACE", 1); return v != 0; }
+// interior kernel as a persistent, software-pipelined kernel (cp.async prefetch of the next tile; k_fused_pipe); 0 = one thread per site
+bool opt_pipe() { static int v = env_int("PANSLBM_PIPE", 1); return v != 0; }
+int device_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148; }
+    return n;
+}
 
 // Spare population buffers.  A lattice owns ONE buffer; the operations that cannot work in place — a standalone Stream()/iStream(),
 // the conversion of the streamed layout back to the natural one, the two-buffer passes of PANSLBM_INPLACE=0 — write into a buffer
@@ -1108,7 +1115,6 @@ void plan_pass_done(pl_plan* p, int mode) {
         l->streamed = 0;
     }
     p->xphase ^= 1;
-    if (mode != PASS_COPY) g_spares.inplace_pass();
 }
 int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, int mode);
 // fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1 —
@@ -1118,6 +1124,7 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
     const bool xstale = p->nxlist && (p->xver[0] != p->f->version || (p->g && p->xver[1] != p->g->version));      // the one-off refill must not be captured
     int mode, r;
     if ((r = plan_pass_mode(p, mode))) return r;
+    if (mode != PASS_COPY) g_spares.inplace_pass();      // (never under stream capture: it may synchronise and free)
     if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial() || xstale || mode == PASS_COPY) return plan_fused_body(p, bc_parity, col_parity, full_save, mode);
     if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity, full_save, mode); }
     pl_plan::Graph& G = p->graphs[bc_parity][mode][p->xphase][full_save ? 1 : 0];
@@ -1171,6 +1178,7 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, i
         if (!fdst || (g && !gdst)) return fail(PL_ERR_CUDA, "out of device memory for the second population buffer (PANSLBM_INPLACE=0)");
     }
     A.fd = fdst; A.gd = gdst;
+    A.pipe = opt_pipe() ? 1 : 0; A.sms = device_sms();
     A.list = p->list; A.ent = p->ent; A.nlist = p->nlist; A.ndirect = p->ndirect; A.tube_f = p->tube_f; A.tube_g = p->tube_g; A.tube_info = p->tube_info;
     if ((r = halo_view(p->f, A.HF))) return r;
     if (g && (r = halo_view(g, A.HG))) return r;
