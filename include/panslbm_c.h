@@ -30,6 +30,9 @@ typedef struct pl_plan pl_plan;
 
 /* ---- library ------------------------------------------------------------------------------- */
 const char* pl_last_error(void);
+/* != 0 while the calling thread is inside an entry point that passes caller host pointers to the CUDA runtime (used by the
+ * coherence layer of the host-pointer surface to refuse serving a page fault from in there) */
+int pl_in_call(void);
 const char* pl_version(void);
 int pl_device_count(void);
 int pl_set_device(int device);
@@ -154,6 +157,9 @@ pl_bc* pl_bc_create(pl_lattice*, int type, int axis, int coord, int dir,
                     const uint8_t* mask_host, const double* v0_host, const double* v1_host, const double* v2_host);
 int pl_bc_destroy(pl_bc*);
 int pl_bc_is_empty(const pl_bc*);
+/* Replace the per-site VALUES of a plane (same arrays as at creation, host pointers; the mask stays): a time-dependent inlet
+ * profile keeps its handle — and every plan that holds it — while its numbers change.  Stream-ordered behind the passes queued. */
+int pl_bc_update_values(pl_bc*, const double* v0, const double* v1, const double* v2);
 
 /* Per-site fields some closures read at the boundary site (device pointers, nxyz doubles; unused = NULL):
  * the velocities saved by the collide of the same step (advection.h:1083-1090), the per-cell diffusivity
@@ -271,6 +277,17 @@ int pl_residual(const double* ux, const double* uy, const double* uz,
                 const double* uxp, const double* uyp, const double* uzp, size_t n, double* out_host);
 int pl_reduce_sum(const double* v, size_t n, double* out_host);
 int pl_reduce_absmax(const double* v, size_t n, double* out_host);
+/* Sum of a per-site field over the box [i0,i1) x [j0,j1) x [k0,k1) of GLOBAL coordinates, clipped to this rank's block and summed
+ * over the ranks: the objective of the heatsink drivers (mean temperature of the heat patch, production/heatsink3D.cpp:227-240,
+ * with its MPI_Allreduce) without bringing the whole field to the host. */
+int pl_reduce_box_sum(const pl_lattice*, const double* v, int i0, int i1, int j0, int j1, int k0, int k1, double* out_host);
+/* The design map of the heatsink drivers on the device (production/heatsink3D.cpp:114-119): from the filtered design ss the
+ * diffusivity, the Brinkman coefficient and their derivatives, alpha0 = alphamax/(ly - 1); the reference's operation order. */
+int pl_design_map(const double* ss, size_t n, double diff_fluid, double diff_solid, double qg, double alpha0, double qf,
+                  double* diffusivity, double* alpha, double* dkds, double* dads);
+/* Every rank's block of a per-site field assembled into the field of the global domain (lx*ly*lz doubles, host) on every rank:
+ * what the reference's VTK writers gather with MPI_Isend/Irecv (src/utility/vtkxmlexport.h:172-214). */
+int pl_comm_gather_field(const pl_lattice*, const double* v_dev, double* out_host_global);
 /* Normalize (src/utility/normalize.h:8-24) */
 int pl_normalize(double* v, size_t n);
 
@@ -302,6 +319,12 @@ int pl_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, co
  * heavisidefilter.h:291-400); the weights then cover neighbours anywhere in the GLOBAL domain. */
 typedef struct pl_filter pl_filter;
 pl_filter* pl_filter_create(pl_lattice*, int nR, const double* weights_host);
+/* The same from weight PATTERNS: patterns[p*K + o] (K = (2nR+1)^3) for the sites with pattern_of_site[idx] == p.  The weights of the
+ * reference's drivers depend on the offset and on which side of the design box the two sites lie (production/heatsink3D.cpp:87-93) —
+ * a few hundred distinct patterns whatever the lattice size; the drop-in headers bake the callable straight into this form (no
+ * dense table is ever built), pl_filter_create folds its dense input into it.  pl_filter_patterns: how many patterns a filter holds. */
+pl_filter* pl_filter_create_patterns(pl_lattice*, int nR, const double* patterns, int npatterns, const int* pattern_of_site);
+int pl_filter_patterns(const pl_filter*);
 int pl_filter_destroy(pl_filter*);
 int pl_filter_apply(pl_filter*, int mode, double beta, const double* v, const double* dfdrho, double* out);
 
@@ -317,6 +340,9 @@ const char* plh_last_error(void);
 void* plh_alloc(size_t bytes);
 void plh_free(void* p);
 int plh_owns(const void* p);
+int plh_owns_range(const void* p);   /* p lies anywhere inside a mirrored block (arrays and population views) */
+/* pl_bc_update_values behind the passes the fusion engine still holds back */
+int plh_bc_update_values(pl_bc*, const double* v0, const double* v1, const double* v2);
 /* The public `T *f0, *f` members of D2Q9/D3Q15 (d3q15.h:225): host views in the reference layout, kept coherent with
  * the device populations on demand (test/d2q9.cpp, test/d3q15.cpp read and write them directly). */
 int plh_lattice_attach_views(pl_lattice*, double** f0, double** f);
@@ -333,6 +359,11 @@ int plh_sensitivity(pl_lattice*, const pl_sens_args* host_args);
 int plh_sensitivity_heat_source(pl_lattice*, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
                                 const double* igsnap, const double* diffusivity, const double* dkds);
 int plh_filter_apply(pl_filter*, int mode, double beta, const double* v_host, const double* dfdrho_host, double* out_host, size_t n);
+/* Before handing a mirrored host array to code that is not this program's own loads and stores — a system call (fwrite of a whole
+ * field), another library, a device-pointer entry point of this one (pl_comm_*, pl_array_upload): make [p, p + bytes) current and
+ * readable on the host (for_write: writable, the host copy becomes the only current one).  The page-fault path serves ordinary
+ * accesses transparently; those callers it cannot serve (EFAULT, or a fault inside the CUDA runtime, which aborts with a message). */
+int plh_host_acquire(const void* p, size_t bytes, int for_write);
 /* Execute whatever is still checked off and wait for the device. */
 int plh_sync(void);
 /* out[0..7] = fused steps, calls executed one by one, uploads, downloads, page faults served, plans built, settles, stagings */

@@ -68,12 +68,14 @@ _PROTOS = {
     "pl_lattice_streamed": (C.c_int, [C.c_void_p]),
     "pl_memory_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
     "pl_memory_trim": (C.c_int, []),
+    "pl_in_call": (C.c_int, []),
     "pl_stream": (C.c_int, [C.c_void_p, C.c_int]),
     "pl_smooth_corner": (C.c_int, [C.c_void_p]),
     "pl_smooth_corner_at": (C.c_int, [C.c_void_p] + [C.c_int] * 6),
     "pl_bc_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_bc_destroy": (C.c_int, [C.c_void_p]),
     "pl_bc_is_empty": (C.c_int, [C.c_void_p]),
+    "pl_bc_update_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_bc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BcAux)]),
     "pl_collide": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(CollideArgs)]),
     "pl_snapshot_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -101,6 +103,11 @@ _PROTOS = {
     "pl_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
     "pl_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
     "pl_filter_create": (C.c_void_p, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pl_filter_create_patterns": (C.c_void_p, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "pl_filter_patterns": (C.c_int, [C.c_void_p]),
+    "pl_reduce_box_sum": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int]*6 + [c_double_p]),
+    "pl_design_map": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_double]*5 + [C.c_void_p]*4),
+    "pl_comm_gather_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_filter_destroy": (C.c_int, [C.c_void_p]),
     "pl_filter_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     # host-pointer surface (bound by the C++ drop-in headers; declared here so that the export test covers it)
@@ -108,6 +115,8 @@ _PROTOS = {
     "plh_alloc": (C.c_void_p, [C.c_size_t]),
     "plh_free": (None, [C.c_void_p]),
     "plh_owns": (C.c_int, [C.c_void_p]),
+    "plh_owns_range": (C.c_int, [C.c_void_p]),
+    "plh_bc_update_values": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "plh_lattice_attach_views": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "plh_lattice_detach": (C.c_int, [C.c_void_p]),
     "plh_collide": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(CollideArgs)]),
@@ -121,6 +130,7 @@ _PROTOS = {
     "plh_sensitivity": (C.c_int, [C.c_void_p, C.POINTER(SensArgs)]),
     "plh_sensitivity_heat_source": (C.c_int, [C.c_void_p] * 9),
     "plh_filter_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "plh_host_acquire": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int]),
     "plh_sync": (C.c_int, []),
     "plh_stats": (C.c_int, [C.POINTER(C.c_uint64)]),
     "plh_store_stats": (C.c_int, [C.POINTER(C.c_uint64)]),

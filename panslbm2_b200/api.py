@@ -704,6 +704,114 @@ def Normalize(v, n):
 
 
 # ----------------------------------------------------------------------------------------------------------
+class ConeFilter:
+    """DensityFilter / HeavisideFilter of the reference (src/utility/densityfilter.h:389-497, heavisidefilter.h:404-894) on one
+    lattice: the weight callable `weight(i1, j1, k1, i2, j2, k2)` (global coordinates, vectorised over numpy arrays; None = the
+    default cone (R - d)/R) is evaluated once and folded into weight patterns (pl_filter_create_patterns)."""
+
+    def __init__(self, lattice, R, weight=None):
+        L = _lib.lib()
+        self.p, self.R = lattice, float(R)
+        p = lattice
+        nR = int(R)
+        side = 2*nR + 1
+        K = side**3
+        n = p.nxyz
+        idx = np.arange(n)
+        i1, j1, k1 = idx % p.nx + p.offsetx, (idx//p.nx) % p.ny + p.offsety, idx//(p.nx*p.ny) + p.offsetz
+        if weight is None:
+            weight = lambda a, b, c, d, e, f: (self.R - np.sqrt((a - d)**2.0 + (b - e)**2.0 + (c - f)**2.0))/self.R
+        rng = np.random.default_rng(12345)
+        mult = rng.integers(1, 2**63, size=K, dtype=np.uint64) | np.uint64(1)
+        h = np.zeros(n, dtype=np.uint64)
+        cols = []
+        o = 0
+        for di in range(-nR, nR + 1):
+            for dj in range(-nR, nR + 1):
+                for dk in range(-nR, nR + 1):
+                    w = np.zeros(n)
+                    i2, j2, k2 = i1 + di, j1 + dj, k1 + dk
+                    ok = (i2 >= 0) & (i2 < p.lx) & (j2 >= 0) & (j2 < p.ly) & (k2 >= 0) & (k2 < max(p.lz, 1))
+                    if p.nd == 2:
+                        ok &= dk == 0
+                    ok &= np.sqrt(float(di)**2.0 + float(dj)**2.0 + float(dk)**2.0) <= self.R
+                    if ok.any():
+                        w[ok] = np.asarray(weight(i1[ok], j1[ok], k1[ok], i2[ok], j2[ok], k2[ok]), dtype=np.float64)
+                    with np.errstate(over="ignore"):
+                        h += (w + 0.0).view(np.uint64)*mult[o]
+                    cols.append(w)
+                    o += 1
+        _, first, pid = np.unique(h, return_index=True, return_inverse=True)
+        patterns = np.ascontiguousarray(np.stack([c[first] for c in cols], axis=1))      # [npat][K]
+        pid = np.ascontiguousarray(pid.reshape(-1), dtype=np.int32)
+        self.npatterns = int(patterns.shape[0])
+        self._h = L.pl_filter_create_patterns(p._h, nR, patterns.ctypes.data, self.npatterns, pid.ctypes.data)
+        if not self._h:
+            raise _lib.PanslbmError(L.pl_last_error().decode())
+
+    def _apply(self, mode, beta, v, aux=None):
+        out = DeviceArray(self.p.nxyz)
+        check(_lib.lib().pl_filter_apply(self._h, mode, float(beta), dptr(v), dptr(aux), out.ptr))
+        return out
+
+    def density(self, v):
+        """DensityFilter::GetFilteredValue"""
+        return self._apply(0, 0.0, v)
+
+    def heaviside(self, s, beta):
+        """HeavisideFilter::GetFilteredVariable"""
+        return self._apply(1, beta, s)
+
+    def heaviside_sensitivity(self, s, dfdrho, beta):
+        """HeavisideFilter::GetFilteredSensitivity"""
+        return self._apply(2, beta, s, dfdrho)
+
+    def free(self):
+        if getattr(self, "_h", None):
+            _lib.lib().pl_filter_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def design_map(ss, diff_fluid, diff_solid, qg, alpha0, qf):
+    """production/heatsink3D.cpp:114-119 on the device: filtered design -> (diffusivity, alpha, dkds, dads); alpha0 = alphamax/(ly - 1)"""
+    out = [DeviceArray(ss.n) for _ in range(4)]
+    check(_lib.lib().pl_design_map(ss.ptr, ss.n, float(diff_fluid), float(diff_solid), float(qg), float(alpha0), float(qf), *[o.ptr for o in out]))
+    return out
+
+
+def box_sum(lattice, v, i0, i1, j0, j1, k0=0, k1=1):
+    """sum of a per-site field over a box of GLOBAL coordinates, over all ranks (the heat-patch objective, heatsink3D.cpp:227-240)"""
+    out = C.c_double(0.0)
+    check(_lib.lib().pl_reduce_box_sum(lattice._h, dptr(v), int(i0), int(i1), int(j0), int(j1), int(k0), int(k1), C.byref(out)))
+    return out.value
+
+
+def reduce_sum(v):
+    out = C.c_double(0.0)
+    check(_lib.lib().pl_reduce_sum(dptr(v), v.n, C.byref(out)))
+    return out.value
+
+
+def reduce_absmax(v):
+    out = C.c_double(0.0)
+    check(_lib.lib().pl_reduce_absmax(dptr(v), v.n, C.byref(out)))
+    return out.value
+
+
+def gather_field(lattice, v):
+    """the field of the GLOBAL domain from every rank's block, on every rank (what the VTK writers gather, vtkxmlexport.h:172-214)"""
+    out = np.zeros(lattice.lx*lattice.ly*max(lattice.lz, 1))
+    check(_lib.lib().pl_comm_gather_field(lattice._h, dptr(v), out.ctypes.data))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
 class StepPlan:
     """Fused time stepping (pl_plan_*): record one loop iteration, then advance it with one fused
     stream+closures+collide pass per step.  Results are identical to issuing the calls one by one."""

@@ -431,7 +431,7 @@ PL_D void boundary_path_sh(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], doubl
 // PANSLBM_BUILD_TAG: an A/B variant of the library)
 #ifndef PLK_FUSED_THREADS
 #define PLK_FUSED_THREADS 256
-#define PLK_FUSED_MINB 1
+#define PLK_FUSED_MINB 2
 #endif
 template <int D, int M, int MODE>
 __global__ void __launch_bounds__(PLK_FUSED_THREADS, PLK_FUSED_MINB) k_fused(Geom G, const double* fs, double* fd, const double* gs, double* gd,
@@ -462,6 +462,92 @@ __global__ void __launch_bounds__(PLK_FUSED_THREADS, PLK_FUSED_MINB) k_fused(Geo
     pass_store<D, MODE>(f, fd, G.pitch, idx, n);
     if constexpr (HASG) pass_store<D, MODE>(g, gd, G.pitch, idx, n);
     wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
+}
+
+// The same pass, software-pipelined.  ncu on k_fused (round 2): 124-128 registers allow 2 CTAs = 16 warps per SM; every warp issues
+// its thirty loads, waits for them (long-scoreboard stall: two thirds of its life), computes, stores — with 14 warps resident the
+// loads in flight per SM do not cover the DRAM latency once the pass moves only 496 B per site (5.4 of 6.5 TB/s).  Here a
+// PERSISTENT CTA walks over tiles of 256 sites and copies the populations of its NEXT tile into shared memory with cp.async
+// (8 bytes per thread and population, no registers held while in flight) before it computes the current one: 61 KB per CTA
+// are always on their way, whatever the register budget.  Every thread reads back only the column it copied itself, so the
+// pipeline needs no barrier.  Same arithmetic, same locations, same XWall traffic as k_fused.
+PL_D void cp_async8(double* smem, const double* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(s), "l"(gmem) : "memory");
+}
+PL_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+PL_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+constexpr int PIPE_THREADS = 256;
+// what the interior kernel does with site (i,j,k): false = the boundary pass owns it
+PL_D bool interior_site(const ShellMask& S, int i, int j, int k, unsigned long long& entries, int& wside) {
+    entries = 0ull; wside = -1;
+    const unsigned long long wx = S.x[i], wy = S.y[j], wz = S.z[k];
+    if ((wx | wy | wz) == 0ull) return true;
+    if (((wy | wz) & ~TUBE_BIT) != 0ull || (wx & (SLAB_BIT | HALO_BIT)) != 0ull || in_tube(wx, wy, wz)) return false;
+    entries = wx & ENTRY_BITS;
+    if ((wx & GHOST_BIT) != 0ull) wside = i == 0 ? 0 : 1;
+    return true;
+}
+template <int D, int M, int MODE>
+__global__ void __launch_bounds__(PIPE_THREADS, 2) k_fused_pipe(Geom G, const double* fs, double* fd, const double* gs, double* gd,
+                                                                CollideParams P, ShellMask S, int inverse, XWall W) {
+    constexpr unsigned FL = ModelFlags<M>::v;
+    constexpr bool HASG = (FL & F_G) != 0;
+    constexpr int NC = LT<D>::nc;
+    extern __shared__ double stage[];      // [(HASG ? 2 : 1)*NC][PIPE_THREADS]: one column per thread
+    double* col = stage + threadIdx.x;
+    const long long ntiles = (G.npacked + PIPE_THREADS - 1)/PIPE_THREADS;
+    auto prefetch = [&](long long tile) {
+        const long long idx = tile*PIPE_THREADS + threadIdx.x;
+        if (idx >= G.npacked) return;
+        int i, j, k, wside;
+        unsigned long long entries;
+        decompose(G, idx, i, j, k);
+        if (!interior_site(S, i, j, k, entries, wside)) return;
+        Nbr n = neighbours(G, i, j, k);
+        orient(n, inverse);
+        const size_t wt = (size_t)(j + G.ny*k);
+        sfor<0, NC>([&](auto C) {
+            constexpr int c = decltype(C)::value;
+            constexpr int X = LT<D>::cx(c);
+            const size_t loc = read_loc<D, MODE, c>(G.pitch, idx, n);
+            const double *pf = fs + loc, *pg = HASG ? gs + loc : nullptr;
+            if constexpr (X != 0) {
+                if (wside >= 0 && (inverse ? -X : X) == (wside ? -1 : 1)) {
+                    const size_t o = (size_t)(wside*NC + c)*W.np + wt;
+                    pf = W.res_f + o;
+                    if constexpr (HASG) pg = W.res_g + o;
+                }
+            }
+            cp_async8(col + c*PIPE_THREADS, pf);
+            if constexpr (HASG) cp_async8(col + (NC + c)*PIPE_THREADS, pg);
+        });
+    };
+    long long tile = blockIdx.x;
+    if (tile < ntiles) prefetch(tile);
+    cp_async_commit();
+    for (; tile < ntiles; tile += gridDim.x) {
+        cp_async_wait_all();
+        const long long idx = tile*PIPE_THREADS + threadIdx.x;
+        int i = 0, j = 0, k = 0, wside = -1;
+        unsigned long long entries = 0ull;
+        bool mine = idx < G.npacked;
+        if (mine) { decompose(G, idx, i, j, k); mine = interior_site(S, i, j, k, entries, wside); }
+        double f[NC], g[NC];
+        if (mine) sfor<0, NC>([&](auto C) { constexpr int c = decltype(C)::value; f[c] = col[c*PIPE_THREADS]; if constexpr (HASG) g[c] = col[(NC + c)*PIPE_THREADS]; });
+        // this thread's column is in registers: the next tile may land in it while the current one is computed
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) prefetch(next);
+        cp_async_commit();
+        if (mine) {
+            Nbr n = neighbours(G, i, j, k);
+            orient(n, inverse);
+            collide_site<D, FL, false>(f, g, P, (size_t)idx, P.issave == 1 || (P.issave == 2 && entries != 0ull));
+            pass_store<D, MODE>(f, fd, G.pitch, idx, n);
+            if constexpr (HASG) pass_store<D, MODE>(g, gd, G.pitch, idx, n);
+            wall_scatter<D, HASG>(W, f, g, G, i, j, k, inverse);
+        }
+    }
 }
 
 // The boundary pass of a fused step, one thread per listed site: Stream (pull), the closure program, and then either the

@@ -20,6 +20,8 @@ struct FusedArgs {
     const int* list; const unsigned long long* ent; int nlist, ndirect;
     double *tube_f, *tube_g; const TubeSite* tube_info;
     HaloView HF, HG;
+    int pipe;                    // interior kernel: the software-pipelined persistent form (k_fused_pipe) on `sms` multiprocessors
+    int sms;
 };
 struct ModelLaunch {
     cudaError_t (*collide)(cudaStream_t, const Geom&, double* fb, double* gb, const CollideParams&, const int* list, long long count);

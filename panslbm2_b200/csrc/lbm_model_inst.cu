@@ -1,6 +1,7 @@
 // One (lattice, collide model) pair of the per-model kernels: compiled once per pair with -DPLI_DIM=<2|3> -DPLI_MODEL=<1..12>
 // (panslbm2_b200/build.py), so that the 23 pairs build in parallel.  See lbm_launch.h.
 #include "lbm_launch.h"
+#include <algorithm>
 
 #if !defined(PLI_DIM) || !defined(PLI_MODEL)
 #error "compile with -DPLI_DIM=<2|3> -DPLI_MODEL=<model>"
@@ -21,8 +22,29 @@ template <int MODE> cudaError_t fused_m(cudaStream_t st, const FusedArgs& A) {
     k_fused<PLI_DIM, PLI_MODEL, MODE><<<blocks(A.G.npacked, PLK_FUSED_THREADS), PLK_FUSED_THREADS, 0, st>>>(A.G, A.fs, A.fd, A.gs, A.gd, A.P, A.S, A.prog, A.inverse, A.W);
     return cudaGetLastError();
 }
+template <int MODE> cudaError_t fused_pipe_m(cudaStream_t st, const FusedArgs& A) {
+    constexpr bool hasg = (ModelFlags<PLI_MODEL>::v & F_G) != 0;
+    constexpr size_t smem = (size_t)(hasg ? 2 : 1)*LT<PLI_DIM>::nc*PIPE_THREADS*sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_fused_pipe<PLI_DIM, PLI_MODEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const long long ntiles = (A.G.npacked + PIPE_THREADS - 1)/PIPE_THREADS;
+    const unsigned grid = (unsigned)std::min<long long>(ntiles, 2LL*(A.sms > 0 ? A.sms : 148));
+    k_fused_pipe<PLI_DIM, PLI_MODEL, MODE><<<grid, PIPE_THREADS, smem, st>>>(A.G, A.fs, A.fd, A.gs, A.gd, A.P, A.S, A.inverse, A.W);
+    return cudaGetLastError();
+}
 cudaError_t fused_(cudaStream_t st, const FusedArgs& A, int mode) {
     if (A.G.npacked == 0) return cudaSuccess;
+    if (A.pipe && A.prog == nullptr) {
+        switch (mode) {
+            case PASS_GATHER: return fused_pipe_m<PASS_GATHER>(st, A);
+            case PASS_LOCAL: return fused_pipe_m<PASS_LOCAL>(st, A);
+            default: return fused_pipe_m<PASS_COPY>(st, A);
+        }
+    }
     switch (mode) {
         case PASS_GATHER: return fused_m<PASS_GATHER>(st, A);
         case PASS_LOCAL: return fused_m<PASS_LOCAL>(st, A);

@@ -97,9 +97,13 @@ __global__ void __launch_bounds__(256) k_absmax_final(const double* __restrict__
 
 // ---------------------------------------------------------------------------------------------------------
 // Cone density filter / Heaviside projection (src/utility/densityfilter.h:389-497, heavisidefilter.h:459-563, 641-857).
-// w[o*nxyz + idx] is the baked weight of the pair (site idx, neighbour idx + offset o), o running over the (2nR+1)^3 cube in
-// the reference's loop order (i2 outermost, k2 innermost); pairs beyond R or outside the domain carry weight 0 and are
-// skipped, which leaves both running sums bit-identical to the reference's.  `v` is a field of the GLOBAL domain.
+// The weight callable of the reference is baked into PATTERNS: wtab[p*K + o] is the weight of the pair (site, neighbour at
+// offset o) for every site whose pattern is p = pid[site], o running over the K = (2nR+1)^3 cube in the reference's loop order (i2
+// outermost, k2 innermost).  The weights of the reference drivers depend on the offset and on which side of the design box
+// the two sites lie (production/heatsink3D.cpp:87-93): a few hundred distinct patterns whatever the lattice size, so the table
+// lives in L1/L2 and a call moves ~20 B per site (a dense per-site table was 8K B per site: 1 GB at 81 x 161 x 81).  Pairs
+// beyond R or outside the domain carry weight 0 and are skipped, which leaves both running sums bit-identical to the
+// reference's.  `v` is a field of the GLOBAL domain.
 struct FilterGeom {
     int nx, ny, nz, nR;          // this rank's block
     long long nxyz;
@@ -118,13 +122,14 @@ __global__ void __launch_bounds__(256) k_filter_scatter(FilterGeom F, const doub
 // mode 1: out = 0.5 (tanh(b/2) + tanh(b (sum(w v)/sum(w) - 1/2)))/tanh(b/2)     HeavisideFilter::GetFilteredVariable
 // mode 2: out = aux * 0.5 b (1 - tanh(b (sum(w v)/sum(w) - 1/2))^2)/tanh(b/2)   first pass of GetFilteredSensitivity (aux = dfdrho)
 // mode 3: out = sum(w v)/sum(w) with out accumulated from 0 and divided last    second pass of GetFilteredSensitivity
-__global__ void __launch_bounds__(256) k_filter(FilterGeom F, const double* __restrict__ w, const double* __restrict__ v, const double* __restrict__ aux,
-                                                double beta, int mode, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_filter(FilterGeom F, const double* __restrict__ wtab, const int* __restrict__ pid, const double* __restrict__ v,
+                                                const double* __restrict__ aux, double beta, int mode, double* __restrict__ out) {
     const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
     if (idx >= F.nxyz) return;
     const int nxy = F.nx*F.ny;
     const int k1 = (int)(idx/nxy), r = (int)(idx - (long long)k1*nxy), j1 = r/F.nx, i1 = r - j1*F.nx;
     const int side = 2*F.nR + 1;
+    const double* __restrict__ w = wtab + (size_t)pid[idx]*(size_t)(side*side*side);
     double wv = 0.0, ws = 0.0;
     int o = 0;
     for (int di = -F.nR; di <= F.nR; ++di)
@@ -132,17 +137,45 @@ __global__ void __launch_bounds__(256) k_filter(FilterGeom F, const double* __re
             for (int dk = -F.nR; dk <= F.nR; ++dk, ++o) {
                 const int i2 = i1 + F.ox + di, j2 = j1 + F.oy + dj, k2 = k1 + F.oz + dk;     // global coordinates of the neighbour
                 if (i2 < 0 || i2 >= F.gx || j2 < 0 || j2 >= F.gy || k2 < 0 || k2 >= F.gz) continue;
-                const double wt = w[(size_t)o*(size_t)F.nxyz + (size_t)idx];
+                const double wt = w[o];
                 if (wt == 0.0) continue;
                 wv = wv + wt*v[(size_t)i2 + (size_t)F.gx*((size_t)j2 + (size_t)F.gy*(size_t)k2)];
                 ws = ws + wt;
             }
-    (void)side;
     double res;
     if (mode == 0 || mode == 3) res = wv/ws;
     else if (mode == 1) res = 0.5*(tanh(0.5*beta) + tanh(beta*(wv/ws - 0.5)))/tanh(0.5*beta);
     else { const double th = tanh(beta*(wv/ws - 0.5)); res = aux[idx]*(0.5*beta*(1.0 - th*th)/tanh(0.5*beta)); }
     out[idx] = res;
+}
+
+// the design map of the heatsink drivers (production/heatsink3D.cpp:114-119, heatsink.cpp:106-111), site by site:
+//   diffusivity = ks + (kf - ks) ss (1 + qg)/(ss + qg)          alpha = a0 qf (1 - ss)/(ss + qf)
+//   dkds = (kf - ks) qg (1 + qg)/pow(ss + qg, 2)                dads = -a0 qf (1 + qf)/pow(ss + qf, 2)      (a0 = alphamax/(ly - 1))
+// in the reference's operation order; pow(x, 2.0) is x*x in glibc as on the device (exact).
+__global__ void __launch_bounds__(256) k_design_map(const double* __restrict__ ss, long long n, double kf, double ks, double qg, double a0, double qf,
+                                                    double* __restrict__ diffusivity, double* __restrict__ alpha, double* __restrict__ dkds, double* __restrict__ dads) {
+    const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const double s = ss[idx];
+    diffusivity[idx] = ks + (kf - ks)*s*(1.0 + qg)/(s + qg);
+    alpha[idx] = a0*qf*(1.0 - s)/(s + qf);
+    const double pg = s + qg, pf = s + qf;
+    dkds[idx] = (kf - ks)*qg*(1.0 + qg)/(pg*pg);
+    dads[idx] = -a0*qf*(1.0 + qf)/(pf*pf);
+}
+// sum of v over the box [i0,i1) x [j0,j1) x [k0,k1) of LOCAL coordinates (the objective of the heatsink drivers: the mean
+// temperature of the heat patch, heatsink3D.cpp:227-240); fixed grid, deterministic
+__global__ void __launch_bounds__(256) k_box_sum_partial(const double* __restrict__ v, int nx, int ny, int i0, int i1, int j0, int j1, int k0, int k1,
+                                                         double* __restrict__ out) {
+    const long long bi = i1 - i0, bj = j1 - j0, total = bi*bj*(long long)(k1 - k0);
+    double s = 0.0;
+    for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x*blockDim.x) {
+        const long long i = t%bi, r = t/bi, j = r%bj, k = r/bj;
+        s += v[(size_t)(i0 + i) + (size_t)nx*((size_t)(j0 + j) + (size_t)ny*(size_t)(k0 + k))];
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
 }  // namespace plb

@@ -39,6 +39,10 @@ cudaStream_t g_stream = 0;          // legacy default stream unless the caller i
 uint64_t g_launches = 0;
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
+// entry points that hand CALLER host pointers to the CUDA runtime mark themselves: the coherence layer of the host-pointer surface
+// (panslbm_host.cpp) must not try to serve a page fault taken in there
+thread_local int g_in_call = 0;
+struct InCall { InCall() { ++g_in_call; } ~InCall() { --g_in_call; } };
 #define CU(call)                                                                                        \
     do {                                                                                                \
         cudaError_t e__ = (call);                                                                       \
@@ -83,6 +87,13 @@ bool opt_xinline() { static int v = env_int("PANSLBM_XINLINE", 0); return v != 0
 // fused passes update the ONE population buffer of a lattice in place (AA pattern: gather pass, local pass, ...);
 // 0 = every pass goes from the buffer to a second one borrowed from the spare pool (the reference's f / fnext scheme)
 bool opt_inplace() { static int v = env_int("PANSLBM_INPLACE", 1); return v != 0; }
+// interior kernel as a persistent, software-pipelined kernel (cp.async prefetch of the next tile; k_fused_pipe); 0 = one thread per site
+bool opt_pipe() { static int v = env_int("PANSLBM_PIPE", 1); return v != 0; }
+int device_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148; }
+    return n;
+}
 
 // Spare population buffers.  A lattice owns ONE buffer; the operations that cannot work in place — a standalone Stream()/iStream(),
 // the conversion of the streamed layout back to the natural one, the two-buffer passes of PANSLBM_INPLACE=0 — write into a buffer
@@ -405,6 +416,7 @@ int make_natural(pl_lattice* l) {
 extern "C" {
 
 const char* pl_last_error(void) { return g_err.c_str(); }
+int pl_in_call(void) { return g_in_call; }
 const char* pl_version(void) { return "panslbm_b200 0.1 (sm_100a, fp64, fmad=off)"; }
 int pl_device_count(void) {
     int n = 0;
@@ -425,11 +437,13 @@ double* pl_array_alloc(size_t n) {
 }
 int pl_array_free(double* dev) { CU(cudaFree(dev)); return PL_OK; }
 int pl_array_upload(double* dev, const double* host, size_t n) {
+    InCall in_call_;
     CU(cudaMemcpyAsync(dev, host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
 }
 int pl_array_download(double* host, const double* dev, size_t n) {
+    InCall in_call_;
     CU(cudaMemcpyAsync(host, dev, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
     CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
@@ -550,6 +564,7 @@ int pl_lattice_info(const pl_lattice* l, int* o) {
     return PL_OK;
 }
 int pl_lattice_set_host(pl_lattice* l, const double* f0, const double* f) {
+    InCall in_call_;
     if (!l || !f0 || !f) return fail(PL_ERR_ARG, "pl_lattice_set_host: null");
     size_t n = (size_t)l->g.nxyz, nf = n*(l->nc - 1);
     double *d0 = nullptr, *d1 = nullptr;
@@ -566,6 +581,7 @@ int pl_lattice_set_host(pl_lattice* l, const double* f0, const double* f) {
     return PL_OK;
 }
 int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
+    InCall in_call_;
     if (!l || !f0 || !f) return fail(PL_ERR_ARG, "pl_lattice_get_host: null");
     { int r = make_natural(l); if (r) return r; }
     size_t n = (size_t)l->g.nxyz, nf = n*(l->nc - 1);
@@ -923,6 +939,19 @@ int pl_bc_destroy(pl_bc* bc) {
     return PL_OK;
 }
 int pl_bc_is_empty(const pl_bc* bc) { return bc ? (bc->empty ? 1 : 0) : 1; }
+int pl_bc_update_values(pl_bc* bc, const double* v0, const double* v1, const double* v2) {
+    InCall in_call_;
+    if (!bc) return fail(PL_ERR_ARG, "pl_bc_update_values: null");
+    if (bc->empty) return PL_OK;
+    if ((v0 != nullptr) != (bc->v0 != nullptr) || (v1 != nullptr) != (bc->v1 != nullptr) || (v2 != nullptr) != (bc->v2 != nullptr))
+        return fail(PL_ERR_ARG, "pl_bc_update_values: the plane was created with other value arrays");
+    const size_t nb = (size_t)bc->pl.n1*bc->pl.n2*sizeof(double);
+    // pageable source: the runtime stages it before returning, the device copy is ordered behind every pass already queued
+    if (v0) CU(cudaMemcpyAsync(bc->v0, v0, nb, cudaMemcpyHostToDevice, g_stream));
+    if (v1) CU(cudaMemcpyAsync(bc->v1, v1, nb, cudaMemcpyHostToDevice, g_stream));
+    if (v2) CU(cudaMemcpyAsync(bc->v2, v2, nb, cudaMemcpyHostToDevice, g_stream));
+    return PL_OK;
+}
 int pl_bc_apply(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* aux) {
     if (!l || !bc) return fail(PL_ERR_ARG, "pl_bc_apply: null");
     return do_bc(l, other, bc, aux);
@@ -1086,7 +1115,6 @@ void plan_pass_done(pl_plan* p, int mode) {
         l->streamed = 0;
     }
     p->xphase ^= 1;
-    if (mode != PASS_COPY) g_spares.inplace_pass();
 }
 int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, int mode);
 // fused F: Stream + closures + SmoothCorner of step t (argument set `bc_parity`) followed by the collide of step t+1 —
@@ -1096,6 +1124,7 @@ int plan_fused(pl_plan* p, int bc_parity, int col_parity, bool full_save) {
     const bool xstale = p->nxlist && (p->xver[0] != p->f->version || (p->g && p->xver[1] != p->g->version));      // the one-off refill must not be captured
     int mode, r;
     if ((r = plan_pass_mode(p, mode))) return r;
+    if (mode != PASS_COPY) g_spares.inplace_pass();      // (never under stream capture: it may synchronise and free)
     if (!opt_graph() || p->f->halo.on || p->profile || opt_shell_serial() || xstale || mode == PASS_COPY) return plan_fused_body(p, bc_parity, col_parity, full_save, mode);
     if (p->graph_cooldown > 0) { --p->graph_cooldown; return plan_fused_body(p, bc_parity, col_parity, full_save, mode); }
     pl_plan::Graph& G = p->graphs[bc_parity][mode][p->xphase][full_save ? 1 : 0];
@@ -1149,6 +1178,7 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, i
         if (!fdst || (g && !gdst)) return fail(PL_ERR_CUDA, "out of device memory for the second population buffer (PANSLBM_INPLACE=0)");
     }
     A.fd = fdst; A.gd = gdst;
+    A.pipe = opt_pipe() ? 1 : 0; A.sms = device_sms();
     A.list = p->list; A.ent = p->ent; A.nlist = p->nlist; A.ndirect = p->ndirect; A.tube_f = p->tube_f; A.tube_g = p->tube_g; A.tube_info = p->tube_info;
     if ((r = halo_view(p->f, A.HF))) return r;
     if (g && (r = halo_view(g, A.HG))) return r;
@@ -1792,6 +1822,7 @@ int pl_comm_info(int* mode, int* rank, int* nranks) {
     return PL_OK;
 }
 int pl_comm_allreduce_v(void* inout_host, size_t n, int dtype, int op) {
+    InCall in_call_;
     if (!inout_host || (dtype != 0 && dtype != 1) || op < 0 || op > 2) return fail(PL_ERR_ARG, "pl_comm_allreduce_v: dtype 0 (f64) / 1 (i32), op 0 (sum) / 1 (max) / 2 (min)");
     if (g_comm.mode != COMM_NCCL || n == 0) return PL_OK;   // a world of one
     const size_t bytes = n*(dtype == 0 ? sizeof(double) : sizeof(int));
@@ -1805,6 +1836,7 @@ int pl_comm_allreduce_v(void* inout_host, size_t n, int dtype, int op) {
     return PL_OK;
 }
 int pl_comm_p2p(const pl_p2p_op* ops, int n) {
+    InCall in_call_;
     if (n < 0 || (n > 0 && !ops)) return fail(PL_ERR_ARG, "pl_comm_p2p: bad arguments");
     if (n == 0) return PL_OK;
     if (g_comm.mode != COMM_NCCL) return fail(PL_ERR_ARG, "pl_comm_p2p: no NCCL communicator");
@@ -1829,6 +1861,7 @@ int pl_comm_p2p(const pl_p2p_op* ops, int n) {
     return PL_OK;
 }
 int pl_comm_allreduce(double* inout_host, int n, int op) {
+    InCall in_call_;
     if (!inout_host || n < 1 || n > 4 || (op != 0 && op != 1)) return fail(PL_ERR_ARG, "pl_comm_allreduce: 1..4 values, op 0 (sum) / 1 (max)");
     if (g_comm.mode != COMM_NCCL) return PL_OK;   // a world of one
     CU(cudaMemcpyAsync(g_comm.red, inout_host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
@@ -1913,40 +1946,68 @@ int pl_normalize(double* v, size_t n) {
 struct pl_filter {
     FilterGeom F;
     bool global = false;           // decomposed block: fields are assembled over all ranks first
-    double* w = nullptr;
+    double* wtab = nullptr;        // [npat][K] weight patterns
+    int* pid = nullptr;            // pattern of each site
+    int npat = 0;
     double* tmp = nullptr;         // first pass of the sensitivity filter (block)
     double* gv = nullptr;          // field of the global domain
 };
-pl_filter* pl_filter_create(pl_lattice* l, int nR, const double* weights_host) {
-    if (!l || nR < 0 || nR > 8 || !weights_host) { fail(PL_ERR_ARG, "pl_filter_create: bad arguments"); return nullptr; }
-    if (l->halo.on && g_comm.mode != COMM_NCCL) {
-        fail(PL_ERR_UNSUPPORTED, "pl_filter_create: filters on a block-decomposed lattice need the NCCL communicator (pl_comm_init)");
-        return nullptr;
-    }
+static pl_filter* filter_from_patterns(pl_lattice* l, int nR, const double* patterns, int npat, const int* pattern_of_site) {
     pl_filter* f = new pl_filter();
     FilterGeom& F = f->F;
     F.nx = l->g.nx; F.ny = l->g.ny; F.nz = l->g.nz; F.nR = nR; F.nxyz = l->g.nxyz;
     F.gx = l->g.lx; F.gy = l->g.ly; F.gz = l->g.lz; F.ox = l->g.offx; F.oy = l->g.offy; F.oz = l->g.offz;
     f->global = l->halo.on;
+    f->npat = npat;
     const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz, gn = (size_t)F.gx*F.gy*F.gz;
-    bool ok = cudaMalloc(&f->w, K*n*sizeof(double)) == cudaSuccess && cudaMalloc(&f->tmp, n*sizeof(double)) == cudaSuccess;
+    bool ok = cudaMalloc(&f->wtab, std::max<size_t>(1, K*npat)*sizeof(double)) == cudaSuccess && cudaMalloc(&f->pid, n*sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&f->tmp, n*sizeof(double)) == cudaSuccess;
     if (ok && f->global) ok = cudaMalloc(&f->gv, gn*sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMemcpy(f->wtab, patterns, K*npat*sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(f->pid, pattern_of_site, n*sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
-        fail(PL_ERR_CUDA, std::string("pl_filter_create: cudaMalloc: ") + cudaGetErrorString(cudaGetLastError()));
-        cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv); delete f;
-        return nullptr;
-    }
-    if (cudaMemcpy(f->w, weights_host, K*n*sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
-        fail(PL_ERR_CUDA, "pl_filter_create: upload failed");
-        cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv); delete f;
+        fail(PL_ERR_CUDA, std::string("pl_filter_create: ") + cudaGetErrorString(cudaGetLastError()));
+        cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gv); delete f;
         return nullptr;
     }
     return f;
 }
+static bool filter_args_ok(pl_lattice* l, int nR, const void* a, const void* b) {
+    if (!l || nR < 0 || nR > 8 || !a || !b) { fail(PL_ERR_ARG, "pl_filter_create: bad arguments"); return false; }
+    if (l->halo.on && g_comm.mode != COMM_NCCL) {
+        fail(PL_ERR_UNSUPPORTED, "pl_filter_create: filters on a block-decomposed lattice need the NCCL communicator (pl_comm_init)");
+        return false;
+    }
+    return true;
+}
+pl_filter* pl_filter_create_patterns(pl_lattice* l, int nR, const double* patterns, int npatterns, const int* pattern_of_site) {
+    InCall in_call_;
+    if (!filter_args_ok(l, nR, patterns, pattern_of_site) || npatterns < 1) { if (npatterns < 1) fail(PL_ERR_ARG, "pl_filter_create_patterns: no pattern"); return nullptr; }
+    for (long long i = 0; i < l->g.nxyz; ++i)
+        if (pattern_of_site[i] < 0 || pattern_of_site[i] >= npatterns) { fail(PL_ERR_ARG, "pl_filter_create_patterns: pattern index out of range"); return nullptr; }
+    return filter_from_patterns(l, nR, patterns, npatterns, pattern_of_site);
+}
+// dense per-site table (weights_host[o*nxyz + idx]): sites with the same K weights share one pattern
+pl_filter* pl_filter_create(pl_lattice* l, int nR, const double* weights_host) {
+    InCall in_call_;
+    if (!filter_args_ok(l, nR, weights_host, weights_host)) return nullptr;
+    const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz;
+    std::unordered_map<std::string, int> seen;
+    std::vector<double> patterns, row(K);
+    std::vector<int> pid(n);
+    for (size_t i = 0; i < n; ++i) {
+        for (size_t o = 0; o < K; ++o) row[o] = weights_host[o*n + i];
+        auto r = seen.emplace(std::string(reinterpret_cast<const char*>(row.data()), K*sizeof(double)), (int)seen.size());
+        if (r.second) patterns.insert(patterns.end(), row.begin(), row.end());
+        pid[i] = r.first->second;
+    }
+    return filter_from_patterns(l, nR, patterns.data(), (int)seen.size(), pid.data());
+}
+int pl_filter_patterns(const pl_filter* f) { return f ? f->npat : 0; }
 int pl_filter_destroy(pl_filter* f) {
     if (!f) return PL_OK;
     cudaStreamSynchronize(g_stream);
-    cudaFree(f->w); cudaFree(f->tmp); cudaFree(f->gv);
+    cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gv);
     delete f;
     return PL_OK;
 }
@@ -1970,12 +2031,61 @@ int pl_filter_apply(pl_filter* f, int mode, double beta, const double* v, const 
     const double* field;
     int r = filter_field(f, v, &field);
     if (r) return r;
-    if (mode < 2) LAUNCH(k_filter, nb, 256, f->F, f->w, field, nullptr, beta, mode, out);
+    if (mode < 2) LAUNCH(k_filter, nb, 256, f->F, f->wtab, f->pid, field, nullptr, beta, mode, out);
     else {
-        LAUNCH(k_filter, nb, 256, f->F, f->w, field, dfdrho, beta, 2, f->tmp);
+        LAUNCH(k_filter, nb, 256, f->F, f->wtab, f->pid, field, dfdrho, beta, 2, f->tmp);
         if ((r = filter_field(f, f->tmp, &field))) return r;
-        LAUNCH(k_filter, nb, 256, f->F, f->w, field, nullptr, beta, 3, out);
+        LAUNCH(k_filter, nb, 256, f->F, f->wtab, f->pid, field, nullptr, beta, 3, out);
     }
+    return PL_OK;
+}
+int pl_design_map(const double* ss, size_t n, double diff_fluid, double diff_solid, double qg, double alpha0, double qf, double* diffusivity, double* alpha,
+                  double* dkds, double* dads) {
+    if (!ss || !diffusivity || !alpha || !dkds || !dads) return fail(PL_ERR_ARG, "pl_design_map: null");
+    if (n == 0) return PL_OK;
+    LAUNCH(k_design_map, blocks_for((long long)n, 256), 256, ss, (long long)n, diff_fluid, diff_solid, qg, alpha0, qf, diffusivity, alpha, dkds, dads);
+    return PL_OK;
+}
+int pl_reduce_box_sum(const pl_lattice* l, const double* v, int i0, int i1, int j0, int j1, int k0, int k1, double* out) {
+    if (!l || !v || !out) return fail(PL_ERR_ARG, "pl_reduce_box_sum: null");
+    const Geom& g = l->g;
+    // global coordinates, clipped to this rank's block (the drivers' `(i + offsetx) < L` tests, heatsink3D.cpp:229-235)
+    i0 = std::max(i0 - g.offx, 0); i1 = std::min(i1 - g.offx, g.nx); j0 = std::max(j0 - g.offy, 0); j1 = std::min(j1 - g.offy, g.ny);
+    k0 = std::max(k0 - g.offz, 0); k1 = std::min(k1 - g.offz, g.nz);
+    const int nb = 256;
+    double* scratch = (double*)g_scratch.get((nb + 1)*sizeof(double));
+    if (!scratch) return fail(PL_ERR_CUDA, "pl_reduce_box_sum: scratch allocation failed");
+    if (i1 <= i0 || j1 <= j0 || k1 <= k0) { *out = 0.0; }
+    else {
+        LAUNCH(k_box_sum_partial, nb, 256, v, g.nx, g.ny, i0, i1, j0, j1, k0, k1, scratch);
+        LAUNCH(k_sum_final, 1, 256, scratch, nb, 1, scratch + nb);
+    }
+    if (i1 <= i0 || j1 <= j0 || k1 <= k0) CU(cudaMemsetAsync(scratch + nb, 0, sizeof(double), g_stream));
+    // the drivers' MPI_Allreduce(SUM) of the partial objective (heatsink3D.cpp:236)
+    if (g_comm.mode == COMM_NCCL) { NC(g_nccl.AllReduce(scratch + nb, scratch + nb, 1, NCCL_F64, NCCL_SUM, g_comm.nccl, g_stream)); ++g_launches; }
+    CU(cudaMemcpyAsync(out, scratch + nb, sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    return PL_OK;
+}
+// every rank's block of a per-site field into the field of the GLOBAL domain, on every rank (what the VTK writers of the
+// reference gather block by block with MPI_Isend/Irecv, vtkxmlexport.h:172-214): device-side scatter + one all-reduce
+int pl_comm_gather_field(const pl_lattice* l, const double* v, double* out_host_global) {
+    InCall in_call_;
+    if (!l || !v || !out_host_global) return fail(PL_ERR_ARG, "pl_comm_gather_field: null");
+    const Geom& g = l->g;
+    const size_t gn = (size_t)g.lx*g.ly*g.lz;
+    if (!l->halo.on) { CU(cudaMemcpyAsync(out_host_global, v, gn*sizeof(double), cudaMemcpyDeviceToHost, g_stream)); CU(cudaStreamSynchronize(g_stream)); return PL_OK; }
+    if (g_comm.mode != COMM_NCCL) return fail(PL_ERR_UNSUPPORTED, "pl_comm_gather_field: a block-decomposed lattice needs the NCCL communicator");
+    double* gv = (double*)g_scratch.get(gn*sizeof(double));
+    if (!gv) return fail(PL_ERR_CUDA, "pl_comm_gather_field: scratch allocation failed");
+    FilterGeom F;
+    F.nx = g.nx; F.ny = g.ny; F.nz = g.nz; F.nR = 0; F.nxyz = g.nxyz; F.gx = g.lx; F.gy = g.ly; F.gz = g.lz; F.ox = g.offx; F.oy = g.offy; F.oz = g.offz;
+    CU(cudaMemsetAsync(gv, 0, gn*sizeof(double), g_stream));
+    LAUNCH(k_filter_scatter, blocks_for(g.nxyz, 256), 256, F, v, gv);
+    NC(g_nccl.AllReduce(gv, gv, gn, NCCL_F64, NCCL_SUM, g_comm.nccl, g_stream));
+    ++g_launches;
+    CU(cudaMemcpyAsync(out_host_global, gv, gn*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
     return PL_OK;
 }
 

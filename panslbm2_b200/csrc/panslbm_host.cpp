@@ -68,6 +68,14 @@ struct Block {
     bool spilled = false;           // its mirror was given up under memory pressure
 };
 std::map<uintptr_t, Block> g_blocks;              // by base address
+// The allocation hook (operator new of the drop-in headers) may be reached from any thread of the caller — an OpenMP region, a
+// library thread — while the fault handler and every call of this file walk the map: a spin lock around the map itself (never
+// held across anything that can fault or block; map nodes are stable, so a Block* stays valid after the lock is dropped).
+std::atomic_flag g_blocks_lock = ATOMIC_FLAG_INIT;
+struct BlocksLock {
+    BlocksLock() { while (g_blocks_lock.test_and_set(std::memory_order_acquire)) {} }
+    ~BlocksLock() { g_blocks_lock.clear(std::memory_order_release); }
+};
 struct Views { Block *f0 = nullptr, *f = nullptr; };
 std::map<pl_lattice*, Views> g_views;
 uint64_t g_stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // fused steps, unfused ops, uploads, downloads, faults, plans, settles, transient stagings
@@ -132,6 +140,7 @@ struct DevPool {
 } g_pool;
 
 Block* find_block(const void* p) {
+    BlocksLock lock_;
     if (g_blocks.empty()) return nullptr;
     auto it = g_blocks.upper_bound((uintptr_t)p);
     if (it == g_blocks.begin()) return nullptr;
@@ -168,6 +177,15 @@ void fetch(Block* b) {
 
 std::atomic_flag g_fault_lock = ATOMIC_FLAG_INIT;     // host threads of the caller (OpenMP loops over its arrays) may fault together
 void on_fault(int sig, siginfo_t* si, void* uc) {
+    // A fault taken while this thread is INSIDE a library call (the CUDA runtime reading a caller's buffer whose host copy is
+    // stale, e.g. a raw pointer handed to pl_comm_* or pl_array_upload) cannot be served: fetching would re-enter the CUDA
+    // runtime from its own signal context.  Such pointers must go through plh_host_acquire first (the mpi.h shim does).
+    if (pl_in_call() && find_block(si->si_addr)) {
+        static const char msg[] = "panslbm_b200: a host array whose current copy lives on the device was handed to a device-pointer entry point "
+                                  "(pl_*); call plh_host_acquire(ptr, bytes, for_write) on it first\n";
+        ssize_t w = write(2, msg, sizeof(msg) - 1); (void)w;
+        abort();
+    }
     while (g_fault_lock.test_and_set(std::memory_order_acquire)) {}
     Block* b = find_block(si->si_addr);
     if (b && b->state == ST_DEVICE) { ++g_stat[4]; fetch(b); g_fault_lock.clear(std::memory_order_release); return; }
@@ -215,6 +233,7 @@ Block* new_block(size_t bytes, int kind, pl_lattice* lat, int state, int prot) {
         madvise(p, mb, MADV_HUGEPAGE);
     }
     Block b;
+    BlocksLock lock_;
     b.base = (char*)p; b.bytes = bytes; b.map_bytes = mb; b.kind = kind; b.lat = lat; b.state = state; b.seq = ++g_seq;
     auto r = g_blocks.emplace((uintptr_t)p, b);
     return &r.first->second;
@@ -222,7 +241,7 @@ Block* new_block(size_t bytes, int kind, pl_lattice* lat, int state, int prot) {
 void drop_block(Block* b) {
     if (b->dev) { g_pool.put(b->dev, b->map_bytes); g_store[2] -= b->map_bytes; }
     char* base = b->base; size_t mb = b->map_bytes;
-    g_blocks.erase((uintptr_t)base);
+    { BlocksLock lock_; g_blocks.erase((uintptr_t)base); }
     munmap(base, mb);
 }
 
@@ -273,6 +292,7 @@ int spill(Block* v, double** keep) {
 // the mirror farthest behind the direction of travel among those not used in this or the previous iteration
 Block* pick_victim(const Block* need, bool same_size) {
     Block* best = nullptr;
+    BlocksLock lock_;
     for (auto& kv : g_blocks) {
         Block& c = kv.second;
         if (c.kind != BK_ARRAY || !c.dev || &c == need || c.last + 1 >= g_tick) continue;
@@ -694,13 +714,50 @@ void* plh_alloc(size_t bytes) {
     return b ? b->base : nullptr;
 }
 int plh_owns(const void* p) {
+    BlocksLock lock_;
     auto it = g_blocks.find((uintptr_t)p);
     return it != g_blocks.end() && it->second.kind == BK_ARRAY;
 }
+int plh_owns_range(const void* p) { return find_block(p) != nullptr; }
+int plh_bc_update_values(pl_bc* bc, const double* v0, const double* v1, const double* v2) {
+    int rc = flush_pending();      // they were called with the previous values
+    if (rc) return rc;
+    return pl_bc_update_values(bc, v0, v1, v2) ? hfail("pl_bc_update_values") : PL_OK;
+}
 void plh_free(void* p) {
     flush_pending();
-    auto it = g_blocks.find((uintptr_t)p);
-    if (it != g_blocks.end()) drop_block(&it->second);
+    Block* b = nullptr;
+    { BlocksLock lock_; auto it = g_blocks.find((uintptr_t)p); if (it != g_blocks.end()) b = &it->second; }
+    if (b) drop_block(b);
+}
+
+// Make [p, p + bytes) readable (and, with for_write, writable) by ordinary host code, system calls and other libraries — which,
+// unlike a load or store of the program itself, cannot be served by the fault handler: an fwrite of a stale array fails with
+// EFAULT, an MPI / NCCL staging copy faults inside the CUDA runtime.  Brings the host copy up to date if the device holds the
+// current one; for_write also makes the host copy the only current one.  The range may span several blocks; foreign memory is
+// left alone.
+int plh_host_acquire(const void* p, size_t bytes, int for_write) {
+    if (!p || bytes == 0) return PL_OK;
+    const char* a = (const char*)p;
+    const char* end = a + bytes;
+    while (a < end) {
+        Block* b = find_block(a);
+        if (!b) {      // not ours: skip to the next block that starts inside the range, if any
+            const char* next = nullptr;
+            { BlocksLock lock_; auto it = g_blocks.upper_bound((uintptr_t)a); if (it != g_blocks.end()) next = it->second.base; }
+            if (!next || next >= end) break;
+            a = next;
+            continue;
+        }
+        if (b->state == ST_DEVICE) { ++g_stat[4]; fetch(b); }
+        if (for_write && b->kind == BK_ARRAY && b->state == ST_SHARED) { flush_pending(); protect(b, PROT_READ | PROT_WRITE); b->state = ST_HOST; }
+        if (for_write && b->kind != BK_ARRAY) {
+            Views& v = g_views[b->lat];
+            for (Block* q : {v.f0, v.f}) if (q->state == ST_SHARED) { protect(q, PROT_READ | PROT_WRITE); q->state = ST_HOST; }
+        }
+        a = b->base + b->map_bytes;
+    }
+    return PL_OK;
 }
 
 int plh_lattice_attach_views(pl_lattice* l, double** f0, double** f) {

@@ -88,7 +88,12 @@ inline int MPI_Init(int*, char***) {
 inline int MPI_Finalize() { plh_sync(); pl_comm_destroy(); panslbm_mpi::st().up = false; return MPI_SUCCESS; }
 inline int MPI_Comm_size(MPI_Comm, int* n) { *n = panslbm_mpi::st().size; return MPI_SUCCESS; }
 inline int MPI_Comm_rank(MPI_Comm, int* r) { *r = panslbm_mpi::st().rank; return MPI_SUCCESS; }
+// Buffers may be the program's mirrored field arrays (MPI_Allreduce(MPI_IN_PLACE, dfds, ...), an Isend of a field): the staging
+// copies below run inside the CUDA runtime, where a stale host copy cannot be fetched on demand — bring them up to date first.
 inline int MPI_Allreduce(const void* send, void* recv, int count, MPI_Datatype type, MPI_Op op, MPI_Comm) {
+    const size_t nbytes = (size_t)count*panslbm_mpi::type_size(type);
+    if (send != MPI_IN_PLACE && send != recv) plh_host_acquire(send, nbytes, 0);
+    plh_host_acquire(recv, nbytes, 1);
     if (send != MPI_IN_PLACE && send != recv) std::memcpy(recv, send, (size_t)count*panslbm_mpi::type_size(type));
     if (pl_comm_allreduce_v(recv, (size_t)count, type == MPI_DOUBLE ? 0 : 1, op)) panslbm_mpi::die("MPI_Allreduce");
     return MPI_SUCCESS;
@@ -98,6 +103,8 @@ inline int MPI_Barrier(MPI_Comm) { double one = 1.0; if (pl_comm_allreduce(&one,
 inline int MPI_Gather(const void* send, int scount, MPI_Datatype stype, void* recv, int, MPI_Datatype, int root, MPI_Comm) {
     using namespace panslbm_mpi;
     const size_t bytes = (size_t)scount*type_size(stype);
+    plh_host_acquire(send, bytes, 0);
+    if (st().rank == root) plh_host_acquire(recv, bytes*(size_t)st().size, 1);
     std::vector<char> all(bytes*(size_t)st().size, 0);
     std::memcpy(all.data() + bytes*(size_t)st().rank, send, bytes);
     if (pl_comm_allreduce_v(all.data(), (size_t)scount*(size_t)st().size, stype == MPI_DOUBLE ? 0 : 1, 0)) die("MPI_Gather");
@@ -117,6 +124,7 @@ inline int MPI_Irecv(void* buf, int count, MPI_Datatype type, int source, int, M
 }
 inline int MPI_Waitall(int, MPI_Request*, MPI_Status*) {
     auto& p = panslbm_mpi::st().pending;
+    for (auto& o : p) plh_host_acquire(o.host, o.bytes, o.is_send ? 0 : 1);
     if (!p.empty() && pl_comm_p2p(p.data(), (int)p.size())) panslbm_mpi::die("MPI_Waitall");
     p.clear();
     return MPI_SUCCESS;

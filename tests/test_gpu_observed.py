@@ -20,7 +20,7 @@ def _observer(log):
         snap["gsnap"], snap["igsnap"] = gsnap.to_host(), igsnap.to_host()
         n = A["ux"].n
         fw = [A[k] for k in ("ux", "uy", "uz") if k in A] + [A[k] for k in ("uxp", "uyp", "uzp") if k in A]
-        snap["residual_u"] = np.array([pl.Residual(*fw, n)])
+        snap["residual_u"] = np.nan_to_num(np.array([pl.Residual(*fw, n)]), nan=-1.0)      # 0/0 right after the first collide of a fluid at rest
         log.append(snap)
     return look
 
