@@ -765,6 +765,19 @@ __global__ void k_snapshot_to_ref(Geom G, const double* __restrict__ snap, size_
     }
 }
 
+// ... and back: a snapshot the host holds in the reference layout -> device SoA
+template <int D>
+__global__ void k_snapshot_from_ref(Geom G, const double* __restrict__ in, double* __restrict__ snap, size_t spitch) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    constexpr int NC = LT<D>::nc;
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        size_t o = idx < G.npacked ? (size_t)(idx/4)*4*NC + 4*c + idx%4 : (size_t)NC*idx + c;
+        snap[(size_t)c*spitch + idx] = in[o];
+    }
+}
+
 // InitialCondition: populations = scalar-order equilibrium (navierstokes.h:550-572, advection.h:1048-1070,
 // adjointnavierstokes.h:474-498, adjointadvection.h:1359-1381).  a0..a6 by family as in pl_initial_condition.
 template <int D>

@@ -970,6 +970,7 @@ int pl_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* a) {
 }
 
 int pl_snapshot_to_host(const pl_lattice* l, const double* snap, double* out) {
+    InCall in_call_;
     if (!l || !snap || !out) return fail(PL_ERR_ARG, "pl_snapshot_to_host: null");
     size_t n = (size_t)l->g.nxyz*l->nc;
     double* d = nullptr;
@@ -977,6 +978,20 @@ int pl_snapshot_to_host(const pl_lattice* l, const double* snap, double* out) {
     if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_to_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, (size_t)l->g.nxyz, d);
     else LAUNCH(k_snapshot_to_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, (size_t)l->g.nxyz, d);
     CU(cudaMemcpyAsync(out, d, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(d);
+    return PL_OK;
+}
+
+int pl_snapshot_from_host(const pl_lattice* l, const double* in_host, double* snap) {
+    InCall in_call_;
+    if (!l || !snap || !in_host) return fail(PL_ERR_ARG, "pl_snapshot_from_host: null");
+    size_t n = (size_t)l->g.nxyz*l->nc;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, n*sizeof(double)));
+    CU(cudaMemcpyAsync(d, in_host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_from_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, d, snap, (size_t)l->g.nxyz);
+    else LAUNCH(k_snapshot_from_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, d, snap, (size_t)l->g.nxyz);
     CU(cudaStreamSynchronize(g_stream));
     cudaFree(d);
     return PL_OK;
