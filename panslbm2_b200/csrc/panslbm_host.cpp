@@ -37,6 +37,7 @@
 #include "../../include/panslbm_c.h"
 
 #include <fcntl.h>
+#include <pthread.h>
 #include <signal.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -75,10 +76,19 @@ std::map<uintptr_t, Block> g_blocks;              // by base address
 // The allocation hook (operator new of the drop-in headers) may be reached from any thread of the caller — an OpenMP region, a
 // library thread — while the fault handler and every call of this file walk the map: a spin lock around the map itself (never
 // held across anything that can fault or block; map nodes are stable, so a Block* stays valid after the lock is dropped).
-std::atomic_flag g_blocks_lock = ATOMIC_FLAG_INIT;
+// Recursive: the map's own node allocations go through the program's replaced operator new / delete, and the delete hook asks
+// plh_owns() — on the thread that already holds the lock.
+std::atomic<unsigned long> g_blocks_owner{0};
+int g_blocks_depth = 0;
 struct BlocksLock {
-    BlocksLock() { while (g_blocks_lock.test_and_set(std::memory_order_acquire)) {} }
-    ~BlocksLock() { g_blocks_lock.clear(std::memory_order_release); }
+    BlocksLock() {
+        const unsigned long me = (unsigned long)pthread_self();
+        if (g_blocks_owner.load(std::memory_order_acquire) == me) { ++g_blocks_depth; return; }
+        unsigned long none = 0;
+        while (!g_blocks_owner.compare_exchange_weak(none, me, std::memory_order_acquire)) none = 0;
+        g_blocks_depth = 1;
+    }
+    ~BlocksLock() { if (--g_blocks_depth == 0) g_blocks_owner.store(0, std::memory_order_release); }
 };
 struct Views { Block *f0 = nullptr, *f = nullptr; };
 std::map<pl_lattice*, Views> g_views;
