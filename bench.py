@@ -492,6 +492,11 @@ def run_ours(args):
         import gc
         gc.collect()
         extra["ns_cavity"] = ns_cavity(pl, api, L, torch, args.ns_size, max(10, K//2), W, barrier, maxms, world, rank, m, save_last, strong=bool(args.global_size))
+    if world == 1 and args.filter_size > 0 and args.config != "heatsink3d":
+        try:
+            extra["filter"] = filter_subline(pl, torch, args.filter_size, with_reference=not args.no_cpu)
+        except Exception as ex:
+            extra["filter"] = {"error": repr(ex)}
 
     if world > 1:
         barrier()
@@ -551,6 +556,58 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+def filter_subline(pl, torch, S, with_reference=True):
+    """HeavisideFilter::GetFilteredVariable with the drivers' design-box weight (production/heatsink3D.cpp:44, 87-103: R = 2.4) on an S^3
+    lattice: one GPU kernel per call over the baked weight patterns, next to the reference's serial host loops (SURVEY.md §6:
+    1.3 s per call at 128^3, three calls per optimisation iteration)"""
+    import numpy as np
+    R, beta = 2.4, 2.0
+    box = [3*(S - 1)//4 + 1]*3
+
+    def weight(i1, j1, k1, i2, j2, k2):
+        inside = (i1 < box[0]) & (j1 < box[1]) & (k1 < box[2]) & (i2 < box[0]) & (j2 < box[1]) & (k2 < box[2])
+        cone = (R - np.sqrt((i1 - i2)**2.0 + (j1 - j2)**2.0 + (k1 - k2)**2.0))/R
+        return np.where(inside, cone, np.where((i1 == i2) & (j1 == j2) & (k1 == k2), 1.0, 0.0))
+    p = pl.D3Q15(S, S, S)
+    t0 = time.perf_counter()
+    f = pl.ConeFilter(p, R, weight)
+    bake_s = time.perf_counter() - t0
+    n = S**3
+    idx = np.arange(n)
+    v = 0.5 + 0.4*np.sin(0.37*(idx % S))*np.cos(0.23*((idx//S) % S))*np.sin(0.31*(idx//(S*S)) + 0.5)
+    dv = pl.DeviceArray.from_host(v)
+    for _ in range(3):
+        out = f.heaviside(dv, beta)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        out = f.heaviside(dv, beta)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)/reps
+    line = {"workload": f"HeavisideFilter::GetFilteredVariable, design-box cone weight R = {R}, {S}^3 (production/heatsink3D.cpp:87-103)", "gpu_ms_per_call": ms,
+            "weight_patterns": f.npatterns, "device_table_bytes": f.npatterns*125*8 + 4*n, "bake_seconds_once": bake_s,
+            "algorithmic_bytes_per_site": 20.0, "achieved_GBs": 20.0*n/(ms*1e-3)/1e9}
+    if with_reference:
+        try:
+            from oracle import oracle as O
+            if O.have_ref(3):
+                ref = O.Backend("ref", 3)
+                l = ref.lattice(S, S, S)
+                res = np.zeros(n)
+                t0 = time.perf_counter()
+                ref._call("filter", l, 1, float(R), float(beta), np.ascontiguousarray(v), None, res, *box)
+                line["reference_ms_per_call"] = 1e3*(time.perf_counter() - t0)
+                line["max_abs_diff_vs_reference"] = float(np.max(np.abs(out.to_host() - res)))
+                l.free()
+        except Exception as ex:
+            line["reference_ms_per_call"] = None
+            line["reference_error"] = repr(ex)
+    return line
+
+
 def ns_cavity(pl, api, L, torch, S, K, W, barrier, maxms, world, rank=0, m=(1, 1, 1), save_last=SAVE_LAST, strong=False):
     """test/cavityflow3D.cpp:44-59 scaled to S^3 per GPU (S^3 in total with --global-size): NS::MacroCollide(save) + Stream + 5 BARRIER walls + lid SetU + SmoothCorner"""
     import math
@@ -605,6 +662,7 @@ def main():
                     help="heatsink3d = BASELINE configs[3] as written: 81x161x81 in total on the PE grid (2x2x2 on 8 GPUs), strong scaling, checked against the reference fixture")
     ap.add_argument("--global-size", type=int, default=0, help="strong scaling: edge of the cubic GLOBAL domain split over the GPUs (BASELINE.md: 512)")
     ap.add_argument("--ns-size", type=int, default=512, help="edge of the secondary NS cavity sweep (0 = skip)")
+    ap.add_argument("--filter-size", type=int, default=128, help="edge of the Heaviside-filter sub-line (0 = skip)")
     ap.add_argument("--save-every-step", action="store_true", help="every collide stores macros + snapshot at every site (the reference's own cadence) instead of the observed policy")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--cpu-size", type=int, default=128)

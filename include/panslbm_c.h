@@ -213,6 +213,9 @@ int pl_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args*);
 /* Export a device snapshot (SoA) into the reference's host layout ([pack][c][lane] for idx < 4*(nxyz/4),
  * [idx][c] for the tail; adjointadvection_avx.h:20-22) — used only by parity tests. */
 int pl_snapshot_to_host(const pl_lattice*, const double* snapshot_dev, double* out_host);
+/* ... and back: a snapshot held by the host in the reference's layout into the device layout.  The host-pointer surface uses
+ * the pair to keep a caller's `_g` / `_ig` array in the REFERENCE layout whenever the host looks at it or has written it. */
+int pl_snapshot_from_host(const pl_lattice*, const double* in_host, double* snapshot_dev);
 
 /* InitialCondition of NS / AD / ANS / AAD (navierstokes.h:550-572, advection.h:1048-1070,
  * adjointnavierstokes.h:474-498, adjointadvection.h:1359-1381). family: 1=NS(rho,ux,uy,uz) 2=AD(tem,ux,uy,uz)

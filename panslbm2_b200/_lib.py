@@ -79,6 +79,7 @@ _PROTOS = {
     "pl_bc_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(BcAux)]),
     "pl_collide": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(CollideArgs)]),
     "pl_snapshot_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pl_snapshot_from_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_initial_condition": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
     "pl_plan_create": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "pl_plan_destroy": (C.c_int, [C.c_void_p]),

@@ -232,6 +232,7 @@ __global__ void __launch_bounds__(128) k_sens_heat_source(Geom G, ClosureArgs A,
 struct ShellMask {
     const unsigned long long *x, *y, *z;
     int prefetch;      // closure inputs ahead of the pull (PANSLBM_PREFETCH): 0 = off, 1 = prefetch.global.L2, 2 = prefetch.global.L1, 3 = plain loads
+    int l2_ahead;      // interior kernel: sites ahead of its own for which a thread asks L2 to fetch the lines it will need (0 = off)
 };
 constexpr unsigned long long TUBE_BIT = 1ull << 63, SLAB_BIT = 1ull << 62, HALO_BIT = 1ull << 61, GHOST_BIT = 1ull << 60,
                              ENTRY_BITS = ~(TUBE_BIT | SLAB_BIT | HALO_BIT | GHOST_BIT);
@@ -433,8 +434,35 @@ PL_D void boundary_path_sh(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], doubl
 #define PLK_FUSED_THREADS 256
 #define PLK_FUSED_MINB 2
 #endif
+// one-lattice models need half the registers: 3 CTAs per SM (an explicit bound of 2 would let ptxas spend 128 registers on them)
+template <int M> constexpr int fused_min_blocks() { return (ModelFlags<M>::v & F_G) != 0 ? PLK_FUSED_MINB : (PLK_FUSED_MINB*3)/2; }
+// The pass is latency-bound, not bandwidth-bound, once it moves 496 B per site: 124-128 registers allow 16 warps per SM, and a warp
+// spends more than half of its life waiting for its thirty loads (ncu: long-scoreboard stall 5.3 of 9.2 cycles per issue, 5.7 of
+// 6.5 TB/s).  Registers cannot hold more loads in flight — but L2 can: every thread also asks L2 for the lines the thread
+// `l2_ahead` sites further on will load (prefetch.global.L2: no register, no L1 line), i.e. for the CTA that follows on this SM;
+// when that CTA issues its loads they cost an L2 hit instead of a DRAM round trip.  DRAM traffic is unchanged (each line is
+// fetched once, the 126 MB L2 holds the ~20 MB in flight).
+PL_D void l2_fetch(const double* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+template <int D, int MODE, unsigned FL>
+PL_D void l2_ahead(const double* fs, const double* gs, const CollideParams& P, const Geom& G, long long idx, const Nbr& n, int ahead) {
+    const long long a = idx + ahead;
+    if (ahead <= 0 || a >= G.npacked) return;
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        const size_t loc = read_loc<D, MODE, c>(G.pitch, a, n);      // the offsets of THIS site: right for every interior site
+        l2_fetch(fs + loc);
+        if constexpr ((FL & F_G) != 0) l2_fetch(gs + loc);
+    });
+    if constexpr ((FL & F_KFIELD) != 0) l2_fetch(P.kappa + a);
+    if constexpr ((FL & F_BRINK) != 0 || ((FL & F_ADJ) != 0 && (FL & F_G) != 0)) l2_fetch(P.alpha + a);
+    if constexpr ((FL & F_ADJ) != 0) {
+        l2_fetch(P.rho + a); l2_fetch(P.ux + a); l2_fetch(P.uy + a);
+        if constexpr (D == 3) l2_fetch(P.uz + a);
+        if constexpr ((FL & F_G) != 0) l2_fetch(P.tem + a);
+    }
+}
 template <int D, int M, int MODE>
-__global__ void __launch_bounds__(PLK_FUSED_THREADS, PLK_FUSED_MINB) k_fused(Geom G, const double* fs, double* fd, const double* gs, double* gd,
+__global__ void __launch_bounds__(PLK_FUSED_THREADS, fused_min_blocks<M>()) k_fused(Geom G, const double* fs, double* fd, const double* gs, double* gd,
                                                CollideParams P, ShellMask S, const ClosureArgs* __restrict__ prog, int inverse, XWall W) {
     constexpr unsigned FL = ModelFlags<M>::v;
     constexpr bool HASG = (FL & F_G) != 0;
@@ -455,6 +483,7 @@ __global__ void __launch_bounds__(PLK_FUSED_THREADS, PLK_FUSED_MINB) k_fused(Geo
     orient(n, inverse);
     double f[LT<D>::nc], g[LT<D>::nc];
     pass_load_wall<D, MODE, HASG>(f, g, fs, gs, G.pitch, idx, n, W, wside, (size_t)(j + G.ny*k), inverse);
+    l2_ahead<D, MODE, FL>(fs, gs, P, G, idx, n, S.l2_ahead);
     if (entries && prog) boundary_path<D, HASG>(f, g, prog, entries, i, j, k, idx);
     // a step nobody observes (issave == 2) stores its macros only where the closures of the next step read them: on the x
     // closure planes this kernel owns (the sites of every other closure plane belong to the boundary pass, which always stores)
@@ -762,6 +791,19 @@ __global__ void k_snapshot_to_ref(Geom G, const double* __restrict__ snap, size_
     for (int c = 0; c < NC; ++c) {
         size_t o = idx < G.npacked ? (size_t)(idx/4)*4*NC + 4*c + idx%4 : (size_t)NC*idx + c;
         out[o] = snap[(size_t)c*spitch + idx];
+    }
+}
+
+// ... and back: a snapshot the host holds in the reference layout -> device SoA
+template <int D>
+__global__ void k_snapshot_from_ref(Geom G, const double* __restrict__ in, double* __restrict__ snap, size_t spitch) {
+    long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= G.nxyz) return;
+    constexpr int NC = LT<D>::nc;
+    #pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        size_t o = idx < G.npacked ? (size_t)(idx/4)*4*NC + 4*c + idx%4 : (size_t)NC*idx + c;
+        snap[(size_t)c*spitch + idx] = in[o];
     }
 }
 

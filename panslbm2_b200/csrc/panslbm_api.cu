@@ -88,7 +88,9 @@ bool opt_xinline() { static int v = env_int("PANSLBM_XINLINE", 0); return v != 0
 // 0 = every pass goes from the buffer to a second one borrowed from the spare pool (the reference's f / fnext scheme)
 bool opt_inplace() { static int v = env_int("PANSLBM_INPLACE", 1); return v != 0; }
 // interior kernel as a persistent, software-pipelined kernel (cp.async prefetch of the next tile; k_fused_pipe); 0 = one thread per site
-bool opt_pipe() { static int v = env_int("PANSLBM_PIPE", 1); return v != 0; }
+bool opt_pipe() { static int v = env_int("PANSLBM_PIPE", 0); return v != 0; }
+// interior kernel: L2 prefetch distance in CTAs (the CTA that follows on the same SM slot is 2*SMs CTAs further on); 0 = off
+int opt_l2_ahead() { static int v = std::max(0, env_int("PANSLBM_L2_AHEAD", 296)); return v; }
 int device_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148; }
@@ -970,6 +972,7 @@ int pl_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* a) {
 }
 
 int pl_snapshot_to_host(const pl_lattice* l, const double* snap, double* out) {
+    InCall in_call_;
     if (!l || !snap || !out) return fail(PL_ERR_ARG, "pl_snapshot_to_host: null");
     size_t n = (size_t)l->g.nxyz*l->nc;
     double* d = nullptr;
@@ -977,6 +980,20 @@ int pl_snapshot_to_host(const pl_lattice* l, const double* snap, double* out) {
     if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_to_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, (size_t)l->g.nxyz, d);
     else LAUNCH(k_snapshot_to_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, snap, (size_t)l->g.nxyz, d);
     CU(cudaMemcpyAsync(out, d, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    CU(cudaStreamSynchronize(g_stream));
+    cudaFree(d);
+    return PL_OK;
+}
+
+int pl_snapshot_from_host(const pl_lattice* l, const double* in_host, double* snap) {
+    InCall in_call_;
+    if (!l || !snap || !in_host) return fail(PL_ERR_ARG, "pl_snapshot_from_host: null");
+    size_t n = (size_t)l->g.nxyz*l->nc;
+    double* d = nullptr;
+    CU(cudaMalloc(&d, n*sizeof(double)));
+    CU(cudaMemcpyAsync(d, in_host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
+    if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_from_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, d, snap, (size_t)l->g.nxyz);
+    else LAUNCH(k_snapshot_from_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, d, snap, (size_t)l->g.nxyz);
     CU(cudaStreamSynchronize(g_stream));
     cudaFree(d);
     return PL_OK;
@@ -1169,7 +1186,7 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, i
     if (p->g && (r = halo_prepare(p->g, p->inverse))) return r;
     FusedArgs A;
     memset(&A, 0, sizeof(A));
-    A.G = p->f->g; A.P = P; A.S = ShellMask{p->mx, p->my, p->mz, opt_prefetch()}; A.inverse = p->inverse;
+    A.G = p->f->g; A.P = P; A.S = ShellMask{p->mx, p->my, p->mz, opt_prefetch(), opt_l2_ahead()*PLK_FUSED_THREADS}; A.inverse = p->inverse;
     A.fs = p->f->buf; A.gs = g ? g->buf : nullptr;
     double *fdst = p->f->buf, *gdst = g ? g->buf : nullptr;
     if (mode == PASS_COPY) {

@@ -37,6 +37,7 @@
 #include "../../include/panslbm_c.h"
 
 #include <fcntl.h>
+#include <pthread.h>
 #include <signal.h>
 #include <sys/mman.h>
 #include <unistd.h>
@@ -66,15 +67,28 @@ struct Block {
     uint64_t last = 0;              // loop iteration (g_tick) of the last device use
     bool maybe_fresh = true;        // no device use yet: the host may never have touched it (see untouched())
     bool spilled = false;           // its mirror was given up under memory pressure
+    // a thermal snapshot (`_g` / `_ig` of the collides, consumed by Sensitivity*): the device keeps it SoA [c][nxyz], the reference's
+    // host layout is [pack][c][lane] / [idx][c] (advection_avx.h:1046-1052, 1093-1098) — converted whenever it crosses, so that a
+    // driver that reads, checkpoints or provides one sees the reference's layout
+    pl_lattice* snap = nullptr;
 };
 std::map<uintptr_t, Block> g_blocks;              // by base address
 // The allocation hook (operator new of the drop-in headers) may be reached from any thread of the caller — an OpenMP region, a
 // library thread — while the fault handler and every call of this file walk the map: a spin lock around the map itself (never
 // held across anything that can fault or block; map nodes are stable, so a Block* stays valid after the lock is dropped).
-std::atomic_flag g_blocks_lock = ATOMIC_FLAG_INIT;
+// Recursive: the map's own node allocations go through the program's replaced operator new / delete, and the delete hook asks
+// plh_owns() — on the thread that already holds the lock.
+std::atomic<unsigned long> g_blocks_owner{0};
+int g_blocks_depth = 0;
 struct BlocksLock {
-    BlocksLock() { while (g_blocks_lock.test_and_set(std::memory_order_acquire)) {} }
-    ~BlocksLock() { g_blocks_lock.clear(std::memory_order_release); }
+    BlocksLock() {
+        const unsigned long me = (unsigned long)pthread_self();
+        if (g_blocks_owner.load(std::memory_order_acquire) == me) { ++g_blocks_depth; return; }
+        unsigned long none = 0;
+        while (!g_blocks_owner.compare_exchange_weak(none, me, std::memory_order_acquire)) none = 0;
+        g_blocks_depth = 1;
+    }
+    ~BlocksLock() { if (--g_blocks_depth == 0) g_blocks_owner.store(0, std::memory_order_release); }
 };
 struct Views { Block *f0 = nullptr, *f = nullptr; };
 std::map<pl_lattice*, Views> g_views;
@@ -161,7 +175,8 @@ void fetch(Block* b) {
     pl_synchronize();
     if (b->kind == BK_ARRAY) {
         protect(b, PROT_READ | PROT_WRITE);
-        pl_array_download((double*)b->base, b->dev, b->bytes/sizeof(double));
+        if (b->snap) pl_snapshot_to_host(b->snap, b->dev, (double*)b->base);
+        else pl_array_download((double*)b->base, b->dev, b->bytes/sizeof(double));
         protect(b, PROT_READ);
         b->state = ST_SHARED;
     } else {
@@ -275,7 +290,7 @@ int spill(Block* v, double** keep) {
     if (v->state == ST_DEVICE) {
         pl_synchronize();
         protect(v, PROT_READ | PROT_WRITE);
-        if (pl_array_download((double*)v->base, v->dev, v->bytes/sizeof(double))) return hfail("spill download");
+        if (v->snap ? pl_snapshot_to_host(v->snap, v->dev, (double*)v->base) : pl_array_download((double*)v->base, v->dev, v->bytes/sizeof(double))) return hfail("spill download");
         ++g_stat[3];
     } else if (v->state == ST_SHARED) {
         pl_synchronize();
@@ -362,7 +377,7 @@ int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
         b->maybe_fresh = false;
         if (!overwrite && b->state == ST_HOST) {      // also before a partial write: the rest of the array must survive
             flush_pending();            // passes held back were called with the previous content of the mirror
-            if (pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
+            if (b->snap ? pl_snapshot_from_host(b->snap, (const double*)b->base, b->dev) : pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
             ++g_stat[2];
             b->state = ST_SHARED;
             if (!wr) protect(b, PROT_READ);
@@ -382,6 +397,12 @@ int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
     g_staged.push_back(s);
     *out = s.dev;
     return PL_OK;
+}
+// `h` is a thermal snapshot of lattice `l` (only whole blocks of exactly nc*nxyz doubles can be converted)
+void tag_snapshot(const double* h, pl_lattice* l, size_t n_nc) {
+    if (!h || !l) return;
+    Block* b = find_block(h);
+    if (b && b->kind == BK_ARRAY && (const char*)h == b->base && b->bytes == n_nc*sizeof(double)) b->snap = l;
 }
 int unstage() {
     int rc = PL_OK;
@@ -776,6 +797,16 @@ int plh_lattice_attach_views(pl_lattice* l, double** f0, double** f) {
 }
 int plh_lattice_detach(pl_lattice* l) {
     int rc = quiesce(l);
+    // snapshots of this lattice that outlive it: bring them home in the reference layout while the lattice still exists
+    {
+        std::vector<Block*> snaps;
+        { BlocksLock lock_; for (auto& kv : g_blocks) if (kv.second.snap == l) snaps.push_back(&kv.second); }
+        for (Block* b : snaps) {
+            if (b->state == ST_DEVICE) fetch(b);
+            if (b->state == ST_SHARED) { protect(b, PROT_READ | PROT_WRITE); b->state = ST_HOST; }
+            b->snap = nullptr;
+        }
+    }
     drop_plans_of(l);
     auto it = g_views.find(l);
     if (it != g_views.end()) {
@@ -812,6 +843,7 @@ int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* h) {
     WR(imx); WR(imy); WR(imz); WR(item); WR(iqx); WR(iqy); WR(iqz);
 #undef RD
 #undef WR
+    tag_snapshot(h->snapshot, g ? g : f, n*nc);
     if ((rc = xlate(h->snapshot, n*nc, false, save, &d.snapshot))) return rc;
     const bool staged = !g_staged.empty();
     rc = do_collide(f, g, d, staged);
@@ -922,6 +954,7 @@ int plh_sensitivity(pl_lattice* l, const pl_sens_args* h) {
     int rc;
     if ((rc = flush_pending())) return rc;
     g_staged.clear();
+    tag_snapshot(h->gsnap, l, n*nc); tag_snapshot(h->igsnap, l, n*nc);
     if ((rc = xlate(h->dfds, n, true, true, &d.dfds))) return rc;
 #define RD(field, len) if ((rc = xlate(h->field, len, true, false, (double**)&d.field))) return rc
     RD(ux, n); RD(uy, n); RD(uz, n); RD(imx, n); RD(imy, n); RD(imz, n); RD(dads, n); RD(tem, n); RD(item, n); RD(iqx, n); RD(iqy, n); RD(iqz, n);
@@ -942,6 +975,7 @@ int plh_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds,
     double *d_dfds, *d_ux, *d_uy, *d_uz, *d_ig, *d_k, *d_dk;
     int rc;
     if ((rc = flush_pending())) return rc;
+    tag_snapshot(igsnap, l, n*nc);
     g_staged.clear();
     if ((rc = xlate(dfds, n, true, true, &d_dfds)) || (rc = xlate(ux, n, true, false, &d_ux)) || (rc = xlate(uy, n, true, false, &d_uy)) ||
         (rc = xlate(uz, n, true, false, &d_uz)) || (rc = xlate(igsnap, n*nc, true, false, &d_ig)) || (rc = xlate(diffusivity, n, true, false, &d_k)) ||

@@ -105,6 +105,7 @@ int main(int argc, char** argv) {
         double* arrs[] = {rho, ux, uy, uz, tem, qx, qy, qz, irho, iux, iuy, iuz, imx, imy, imz, item, iqx, iqy, iqz};
         for (int a = 0; a < 19; ++a) wr(names[a], arrs[a], n);
         wr("dfdss", dfdss.data(), n);
+        wr("gsnap", gi, (size_t)n*pg.nc); wr("igsnap", igi, (size_t)n*pg.nc);     // the reference's layout: [pack][c][lane], tail [idx][c]
         wr("f.f0", pf.f0, n); wr("f.f", pf.f, (size_t)n*(pf.nc - 1)); wr("g.f0", pg.f0, n); wr("g.f", pg.f, (size_t)n*(pg.nc - 1));
         double extra[2] = {f_buffer, residual};
         wr("extra", extra, 2);
@@ -162,6 +163,7 @@ int main(int argc, char** argv) {
         double* arrs[] = {rho, ux, uy, tem, qx, qy, irho, iux, iuy, imx, imy, item, iqx, iqy};
         for (int a = 0; a < 14; ++a) wr(names[a], arrs[a], n);
         wr("dfdss", dfdss.data(), n);
+        wr("gsnap", gi, (size_t)n*pg.nc); wr("igsnap", igi, (size_t)n*pg.nc);
         wr("f.f0", pf.f0, n); wr("f.f", pf.f, (size_t)n*(pf.nc - 1)); wr("g.f0", pg.f0, n); wr("g.f", pg.f, (size_t)n*(pg.nc - 1));
         double extra[2] = {f_buffer, residual};
         wr("extra", extra, 2);

@@ -11,6 +11,14 @@
 // (heatsink3D_transient.cpp:97, nitr = 500); the printed timings are those of the last repetition (the first one also pays for
 // the first-touch allocation of the per-step arrays).
 #define _USE_AVX_DEFINES
+// Multi-rank runs (drop-in build only; the container has no MPI for the reference): TRANSIENT_PE="mx,my,mz" with one process per
+// GPU under tools/mpiexec_b200 decomposes the 3-D lattice as the MPI build of production/heatsink3D_transient.cpp:28-48 does
+// (rank = PEid, MPI_Allreduce of the objective); every rank reads the GLOBAL input fields, takes its block, and writes its
+// block of every output as <name>.r<rank>.out plus block.r<rank>.out = (offsets, extents).  The single-rank fixture is the oracle.
+#if defined(PANSLBM_B200_DROPIN) && defined(TRANSIENT_MPI)
+#define _USE_MPI_DEFINES
+#include "mpi/mpi.h"
+#endif
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -36,10 +44,11 @@ static void rd(const char* name, double* p, size_t n) {
     if (!f || fread(p, sizeof(double), n, f) != n) { fprintf(stderr, "cannot read %s\n", name); exit(2); }
     fclose(f);
 }
+static std::string rank_suffix;
 static void wr(const std::string& name, const double* p, size_t n) {
     volatile double first = n ? p[0] : 0.0;     // user-space touch first (see tests/dropin/heatsink_dump.cpp)
     (void)first;
-    FILE* f = fopen((dir + "/" + name + ".out").c_str(), "wb");
+    FILE* f = fopen((dir + "/" + name + rank_suffix + ".out").c_str(), "wb");
     fwrite(p, sizeof(double), n, f);
     fclose(f);
 }
@@ -65,7 +74,19 @@ int main(int argc, char** argv) {
     if (dim != TRANSIENT_DIM) { fprintf(stderr, "built for dim %d\n", TRANSIENT_DIM); return 2; }
 #if TRANSIENT_DIM == 3
     {
-        D3Q15<double> pf(lx, ly, lz), pg(lx, ly, lz);
+        int MyRank = 0, pex = 1, pey = 1, pez = 1;
+#ifdef _USE_MPI_DEFINES
+        {
+            int PeTot;
+            MPI_Init(&argc, &argv);
+            MPI_Comm_size(MPI_COMM_WORLD, &PeTot);
+            MPI_Comm_rank(MPI_COMM_WORLD, &MyRank);
+            const char* pe = getenv("TRANSIENT_PE");
+            if (!pe || sscanf(pe, "%d,%d,%d", &pex, &pey, &pez) != 3 || pex*pey*pez != PeTot) { fprintf(stderr, "TRANSIENT_PE=mx,my,mz must match the number of ranks\n"); return 2; }
+            if (PeTot > 1) rank_suffix = ".r" + std::to_string(MyRank);
+        }
+#endif
+        D3Q15<double> pf(lx, ly, lz, MyRank, pex, pey, pez), pg(lx, ly, lz, MyRank, pex, pey, pez);
         const int n = pf.nxyz;
         double **rho = new double*[nt], **ux = new double*[nt], **uy = new double*[nt], **uz = new double*[nt];
         double **tem = new double*[nt], **qx = new double*[nt], **qy = new double*[nt], **qz = new double*[nt];
@@ -79,7 +100,18 @@ int main(int argc, char** argv) {
         double *item = filled(n, 0.0), *iqx = filled(n, 0.0), *iqy = filled(n, 0.0), *iqz = filled(n, 0.0);
         double *alpha = new double[n], *diffusivity = new double[n], *dads = new double[n], *dkds = new double[n];
         double *igi = new double[n*pg.nc];
-        rd("alpha.bin", alpha, n); rd("kappa.bin", diffusivity, n); rd("dads.bin", dads, n); rd("dkds.bin", dkds, n);
+        {
+            // the input files hold the fields of the GLOBAL domain: every rank takes its block
+            const size_t gn = (size_t)lx*ly*lz;
+            std::vector<double> gbuf(gn);
+            const char* files[4] = {"alpha.bin", "kappa.bin", "dads.bin", "dkds.bin"};
+            double* dst[4] = {alpha, diffusivity, dads, dkds};
+            for (int a = 0; a < 4; ++a) {
+                rd(files[a], gbuf.data(), gn);
+                for (int k = 0; k < pf.nz; ++k) for (int j = 0; j < pf.ny; ++j) for (int i = 0; i < pf.nx; ++i)
+                    dst[a][pf.Index(i, j, k)] = gbuf[(size_t)(i + pf.offsetx) + (size_t)lx*((size_t)(j + pf.offsety) + (size_t)ly*(size_t)(k + pf.offsetz))];
+            }
+        }
 
         std::vector<double> dfdss(n, 0.0);
         for (int it = 0; it < iterations; ++it) {
@@ -135,7 +167,11 @@ int main(int argc, char** argv) {
         // objective: heat-patch temperature summed over every stored step (heatsink3D_transient.cpp:221-231)
         // t = 0 holds the initial condition the driver wrote; steps 1..nt-1 what the collides saved
         for (int t = 0; t < nt; ++t)
-            for (int i = 0; i < pf.nx; ++i) for (int k = 0; k < pf.nz; ++k) if (i < L && k < L) f_buffer += tem[t][pf.Index(i, 0, k)];
+            for (int i = 0; i < pf.nx; ++i) for (int k = 0; k < pf.nz; ++k) if ((i + pf.offsetx) < L && (k + pf.offsetz) < L && pf.PEy == 0) f_buffer += tem[t][pf.Index(i, 0, k)];
+#ifdef _USE_MPI_DEFINES
+        { double f_all = 0.0; MPI_Allreduce(&f_buffer, &f_all, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD); f_buffer = f_all; }
+        { double blk[6] = {(double)pf.offsetx, (double)pf.offsety, (double)pf.offsetz, (double)pf.nx, (double)pf.ny, (double)pf.nz}; wr("block", blk, 6); }
+#endif
         const int tq[3] = {1, nt/2, nt - 1};
         for (int q = 0; q < 3; ++q) {
             const std::string s = "@" + std::to_string(q);
@@ -240,6 +276,9 @@ int main(int argc, char** argv) {
     plh_store_stats(ss);
     printf("state store: spilled %llu mirrors, restored %llu, device bytes now %llu, peak %llu\n", (unsigned long long)ss[0], (unsigned long long)ss[1],
            (unsigned long long)ss[2], (unsigned long long)ss[3]);
+#endif
+#ifdef _USE_MPI_DEFINES
+    MPI_Finalize();
 #endif
     return 0;
 }

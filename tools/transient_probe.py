@@ -16,16 +16,20 @@ import numpy as np
 import heatsink_case as H
 from helpers import gcoords
 
+# PROBE_PE="mx,my,mz": the same on a PE grid, one process per GPU under tools/mpiexec_b200 (strong scaling of the 81 x 161 x 81 domain)
 nt = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 budget = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 cpu_nt = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 size = (81, 161, 81)
 env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
 lib = os.path.join(ROOT, "panslbm2_b200")
-out = {"workload": f"transient heatsink loops 81x161x81, nt={nt} stored steps ({23*8*size[0]*size[1]*size[2]*nt/1e9:.1f} GB of states)"}
+out = {"workload": f"transient heatsink loops 81x161x81, nt={nt} stored steps ({23*8*size[0]*size[1]*size[2]*nt/1e9:.1f} GB of states)" +
+                   (f", PE grid {os.environ['PROBE_PE']} (one process per GPU)" if os.environ.get("PROBE_PE") else "")}
 with tempfile.TemporaryDirectory() as d:
     exe = os.path.join(d, "td3")
-    subprocess.check_call(["g++", "-O2", "-mavx", "-ffp-contract=off", "-w", "-DTRANSIENT_DIM=3", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(ROOT, "include"),
+    pe = os.environ.get("PROBE_PE", "")
+    nranks = eval(pe.replace(",", "*")) if pe else 1
+    subprocess.check_call(["g++", "-O2", "-mavx", "-ffp-contract=off", "-w", "-DTRANSIENT_DIM=3", "-DPANSLBM_B200_DROPIN"] + (["-DTRANSIENT_MPI"] if pe else []) + ["-I" + os.path.join(ROOT, "include"),
                            "-I" + os.path.join(lib, "src"), os.path.join(ROOT, "tests", "dropin", "transient_dump.cpp"), "-o", exe,
                            "-L" + lib, "-lpanslbm_b200", "-Wl,-rpath," + lib], env=env)
     p = H.params(3, size)
@@ -35,6 +39,9 @@ with tempfile.TemporaryDirectory() as d:
 
     def run(cmd, extra_env=None):
         e = dict(env); e.update(extra_env or {})
+        if pe and cmd[0] == exe:
+            e.update(TRANSIENT_PE=pe, PANSLBM_RDV_DIR=d)
+            cmd = [os.path.join(ROOT, "tools", "mpiexec_b200"), "-n", str(nranks)] + cmd
         r = subprocess.run(cmd, capture_output=True, text=True, env=e)
         sys.stderr.write(r.stderr)
         if r.returncode:
