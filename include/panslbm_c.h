@@ -216,6 +216,8 @@ int pl_snapshot_to_host(const pl_lattice*, const double* snapshot_dev, double* o
 /* ... and back: a snapshot held by the host in the reference's layout into the device layout.  The host-pointer surface uses
  * the pair to keep a caller's `_g` / `_ig` array in the REFERENCE layout whenever the host looks at it or has written it. */
 int pl_snapshot_from_host(const pl_lattice*, const double* in_host, double* snapshot_dev);
+/* the same for a lattice shape given by kind (PL_D2Q9 / PL_D3Q15) and site count alone; to_host: device layout -> reference layout */
+int pl_snapshot_convert(int kind, long long nxyz, const double* in, double* out, int to_host);
 
 /* InitialCondition of NS / AD / ANS / AAD (navierstokes.h:550-572, advection.h:1048-1070,
  * adjointnavierstokes.h:474-498, adjointadvection.h:1359-1381). family: 1=NS(rho,ux,uy,uz) 2=AD(tem,ux,uy,uz)

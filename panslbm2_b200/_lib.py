@@ -80,6 +80,7 @@ _PROTOS = {
     "pl_collide": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(CollideArgs)]),
     "pl_snapshot_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_snapshot_from_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pl_snapshot_convert": (C.c_int, [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]),
     "pl_initial_condition": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int]),
     "pl_plan_create": (C.c_void_p, [C.c_void_p, C.c_void_p]),
     "pl_plan_destroy": (C.c_int, [C.c_void_p]),

@@ -90,7 +90,7 @@ bool opt_inplace() { static int v = env_int("PANSLBM_INPLACE", 1); return v != 0
 // interior kernel as a persistent, software-pipelined kernel (cp.async prefetch of the next tile; k_fused_pipe); 0 = one thread per site
 bool opt_pipe() { static int v = env_int("PANSLBM_PIPE", 0); return v != 0; }
 // interior kernel: L2 prefetch distance in CTAs (the CTA that follows on the same SM slot is 2*SMs CTAs further on); 0 = off
-int opt_l2_ahead() { static int v = std::max(0, env_int("PANSLBM_L2_AHEAD", 296)); return v; }
+int opt_l2_ahead() { static int v = std::max(0, env_int("PANSLBM_L2_AHEAD", 148)); return v; }
 int device_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148; }
@@ -985,18 +985,33 @@ int pl_snapshot_to_host(const pl_lattice* l, const double* snap, double* out) {
     return PL_OK;
 }
 
-int pl_snapshot_from_host(const pl_lattice* l, const double* in_host, double* snap) {
+// snapshot layout conversion for a lattice shape given by (kind, nxyz) alone: the host-pointer surface keeps converting a caller's
+// snapshot array after the lattice that produced it is gone
+int pl_snapshot_convert(int kind, long long nxyz, const double* in, double* out, int to_host) {
     InCall in_call_;
-    if (!l || !snap || !in_host) return fail(PL_ERR_ARG, "pl_snapshot_from_host: null");
-    size_t n = (size_t)l->g.nxyz*l->nc;
+    if ((kind != PL_D2Q9 && kind != PL_D3Q15) || nxyz <= 0 || !in || !out) return fail(PL_ERR_ARG, "pl_snapshot_convert: bad arguments");
+    Geom g;
+    memset(&g, 0, sizeof(g));
+    g.nxyz = nxyz; g.npacked = 4*(nxyz/4);
+    const size_t n = (size_t)nxyz*(kind == PL_D2Q9 ? 9 : 15);
     double* d = nullptr;
     CU(cudaMalloc(&d, n*sizeof(double)));
-    CU(cudaMemcpyAsync(d, in_host, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
-    if (l->kind == PL_D2Q9) LAUNCH(k_snapshot_from_ref<2>, blocks_for(l->g.nxyz, 256), 256, l->g, d, snap, (size_t)l->g.nxyz);
-    else LAUNCH(k_snapshot_from_ref<3>, blocks_for(l->g.nxyz, 256), 256, l->g, d, snap, (size_t)l->g.nxyz);
+    if (to_host) {
+        if (kind == PL_D2Q9) LAUNCH(k_snapshot_to_ref<2>, blocks_for(nxyz, 256), 256, g, in, (size_t)nxyz, d);
+        else LAUNCH(k_snapshot_to_ref<3>, blocks_for(nxyz, 256), 256, g, in, (size_t)nxyz, d);
+        CU(cudaMemcpyAsync(out, d, n*sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+    } else {
+        CU(cudaMemcpyAsync(d, in, n*sizeof(double), cudaMemcpyHostToDevice, g_stream));
+        if (kind == PL_D2Q9) LAUNCH(k_snapshot_from_ref<2>, blocks_for(nxyz, 256), 256, g, d, out, (size_t)nxyz);
+        else LAUNCH(k_snapshot_from_ref<3>, blocks_for(nxyz, 256), 256, g, d, out, (size_t)nxyz);
+    }
     CU(cudaStreamSynchronize(g_stream));
     cudaFree(d);
     return PL_OK;
+}
+int pl_snapshot_from_host(const pl_lattice* l, const double* in_host, double* snap) {
+    if (!l) return fail(PL_ERR_ARG, "pl_snapshot_from_host: null");
+    return pl_snapshot_convert(l->kind, l->g.nxyz, in_host, snap, 0);
 }
 
 int pl_initial_condition(pl_lattice* l, int family, const double* const* a, int na) {

@@ -70,7 +70,8 @@ struct Block {
     // a thermal snapshot (`_g` / `_ig` of the collides, consumed by Sensitivity*): the device keeps it SoA [c][nxyz], the reference's
     // host layout is [pack][c][lane] / [idx][c] (advection_avx.h:1046-1052, 1093-1098) — converted whenever it crosses, so that a
     // driver that reads, checkpoints or provides one sees the reference's layout
-    pl_lattice* snap = nullptr;
+    int snap_kind = 0;              // 0 = not a snapshot, else PL_D2Q9 / PL_D3Q15 of the lattice it belongs to (its nxyz = bytes/8/nc)
+    long long snap_n() const { return (long long)(bytes/sizeof(double)/(snap_kind == PL_D2Q9 ? 9 : 15)); }
 };
 std::map<uintptr_t, Block> g_blocks;              // by base address
 // The allocation hook (operator new of the drop-in headers) may be reached from any thread of the caller — an OpenMP region, a
@@ -175,7 +176,7 @@ void fetch(Block* b) {
     pl_synchronize();
     if (b->kind == BK_ARRAY) {
         protect(b, PROT_READ | PROT_WRITE);
-        if (b->snap) pl_snapshot_to_host(b->snap, b->dev, (double*)b->base);
+        if (b->snap_kind) pl_snapshot_convert(b->snap_kind, b->snap_n(), b->dev, (double*)b->base, 1);
         else pl_array_download((double*)b->base, b->dev, b->bytes/sizeof(double));
         protect(b, PROT_READ);
         b->state = ST_SHARED;
@@ -290,7 +291,7 @@ int spill(Block* v, double** keep) {
     if (v->state == ST_DEVICE) {
         pl_synchronize();
         protect(v, PROT_READ | PROT_WRITE);
-        if (v->snap ? pl_snapshot_to_host(v->snap, v->dev, (double*)v->base) : pl_array_download((double*)v->base, v->dev, v->bytes/sizeof(double))) return hfail("spill download");
+        if (v->snap_kind ? pl_snapshot_convert(v->snap_kind, v->snap_n(), v->dev, (double*)v->base, 1) : pl_array_download((double*)v->base, v->dev, v->bytes/sizeof(double))) return hfail("spill download");
         ++g_stat[3];
     } else if (v->state == ST_SHARED) {
         pl_synchronize();
@@ -377,7 +378,7 @@ int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
         b->maybe_fresh = false;
         if (!overwrite && b->state == ST_HOST) {      // also before a partial write: the rest of the array must survive
             flush_pending();            // passes held back were called with the previous content of the mirror
-            if (b->snap ? pl_snapshot_from_host(b->snap, (const double*)b->base, b->dev) : pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
+            if (b->snap_kind ? pl_snapshot_convert(b->snap_kind, b->snap_n(), (const double*)b->base, b->dev, 0) : pl_array_upload(b->dev, (const double*)b->base, b->bytes/sizeof(double))) return hfail("upload");
             ++g_stat[2];
             b->state = ST_SHARED;
             if (!wr) protect(b, PROT_READ);
@@ -402,7 +403,11 @@ int xlate(const double* h, size_t n, bool rd, bool wr, double** out) {
 void tag_snapshot(const double* h, pl_lattice* l, size_t n_nc) {
     if (!h || !l) return;
     Block* b = find_block(h);
-    if (b && b->kind == BK_ARRAY && (const char*)h == b->base && b->bytes == n_nc*sizeof(double)) b->snap = l;
+    if (b && b->kind == BK_ARRAY && (const char*)h == b->base && b->bytes == n_nc*sizeof(double)) {
+        int info[18];
+        pl_lattice_info(l, info);
+        b->snap_kind = info[17] == 9 ? PL_D2Q9 : PL_D3Q15;
+    }
 }
 int unstage() {
     int rc = PL_OK;
@@ -797,16 +802,6 @@ int plh_lattice_attach_views(pl_lattice* l, double** f0, double** f) {
 }
 int plh_lattice_detach(pl_lattice* l) {
     int rc = quiesce(l);
-    // snapshots of this lattice that outlive it: bring them home in the reference layout while the lattice still exists
-    {
-        std::vector<Block*> snaps;
-        { BlocksLock lock_; for (auto& kv : g_blocks) if (kv.second.snap == l) snaps.push_back(&kv.second); }
-        for (Block* b : snaps) {
-            if (b->state == ST_DEVICE) fetch(b);
-            if (b->state == ST_SHARED) { protect(b, PROT_READ | PROT_WRITE); b->state = ST_HOST; }
-            b->snap = nullptr;
-        }
-    }
     drop_plans_of(l);
     auto it = g_views.find(l);
     if (it != g_views.end()) {
