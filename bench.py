@@ -126,8 +126,6 @@ class HeatsinkSweep:
         for k in ("ux", "uy", "uz", "tem"):
             if A[k] is not None:
                 A[k].fill(0.0)
-        for k in ("ux", "uy", "uz", "tem"):
-            pass
         u = [A[k] for k in ("ux", "uy", "uz") if A[k] is not None]
         pl.NS.InitialCondition(self.f, A["rho"], *u)
         pl.AD.InitialCondition(self.g, A["tem"], *u)
