@@ -84,13 +84,15 @@ class HeatsinkSweep:
     """forward + adjoint plans of the heatsink3D loop bodies on one block (tests/heatsink_case.py holds the same sequence
     call by call for the parity tests)"""
 
-    def __init__(self, pl, api, size, peid=0, m=(1, 1, 1)):
+    def __init__(self, pl, api, size, peid=0, m=(1, 1, 1), dim=3):
         import heatsink_case as H
         import numpy as np
-        self.pl, self.api, self.H = pl, api, H
-        self.p = p = H.params(3, size)
-        self.f = pl.D3Q15(*size, peid, *m)
-        self.g = pl.D3Q15(*size, peid, *m)
+        self.pl, self.api, self.H, self.dim = pl, api, H, dim
+        self.p = p = H.params(dim, size)
+        if dim == 3:
+            self.f, self.g = pl.D3Q15(*size, peid, *m), pl.D3Q15(*size, peid, *m)
+        else:       # production/heatsink.cpp: the same loop bodies on D2Q9
+            self.f, self.g = pl.D2Q9(size[0], size[1], peid, m[0], m[1]), pl.D2Q9(size[0], size[1], peid, m[0], m[1])
         self.n = n = self.f.nxyz
         f = self.f
 
@@ -100,9 +102,13 @@ class HeatsinkSweep:
         self.alpha, self.kappa, self.dads, self.dkds = [pl.DeviceArray(n) for _ in range(4)]
         names = H.FWD + H.ADJ + ["uxp", "uyp", "uzp", "qxp", "qyp", "qzp", "iuxp", "iuyp", "iuzp", "iqxp", "iqyp", "iqzp"]
         self.A = {k: pl.DeviceArray(n, 0.0) for k in names}
-        self.gsnap, self.igsnap = pl.DeviceArray(n*15), pl.DeviceArray(n*15)
+        self.gsnap, self.igsnap = pl.DeviceArray(n*self.f.nc), pl.DeviceArray(n*self.f.nc)
         self.dfdss = pl.DeviceArray(n, 0.0)
-        self.P = H.predicates(p)
+        P3 = H.predicates(p)
+        self.P = P3 if dim == 3 else {k: (lambda fn: (lambda i, j: fn(i, j, 0)))(v) for k, v in P3.items()}
+        if dim == 2:
+            for k in [k for k in self.A if k.rstrip("p").endswith("z")]:
+                self.A[k] = None
         self.fplan = self.aplan = None
 
     def upload_design(self, pinned=None):
@@ -118,9 +124,11 @@ class HeatsinkSweep:
         pl, A = self.pl, self.A
         A["rho"].fill(1.0)
         for k in ("ux", "uy", "uz", "tem"):
-            A[k].fill(0.0)
-        pl.NS.InitialCondition(self.f, A["rho"], A["ux"], A["uy"], A["uz"])
-        pl.AD.InitialCondition(self.g, A["tem"], A["ux"], A["uy"], A["uz"])
+            if A[k] is not None:
+                A[k].fill(0.0)
+        u = [A[k] for k in ("ux", "uy", "uz") if A[k] is not None]
+        pl.NS.InitialCondition(self.f, A["rho"], *u)
+        pl.AD.InitialCondition(self.g, A["tem"], *u)
         if self.fplan is None:
             self.fplan = self._forward_plan()
 
@@ -129,10 +137,10 @@ class HeatsinkSweep:
 
         def args(sw):
             s = "p" if sw else ""
-            arrs = dict(ux=A["ux" + s], uy=A["uy" + s], uz=A["uz" + s], qx=A["qx" + s], qy=A["qy" + s], qz=A["qz" + s])
+            arrs = {k: A[k + s] for k in ("ux", "uy", "uz", "qx", "qy", "qz") if A[k + s] is not None}
             ca = pl.collide_args(api.M_AD_BRINKMAN_NAT_CONV, True, p["nu"], gx=p["gx"], gy=p["gy"], gz=p["gz"], tem0=p["tem0"], rho=A["rho"], tem=A["tem"],
                                  alpha=self.alpha, diffusivity=self.kappa, snapshot=self.gsnap, **arrs)
-            return ca, pl.bc_aux(ux=arrs["ux"], uy=arrs["uy"], uz=arrs["uz"], diffusivity=self.kappa)
+            return ca, pl.bc_aux(ux=arrs["ux"], uy=arrs["uy"], uz=arrs.get("uz"), diffusivity=self.kappa)
         (c0, a0), (c1, a1) = args(False), args(True)
         plan = pl.StepPlan(f, g).set_collide(c0, c1).set_stream(False)
         plan.add_bounce(f, P["f_wall"])
@@ -144,9 +152,11 @@ class HeatsinkSweep:
     def init_adjoint(self):
         pl, A = self.pl, self.A
         for k in ("ip", "iux", "iuy", "iuz", "item", "iqx", "iqy", "iqz"):
-            A[k].fill(0.0)
-        pl.ANS.InitialCondition(self.f, A["ux"], A["uy"], A["uz"], A["ip"], A["iux"], A["iuy"], A["iuz"])
-        pl.AAD.InitialCondition(self.g, A["ux"], A["uy"], A["uz"], A["item"], A["iqx"], A["iqy"], A["iqz"])
+            if A[k] is not None:
+                A[k].fill(0.0)
+        V = lambda *names: [A[k] for k in names if A[k] is not None]
+        pl.ANS.InitialCondition(self.f, *V("ux", "uy", "uz"), A["ip"], *V("iux", "iuy", "iuz"))
+        pl.AAD.InitialCondition(self.g, *V("ux", "uy", "uz"), A["item"], *V("iqx", "iqy", "iqz"))
         if self.aplan is None:
             self.aplan = self._adjoint_plan()
 
@@ -155,8 +165,8 @@ class HeatsinkSweep:
 
         def args(sw):
             s = "p" if sw else ""
-            arrs = dict(iux=A["iux" + s], iuy=A["iuy" + s], iuz=A["iuz" + s], iqx=A["iqx" + s], iqy=A["iqy" + s], iqz=A["iqz" + s])
-            fixed = {k: A[k] for k in ("rho", "ux", "uy", "uz", "tem", "ip", "imx", "imy", "imz", "item")}
+            arrs = {k: A[k + s] for k in ("iux", "iuy", "iuz", "iqx", "iqy", "iqz") if A[k + s] is not None}
+            fixed = {k: A[k] for k in ("rho", "ux", "uy", "uz", "tem", "ip", "imx", "imy", "imz", "item") if A[k] is not None}
             return pl.collide_args(api.M_AAD_NAT_CONV, True, p["nu"], gx=p["gx"], gy=p["gy"], gz=p["gz"], alpha=self.alpha, diffusivity=self.kappa,
                                    snapshot=self.igsnap, **fixed, **arrs)
         aux0 = pl.bc_aux(ux=A["ux"], uy=A["uy"], uz=A["uz"])
@@ -172,8 +182,9 @@ class HeatsinkSweep:
     def sensitivity(self):
         pl, A, P = self.pl, self.A, self.P
         self.dfdss.fill(0.0)
-        pl.AAD.SensitivityTemperatureAtHeatSource(self.g, self.dfdss, A["ux"], A["uy"], A["uz"], A["imx"], A["imy"], A["imz"], self.dads, A["tem"], A["item"],
-                                                  A["iqx"], A["iqy"], A["iqz"], self.gsnap, self.igsnap, self.kappa, self.dkds, P["qn"], P["source"])
+        V = lambda *names: [A[k] for k in names if A[k] is not None]
+        pl.AAD.SensitivityTemperatureAtHeatSource(self.g, self.dfdss, *V("ux", "uy", "uz"), *V("imx", "imy", "imz"), self.dads, A["tem"], A["item"],
+                                                  *V("iqx", "iqy", "iqz"), self.gsnap, self.igsnap, self.kappa, self.dkds, P["qn"], P["source"])
 
 
 def read_profile(L, plan):
@@ -492,6 +503,11 @@ def run_ours(args):
         import gc
         gc.collect()
         extra["ns_cavity"] = ns_cavity(pl, api, L, torch, args.ns_size, max(10, K//2), W, barrier, maxms, world, rank, m, save_last, strong=bool(args.global_size))
+    if world == 1 and not args.no_small and args.config != "heatsink3d":
+        try:
+            extra["small_domains"] = small_domains(pl, api, torch, with_reference=not args.no_cpu)
+        except Exception as ex:
+            extra["small_domains"] = {"error": repr(ex)}
     if world == 1 and args.filter_size > 0 and args.config != "heatsink3d":
         try:
             extra["filter"] = filter_subline(pl, torch, args.filter_size, with_reference=not args.no_cpu)
@@ -554,6 +570,71 @@ def run_ours(args):
         except Exception as ex:   # the checker must never take the bench down
             line["cpu_baseline"] = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
     print(json.dumps(line), flush=True)
+
+
+def small_domains(pl, api, torch, with_reference=True):
+    """BASELINE configs[0] / configs[1] at their committed sizes: test/cavityflow.cpp (D2Q9 NS, 101 x 101) and the forward + adjoint loops
+    of production/heatsink.cpp (D2Q9 NS+AD, 141 x 161) — domains of a few 10^4 sites that live in L2, where a step is bound by kernel
+    launches, not by bandwidth.  us per lattice update through the fused plan, with the reference's loops on the host
+    cores beside them where oracle/_ref travelled."""
+    import math
+    import numpy as np
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # --- cavity 101^2 (test/cavityflow.cpp:31-66)
+    lx = ly = 101
+    pf = pl.D2Q9(lx, ly)
+    n = pf.nxyz
+    rho, u = pl.DeviceArray(n, 1.0), [pl.DeviceArray(n, 0.0) for _ in range(2)]
+    pl.NS.InitialCondition(pf, rho, *u)
+    plan = pl.StepPlan(pf).set_collide(pl.collide_args(api.M_NS_COLLIDE, True, 0.1, rho=rho, ux=u[0], uy=u[1]))
+    plan.add_bounce(pf, lambda i, j: np.where((i == 0) | (i == lx - 1) | (j == 0), 1, 0))
+    plan.add_closure(pf, api.BC_NS_SET_U, lambda i, j: j == ly - 1, [lambda i, j: 0.1, lambda i, j: 0.0]).set_smooth_corner(True).finalize()
+    plan.advance(200, end_streamed=False, save_last=SAVE_LAST)
+    K = 2000
+    e0, e1 = ev(), ev()
+    torch.cuda.synchronize(); e0.record()
+    plan.advance(K, end_streamed=False, save_last=SAVE_LAST)
+    e1.record(); torch.cuda.synchronize()
+    us = 1e3*e0.elapsed_time(e1)/K
+    out["cavity2d_101x101"] = {"workload": "test/cavityflow.cpp loop body (D2Q9 NS), 101 x 101", "us_per_step": us, "mlups": n/us}
+    # --- heatsink 141 x 161 (production/heatsink.cpp:41, loop bodies :140-214)
+    size = (141, 161, 1)
+    sw = HeatsinkSweep(pl, api, size, dim=2)
+    sw.upload_design()
+    sw.init_forward()
+    sw.fplan.advance(200, end_streamed=False, save_last=SAVE_LAST)
+    K = 1000
+    e = [ev() for _ in range(4)]
+    torch.cuda.synchronize(); e[0].record()
+    sw.fplan.advance(K, end_streamed=False, save_last=SAVE_LAST)
+    e[1].record(); torch.cuda.synchronize()
+    sw.fplan.advance(0, end_streamed=True)
+    sw.init_adjoint()
+    sw.aplan.advance(200, end_streamed=False, save_last=SAVE_LAST)
+    torch.cuda.synchronize(); e[2].record()
+    sw.aplan.advance(K, end_streamed=False, save_last=SAVE_LAST)
+    e[3].record(); torch.cuda.synchronize()
+    uf, ua = 1e3*e[0].elapsed_time(e[1])/K, 1e3*e[2].elapsed_time(e[3])/K
+    out["heatsink2d_141x161"] = {"workload": "production/heatsink.cpp forward + adjoint loop bodies (D2Q9 NS+AD), 141 x 161", "forward_us_per_step": uf,
+                                 "adjoint_us_per_step": ua, "mlups": 2*sw.n/(uf + ua)}
+    if with_reference:
+        try:
+            from oracle import oracle as O
+            import heatsink_case as H
+            if O.have_ref(2):
+                be = O.Backend("ref", 2)
+                be.lib.ref_set_threads(host_threads())
+                p = H.params(2, size)
+                alpha, kappa, _, _ = [np.ascontiguousarray(a) for a in H.design_fields(p, *H.gcoords(*size))]
+                secs = np.zeros(2)
+                be.time_heatsink(size[0], size[1], 1, alpha, kappa, p["nu"], p["gx"], p["gy"], p["gz"], p["tem0"], p["qn0"], p["L"], 2000, 100, secs)
+                out["heatsink2d_141x161"]["reference_us_per_step"] = [1e6*float(secs[0])/2000, 1e6*float(secs[1])/2000]
+                out["heatsink2d_141x161"]["reference_mlups"] = 2*sw.n*2000/float(secs.sum())/1e6
+                out["heatsink2d_141x161"]["reference_threads"] = int(be.lib.ref_max_threads())
+        except Exception as ex:
+            out["heatsink2d_141x161"]["reference_error"] = repr(ex)
+    return out
 
 
 def filter_subline(pl, torch, S, with_reference=True):
@@ -665,6 +746,7 @@ def main():
     ap.add_argument("--filter-size", type=int, default=128, help="edge of the Heaviside-filter sub-line (0 = skip)")
     ap.add_argument("--save-every-step", action="store_true", help="every collide stores macros + snapshot at every site (the reference's own cadence) instead of the observed policy")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the configs[0]/[1] sub-lines (2-D domains at their committed sizes)")
     ap.add_argument("--cpu-size", type=int, default=128)
     ap.add_argument("--cpu-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")

@@ -5,7 +5,7 @@ O=gpurun_out
 (timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 --timeout=400 2>&1 | tail -150) > $O/r02d_tests.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 > $O/r02d_smoke.log
 B="timeout 400 python bench.py --steps 20 --warmup 5"
-Q="--ns-size 0 --filter-size 0 --no-cpu"
+Q="--ns-size 0 --filter-size 0 --no-small --no-cpu"
 $B > $O/r02d_bench_n1.json 2> $O/r02d_bench_n1.err
 for a in 0 148 592 1184; do PANSLBM_L2_AHEAD=$a $B $Q > $O/r02d_bench_n1_ahead$a.json 2> $O/r02d_bench_a$a.err; done
 PANSLBM_INPLACE=0 $B $Q > $O/r02d_bench_n1_two_buffers.json 2> $O/r02d_bench_tb.err

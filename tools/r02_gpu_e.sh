@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 O=gpurun_out
 (timeout 600 python -m pytest tests/test_gpu_dropin.py tests/test_gpu_transient.py tests/test_gpu_closure_values.py tests/test_gpu_inplace.py -m gpu -q --maxfail=10 --timeout=300 2>&1 | tail -40) > $O/r02e_tests.log
 B="timeout 300 python bench.py --steps 20 --warmup 5"
-Q="--ns-size 0 --filter-size 0 --no-cpu"
+Q="--ns-size 0 --filter-size 0 --no-small --no-cpu"
 for a in 18 37 74 111 148 185 222; do
   PANSLBM_L2_AHEAD=$a $B $Q > $O/r02e_bench_n1_ahead$a.json 2> $O/r02e_a$a.err
   PANSLBM_L2_AHEAD=$a $B --dims 81,161,81 $Q > $O/r02e_bench_81x161x81_ahead$a.json 2> $O/r02e_81a$a.err
