@@ -3,6 +3,7 @@
 // panslbm_api.cu reaches them through this table.  Host-side plumbing only.
 #pragma once
 #include "lbm_kernels.cuh"
+#include "lbm_steps.cuh"
 #include <cuda_runtime.h>
 
 namespace plb {
@@ -27,6 +28,8 @@ struct ModelLaunch {
     cudaError_t (*collide)(cudaStream_t, const Geom&, double* fb, double* gb, const CollideParams&, const int* list, long long count);
     cudaError_t (*fused)(cudaStream_t, const FusedArgs&, int mode);
     cudaError_t (*shell)(cudaStream_t, const FusedArgs&, int mode);     // k_shell (+ k_tubes right behind it when the plan has tube sites)
+    // k_steps: A.nsteps fused passes in one cooperative launch; *max_blocks = co-resident CTAs the device can hold (0: unsupported)
+    cudaError_t (*steps)(cudaStream_t, const StepsArgs&, int sms, int* grid_used);
 };
 // nullptr: the model does not exist for this lattice (PL_AAD_NAT_CONV_MASSFLOW is D2Q9 only)
 const ModelLaunch* model_launch(int D, int M);

@@ -73,11 +73,25 @@ cudaError_t shell_(cudaStream_t st, const FusedArgs& A, int mode) {
     }
 }
 
+cudaError_t steps_(cudaStream_t st, const StepsArgs& A, int sms, int* grid_used) {
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_steps<PLI_DIM, PLI_MODEL>, STEPS_THREADS, 0);
+        if (e != cudaSuccess) { per_sm = -1; return e; }
+    }
+    if (per_sm < 1) return cudaErrorCooperativeLaunchTooLarge;
+    const long long want = std::max<long long>(1, (std::max<long long>(A.G.npacked, (long long)A.nlist*2) + STEPS_THREADS - 1)/STEPS_THREADS);
+    const int grid = (int)std::min<long long>(want, (long long)per_sm*(sms > 0 ? sms : 148));
+    if (grid_used) *grid_used = grid;
+    void* args[] = {(void*)&A};
+    return cudaLaunchCooperativeKernel((const void*)k_steps<PLI_DIM, PLI_MODEL>, dim3(grid), dim3(STEPS_THREADS), args, 0, st);
+}
+
 }  // namespace
 
 #define PL_CAT_(a, b, c) a##b##_##c
 #define PL_CAT(a, b, c) PL_CAT_(a, b, c)
 extern const ModelLaunch PL_CAT(model_launch_, PLI_DIM, PLI_MODEL);
-const ModelLaunch PL_CAT(model_launch_, PLI_DIM, PLI_MODEL) = {collide_, fused_, shell_};
+const ModelLaunch PL_CAT(model_launch_, PLI_DIM, PLI_MODEL) = {collide_, fused_, shell_, steps_};
 
 }  // namespace plb

@@ -91,6 +91,9 @@ bool opt_inplace() { static int v = env_int("PANSLBM_INPLACE", 1); return v != 0
 bool opt_pipe() { static int v = env_int("PANSLBM_PIPE", 0); return v != 0; }
 // interior kernel: L2 prefetch distance in CTAs (the CTA that follows on the same SM slot is 2*SMs CTAs further on); 0 = off
 int opt_l2_ahead() { static int v = std::max(0, env_int("PANSLBM_L2_AHEAD", 148)); return v; }
+// lattices of up to this many sites run several fused passes per cooperative launch (k_steps: grid barriers instead of kernel
+// boundaries; the 2-D configs and L2-sized 3-D blocks are bound by launch latency); 0 = never
+long long opt_coop_sites() { static long long v = std::max(0, env_int("PANSLBM_COOP_SITES", 400000)); return v; }
 int device_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148; }
@@ -1298,6 +1301,47 @@ int plan_fused_body(pl_plan* p, int bc_parity, int col_parity, bool full_save, i
     if (p->g && (r = halo_prepare(p->g, p->inverse, true))) return r;
     return PL_OK;
 }
+// `n` fused passes in one cooperative launch (lbm_steps.cuh), for single blocks that live in L2.  false in *done: not applicable
+// (the caller runs the passes one by one).
+int plan_steps(pl_plan* p, int n, int save_last_of_call, int remaining_after, bool* done) {
+    *done = false;
+    if (n < 2 || opt_coop_sites() <= 0 || p->f->g.nxyz > opt_coop_sites() || !opt_inplace() || p->f->halo.on || p->profile || opt_graph() || opt_xinline() ||
+        opt_shell_serial() || opt_pipe()) return PL_OK;
+    int mode, r;
+    if ((r = plan_pass_mode(p, mode))) return r;
+    if (mode == PASS_COPY) return PL_OK;
+    if (p->nxlist && (p->xver[0] != p->f->version || (p->g && p->xver[1] != p->g->version))) return PL_OK;     // the first pass refills the wall buffers
+    CollideParams P0, P1; unsigned flags;
+    if ((r = make_params(p->f, p->g, &p->args[0], P0, flags)) || (r = make_params(p->f, p->g, &p->args[1], P1, flags))) return r;
+    pl_lattice* g = (flags & F_G) ? p->g : nullptr;
+    if (p->g && !g) return fail(PL_ERR_ARG, "plan: a single-lattice collide cannot drive a two-lattice plan");
+    const ModelLaunch* ml = launcher(p->f, p->args[0].model);
+    if (!ml) return PL_ERR_UNSUPPORTED;
+    StepsArgs A;
+    memset(&A, 0, sizeof(A));
+    A.G = p->f->g; A.f = p->f->buf; A.g = g ? g->buf : nullptr;
+    A.P[0] = P0; A.P[1] = P1; A.prog[0] = p->prog[0]; A.prog[1] = p->prog[1];
+    A.S = ShellMask{p->mx, p->my, p->mz, 0, 0}; A.inverse = p->inverse;
+    A.list = p->list; A.ent = p->ent; A.nlist = p->nlist; A.ndirect = p->ndirect; A.tube_f = p->tube_f; A.tube_g = p->tube_g; A.tube_info = p->tube_info;
+    A.xlist = p->xlist; A.xent = p->xent; A.nxlist = p->nxlist; A.xneed = p->xneed;
+    for (int b = 0; b < 2; ++b) { A.xout_f[b] = p->xout[0][b]; A.xout_g[b] = g ? p->xout[1][b] : nullptr; }
+    A.xres_f = p->xres[0]; A.xres_g = g ? p->xres[1] : nullptr;
+    A.np = p->f->g.ny*p->f->g.nz; A.xon[0] = p->xon[0]; A.xon[1] = p->xon[1];
+    A.nsteps = n; A.parity = p->parity; A.mode = mode; A.xphase = p->xphase;
+    // passes of this launch that store everywhere: the last save_last collides of the whole pl_plan_advance call
+    A.save_last = save_last_of_call < 0 ? -1 : std::max(0, save_last_of_call - remaining_after);
+    g_spares.inplace_pass();
+    int grid = 0;
+    cudaError_t e = ml->steps(g_stream, A, device_sms(), &grid);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) { cudaGetLastError(); return PL_OK; }
+    CU(e);
+    ++g_launches;
+    for (int s = 0; s < n; ++s) { plan_pass_done(p, mode); mode = mode == PASS_GATHER ? PASS_LOCAL : PASS_GATHER; p->parity ^= 1; }
+    halo_touch(p->f); if (p->g) halo_touch(p->g);
+    p->xver[0] = p->f->version; if (p->g) p->xver[1] = p->g->version;
+    *done = true;
+    return PL_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1793,6 +1837,15 @@ int pl_plan_advance_observed(pl_plan* p, int ncollides, int end_streamed, int sa
     if (ncollides > 0 && p->f->streamed) {
         if ((r = plan_collide_full(p, p->parity))) return r;
         done = 1;
+    }
+    if (done < ncollides && ncollides - done >= 3) {
+        // small lattices: the first pass on its own (it may refill the wall buffers), the rest in one cooperative launch
+        if ((r = plan_fused(p, p->parity, p->parity ^ 1, save_last < 0 || ncollides - done <= save_last))) return r;
+        p->parity ^= 1;
+        ++done;
+        bool coop = false;
+        if ((r = plan_steps(p, ncollides - done, save_last, 0, &coop))) return r;
+        if (coop) done = ncollides;
     }
     while (done < ncollides) {
         // state: just collided with set `parity`; fuse S(parity) with C(parity^1)

@@ -515,6 +515,9 @@ struct Engine {
     // filters), a host access to a mirrored array (page fault), the end of the loop — first queues the held-back passes WITH
     // their stores, which leaves every array exactly as step-by-step execution would.
     int pending = 0;
+    // how many passes may be held back: 2 proves non-observation; small lattices (PANSLBM_COOP_SITES) hold back more, because
+    // the library runs a batch of passes in ONE cooperative launch (k_steps) where a step is bound by launch latency
+    int lag = 2;
     std::vector<Plan*> plans;
 } E;
 
@@ -532,7 +535,8 @@ int flush_pending() {
     if (!E.active || E.pending == 0) return PL_OK;
     const int n = E.pending;
     E.pending = 0;
-    if (pl_plan_advance_observed(E.active->p, n, 0, n)) return hfail("pl_plan_advance");
+    // only the two most recent passes can still be observed: older ones of the batch are overwritten by them
+    if (pl_plan_advance_observed(E.active->p, n, 0, 2)) return hfail("pl_plan_advance");
     return PL_OK;
 }
 int settle() {
@@ -633,6 +637,13 @@ int enter_replay(Plan* pl, int par, const pl_collide_args& d) {
     if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
     ++g_stat[0];
     E.active = pl; E.par = par; E.pos = 0; E.nhist = 0; E.cur = Iter();
+    {
+        static long long coop_sites = -1;
+        if (coop_sites < 0) { const char* v = getenv("PANSLBM_COOP_SITES"); coop_sites = v && *v ? atoll(v) : 400000; }
+        int info[18];
+        pl_lattice_info(pl->f, info);
+        E.lag = (long long)info[13] <= coop_sites ? 32 : 2;
+    }
     return PL_OK;
 }
 
@@ -653,10 +664,11 @@ int do_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args& d, bool stag
                 if (!rc) rc = flush_bindings(pl, next);
                 if (rc) return rc;
                 if (pl_plan_advance(pl->p, 1, 0)) return hfail("pl_plan_advance");
-            } else if (++E.pending > 2) {
-                // the pass accepted two collides ago: its stores can no longer be observed (see Engine::pending)
-                --E.pending;
-                if (pl_plan_advance_observed(pl->p, 1, 0, 0)) return hfail("pl_plan_advance");
+            } else if (++E.pending > E.lag) {
+                // everything but the two most recent passes: their stores can no longer be observed (see Engine::pending)
+                const int n = E.pending - 2;
+                E.pending = 2;
+                if (pl_plan_advance_observed(pl->p, n, 0, 0)) return hfail("pl_plan_advance");
             }
             ++g_stat[0];
             E.par = next; E.pos = 0;

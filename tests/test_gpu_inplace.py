@@ -72,6 +72,30 @@ def test_observation_at_any_pass_parity_sees_the_natural_layout(nt):
     H.compare(b, c, "fused vs call by call")
 
 
+@pytest.mark.parametrize("dim,size,nt,chunks", [(2, (33, 27, 1), 41, (7, 9)), (3, (15, 13, 11), 23, (5, 8))])
+def test_cooperative_multi_step_launch_gives_the_same_numbers(dim, size, nt, chunks):
+    """lattices that live in L2 run the fused passes of one advance call in ONE cooperative launch (k_steps: grid barriers instead
+    of kernel boundaries); PANSLBM_COOP_SITES=0 runs them pass by pass — same numbers, and both equal the call-by-call loop"""
+    code = ("import sys, json, hashlib, numpy as np\n"
+            f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
+            "import heatsink_case as H\n"
+            "from panslbm2_b200 import _lib\n"
+            f"r = H.run_cuda({dim}, {size!r}, {nt}, fused=FUSED, chunks={chunks!r}, save_last=SAVE)\n"
+            "d = {k: hashlib.sha256(np.ascontiguousarray(v + 0.0).tobytes()).hexdigest() for k, v in sorted(r.items())}\n"
+            "d['launches'] = int(_lib.lib().pl_launch_count())\n"
+            "print(json.dumps(d))\n")
+    import json
+    outs = {}
+    for tag, env, fused, save in (("coop", {}, True, 2), ("passes", {"PANSLBM_COOP_SITES": "0"}, True, 2), ("calls", {}, False, None)):
+        r = subprocess.run([sys.executable, "-c", code.replace("FUSED", str(fused)).replace("SAVE", str(save))], capture_output=True, text=True,
+                           env=dict(os.environ, **env), timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = json.loads(r.stdout.strip().splitlines()[-1])
+    launches = {k: v.pop("launches") for k, v in outs.items()}
+    assert outs["coop"] == outs["passes"] == outs["calls"]
+    assert launches["coop"] < launches["passes"]/2, launches      # the batches really went through k_steps
+
+
 def test_two_buffer_schedule_gives_the_same_numbers():
     code = ("import sys, json, hashlib, numpy as np\n"
             f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
