@@ -749,22 +749,22 @@ class ConeFilter:
         if not self._h:
             raise _lib.PanslbmError(L.pl_last_error().decode())
 
-    def _apply(self, mode, beta, v, aux=None):
-        out = DeviceArray(self.p.nxyz)
+    def _apply(self, mode, beta, v, aux=None, out=None):
+        out = DeviceArray(self.p.nxyz) if out is None else out
         check(_lib.lib().pl_filter_apply(self._h, mode, float(beta), dptr(v), dptr(aux), out.ptr))
         return out
 
-    def density(self, v):
+    def density(self, v, out=None):
         """DensityFilter::GetFilteredValue"""
-        return self._apply(0, 0.0, v)
+        return self._apply(0, 0.0, v, out=out)
 
-    def heaviside(self, s, beta):
+    def heaviside(self, s, beta, out=None):
         """HeavisideFilter::GetFilteredVariable"""
-        return self._apply(1, beta, s)
+        return self._apply(1, beta, s, out=out)
 
-    def heaviside_sensitivity(self, s, dfdrho, beta):
+    def heaviside_sensitivity(self, s, dfdrho, beta, out=None):
         """HeavisideFilter::GetFilteredSensitivity"""
-        return self._apply(2, beta, s, dfdrho)
+        return self._apply(2, beta, s, dfdrho, out=out)
 
     def free(self):
         if getattr(self, "_h", None):

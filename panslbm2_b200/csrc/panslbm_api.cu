@@ -92,8 +92,9 @@ bool opt_pipe() { static int v = env_int("PANSLBM_PIPE", 0); return v != 0; }
 // interior kernel: L2 prefetch distance in CTAs (the CTA that follows on the same SM slot is 2*SMs CTAs further on); 0 = off
 int opt_l2_ahead() { static int v = std::max(0, env_int("PANSLBM_L2_AHEAD", 148)); return v; }
 // lattices of up to this many sites run several fused passes per cooperative launch (k_steps: grid barriers instead of kernel
-// boundaries; the 2-D configs and L2-sized 3-D blocks are bound by launch latency); 0 = never
-long long opt_coop_sites() { static long long v = std::max(0, env_int("PANSLBM_COOP_SITES", 400000)); return v; }
+// boundaries); 0 = never, the default: measured SLOWER than the launches it replaces (heatsink 141 x 161: 35 vs 29 us per step,
+// 41 x 81 x 41: 1 718 vs 2 457 MLUPS — three grid barriers per step and no overlap of the boundary pass with the interior)
+long long opt_coop_sites() { static long long v = std::max(0, env_int("PANSLBM_COOP_SITES", 0)); return v; }
 int device_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148; }

@@ -639,7 +639,7 @@ int enter_replay(Plan* pl, int par, const pl_collide_args& d) {
     E.active = pl; E.par = par; E.pos = 0; E.nhist = 0; E.cur = Iter();
     {
         static long long coop_sites = -1;
-        if (coop_sites < 0) { const char* v = getenv("PANSLBM_COOP_SITES"); coop_sites = v && *v ? atoll(v) : 400000; }
+        if (coop_sites < 0) { const char* v = getenv("PANSLBM_COOP_SITES"); coop_sites = v && *v ? atoll(v) : 0; }
         int info[18];
         pl_lattice_info(pl->f, info);
         E.lag = (long long)info[13] <= coop_sites ? 32 : 2;

@@ -56,9 +56,9 @@ def run_dump(exe, d, dim, size, nt, env=None):
 
 @pytest.mark.parametrize("knobs", [{"PANSLBM_XGHOST": "0"}, {"PANSLBM_XGHOST": "0", "PANSLBM_XINLINE": "1"}, {"PANSLBM_GRAPH": "1"},
                                    {"PANSLBM_XGHOST": "0", "PANSLBM_SHELL_SERIAL": "1", "PANSLBM_PREFETCH": "3"}, {"PANSLBM_INPLACE": "0"},
-                                   {"PANSLBM_INPLACE": "0", "PANSLBM_XGHOST": "0"}, {"PANSLBM_GRAPH": "1", "PANSLBM_XGHOST": "0"}, {"PANSLBM_COOP_SITES": "0"},
-                                   {"PANSLBM_COOP_SITES": "0", "PANSLBM_L2_AHEAD": "0"}, {"PANSLBM_PIPE": "1", "PANSLBM_COOP_SITES": "0"}],
-                         ids=["xslab", "xinline", "graph", "serial_prefetch", "two_buffers", "two_buffers_xslab", "graph_xslab", "no_coop", "no_coop_no_l2_ahead", "pipe"])
+                                   {"PANSLBM_INPLACE": "0", "PANSLBM_XGHOST": "0"}, {"PANSLBM_GRAPH": "1", "PANSLBM_XGHOST": "0"}, {"PANSLBM_COOP_SITES": "400000"},
+                                   {"PANSLBM_L2_AHEAD": "0"}, {"PANSLBM_PIPE": "1"}],
+                         ids=["xslab", "xinline", "graph", "serial_prefetch", "two_buffers", "two_buffers_xslab", "graph_xslab", "coop", "no_l2_ahead", "pipe"])
 @pytest.mark.parametrize("tag", ["hs3d", "hs2d"])
 def test_alternative_boundary_schedules_give_the_same_numbers(dump_exe, tmp_path, tag, knobs):
     """the x closure planes can be served three ways (k_xclose ahead of the pass on the compact wall buffers = default, aligned x

@@ -74,8 +74,9 @@ def test_observation_at_any_pass_parity_sees_the_natural_layout(nt):
 
 @pytest.mark.parametrize("dim,size,nt,chunks", [(2, (33, 27, 1), 41, (7, 9)), (3, (15, 13, 11), 23, (5, 8))])
 def test_cooperative_multi_step_launch_gives_the_same_numbers(dim, size, nt, chunks):
-    """lattices that live in L2 run the fused passes of one advance call in ONE cooperative launch (k_steps: grid barriers instead
-    of kernel boundaries); PANSLBM_COOP_SITES=0 runs them pass by pass — same numbers, and both equal the call-by-call loop"""
+    """PANSLBM_COOP_SITES=n runs the fused passes of one advance call in ONE cooperative launch on lattices of up to n sites (k_steps:
+    grid barriers instead of kernel boundaries; an experiment that measured slower and is off by default) — same numbers as pass by
+    pass, and both equal the call-by-call loop"""
     code = ("import sys, json, hashlib, numpy as np\n"
             f"sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})\n"
             "import heatsink_case as H\n"
@@ -86,14 +87,14 @@ def test_cooperative_multi_step_launch_gives_the_same_numbers(dim, size, nt, chu
             "print(json.dumps(d))\n")
     import json
     outs = {}
-    for tag, env, fused, save in (("coop", {}, True, 2), ("passes", {"PANSLBM_COOP_SITES": "0"}, True, 2), ("calls", {}, False, None)):
+    for tag, env, fused, save in (("coop", {"PANSLBM_COOP_SITES": "400000"}, True, 2), ("passes", {"PANSLBM_COOP_SITES": "0"}, True, 2), ("calls", {}, False, None)):
         r = subprocess.run([sys.executable, "-c", code.replace("FUSED", str(fused)).replace("SAVE", str(save))], capture_output=True, text=True,
                            env=dict(os.environ, **env), timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         outs[tag] = json.loads(r.stdout.strip().splitlines()[-1])
     launches = {k: v.pop("launches") for k, v in outs.items()}
     assert outs["coop"] == outs["passes"] == outs["calls"]
-    assert launches["coop"] < launches["passes"]/2, launches      # the batches really went through k_steps
+    assert launches["coop"] < launches["passes"], launches      # the batches really went through k_steps
 
 
 def test_two_buffer_schedule_gives_the_same_numbers():
