@@ -104,7 +104,7 @@ int device_sms() {
 // Spare population buffers.  A lattice owns ONE buffer; the operations that cannot work in place — a standalone Stream()/iStream(),
 // the conversion of the streamed layout back to the natural one, the two-buffer passes of PANSLBM_INPLACE=0 — write into a buffer
 // borrowed here and hand their old one back.  Lattices of one shape share the spares (f and g of a driver stream one after the
-// other through the same one), and the pool is emptied once a run of in-place passes shows that nobody needs them.
+// other through the same one), and the pool is emptied once a run of 64 in-place passes shows that nobody needs them.
 struct SparePool {
     std::multimap<size_t, double*> free_;
     int streak = 0;                    // fused in-place passes since the last borrow
@@ -125,7 +125,9 @@ struct SparePool {
         for (auto& kv : free_) cudaFree(kv.second);
         free_.clear();
     }
-    void inplace_pass() { if (!free_.empty() && ++streak >= 3) trim(); }
+    // 64 passes without a borrow: a production loop (thousands of steps) sheds its spares early, a short loop that closes with a
+    // standalone Stream() every few steps keeps them (cudaMalloc / cudaFree of a 5 GB buffer inside a loop costs milliseconds)
+    void inplace_pass() { if (!free_.empty() && ++streak >= 64) trim(); }
 } g_spares;
 uint64_t g_lattice_bytes = 0, g_conversions = 0;      // population buffers owned by live lattices; streamed -> natural conversions so far
 
