@@ -255,32 +255,42 @@ struct XWall {
     int np;                           // ny*nz
     int on[2];                        // the plane x = 0 / x = nx-1 is handled this way
 };
-// after the collide of site (i,j,k): the populations that stream onto a compact x plane
-template <int D, bool HASG>
-PL_D void wall_scatter(const XWall& W, const double (&f)[LT<D>::nc], const double (&g)[LT<D>::nc], const Geom& G, int i, int j, int k, int inverse) {
+// after the collide of site (i,j,k): the populations that stream onto a compact x plane — also through the periodic wrap: a
+// population no closure of the plane rebuilds keeps the wrapped-around value, exactly as after Stream() (a plane whose closure mask
+// covers only part of it, a lattice without closures on a plane the other lattice has them on).
+// XV = the x component of the populations that take the step (one call per step direction: straight-line code for its five
+// populations, no per-population test — at nx = 81 almost every other warp holds a lane that comes through here)
+template <int D, bool HASG, int XV>
+PL_D void wall_scatter_set(const XWall& W, const double (&f)[LT<D>::nc], const double (&g)[LT<D>::nc], const Geom& G, int side, int j, int k, int inverse) {
     constexpr int NC = LT<D>::nc;
-    if (W.out_f == nullptr || (i > 1 && i < G.nx - 2)) return;
-    PL_UNROLL
-    for (int side = 0; side < 2; ++side) {
-        if (!W.on[side]) continue;
-        // the x step that lands on the plane — also through the periodic wrap: a population no closure of the plane rebuilds keeps
-        // the wrapped-around value, exactly as after Stream() (a plane whose closure mask covers only part of it, a lattice without
-        // closures on a plane the other lattice has them on)
-        int di = (side ? G.nx - 1 : 0) - i;
-        di = di == G.nx - 1 ? -1 : (di == 1 - G.nx ? 1 : di);
-        if (di < -1 || di > 1) continue;
-        sfor<0, NC>([&](auto C) {
-            constexpr int c = decltype(C)::value;
-            constexpr int X = LT<D>::cx(c), Y = LT<D>::cy(c), Z = LT<D>::cz(c);
-            if ((inverse ? -X : X) != di) return;
-            int jt = j + (inverse ? -Y : Y), kt = k + (inverse ? -Z : Z);
-            jt = jt < 0 ? G.ny - 1 : (jt >= G.ny ? 0 : jt);
-            kt = kt < 0 ? G.nz - 1 : (kt >= G.nz ? 0 : kt);
+    sfor<0, NC>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        constexpr int X = LT<D>::cx(c), Y = LT<D>::cy(c), Z = LT<D>::cz(c);
+        if constexpr (X == XV) {
+            int jt = j, kt = k;
+            if constexpr (Y != 0) { jt = j + (inverse ? -Y : Y); jt = jt < 0 ? G.ny - 1 : (jt >= G.ny ? 0 : jt); }
+            if constexpr (Z != 0) { kt = k + (inverse ? -Z : Z); kt = kt < 0 ? G.nz - 1 : (kt >= G.nz ? 0 : kt); }
             const size_t o = (size_t)(side*NC + c)*W.np + (size_t)(jt + G.ny*kt);
             W.out_f[o] = f[c];
             if constexpr (HASG) W.out_g[o] = g[c];
-        });
-    }
+        }
+    });
+}
+template <int D, bool HASG>
+PL_D void wall_scatter(const XWall& W, const double (&f)[LT<D>::nc], const double (&g)[LT<D>::nc], const Geom& G, int i, int j, int k, int inverse) {
+    if (W.out_f == nullptr || (i > 1 && i < G.nx - 2)) return;
+    // (side, di): the plane this site feeds and the x step s*c_x that lands on it (nx >= 4: the four cases are distinct)
+    auto emit = [&](int side, int di) {
+        if (!W.on[side]) return;
+        const int xv = inverse ? -di : di;
+        if (xv == 0) wall_scatter_set<D, HASG, 0>(W, f, g, G, side, j, k, inverse);
+        else if (xv > 0) wall_scatter_set<D, HASG, 1>(W, f, g, G, side, j, k, inverse);
+        else wall_scatter_set<D, HASG, -1>(W, f, g, G, side, j, k, inverse);
+    };
+    if (i == 0) { emit(0, 0); emit(1, -1); }                 // its own plane; the far plane through the periodic wrap
+    else if (i == 1) emit(0, -1);
+    else if (i == G.nx - 2) emit(1, 1);
+    else { emit(1, 0); emit(0, 1); }
 }
 // the load of the interior kernel: a site on a compact x plane (wside = 0: x = 0, 1: x = nx-1; -1: any other site) takes the
 // populations that would come through the periodic wrap from what the closures of the plane made of them (XWall::res) instead —

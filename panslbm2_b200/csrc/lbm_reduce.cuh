@@ -107,9 +107,22 @@ __global__ void __launch_bounds__(256) k_absmax_final(const double* __restrict__
 struct FilterGeom {
     int nx, ny, nz, nR;          // this rank's block
     long long nxyz;
-    int gx, gy, gz;              // global domain: neighbours are looked up in a field of the whole domain (the block itself when undecomposed)
+    int gx, gy, gz;              // global domain (neighbours outside it do not count)
     int ox, oy, oz;              // offset of the block in it
+    // the field the kernel reads: fx*fy*fz doubles with the block's site (0,0,0) at (ax,ay,az) — the block itself (a = 0), or on a
+    // decomposed lattice the block with an nR-wide ghost layer filled from the neighbouring ranks (a = nR along decomposed axes)
+    int fx, fy, fz, ax, ay, az;
 };
+// copy the box [0,ex) x [0,ey) x [0,ez) at origin (sx,sy,sz) of a field of dims (sdx,sdy,.) to origin (dx,dy,dz) of a field of dims (ddx,ddy,.)
+__global__ void __launch_bounds__(256) k_box_copy(const double* __restrict__ src, int sdx, int sdy, int sx, int sy, int sz,
+                                                  double* __restrict__ dst, int ddx, int ddy, int dx, int dy, int dz, int ex, int ey, int ez) {
+    const long long total = (long long)ex*ey*ez;
+    for (long long t = (long long)blockIdx.x*blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x*blockDim.x) {
+        const int i = (int)(t%ex), j = (int)((t/ex)%ey), k = (int)(t/((long long)ex*ey));
+        dst[(size_t)(dx + i) + (size_t)ddx*((size_t)(dy + j) + (size_t)ddy*(size_t)(dz + k))] =
+            src[(size_t)(sx + i) + (size_t)sdx*((size_t)(sy + j) + (size_t)sdy*(size_t)(sz + k))];
+    }
+}
 // block -> its place in a zeroed field of the global domain (summed over the ranks afterwards: x + 0.0 == x)
 __global__ void __launch_bounds__(256) k_filter_scatter(FilterGeom F, const double* __restrict__ v, double* __restrict__ gv) {
     const long long idx = (long long)blockIdx.x*blockDim.x + threadIdx.x;
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(256) k_filter(FilterGeom F, const double* __re
                 if (i2 < 0 || i2 >= F.gx || j2 < 0 || j2 >= F.gy || k2 < 0 || k2 >= F.gz) continue;
                 const double wt = w[o];
                 if (wt == 0.0) continue;
-                wv = wv + wt*v[(size_t)i2 + (size_t)F.gx*((size_t)j2 + (size_t)F.gy*(size_t)k2)];
+                wv = wv + wt*v[(size_t)(i1 + F.ax + di) + (size_t)F.fx*((size_t)(j1 + F.ay + dj) + (size_t)F.fy*(size_t)(k1 + F.az + dk))];
                 ws = ws + wt;
             }
     double res;

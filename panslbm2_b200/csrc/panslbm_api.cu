@@ -104,7 +104,7 @@ int device_sms() {
 // Spare population buffers.  A lattice owns ONE buffer; the operations that cannot work in place — a standalone Stream()/iStream(),
 // the conversion of the streamed layout back to the natural one, the two-buffer passes of PANSLBM_INPLACE=0 — write into a buffer
 // borrowed here and hand their old one back.  Lattices of one shape share the spares (f and g of a driver stream one after the
-// other through the same one), and the pool is emptied once a run of in-place passes shows that nobody needs them.
+// other through the same one), and the pool is emptied once a run of 64 in-place passes shows that nobody needs them.
 struct SparePool {
     std::multimap<size_t, double*> free_;
     int streak = 0;                    // fused in-place passes since the last borrow
@@ -125,7 +125,9 @@ struct SparePool {
         for (auto& kv : free_) cudaFree(kv.second);
         free_.clear();
     }
-    void inplace_pass() { if (!free_.empty() && ++streak >= 3) trim(); }
+    // 64 passes without a borrow: a production loop (thousands of steps) sheds its spares early, a short loop that closes with a
+    // standalone Stream() every few steps keeps them (cudaMalloc / cudaFree of a 5 GB buffer inside a loop costs milliseconds)
+    void inplace_pass() { if (!free_.empty() && ++streak >= 64) trim(); }
 } g_spares;
 uint64_t g_lattice_bytes = 0, g_conversions = 0;      // population buffers owned by live lattices; streamed -> natural conversions so far
 
@@ -2036,7 +2038,12 @@ struct pl_filter {
     int* pid = nullptr;            // pattern of each site
     int npat = 0;
     double* tmp = nullptr;         // first pass of the sensitivity filter (block)
-    double* gv = nullptr;          // field of the global domain
+    // decomposed lattice: the block with an nR-wide ghost layer along the decomposed axes, filled from the neighbouring ranks
+    // (heavisidefilter.h:291-400 exchanges the same layer with 26 MPI messages; here axis by axis, 2 messages each, the slabs of
+    // the later axes carrying the ghosts of the earlier ones, which delivers the edge and corner regions as well)
+    double* gh = nullptr;
+    double *sbuf[2] = {nullptr, nullptr}, *rbuf[2] = {nullptr, nullptr};
+    int dec[3] = {0, 0, 0}, pe[3] = {0, 0, 0}, m[3] = {1, 1, 1};
 };
 static pl_filter* filter_from_patterns(pl_lattice* l, int nR, const double* patterns, int npat, const int* pattern_of_site) {
     pl_filter* f = new pl_filter();
@@ -2045,15 +2052,25 @@ static pl_filter* filter_from_patterns(pl_lattice* l, int nR, const double* patt
     F.gx = l->g.lx; F.gy = l->g.ly; F.gz = l->g.lz; F.ox = l->g.offx; F.oy = l->g.offy; F.oz = l->g.offz;
     f->global = l->halo.on;
     f->npat = npat;
-    const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz, gn = (size_t)F.gx*F.gy*F.gz;
+    f->dec[0] = l->mx > 1; f->dec[1] = l->my > 1; f->dec[2] = l->kind == PL_D3Q15 && l->mz > 1;
+    f->pe[0] = l->pex; f->pe[1] = l->pey; f->pe[2] = l->pez; f->m[0] = l->mx; f->m[1] = l->my; f->m[2] = l->mz;
+    F.ax = f->dec[0] ? nR : 0; F.ay = f->dec[1] ? nR : 0; F.az = f->dec[2] ? nR : 0;
+    F.fx = F.nx + 2*F.ax; F.fy = F.ny + 2*F.ay; F.fz = F.nz + 2*F.az;
+    const size_t side = 2*(size_t)nR + 1, K = side*side*side, n = (size_t)l->g.nxyz, gn = (size_t)F.fx*F.fy*F.fz;
     bool ok = cudaMalloc(&f->wtab, std::max<size_t>(1, K*npat)*sizeof(double)) == cudaSuccess && cudaMalloc(&f->pid, n*sizeof(int)) == cudaSuccess &&
               cudaMalloc(&f->tmp, n*sizeof(double)) == cudaSuccess;
-    if (ok && f->global) ok = cudaMalloc(&f->gv, gn*sizeof(double)) == cudaSuccess;
+    if (ok && f->global) {
+        const size_t slab = (size_t)std::max(1, nR)*std::max({(size_t)F.fy*F.fz, (size_t)F.fx*F.fz, (size_t)F.fx*F.fy});
+        ok = cudaMalloc(&f->gh, gn*sizeof(double)) == cudaSuccess;
+        for (int b = 0; ok && b < 2; ++b) ok = cudaMalloc(&f->sbuf[b], slab*sizeof(double)) == cudaSuccess && cudaMalloc(&f->rbuf[b], slab*sizeof(double)) == cudaSuccess;
+    }
     ok = ok && cudaMemcpy(f->wtab, patterns, K*npat*sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(f->pid, pattern_of_site, n*sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         fail(PL_ERR_CUDA, std::string("pl_filter_create: ") + cudaGetErrorString(cudaGetLastError()));
-        cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gv); delete f;
+        cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gh);
+        for (int b = 0; b < 2; ++b) { cudaFree(f->sbuf[b]); cudaFree(f->rbuf[b]); }
+        delete f;
         return nullptr;
     }
     return f;
@@ -2093,20 +2110,53 @@ int pl_filter_patterns(const pl_filter* f) { return f ? f->npat : 0; }
 int pl_filter_destroy(pl_filter* f) {
     if (!f) return PL_OK;
     cudaStreamSynchronize(g_stream);
-    cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gv);
+    cudaFree(f->wtab); cudaFree(f->pid); cudaFree(f->tmp); cudaFree(f->gh);
+    for (int b = 0; b < 2; ++b) { cudaFree(f->sbuf[b]); cudaFree(f->rbuf[b]); }
     delete f;
     return PL_OK;
 }
-// the field the filter kernel reads: the block itself, or (decomposed) the global field assembled over the ranks — what
-// replaces the 26-neighbour nR-wide halo exchange of heavisidefilter.h:291-400 (three calls per optimisation iteration)
+// the field the filter kernel reads: the block itself, or (decomposed) the block with its nR-wide ghost layer exchanged with the
+// neighbouring ranks — O(block) memory and traffic per rank.  The domain is NOT periodic for the filters (neighbours outside the
+// global domain do not count, heavisidefilter.h:470-556): ranks on a domain face have no partner there.
 static int filter_field(pl_filter* f, const double* v, const double** out) {
     if (!f->global) { *out = v; return PL_OK; }
-    const size_t gn = (size_t)f->F.gx*f->F.gy*f->F.gz;
-    CU(cudaMemsetAsync(f->gv, 0, gn*sizeof(double), g_stream));
-    LAUNCH(k_filter_scatter, blocks_for(f->F.nxyz, 256), 256, f->F, v, f->gv);
-    NC(g_nccl.AllReduce(f->gv, f->gv, gn, NCCL_F64, NCCL_SUM, g_comm.nccl, g_stream));
-    ++g_launches;
-    *out = f->gv;
+    const FilterGeom& F = f->F;
+    const int nR = F.nR;
+    CU(cudaMemsetAsync(f->gh, 0, (size_t)F.fx*F.fy*F.fz*sizeof(double), g_stream));
+    LAUNCH(k_box_copy, blocks_for(F.nxyz, 256), 256, v, F.nx, F.ny, 0, 0, 0, f->gh, F.fx, F.fy, F.ax, F.ay, F.az, F.nx, F.ny, F.nz);
+    if (nR == 0) { *out = f->gh; return PL_OK; }
+    const int n[3] = {F.nx, F.ny, F.nz}, a[3] = {F.ax, F.ay, F.az}, fd[3] = {F.fx, F.fy, F.fz};
+    const int stride[3] = {1, f->m[0], f->m[0]*f->m[1]};
+    for (int ax = 0; ax < 3; ++ax) {
+        if (!f->dec[ax]) continue;
+        // the slab spans the full (ghosted) extent of the axes already exchanged, the interior of the later ones
+        int ext[3], org[3];
+        for (int d = 0; d < 3; ++d) { ext[d] = d < ax ? fd[d] : n[d]; org[d] = d < ax ? 0 : a[d]; }
+        ext[ax] = nR;
+        const long long cnt = (long long)ext[0]*ext[1]*ext[2];
+        const bool lo = f->pe[ax] > 0, hi = f->pe[ax] < f->m[ax] - 1;
+        const int rank = g_comm.rank;
+        // pack: towards the low neighbour the first nR interior layers, towards the high neighbour the last nR
+        for (int side = 0; side < 2; ++side) {
+            if (!(side ? hi : lo)) continue;
+            int so[3] = {org[0], org[1], org[2]};
+            so[ax] = side ? a[ax] + n[ax] - nR : a[ax];
+            LAUNCH(k_box_copy, blocks_for(cnt, 256), 256, f->gh, fd[0], fd[1], so[0], so[1], so[2], f->sbuf[side], ext[0], ext[1], 0, 0, 0, ext[0], ext[1], ext[2]);
+        }
+        NC(g_nccl.GroupStart());
+        if (lo) { NC(g_nccl.Send(f->sbuf[0], (size_t)cnt, NCCL_F64, rank - stride[ax], g_comm.nccl, g_stream)); NC(g_nccl.Recv(f->rbuf[0], (size_t)cnt, NCCL_F64, rank - stride[ax], g_comm.nccl, g_stream)); }
+        if (hi) { NC(g_nccl.Send(f->sbuf[1], (size_t)cnt, NCCL_F64, rank + stride[ax], g_comm.nccl, g_stream)); NC(g_nccl.Recv(f->rbuf[1], (size_t)cnt, NCCL_F64, rank + stride[ax], g_comm.nccl, g_stream)); }
+        NC(g_nccl.GroupEnd());
+        ++g_launches;
+        // unpack into the ghost layers
+        for (int side = 0; side < 2; ++side) {
+            if (!(side ? hi : lo)) continue;
+            int dorg[3] = {org[0], org[1], org[2]};
+            dorg[ax] = side ? a[ax] + n[ax] : 0;
+            LAUNCH(k_box_copy, blocks_for(cnt, 256), 256, f->rbuf[side], ext[0], ext[1], 0, 0, 0, f->gh, fd[0], fd[1], dorg[0], dorg[1], dorg[2], ext[0], ext[1], ext[2]);
+        }
+    }
+    *out = f->gh;
     return PL_OK;
 }
 int pl_filter_apply(pl_filter* f, int mode, double beta, const double* v, const double* dfdrho, double* out) {

@@ -38,13 +38,16 @@ def test_steady_loop_holds_one_buffer_per_lattice():
     sw.init_forward()
     per_lattice = 15*8*((sw.n + 15)//16*16)
     assert mem()[0] - base[0] == 2*per_lattice
-    sw.fplan.advance(9, end_streamed=False, save_last=2)
+    sw.f.Stream(); sw.g.Stream()                                          # a standalone Stream() borrows a spare (f and g share it) ...
+    assert mem()[1] == per_lattice
+    sw.init_forward()
+    sw.fplan.advance(71, end_streamed=False, save_last=2)
     m = mem()
-    assert m[0] - base[0] == 2*per_lattice and m[1] == 0, m          # no second buffer anywhere while the loop runs
+    assert m[0] - base[0] == 2*per_lattice and m[1] == 0, m          # ... which a steady loop gives back: no second buffer anywhere
     borrows = m[2]
     sw.fplan.advance(7, end_streamed=False, save_last=2)
     assert mem()[2] == borrows                                           # ... and none was borrowed on the way
-    # observing the populations in the middle of the loop (15 passes so far: streamed layout inside) converts through ONE spare
+    # observing the populations in the middle of the loop (77 passes so far: streamed layout inside) converts through ONE spare
     conv = mem()[3]
     f0a, fa = sw.f.get_populations()
     m = mem()
