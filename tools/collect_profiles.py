@@ -9,14 +9,14 @@ import shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC, DST = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 COPY = {
-    # final 1-GPU run (tools/r02_gpu_i.sh)
-    "r02i_bench_n1.json": "r02_bench_n1.json", "r02i_bench_reference.json": "r02_bench_reference.json",
-    "r02i_bench_n1_two_buffers.json": "r02_bench_n1_two_buffers.json", "r02i_bench_n1_save_every_step.json": "r02_bench_n1_save_every_step.json",
-    "r02i_bench_81x161x81.json": "r02_bench_81x161x81.json", "r02i_bench_512.json": "r02_bench_512.json",
+    # final 1-GPU runs (tools/r02_gpu_j.sh: final code; tools/r02_gpu_i.sh: the captures that do not depend on the last change)
+    "r02j_bench_n1.json": "r02_bench_n1.json", "r02i_bench_reference.json": "r02_bench_reference.json",
+    "r02j_bench_n1_two_buffers.json": "r02_bench_n1_two_buffers.json", "r02j_bench_n1_save_every_step.json": "r02_bench_n1_save_every_step.json",
+    "r02j_bench_81x161x81.json": "r02_bench_81x161x81.json", "r02j_bench_512.json": "r02_bench_512.json",
     "r02i_transient_81x161x81_nt200_1.json": "r02_transient_81x161x81_nt200_run1.json", "r02i_transient_81x161x81_nt200_2.json": "r02_transient_81x161x81_nt200_run2.json",
     "r02i_transient_81x161x81_nt200_budget8GB.json": "r02_transient_81x161x81_nt200_budget8GB.json",
-    "r02i_launches_bench_default.csv": "r02_launches_bench_default.csv", "r02i_launches_bench_81x161x81.csv": "r02_launches_bench_81x161x81.csv",
-    "r02i_tests.log": "r02_gpu_tests.log",
+    "r02j_launches_bench_default.csv": "r02_launches_bench_default.csv", "r02j_launches_bench_81x161x81.csv": "r02_launches_bench_81x161x81.csv",
+    "r02j_tests.log": "r02_gpu_tests.log",
     # multi-GPU runs (tools/r02_gpu_f.sh: 2 GPUs, tools/r02_gpu_g.sh: 8 GPUs)
     "r02f_bench_n2.json": "r02_bench_n2.json", "r02f_bench_n2_reference.json": "r02_bench_n2_reference_arm_under_torchrun.json", "r02f_bench_n2_strong512.json": "r02_bench_n2_strong512.json",
     "r02f_tests.log": "r02_gpu_tests_2gpus.log",
@@ -26,10 +26,13 @@ COPY = {
     "r02c_bench_n1.json": "r02_exp_bench_n1_cp_async_pipeline.json", "r02c_bench_n1_occ5_nopipe.json": "r02_exp_bench_n1_occ5_96_registers.json",
     "r02c_ncu_full_fused_fwd_gather_raw.csv": "r02_exp_ncu_full_fused_pipe_fwd_gather_raw.csv",
     "r02c_ncu_full_fused_fwd_local_nopipe_raw.csv": "r02_exp_ncu_full_fused_fwd_local_no_l2_ahead_raw.csv",
-    "r02h_bench_41x81x41.json": "r02_exp_bench_41x81x41_cooperative.json", "r02h_bench_41x81x41_nocoop.json": "r02_bench_41x81x41.json",
+    "r02h_bench_41x81x41.json": "r02_exp_bench_41x81x41_cooperative.json", "r02j_bench_41x81x41.json": "r02_bench_41x81x41.json",
+    "r02k_tests_2gpus.log": "r02_gpu_tests_final_2gpus.log", "r02k_tests_8gpus.log": "r02_gpu_tests_final_8gpus.log",
     "r02h_bench_n1.json": "r02_exp_bench_n1_small_domains_cooperative.json", "r02h_bench_n1_nocoop.json": "r02_exp_bench_n1_small_domains_launches.json",
 }
-for k in ("fwd_gather", "fwd_local", "fwd_storing", "adj_gather", "adj_local", "adj_storing", "ns"):
+for k in ("fwd_gather", "fwd_local", "adj_gather", "adj_local"):
+    COPY[f"r02j_ncu_full_fused_{k}_raw.csv"] = f"r02_ncu_full_fused_{k}_raw.csv"
+for k in ("fwd_storing", "adj_storing", "ns"):
     COPY[f"r02i_ncu_full_fused_{k}_raw.csv"] = f"r02_ncu_full_fused_{k}_raw.csv"
 for k in ("k_xclose", "k_shell", "k_tubes", "k_sensitivity", "k_filter", "k_residual"):
     COPY[f"r02i_ncu_full_{k}_raw.csv"] = f"r02_ncu_full_{k}_raw.csv"
