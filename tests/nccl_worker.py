@@ -43,6 +43,36 @@ def run(pl, api, size, rank, m, nt):
     return s.f, out, res_mid
 
 
+def collectives(rank, world):
+    """the communicator entry points the mpi.h shim maps MPI onto (src/mpi/mpi.h): pl_comm_allreduce (<= 4 doubles), pl_comm_allreduce_v
+    (any count, f64 / i32, sum / max / min), pl_comm_p2p (grouped sends and receives matched in issue order), pl_reduce_box_sum and
+    pl_comm_gather_field — against what MPI would return"""
+    import ctypes as C
+    import panslbm2_b200 as pl
+    from panslbm2_b200 import _lib
+    L = _lib.lib()
+    ok = True
+    v = np.array([rank + 1.0, 10.0*(rank + 1)])
+    _lib.check(L.pl_comm_allreduce(v.ctypes.data, 2, 0))
+    ok &= np.array_equal(v, [world*(world + 1)/2.0, 10.0*world*(world + 1)/2.0])
+    for dtype, arr in ((0, np.arange(1000, dtype=np.float64)*(rank + 1)), (1, (np.arange(333, dtype=np.int32) % 7)*(rank + 1))):
+        for op, fn in ((0, lambda a: a*(world*(world + 1)//2)), (1, lambda a: a*world), (2, lambda a: a*1)):
+            base = arr/(rank + 1) if dtype == 0 else arr//(rank + 1)
+            x = np.ascontiguousarray(arr.copy())
+            _lib.check(L.pl_comm_allreduce_v(x.ctypes.data, x.size, dtype, op))
+            ok &= np.array_equal(x, fn(base).astype(x.dtype))
+    # ring: every rank sends 4096 doubles to rank + 1 and receives from rank - 1 (one group, as MPI_Isend / Irecv / Waitall)
+    class P2P(C.Structure):
+        _fields_ = [("host", C.c_void_p), ("bytes", C.c_size_t), ("peer", C.c_int), ("is_send", C.c_int)]
+    out = np.full(4096, float(rank))
+    inp = np.zeros(4096)
+    ops = (P2P*2)(P2P(out.ctypes.data, out.nbytes, (rank + 1) % world, 1), P2P(inp.ctypes.data, inp.nbytes, (rank - 1) % world, 0))
+    L.pl_comm_p2p.restype, L.pl_comm_p2p.argtypes = C.c_int, [C.c_void_p, C.c_int]
+    _lib.check(L.pl_comm_p2p(ops, 2))
+    ok &= bool(np.all(inp == float((rank - 1) % world)))
+    return bool(ok)
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -58,12 +88,13 @@ def main():
     rank, world = pl.comm_init_torch()
     assert world == m[0]*m[1]*m[2]
     lat, got, res_d = run(pl, api, size, rank, m, nt)
+    coll_ok = collectives(rank, world)
     offs = type("B", (), dict(offsetx=lat.offsetx, offsety=lat.offsety, offsetz=lat.offsetz, nx=lat.nx, ny=lat.ny, nz=lat.nz))
     del lat
     pl.comm_destroy()
     _, want, res_s = run(pl, api, size, 0, (1, 1, 1), nt)
     bad = [k for k in want if not np.array_equal(got[k], block(offs, want[k], size))]
-    ok = not bad and abs(res_d - res_s) <= 1e-12*abs(res_s)
+    ok = not bad and abs(res_d - res_s) <= 1e-12*abs(res_s) and coll_ok
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     print(f"rank {rank}: {'OK' if ok else 'MISMATCH ' + ','.join(bad[:8])} residual {res_d:.17g} vs {res_s:.17g}", flush=True)
