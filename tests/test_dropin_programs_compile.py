@@ -12,7 +12,8 @@ LIB = os.path.join(ROOT, "panslbm2_b200")
 
 PROGRAMS = [("heatsink_dump.cpp", []), ("transient_dump.cpp", ["-DTRANSIENT_DIM=3", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("transient_dump.cpp", ["-DTRANSIENT_DIM=2", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
-            ("ncpump_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]), ("filter_dump.cpp", [])]
+            ("ncpump_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]), ("filter_dump.cpp", []),
+            ("nsopt_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")])]
 
 
 @pytest.mark.parametrize("src,flags", PROGRAMS, ids=[p[0] + "".join(f for f in p[1] if f.startswith("-DTRANSIENT")) for p in PROGRAMS])
