@@ -13,6 +13,7 @@ LIB = os.path.join(ROOT, "panslbm2_b200")
 PROGRAMS = [("heatsink_dump.cpp", []), ("transient_dump.cpp", ["-DTRANSIENT_DIM=3", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("transient_dump.cpp", ["-DTRANSIENT_DIM=2", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("ncpump_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]), ("filter_dump.cpp", []),
+            ("ncpump_periodic_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("nsopt_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")])]
 
 

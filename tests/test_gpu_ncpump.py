@@ -54,3 +54,41 @@ def test_ncpump_loops_match_reference_fixture(exe, tmp_path, tag):
         assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() == bytes(z[f"{tag}/{k}/sha"]), f"{tag}: {k} digest"
     # both loops replay as fused passes: closures after SmoothCorner and the SmoothCornerAt points are part of the plan
     assert res["stats"][0] >= 2*(nt - 4), r.stdout
+
+
+# ---------------------------------------------------------------------------------------------------------
+# production/ncpump_periodic.cpp:107-305 — the time-periodic pump: per-step arrays, a SetT value that changes every step, the
+# objective read on the host after every forward step, direction fields rewritten on the host before every adjoint step,
+# a sensitivity call per adjoint step, a second optimisation iteration restarting from the last stored step.
+def periodic_cases():
+    spec = importlib.util.spec_from_file_location("make_ncpump_periodic_golden", os.path.join(G, "make_ncpump_periodic_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.NCPUMP_PERIODIC_CASES
+
+
+@pytest.fixture(scope="session")
+def periodic_exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("ncpump_periodic") / "ncpump_periodic_dump")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    lib = os.path.join(ROOT, "panslbm2_b200")
+    subprocess.check_call(["g++", "-O2", "-mavx", "-ffp-contract=off", "-w", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(lib, "src"),
+                           os.path.join(HERE, "dropin", "ncpump_periodic_dump.cpp"), "-o", out, "-L" + lib, "-lpanslbm_b200", "-Wl,-rpath," + lib], env=env)
+    return out
+
+
+@pytest.mark.parametrize("tag", ["ncpp_small", "ncpp"])
+def test_ncpump_periodic_loops_match_reference_fixture(periodic_exe, tmp_path, tag):
+    args = periodic_cases()[tag]
+    r = subprocess.run([periodic_exe, *[str(a) for a in args], str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = {f[:-4]: np.fromfile(os.path.join(str(tmp_path), f)) for f in os.listdir(str(tmp_path)) if f.endswith(".out")}
+    z = np.load(os.path.join(G, "ncpump_periodic.npz"))
+    keys = sorted(k.split("/")[1] for k in z.files if k.startswith(tag + "/") and k.endswith("/sha"))
+    assert len(keys) >= 28
+    for k in keys:
+        a = res[k] + 0.0
+        want = z[f"{tag}/{k}/s5"]
+        got = a if len(want) == len(a) else a[::5]
+        assert np.array_equal(got, want), f"{tag}: {k} differs from the reference fixture (max abs {np.max(np.abs(got - want)):.3e})\n{r.stdout}"
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() == bytes(z[f"{tag}/{k}/sha"]), f"{tag}: {k} digest"
