@@ -252,6 +252,20 @@ def test_golden_cavity3d_reference_fixture():
         assert same(x[::37], z[f"b_{name}_s37"]), name
 
 
+def test_golden_cavity3d_128_cube_200_steps():
+    """SURVEY §8d cfg 3 parity case: test/cavityflow3D.cpp scaled to 128^3, 200 steps, fused in-place passes, against the
+    fixture of the reference build: every 997th value and the SHA-256 of each whole field — bit for bit"""
+    import hashlib
+    z = np.load(os.path.join(G, "cavity3d.npz"))
+    lx, ly, lz, nt = [int(v) for v in z["c_shape"]]
+    assert (lx, ly, lz, nt) == (128, 128, 128, 200)
+    c, _ = cavity_cuda(lx, ly, lz, nt, fused=True)
+    for name, x in zip(("rho", "ux", "uy", "uz"), c):
+        assert same(x[::997], z[f"c_{name}_s997"]), (name, float(np.max(np.abs(x[::997] - z[f"c_{name}_s997"]))))
+        assert hashlib.sha256(np.ascontiguousarray(canon(x)).tobytes()).digest() == bytes(z[f"c_{name}_sha256"]), name
+    assert np.max(np.abs(c[1])) > 1e-2
+
+
 def cavity2d_host(be, lx, ly, nt, u0=0.1, nu=0.1):
     """test/cavityflow.cpp:31-66 call by call on a CPU backend (the C oracle / the reference build)"""
     l = be.lattice(lx, ly)
