@@ -152,6 +152,8 @@ int pl_smooth_corner_at(pl_lattice*, int i, int j, int k, int dirx, int diry, in
 #define PL_BC_AAD_ISET_T 9    /* AAD::iBoundaryConditionSetTAlong* adjointadvection.h:154-300; aux ux,uy,uz */
 #define PL_BC_AAD_ISET_Q 10   /* AAD::iBoundaryConditionSetQAlong* adjointadvection.h:304-484; aux ux,uy,uz; eps */
 #define PL_BC_AAD_ISET_RHO 11 /* AAD::iBoundaryConditionSetRhoAlong*Edge (D2Q9 only) adjointadvection.h:488-575 */
+#define PL_BC_NSIN_SET_U 12   /* NSin::BoundaryConditionSetUAlong*Edge (D2Q9 only)   nsincompressible.h:46-94;   v0,v1 = ux,uy */
+#define PL_BC_NSIN_SET_RHO 13 /* NSin::BoundaryConditionSetRhoAlong*Edge (D2Q9 only) nsincompressible.h:96-154;  v0 = rho, v1 = _usbc */
 
 pl_bc* pl_bc_create(pl_lattice*, int type, int axis, int coord, int dir,
                     const uint8_t* mask_host, const double* v0_host, const double* v1_host, const double* v2_host);
@@ -187,6 +189,8 @@ int pl_bc_apply(pl_lattice*, pl_lattice* other, const pl_bc*, const pl_bc_aux* a
 #define PL_AAD_FORCE_CONV 10             /* AAD::MacroBrinkmanCollideForceConvection adjointadvection_avx.h:530-761 */
 #define PL_AAD_NAT_CONV 11               /* AAD::MacroBrinkmanCollideNaturalConvection adjointadvection_avx.h:763-1005 */
 #define PL_AAD_NAT_CONV_MASSFLOW 12      /* AAD::...NaturalConvectionMassFlow (D2Q9)  adjointadvection_avx.h:1007-1129 */
+#define PL_NSIN_COLLIDE 13               /* NSin::MacroCollide (D2Q9, scalar templates only)          nsincompressible.h:158-181 */
+#define PL_NSIN_BRINKMAN 14              /* NSin::MacroBrinkmanCollide (D2Q9)                         nsincompressible.h:183-210 */
 
 typedef struct pl_collide_args {
     int model;
@@ -198,7 +202,7 @@ typedef struct pl_collide_args {
     const double *diffusivity;       /* per-cell diffusivity field (models 6,7,10,11,12) */
     const double *beta;              /* heat-exchange coefficient field (models 5,9) */
     const double *dirx, *diry, *dirz;/* mass-flow direction fields (model 12) */
-    /* forward macros: outputs of models 1-7 (written when issave), inputs of models 8-12 */
+    /* forward macros: outputs of models 1-7, 13, 14 (written when issave), inputs of models 8-12 */
     double *rho, *ux, *uy, *uz, *tem, *qx, *qy, *qz;
     /* adjoint macros: outputs of models 8-12 (written when issave) */
     double *ip, *iux, *iuy, *iuz, *imx, *imy, *imz, *item, *iqx, *iqy, *iqz;
@@ -221,7 +225,8 @@ int pl_snapshot_convert(int kind, long long nxyz, const double* in, double* out,
 
 /* InitialCondition of NS / AD / ANS / AAD (navierstokes.h:550-572, advection.h:1048-1070,
  * adjointnavierstokes.h:474-498, adjointadvection.h:1359-1381). family: 1=NS(rho,ux,uy,uz) 2=AD(tem,ux,uy,uz)
- * 3=ANS(ux,uy,uz,ip,iux,iuy,iuz) 4=AAD(ux,uy,uz,item,iqx,iqy,iqz); a[] holds the device arrays in that order. */
+ * 3=ANS(ux,uy,uz,ip,iux,iuy,iuz) 4=AAD(ux,uy,uz,item,iqx,iqy,iqz) 5=NSin(rho,ux,uy,-; nsincompressible.h:212-223, D2Q9 only);
+ * a[] holds the device arrays in that order. */
 int pl_initial_condition(pl_lattice*, int family, const double* const* a, int na);
 
 /* ---- fused time stepping ------------------------------------------------------------------------

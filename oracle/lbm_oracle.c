@@ -357,6 +357,101 @@ void orc_ns_bc_set_rho(orc_lattice* l, const double* v0, const double* v1, const
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* NSin — incompressible NS on D2Q9: nsincompressible.h (scalar templates only, no AVX overloads: one order for every site) */
+/* Macro: nsincompressible.h:11-24 — rho = sum f, u = sum c f (NOT divided by rho) */
+static void nsin_macro(const L* l, const double* p, double* rho, double* ux, double* uy) {
+    double r = p[0], x = 0.0, y = 0.0;
+    for (int c = 1; c < l->nc; ++c) {
+        r = r + p[c];
+        x = x + l->cx[c]*p[c];
+        y = y + l->cy[c]*p[c];
+    }
+    *rho = r; *ux = x; *uy = y;
+}
+/* Equilibrium: nsincompressible.h:26-34 — feq_c = ei_c*(3 c.u + 4.5 (c.u)^2 + (rho - 1.5 u.u)) */
+static void nsin_eq(const L* l, double* feq, double rho, double ux, double uy) {
+    double rhouu = rho - 1.5*(ux*ux + uy*uy);
+    for (int c = 0; c < l->nc; ++c) {
+        double ciu = l->cx[c]*ux + l->cy[c]*uy;
+        feq[c] = l->ei[c]*(3.0*ciu + 4.5*ciu*ciu + rhouu);
+    }
+}
+/* InitialCondition: nsincompressible.h:212-223 */
+void orc_nsin_init(orc_lattice* l, const double* rho, const double* ux, const double* uy, const double* uz) {
+    (void)uz;
+    double feq[NCMAX];
+    for (int idx = 0; idx < l->nxyz; ++idx) {
+        nsin_eq(l, feq, rho[idx], ux[idx], uy[idx]);
+        scatter(l, idx, feq);
+    }
+}
+/* MacroCollide: nsincompressible.h:158-181; MacroBrinkmanCollide: :183-210 (force = NS's ExternalForceBrinkman, :36-44; macros
+ * re-evaluated after the force and stored after it) */
+static void nsin_collide(L* l, double* rho, double* ux, double* uy, double nu, const double* alpha, int issave) {
+    double omega = 1.0/(3.0*nu + 0.5), iomega = 1.0 - omega;
+    #pragma omp parallel for
+    for (int idx = 0; idx < l->nxyz; ++idx) {
+        double p[NCMAX], feq[NCMAX], r, x, y;
+        gather(l, idx, p);
+        nsin_macro(l, p, &r, &x, &y);
+        if (alpha) {
+            double coef = 3.0*alpha[idx]*r/(r + alpha[idx]);
+            for (int c = 1; c < l->nc; ++c) p[c] = p[c] - coef*l->ei[c]*(l->cx[c]*x + l->cy[c]*y);
+            nsin_macro(l, p, &r, &x, &y);
+        }
+        if (issave) { rho[idx] = r; ux[idx] = x; uy[idx] = y; }
+        nsin_eq(l, feq, r, x, y);
+        relax(l, p, feq, omega, iomega);
+        scatter(l, idx, p);
+    }
+}
+void orc_nsin_macro_collide(orc_lattice* l, double* rho, double* ux, double* uy, double* uz, double nu, int issave) {
+    (void)uz; nsin_collide(l, rho, ux, uy, nu, NULL, issave);
+}
+void orc_nsin_macro_brinkman_collide(orc_lattice* l, double* rho, double* ux, double* uy, double* uz, double nu, const double* alpha, int issave) {
+    (void)uz; nsin_collide(l, rho, ux, uy, nu, alpha, issave);
+}
+/* Edge closures: nsincompressible.h:46-94 (SetU), :96-154 (SetRho).  a = normal axis, t = the other one.
+ *   SetRho first derives the normal velocity: u_a = -dir*(rho - (f0 + f_{+t} + f_{-t} + 2*(sum of the three populations leaving)))
+ *   axis population:  f_in = f_out -dir*2u_a/3
+ *   diagonals:        f_in = f_opp -dir*u_a/6 - c_t*0.5*(f_{+t} - f_{-t} - u_t) */
+static void nsin_bc_site(L* l, int idx, int gidx, int axis, int dir, void* vctx) {
+    nsbc_ctx* b = (nsbc_ctx*)vctx;
+    if (!b->mask[gidx]) return;
+    double p[NCMAX];
+    gather(l, idx, p);
+    int t = 1 - axis, v[3] = {0, 0, 0};
+    v[t] = 1; int cp = find_dir(l, v[0], v[1], v[2]); v[t] = -1; int cm = find_dir(l, v[0], v[1], v[2]);
+    double ua, ut;
+    if (!b->setrho) { ua = axis == 0 ? b->v0[gidx] : b->v1[gidx]; ut = axis == 0 ? b->v1[gidx] : b->v0[gidx]; }
+    else {
+        double s = p[0] + p[cp] + p[cm];
+        double o = 0.0; int first = 1;
+        for (int c = 1; c < l->nc; ++c) if (l->ci[c][axis] == dir) { o = first ? p[c] : o + p[c]; first = 0; }
+        double tot = s + 2.0*o;
+        ua = dir == -1 ? b->v0[gidx] - tot : -b->v0[gidx] + tot;
+        ut = b->v1[gidx];
+    }
+    double T = p[cp] - p[cm] - ut;
+    for (int c = 1; c < l->nc; ++c) {
+        if (l->ci[c][axis] != -dir) continue;
+        double val;
+        if (l->ci[c][t] == 0) val = dir == -1 ? p[l->opp[c]] + 2.0*ua/3.0 : p[l->opp[c]] - 2.0*ua/3.0;
+        else {
+            val = dir == -1 ? p[l->opp[c]] + ua/6.0 : p[l->opp[c]] - ua/6.0;
+            val = l->ci[c][t] > 0 ? val - 0.5*T : val + 0.5*T;
+        }
+        l->f[IF(l, idx, c)] = val;
+    }
+}
+void orc_nsin_bc_set_u(orc_lattice* l, const double* uxg, const double* uyg, const double* uzg, const int* mask) {
+    (void)uzg; nsbc_ctx b = {uxg, uyg, NULL, mask, 0}; for_all_faces(l, nsin_bc_site, &b);
+}
+void orc_nsin_bc_set_rho(orc_lattice* l, const double* v0, const double* v1, const double* v2, const int* mask) {
+    (void)v2; nsbc_ctx b = {v0, v1, NULL, mask, 1}; for_all_faces(l, nsin_bc_site, &b);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* AD (thermal lattice) primitives: advection.h:18-95 (scalar), advection_avx.h:25-102 (AVX)   */
 /* Macro: the same order in both (advection.h:18-51 == advection_avx.h:25-56) */
 static void ad_macro(const L* l, const double* g, double ux, double uy, double uz, double omegag, double* tem, double* qx, double* qy, double* qz) {

@@ -43,6 +43,9 @@ typedef PANSLBM2::D3Q15<double> PT;
 #include "src/equation/advection.h"
 #include "src/equation/adjointnavierstokes.h"
 #include "src/equation/adjointadvection.h"
+#if DIM == 2
+#include "src/equation/nsincompressible.h"
+#endif
 #include "src/utility/residual.h"
 #include "src/utility/normalize.h"
 #include "src/utility/densityfilter.h"
@@ -136,6 +139,33 @@ void ref_ns_bc_set_rho(void* h, const double* v0, const double* v1, const double
     GDEF(L(h));
     NS::BoundaryConditionSetRho(*L(h)->p, FV(v0), FV(v1), Z(FV(v2)) FM(mask));
 }
+
+//---------------------------------------------------------------- NSin (D2Q9 only, scalar templates only: nsincompressible.h)
+#if DIM == 2
+void ref_nsin_init(void* h, const double* rho, const double* ux, const double* uy, const double* uz) {
+    NSin::InitialCondition(*L(h)->p, rho, ux, uy);
+}
+void ref_nsin_macro_collide(void* h, double* rho, double* ux, double* uy, double* uz, double nu, int issave) {
+    NSin::MacroCollide(*L(h)->p, rho, ux, uy, nu, issave != 0);
+}
+void ref_nsin_macro_brinkman_collide(void* h, double* rho, double* ux, double* uy, double* uz, double nu, const double* alpha, int issave) {
+    NSin::MacroBrinkmanCollide(*L(h)->p, rho, ux, uy, nu, alpha, issave != 0);
+}
+void ref_nsin_bc_set_u(void* h, const double* uxg, const double* uyg, const double* uzg, const int* mask) {
+    GDEF(L(h));
+    NSin::BoundaryConditionSetU(*L(h)->p, FV(uxg), FV(uyg), FM(mask));
+}
+// NSin::BoundaryConditionSetRho itself cannot be instantiated (it calls a misspelt helper, nsincompressible.h:238): the four
+// edge calls it stands for, in its order.  v0 = rho, v1 = _usbc.
+void ref_nsin_bc_set_rho(void* h, const double* v0, const double* v1, const double* v2, const int* mask) {
+    GDEF(L(h));
+    PT& p = *L(h)->p;
+    NSin::BoundaryConditionSetRhoAlongXEdge(p, 0, -1, FV(v0), FV(v1), FM(mask));
+    NSin::BoundaryConditionSetRhoAlongXEdge(p, p.lx - 1, 1, FV(v0), FV(v1), FM(mask));
+    NSin::BoundaryConditionSetRhoAlongYEdge(p, 0, -1, FV(v0), FV(v1), FM(mask));
+    NSin::BoundaryConditionSetRhoAlongYEdge(p, p.ly - 1, 1, FV(v0), FV(v1), FM(mask));
+}
+#endif
 
 //---------------------------------------------------------------- AD
 void ref_ad_init(void* hg, const double* tem, const double* ux, const double* uy, const double* uz) {

@@ -33,8 +33,10 @@ BARRIER, MIRROR = 1, 2   # d3q15.h:19-22
 # pl_bc types / collide models (include/panslbm_c.h)
 BC_BOUNCE, BC_IBOUNCE, BC_NS_SET_U, BC_NS_SET_RHO, BC_AD_SET_T, BC_AD_SET_Q = 1, 2, 3, 4, 5, 6
 BC_ANS_ISET_U, BC_ANS_ISET_RHO, BC_AAD_ISET_T, BC_AAD_ISET_Q, BC_AAD_ISET_RHO = 7, 8, 9, 10, 11
+BC_NSIN_SET_U, BC_NSIN_SET_RHO = 12, 13
 (M_NS_COLLIDE, M_NS_BRINKMAN, M_AD_FORCE_CONV, M_AD_NAT_CONV, M_AD_BRINKMAN_HEATEX, M_AD_BRINKMAN_FORCE_CONV,
  M_AD_BRINKMAN_NAT_CONV, M_ANS_BRINKMAN, M_AAD_HEATEX, M_AAD_FORCE_CONV, M_AAD_NAT_CONV, M_AAD_NAT_CONV_MASSFLOW) = range(1, 13)
+M_NSIN_COLLIDE, M_NSIN_BRINKMAN = 13, 14
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -461,6 +463,30 @@ class NS:
         # (rhobc, usbc, [utbc,] bctype)
         *vals, mask = fns
         _closure_faces(p, BC_NS_SET_RHO, mask, vals)
+
+
+class NSin:
+    """src/equation/nsincompressible.h (D2Q9 only, scalar templates only)"""
+
+    @staticmethod
+    def InitialCondition(p, rho, ux, uy):
+        _init(p, 5, [rho, ux, uy, None])
+
+    @staticmethod
+    def MacroCollide(p, rho, ux, uy, viscosity, issave=False):
+        _collide(p, None, collide_args(M_NSIN_COLLIDE, issave, viscosity, rho=rho, ux=ux, uy=uy))
+
+    @staticmethod
+    def MacroBrinkmanCollide(p, rho, ux, uy, viscosity, alpha, issave=False):
+        _collide(p, None, collide_args(M_NSIN_BRINKMAN, issave, viscosity, rho=rho, ux=ux, uy=uy, alpha=alpha))
+
+    @staticmethod
+    def BoundaryConditionSetU(p, uxbc, uybc, bctype):
+        _closure_faces(p, BC_NSIN_SET_U, bctype, [uxbc, uybc])
+
+    @staticmethod
+    def BoundaryConditionSetRho(p, rhobc, usbc, bctype):
+        _closure_faces(p, BC_NSIN_SET_RHO, bctype, [rhobc, usbc])
 
 
 _ZNAMES = {"uz", "qz", "iuz", "imz", "iqz", "gz", "dirz"}

@@ -6,7 +6,7 @@
 -fmad=false: the reference is built with -mavx only (no FMA, README.md:23-25); contracting a*b+c on the GPU would
 change the last bits of every population.  The sweep is HBM-bound, so the extra instruction issue is hidden.
 
-The per-model kernels (k_collide / k_fused / k_shell / k_tubes for each lattice and each of the twelve Macro*Collide* models,
+The per-model kernels (k_collide / k_fused / k_shell / k_tubes for each lattice and each of the fourteen Macro*Collide* models,
 three pass modes each) are compiled as one translation unit per (lattice, model) pair — csrc/lbm_model_inst.cu with
 -DPLI_DIM / -DPLI_MODEL — in parallel; objects land in build/obj/ (git-ignored), the library next to this file.
 """
@@ -26,7 +26,7 @@ CSRC = os.path.join(HERE, "csrc")
 TAG = os.environ.get("PANSLBM_BUILD_TAG", "")
 OBJ = os.path.join(ROOT, "build", "obj" + ("_" + TAG if TAG else ""))
 LIB = os.path.join(HERE, "libpanslbm_b200" + ("_" + TAG if TAG else "") + ".so")
-PAIRS = [(2, m) for m in range(1, 13)] + [(3, m) for m in range(1, 12)]      # model 12 (mass flow) exists for D2Q9 only
+PAIRS = [(2, m) for m in range(1, 15)] + [(3, m) for m in range(1, 12)]      # models 12 (mass flow), 13, 14 (NSin) exist for D2Q9 only
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC"] + \
     os.environ.get("PANSLBM_BUILD_FLAGS", "").split()
 

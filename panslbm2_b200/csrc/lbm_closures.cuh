@@ -19,7 +19,8 @@ namespace plb {
 // closure types (PL_BC_* of include/panslbm_c.h)
 enum : int {
     BC_BOUNCE = 1, BC_IBOUNCE = 2, BC_NS_SET_U = 3, BC_NS_SET_RHO = 4, BC_AD_SET_T = 5, BC_AD_SET_Q = 6,
-    BC_ANS_ISET_U = 7, BC_ANS_ISET_RHO = 8, BC_AAD_ISET_T = 9, BC_AAD_ISET_Q = 10, BC_AAD_ISET_RHO = 11
+    BC_ANS_ISET_U = 7, BC_ANS_ISET_RHO = 8, BC_AAD_ISET_T = 9, BC_AAD_ISET_Q = 10, BC_AAD_ISET_RHO = 11,
+    BC_NSIN_SET_U = 12, BC_NSIN_SET_RHO = 13
 };
 
 // per-site inputs of one closure application
@@ -141,6 +142,47 @@ template <int D, class PA> PL_HD void closure_ns(PA& p, int axis, int dir, const
     }
     PL_UNROLL
     for (int c = 1; c < NC; ++c) p[c] = out[c];
+}
+
+// NSin::BoundaryConditionSetU / SetRho along an edge of a D2Q9 lattice (nsincompressible.h:46-154).  a = normal axis, t = the other.
+//   SetU:   u given.   SetRho: u_t given, u_a = -dir*(rho - (f0 + sum(tan) + 2*sum(out)))  (v0 = rho, v1 = u_t)
+//   f_in(axis)     = f_out - dir*(2 u_a/3)
+//   f_in(diagonal) = f_opp - dir*(u_a/6) - c_t*0.5*(f_{+t} - f_{-t} - u_t)
+template <int D, class PA> PL_HD void closure_nsin(PA& p, int axis, int dir, const SiteVals& V, bool setrho) {
+    if constexpr (D == 2) {
+        const int t = 1 - axis;
+        double ua, ut;
+        if (!setrho) { ua = axis == 0 ? V.v0 : V.v1; ut = axis == 0 ? V.v1 : V.v0; }
+        else {
+            double s = p[0];
+            PL_UNROLL
+            for (int c = 1; c < 9; ++c) if (rdir<2>(c, axis) == 0) s = s + p[c];
+            double o = 0.0; bool first = true;
+            PL_UNROLL
+            for (int c = 1; c < 9; ++c) if (rdir<2>(c, axis) == dir) { o = first ? p[c] : o + p[c]; first = false; }
+            const double tot = s + 2.0*o;
+            ua = dir == -1 ? V.v0 - tot : -V.v0 + tot;
+            ut = V.v1;
+        }
+        const int cp = find_dir<2>(t == 0, t == 1, 0), cm = find_dir<2>(-(t == 0), -(t == 1), 0);
+        const double T = p[cp] - p[cm] - ut;
+        double out[9];
+        PL_UNROLL
+        for (int c = 1; c < 9; ++c) {
+            out[c] = p[c];
+            if (rdir<2>(c, axis) != -dir) continue;
+            const int ct = rdir<2>(c, t);
+            double val;
+            if (ct == 0) val = dir == -1 ? p[ropp<2>(c)] + 2.0*ua/3.0 : p[ropp<2>(c)] - 2.0*ua/3.0;
+            else {
+                val = dir == -1 ? p[ropp<2>(c)] + ua/6.0 : p[ropp<2>(c)] - ua/6.0;
+                val = ct > 0 ? val - 0.5*T : val + 0.5*T;
+            }
+            out[c] = val;
+        }
+        PL_UNROLL
+        for (int c = 1; c < 9; ++c) p[c] = out[c];
+    }
 }
 
 // AD::BoundaryConditionSetT (advection.h:99-238) and SetQ (advection.h:242-524; scalar and per-cell diffusivity):
@@ -326,6 +368,8 @@ PL_HD void apply_closure_on(int type, int axis, int dir, int maskval, PA& p, con
         case BC_AAD_ISET_T: closure_aad_isett<D>(p, axis, dir, V); break;
         case BC_AAD_ISET_Q: closure_aad_isetq<D>(p, axis, dir, V); break;
         case BC_AAD_ISET_RHO: if constexpr (D == 2) closure_aad_isetrho2d(p, q, axis, dir, maskval, V); break;
+        case BC_NSIN_SET_U: closure_nsin<D>(p, axis, dir, V, false); break;
+        case BC_NSIN_SET_RHO: closure_nsin<D>(p, axis, dir, V, true); break;
         default: break;
     }
 }

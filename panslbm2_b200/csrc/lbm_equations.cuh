@@ -18,7 +18,8 @@ enum : unsigned {
     F_HEATEX = 16u,   // heat-exchange source on g
     F_MASSFLOW = 32u, // mass-flow objective source (adjoint, D2Q9)
     F_KFIELD = 64u,   // per-cell diffusivity field (else scalar)
-    F_SNAP = 128u     // model has a snapshot parameter (_g / _ig)
+    F_SNAP = 128u,    // model has a snapshot parameter (_g / _ig)
+    F_INCOMP = 256u   // incompressible NS (NSin, nsincompressible.h): momentum moments, rho only in the rest term of feq; D2Q9, scalar templates only
 };
 
 template <int M> struct ModelFlags;
@@ -34,6 +35,8 @@ template <> struct ModelFlags<9> { static constexpr unsigned v = F_ADJ | F_G | F
 template <> struct ModelFlags<10> { static constexpr unsigned v = F_ADJ | F_G | F_KFIELD | F_SNAP; };
 template <> struct ModelFlags<11> { static constexpr unsigned v = F_ADJ | F_G | F_NATCONV | F_KFIELD | F_SNAP; };
 template <> struct ModelFlags<12> { static constexpr unsigned v = F_ADJ | F_G | F_NATCONV | F_MASSFLOW | F_KFIELD | F_SNAP; };
+template <> struct ModelFlags<13> { static constexpr unsigned v = F_INCOMP; };
+template <> struct ModelFlags<14> { static constexpr unsigned v = F_INCOMP | F_BRINK; };
 
 // kernel-side argument block of one collide (built on the host from pl_collide_args)
 struct CollideParams {
@@ -91,6 +94,27 @@ template <int D> PL_D void ns_brinkman(double (&f)[LT<D>::nc], double rho, doubl
     sfor<1, LT<D>::nc>([&](auto C) {
         constexpr int c = decltype(C)::value;
         f[c] = f[c] - coef*LT<D>::ei(c)*cdot<D, c>(ux, uy, uz);
+    });
+}
+
+// NSin  (nsincompressible.h:11-44): u is the momentum sum itself (no division by rho), rho enters feq only through the rest term.
+// The reference has scalar templates only (no AVX overloads), so every site computes in this one order.
+template <int D> PL_D void nsin_macro(const double (&f)[LT<D>::nc], double& rho, double& ux, double& uy, double& uz) {
+    rho = f[0]; ux = 0.0; uy = 0.0; uz = 0.0;
+    sfor<1, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        rho = rho + f[c];
+        ux = sadd<LT<D>::cx(c)>(ux, f[c]);
+        uy = sadd<LT<D>::cy(c)>(uy, f[c]);
+        if constexpr (D == 3) uz = sadd<LT<D>::cz(c)>(uz, f[c]);
+    });
+}
+template <int D> PL_D void nsin_eq(double (&feq)[LT<D>::nc], double rho, double ux, double uy, double uz) {
+    double rhouu = rho - 1.5*dot<D>(ux, uy, uz, ux, uy, uz);
+    sfor<0, LT<D>::nc>([&](auto C) {
+        constexpr int c = decltype(C)::value;
+        double ciu = cdot<D, c>(ux, uy, uz);
+        feq[c] = LT<D>::ei(c)*(3.0*ciu + 4.5*ciu*ciu + rhouu);
     });
 }
 
@@ -291,14 +315,16 @@ PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Col
     if constexpr (!(FL & F_ADJ)) {
         // ---- forward: advection_avx.h:1011-1066 (and the variants :106-883), navierstokes_avx.h:148-329
         double rho, ux, uy, uz, tem = 0.0, qx = 0.0, qy = 0.0, qz = 0.0;
-        ns_macro<D>(f, rho, ux, uy, uz);
+        constexpr bool INC = (FL & F_INCOMP) != 0;      // NSin::MacroCollide / MacroBrinkmanCollide (nsincompressible.h:158-210)
+        auto fmacro = [&]() { if constexpr (INC) nsin_macro<D>(f, rho, ux, uy, uz); else ns_macro<D>(f, rho, ux, uy, uz); };
+        fmacro();
         if constexpr (G) ad_macro<D>(g, ux, uy, uz, omegag, tem, qx, qy, qz);
         // quirk: the 2-D scalar tail of NS::MacroBrinkmanCollide stores the macros before the force (navierstokes_avx.h:246-254)
         constexpr bool early = SC && D == 2 && FL == F_BRINK;
         if constexpr (early) { if (save) { P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy; } }
         if constexpr ((FL & F_NATCONV) != 0) ad_natconv<D, SC>(f, tem, P);
         if constexpr ((FL & F_BRINK) != 0) ns_brinkman<D>(f, rho, ux, uy, uz, P.alpha[idx]);
-        if constexpr ((FL & (F_NATCONV | F_BRINK)) != 0) ns_macro<D>(f, rho, ux, uy, uz);
+        if constexpr ((FL & (F_NATCONV | F_BRINK)) != 0) fmacro();
         if constexpr ((FL & F_HEATEX) != 0) ad_heatex<D, SC>(g, tem, P.beta[idx]);
         if constexpr (G && (FL & (F_NATCONV | F_BRINK)) != 0) ad_macro<D>(g, ux, uy, uz, omegag, tem, qx, qy, qz);
         if (save) {
@@ -313,7 +339,9 @@ PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Col
             }
         }
         double eq[NC];
-        if constexpr (SC) ns_eq_sc<D>(eq, rho, ux, uy, uz); else ns_eq_avx<D>(eq, rho, ux, uy, uz);
+        if constexpr (INC) nsin_eq<D>(eq, rho, ux, uy, uz);
+        else if constexpr (SC) ns_eq_sc<D>(eq, rho, ux, uy, uz);
+        else ns_eq_avx<D>(eq, rho, ux, uy, uz);
         relax<D>(f, eq, P.omegaf, P.iomegaf);
         if constexpr (G) {
             if constexpr (SC) ad_eq_sc<D>(eq, tem, ux, uy, uz); else ad_eq_avx<D>(eq, tem, ux, uy, uz);

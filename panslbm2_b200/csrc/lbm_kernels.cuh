@@ -831,6 +831,8 @@ __global__ void __launch_bounds__(256) k_init(Geom G, double* __restrict__ dst, 
         ad_eq_sc<D>(eq, a0[idx], a1[idx], a2[idx], D == 3 ? a3[idx] : 0.0);
     } else if (family == 3) {   // ANS: ux, uy, uz, ip, iux, iuy, iuz
         ans_eq<D>(eq, a0[idx], a1[idx], D == 3 ? a2[idx] : 0.0, a3[idx], a4[idx], a5[idx], D == 3 ? a6[idx] : 0.0);
+    } else if (family == 5) {   // NSin: rho, ux, uy (nsincompressible.h:212-223)
+        nsin_eq<D>(eq, a0[idx], a1[idx], a2[idx], D == 3 ? a3[idx] : 0.0);
     } else {                    // AAD: ux, uy, uz, item, iqx, iqy, iqz
         double ux = a0[idx], uy = a1[idx], uz = D == 3 ? a2[idx] : 0.0;
         // scalar order: item + 3*(ux*iqx + uy*iqy + uz*iqz)  (adjointadvection.h:54-68)

@@ -19,15 +19,16 @@ using namespace plb;
 
 namespace plb {
 #define PL_ML(D, M) extern const ModelLaunch model_launch_##D##_##M;
-PL_ML(2, 1) PL_ML(2, 2) PL_ML(2, 3) PL_ML(2, 4) PL_ML(2, 5) PL_ML(2, 6) PL_ML(2, 7) PL_ML(2, 8) PL_ML(2, 9) PL_ML(2, 10) PL_ML(2, 11) PL_ML(2, 12)
+PL_ML(2, 1) PL_ML(2, 2) PL_ML(2, 3) PL_ML(2, 4) PL_ML(2, 5) PL_ML(2, 6) PL_ML(2, 7) PL_ML(2, 8) PL_ML(2, 9) PL_ML(2, 10) PL_ML(2, 11) PL_ML(2, 12) PL_ML(2, 13) PL_ML(2, 14)
 PL_ML(3, 1) PL_ML(3, 2) PL_ML(3, 3) PL_ML(3, 4) PL_ML(3, 5) PL_ML(3, 6) PL_ML(3, 7) PL_ML(3, 8) PL_ML(3, 9) PL_ML(3, 10) PL_ML(3, 11)
 #undef PL_ML
 const ModelLaunch* model_launch(int D, int M) {
-    static const ModelLaunch* const t2[13] = {nullptr, &model_launch_2_1, &model_launch_2_2, &model_launch_2_3, &model_launch_2_4, &model_launch_2_5, &model_launch_2_6,
-                                              &model_launch_2_7, &model_launch_2_8, &model_launch_2_9, &model_launch_2_10, &model_launch_2_11, &model_launch_2_12};
-    static const ModelLaunch* const t3[13] = {nullptr, &model_launch_3_1, &model_launch_3_2, &model_launch_3_3, &model_launch_3_4, &model_launch_3_5, &model_launch_3_6,
-                                              &model_launch_3_7, &model_launch_3_8, &model_launch_3_9, &model_launch_3_10, &model_launch_3_11, nullptr};
-    if (M < 1 || M > 12) return nullptr;
+    static const ModelLaunch* const t2[15] = {nullptr, &model_launch_2_1, &model_launch_2_2, &model_launch_2_3, &model_launch_2_4, &model_launch_2_5, &model_launch_2_6,
+                                              &model_launch_2_7, &model_launch_2_8, &model_launch_2_9, &model_launch_2_10, &model_launch_2_11, &model_launch_2_12,
+                                              &model_launch_2_13, &model_launch_2_14};
+    static const ModelLaunch* const t3[15] = {nullptr, &model_launch_3_1, &model_launch_3_2, &model_launch_3_3, &model_launch_3_4, &model_launch_3_5, &model_launch_3_6,
+                                              &model_launch_3_7, &model_launch_3_8, &model_launch_3_9, &model_launch_3_10, &model_launch_3_11, nullptr, nullptr, nullptr};
+    if (M < 1 || M > 14) return nullptr;
     return D == 2 ? t2[M] : (D == 3 ? t3[M] : nullptr);
 }
 }  // namespace plb
@@ -751,6 +752,10 @@ int make_closure_args(const pl_lattice* l, const pl_lattice* other, const pl_bc*
     const bool vel = A.ux && A.uy && (!d3 || A.uz);
     switch (bc->type) {
         case PL_BC_BOUNCE: case PL_BC_IBOUNCE: case PL_BC_ANS_ISET_RHO: break;
+        case PL_BC_NSIN_SET_U: case PL_BC_NSIN_SET_RHO:
+            if (d3) return fail(PL_ERR_UNSUPPORTED, "closure: the reference's NSin closures exist for D2Q9 only (nsincompressible.h:46-154)");
+            if (!bc->v0 || !bc->v1) return fail(PL_ERR_ARG, "closure: NSin SetU / SetRho need two plane values (ux,uy / rho,us)");
+            break;
         case PL_BC_NS_SET_U: case PL_BC_ANS_ISET_U:
             if (!bc->v0 || !bc->v1 || (d3 && !bc->v2)) return fail(PL_ERR_ARG, "closure: SetU needs ux,uy(,uz) plane values");
             break;
@@ -797,12 +802,14 @@ int do_bc(pl_lattice* l, pl_lattice* other, const pl_bc* bc, const pl_bc_aux* au
 
 // pl_collide_args -> kernel argument block
 int make_params(const pl_lattice* f, const pl_lattice* g, const pl_collide_args* a, CollideParams& P, unsigned& flags) {
-    static const unsigned FLAGS[13] = {0, ModelFlags<1>::v, ModelFlags<2>::v, ModelFlags<3>::v, ModelFlags<4>::v, ModelFlags<5>::v, ModelFlags<6>::v,
-                                       ModelFlags<7>::v, ModelFlags<8>::v, ModelFlags<9>::v, ModelFlags<10>::v, ModelFlags<11>::v, ModelFlags<12>::v};
+    static const unsigned FLAGS[15] = {0, ModelFlags<1>::v, ModelFlags<2>::v, ModelFlags<3>::v, ModelFlags<4>::v, ModelFlags<5>::v, ModelFlags<6>::v,
+                                       ModelFlags<7>::v, ModelFlags<8>::v, ModelFlags<9>::v, ModelFlags<10>::v, ModelFlags<11>::v, ModelFlags<12>::v,
+                                       ModelFlags<13>::v, ModelFlags<14>::v};
     if (!f || !a) return fail(PL_ERR_ARG, "pl_collide: null");
-    if (a->model < 1 || a->model > 12) return fail(PL_ERR_ARG, "pl_collide: unknown model");
+    if (a->model < 1 || a->model > 14) return fail(PL_ERR_ARG, "pl_collide: unknown model");
     flags = FLAGS[a->model];
     const bool d3 = f->kind == PL_D3Q15;
+    if ((flags & F_INCOMP) && d3) return fail(PL_ERR_UNSUPPORTED, "pl_collide: the reference's NSin equations exist for D2Q9 only (nsincompressible.h)");
     if (a->model == PL_AAD_NAT_CONV_MASSFLOW && d3)
         return fail(PL_ERR_UNSUPPORTED, "pl_collide: the reference's D3Q15 NaturalConvectionMassFlow does not compile (adjointadvection_avx.h:1161); D2Q9 only");
     if ((flags & F_G) && (!g || g->kind != f->kind || g->g.nxyz != f->g.nxyz)) return fail(PL_ERR_ARG, "pl_collide: model needs a thermal lattice of the same shape");
@@ -915,9 +922,13 @@ int pl_smooth_corner_at(pl_lattice* l, int gi, int gj, int gk, int dx, int dy, i
 }
 
 pl_bc* pl_bc_create(pl_lattice* l, int type, int axis, int coord, int dir, const uint8_t* mask, const double* v0, const double* v1, const double* v2) {
-    if (!l || type < 1 || type > 11 || (dir != -1 && dir != 1) || axis < 0 || axis >= l->kind) { fail(PL_ERR_ARG, "pl_bc_create: bad arguments"); return nullptr; }
+    if (!l || type < 1 || type > 13 || (dir != -1 && dir != 1) || axis < 0 || axis >= l->kind) { fail(PL_ERR_ARG, "pl_bc_create: bad arguments"); return nullptr; }
     if (type == PL_BC_AAD_ISET_RHO && l->kind == PL_D3Q15) {
         fail(PL_ERR_UNSUPPORTED, "pl_bc_create: the reference's D3Q15 AAD::iBoundaryConditionSetRho does not compile (adjointadvection.h:583); D2Q9 only");
+        return nullptr;
+    }
+    if ((type == PL_BC_NSIN_SET_U || type == PL_BC_NSIN_SET_RHO) && l->kind == PL_D3Q15) {
+        fail(PL_ERR_UNSUPPORTED, "pl_bc_create: the reference's NSin closures exist for D2Q9 only (nsincompressible.h:46-154)");
         return nullptr;
     }
     pl_bc* bc = new pl_bc();
@@ -1021,15 +1032,16 @@ int pl_snapshot_from_host(const pl_lattice* l, const double* in_host, double* sn
 }
 
 int pl_initial_condition(pl_lattice* l, int family, const double* const* a, int na) {
-    if (!l || !a || family < 1 || family > 4) return fail(PL_ERR_ARG, "pl_initial_condition: bad arguments");
-    const int want = family <= 2 ? 4 : 7;
+    if (!l || !a || family < 1 || family > 5) return fail(PL_ERR_ARG, "pl_initial_condition: bad arguments");
+    if (family == 5 && l->kind == PL_D3Q15) return fail(PL_ERR_UNSUPPORTED, "pl_initial_condition: the reference's NSin equations exist for D2Q9 only");
+    const int want = (family <= 2 || family == 5) ? 4 : 7;
     if (na < want) return fail(PL_ERR_ARG, "pl_initial_condition: too few arrays");
     const double* p[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int n = 0; n < want; ++n) p[n] = a[n];
     const bool d3 = l->kind == PL_D3Q15;
     // z-components may be null on D2Q9
     for (int n = 0; n < want; ++n) {
-        bool zslot = family <= 2 ? n == 3 : (n == 2 || n == 6);
+        bool zslot = (family <= 2 || family == 5) ? n == 3 : (n == 2 || n == 6);
         if (!p[n] && !(zslot && !d3)) return fail(PL_ERR_ARG, "pl_initial_condition: null array");
     }
     l->rep = 0;      // every population is overwritten: whatever layout the buffer was in is irrelevant
@@ -1494,7 +1506,8 @@ int pl_plan_finalize(pl_plan* p) {
             for (size_t e = 0; e < prog[0].size() && ok; ++e) {
                 if (!((hx[i] >> e) & 1ull)) continue;
                 const ClosureArgs& A = prog[0][e];
-                const bool fwd = A.type == BC_BOUNCE || A.type == BC_NS_SET_U || A.type == BC_NS_SET_RHO || A.type == BC_AD_SET_T || A.type == BC_AD_SET_Q;
+                const bool fwd = A.type == BC_BOUNCE || A.type == BC_NS_SET_U || A.type == BC_NS_SET_RHO || A.type == BC_AD_SET_T || A.type == BC_AD_SET_Q ||
+                                 A.type == BC_NSIN_SET_U || A.type == BC_NSIN_SET_RHO;
                 ok = A.pl.axis == 0 && A.pl.dir == (i == 0 ? -1 : 1) && fwd == (p->inverse == 0);
             }
             ghost[i] = ok;
@@ -1528,7 +1541,7 @@ int pl_plan_finalize(pl_plan* p) {
             switch (A.type) {
                 case BC_BOUNCE: own = set_of(dir, true); break;
                 case BC_IBOUNCE: own = set_of(-dir, true); break;
-                case BC_NS_SET_U: case BC_NS_SET_RHO: case BC_AD_SET_T: own = set_of(-dir, false); break;
+                case BC_NS_SET_U: case BC_NS_SET_RHO: case BC_AD_SET_T: case BC_NSIN_SET_U: case BC_NSIN_SET_RHO: own = set_of(-dir, false); break;
                 case BC_AD_SET_Q: own = set_of(dir, true); break;
                 case BC_AAD_ISET_RHO: own = set_of(-dir, true); other = own; break;
                 default: own = set_of(-dir, true); break;      // ANS iSetU/iSetRho, AAD iSetT/iSetQ: the known set K

@@ -837,7 +837,7 @@ int plh_collide(pl_lattice* f, pl_lattice* g, const pl_collide_args* h) {
     memset(&d, 0, sizeof(d));
     d.model = h->model; d.issave = h->issave; d.viscosity = h->viscosity; d.diffusivity_const = h->diffusivity_const;
     d.gx = h->gx; d.gy = h->gy; d.gz = h->gz; d.tem0 = h->tem0;
-    const bool adj = h->model >= PL_ANS_BRINKMAN, save = h->issave != 0;
+    const bool adj = h->model >= PL_ANS_BRINKMAN && h->model <= PL_AAD_NAT_CONV_MASSFLOW, save = h->issave != 0;
     g_staged.clear();
 #define RD(field) if ((rc = xlate(h->field, n, true, false, (double**)&d.field))) return rc
 #define WR(field) if ((rc = xlate(h->field, n, false, save, (double**)&d.field))) return rc

@@ -91,6 +91,32 @@ class CudaOps:
         fns = [l.dense(v0), l.dense(v1)] + ([l.dense(v2)] if self.dim == 3 else [])
         pl.NS.BoundaryConditionSetRho(l.p, *fns, l.dense(mask))
 
+    # NSin (D2Q9 only)
+    def nsin_init(self, l, rho, ux, uy, uz):
+        pl.NSin.InitialCondition(l.p, up(rho), up(ux), up(uy))
+
+    def nsin_macro_collide(self, l, rho, ux, uy, uz, nu, issave):
+        host = [rho, ux, uy]
+        dev = self._macros(host)
+        pl.NSin.MacroCollide(l.p, *dev, nu, bool(issave))
+        if issave:
+            for h, d in zip(host, dev):
+                d.to_host(h)
+
+    def nsin_macro_brinkman_collide(self, l, rho, ux, uy, uz, nu, alpha, issave):
+        host = [rho, ux, uy]
+        dev = self._macros(host)
+        pl.NSin.MacroBrinkmanCollide(l.p, *dev, nu, up(alpha), bool(issave))
+        if issave:
+            for h, d in zip(host, dev):
+                d.to_host(h)
+
+    def nsin_bc_set_u(self, l, uxg, uyg, uzg, mask):
+        pl.NSin.BoundaryConditionSetU(l.p, l.dense(uxg), l.dense(uyg), l.dense(mask))
+
+    def nsin_bc_set_rho(self, l, v0, v1, v2, mask):
+        pl.NSin.BoundaryConditionSetRho(l.p, l.dense(v0), l.dense(v1), l.dense(mask))
+
     # utilities
     def residual3(self, ux, uy, uz, uxp, uyp, uzp, n):
         return pl.Residual(up(ux), up(uy), up(uz), up(uxp), up(uyp), up(uzp), n)

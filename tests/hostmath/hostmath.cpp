@@ -104,7 +104,7 @@ template <int D, int M> void collide_all(Lat* f, Lat* g, CollideParams P, double
 }
 template <int M> void collide(Lat* f, Lat* g, const CollideParams& P, double* snap_ref) {
     if (f->kind == 2) collide_all<2, M>(f, g, P, snap_ref);
-    else if constexpr (M != 12) collide_all<3, M>(f, g, P, snap_ref);
+    else if constexpr (M < 12) collide_all<3, M>(f, g, P, snap_ref);
 }
 CollideParams params(const Lat* f, double nu, double kconst, double gx, double gy, double gz, double tem0, int issave) {
     CollideParams P;
@@ -186,6 +186,19 @@ void hm_ns_macro_collide(void* h, double* rho, double* ux, double* uy, double* u
 void hm_ns_macro_brinkman_collide(void* h, double* rho, double* ux, double* uy, double* uz, double nu, const double* alpha, int issave) {
     CollideParams P = params(L(h), nu, 0, 0, 0, 0, 0, issave); SETM(P) P.alpha = alpha; collide<2>(L(h), nullptr, P, nullptr);
 }
+// NSin (D2Q9 only; models 13 / 14, closures 12 / 13, InitialCondition family 5)
+void hm_nsin_macro_collide(void* h, double* rho, double* ux, double* uy, double* uz, double nu, int issave) {
+    CollideParams P = params(L(h), nu, 0, 0, 0, 0, 0, issave); SETM(P) collide<13>(L(h), nullptr, P, nullptr);
+}
+void hm_nsin_macro_brinkman_collide(void* h, double* rho, double* ux, double* uy, double* uz, double nu, const double* alpha, int issave) {
+    CollideParams P = params(L(h), nu, 0, 0, 0, 0, 0, issave); SETM(P) P.alpha = alpha; collide<14>(L(h), nullptr, P, nullptr);
+}
+void hm_nsin_bc_set_u(void* h, const double* ux, const double* uy, const double* uz, const int* mask) {
+    FaceJob J{}; J.type = BC_NSIN_SET_U; J.mask = mask; J.v0 = ux; J.v1 = uy; faces(L(h), nullptr, J);
+}
+void hm_nsin_bc_set_rho(void* h, const double* v0, const double* v1, const double* v2, const int* mask) {
+    FaceJob J{}; J.type = BC_NSIN_SET_RHO; J.mask = mask; J.v0 = v0; J.v1 = v1; faces(L(h), nullptr, J);
+}
 #define SETQ(P) P.tem = tem; P.qx = qx; P.qy = qy; P.qz = qz;
 void hm_ad_macro_collide_force_convection(void* f, double* rho, double* ux, double* uy, double* uz, double nu,
         void* g, double* tem, double* qx, double* qy, double* qz, double diffusivity, int issave) {
@@ -244,6 +257,10 @@ void hm_ns_init(void* h, const double* rho, const double* ux, const double* uy, 
         if (l->kind == 2) { double e[9]; ns_eq_sc<2>(e, rho[i], ux[i], uy[i], 0.0); store<2>(l, i, e); }
         else { double e[15]; ns_eq_sc<3>(e, rho[i], ux[i], uy[i], uz[i]); store<3>(l, i, e); }
     }
+}
+void hm_nsin_init(void* h, const double* rho, const double* ux, const double* uy, const double* uz) {
+    Lat* l = L(h);
+    for (long long i = 0; i < l->nxyz; ++i) { double e[9]; nsin_eq<2>(e, rho[i], ux[i], uy[i], 0.0); store<2>(l, i, e); }
 }
 void hm_ad_init(void* h, const double* tem, const double* ux, const double* uy, const double* uz) {
     Lat* l = L(h);

@@ -4,7 +4,7 @@ tests/cuda_ops.py).  A scenario takes a backend and returns a list of (name, arr
 all arrays are equal bit for bit.  Inputs are seeded numpy draws; nothing is read from disk."""
 import numpy as np
 
-from helpers import i32, random_field, random_pops
+from helpers import gcoords, i32, random_field, random_pops
 
 NU = 0.07
 
@@ -198,6 +198,59 @@ def inits(be, dim, size, seed, peid=0, m=(1, 1, 1)):
             be.aad_init(l, F.ux, F.uy, F.uz, F.item, F.iqx, F.iqy, F.iqz)
         res += pops(fam, l)
         l.free()
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NSin (src/equation/nsincompressible.h; D2Q9 only): InitialCondition, both collides with and without issave, SetU and SetRho on all
+# four edges with random masks and values, and a short loop collide - Stream - bounce - SetU - SetRho - SmoothCorner
+def nsin(be, size, seed, steps=6):
+    lx, ly = size[0], size[1]
+    l = be.lattice(lx, ly, 1)
+    n = l.nxyz
+    F = Fields(n, seed)
+    res = []
+    be.nsin_init(l, F.rho, F.ux, F.uy, F.uz)
+    res += pops("init", l)
+    l.set(*random_pops(n, l.nc, seed))
+    for k, (issave, nu, alpha) in enumerate(((1, NU, None), (0, 0.021, None), (1, 0.1, F.alpha), (0, 0.03, F.alpha))):
+        rho, ux, uy, uz = out(n, 4)
+        if alpha is None:
+            be.nsin_macro_collide(l, rho, ux, uy, uz, nu, issave)
+        else:
+            be.nsin_macro_brinkman_collide(l, rho, ux, uy, uz, nu, alpha, issave)
+        if issave:
+            res += [(f"rho{k}", rho.copy()), (f"ux{k}", ux.copy()), (f"uy{k}", uy.copy())]
+        res += pops(f"c{k}", l)
+    Gn = lx*ly
+    rs = np.random.RandomState(seed + 7)
+    mask = i32(rs.randint(0, 2, size=Gn))
+    v = [random_field(Gn, seed*10 + d, -0.1, 0.1) for d in range(2)]
+    rg = random_field(Gn, seed*10 + 3, 0.95, 1.05)
+    be.nsin_bc_set_u(l, v[0], v[1], None, mask)
+    res += pops("setu", l)
+    be.nsin_bc_set_rho(l, rg, v[1], None, mask)
+    res += pops("setrho", l)
+    if steps <= 0:      # backends without Stream / SmoothCorner (tests/hostmath: site math only)
+        l.free()
+        return res
+    # a short driver-style loop: lid-driven box with a pressure outlet patch on ymin
+    i, j, _ = gcoords(lx, ly, 1)
+    wall = i32(np.where((i == 0) | (i == lx - 1) | ((j == 0) & (i < lx//2)), 1, 0))
+    lid = i32(j == ly - 1)
+    outlet = i32((j == 0) & (i >= lx//2))
+    uxg, uyg = np.full(Gn, 0.05), np.zeros(Gn)
+    rho, ux, uy, uz = np.ones(n), np.zeros(n), np.zeros(n), np.zeros(n)
+    be.nsin_init(l, rho, ux, uy, uz)
+    for _ in range(steps):
+        be.nsin_macro_brinkman_collide(l, rho, ux, uy, uz, 0.1, F.alpha*0.01, 1)
+        be.stream(l)
+        be.bc(l, wall, 0)
+        be.nsin_bc_set_u(l, uxg, uyg, None, lid)
+        be.nsin_bc_set_rho(l, np.ones(Gn), uyg, None, outlet)
+        be.smooth_corner(l)
+    res += [("loop.rho", rho.copy()), ("loop.ux", ux.copy()), ("loop.uy", uy.copy())] + pops("loop", l)
+    l.free()
     return res
 
 

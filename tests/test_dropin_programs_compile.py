@@ -14,6 +14,7 @@ PROGRAMS = [("heatsink_dump.cpp", []), ("transient_dump.cpp", ["-DTRANSIENT_DIM=
             ("transient_dump.cpp", ["-DTRANSIENT_DIM=2", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("ncpump_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]), ("filter_dump.cpp", []),
             ("ncpump_periodic_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
+            ("nsin_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("nsopt_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")])]
 
 

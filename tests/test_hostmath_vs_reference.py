@@ -62,3 +62,15 @@ def test_closures_on_decomposed_blocks(dim):
     for peid in range(m[0]*m[1]*m[2]):
         for kind in ("ad_set_t", "ad_set_q_field", "aad_iset_q"):
             S.assert_same(S.closure(ref, dim, kind, size, 20 + peid, peid, m), S.closure(hm, dim, kind, size, 20 + peid, peid, m), f"{kind} pe{peid}")
+
+
+def test_nsin_site_math():
+    """NSin (nsincompressible.h, D2Q9 only): collide models 13 / 14, closures 12 / 13 and InitialCondition family 5 of the product code
+    against the reference headers"""
+    if 2 not in DIMS:
+        pytest.skip("oracle/_ref (2-D) not built")
+    ref, hm = both(2)
+    if not ref.has("nsin_macro_collide"):
+        pytest.skip("oracle/_ref predates the NSin entry points: make -C oracle ref")
+    for n, size in enumerate(SIZES[2] + [(23, 17, 1)]):
+        S.assert_same(S.nsin(ref, size, 4 + n, steps=0), S.nsin(hm, size, 4 + n, steps=0), f"NSin {size}")

@@ -244,3 +244,15 @@ def test_heatsink_iteration_sequence(dim):
     assert sorted(a) == sorted(b)
     for k in a:
         assert same(a[k], b[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NSin (src/equation/nsincompressible.h, D2Q9 only): the C restatement against the reference headers
+@pytest.mark.skipif(not O.have_ref(2), reason="oracle/_ref not built (no /root/reference here)")
+@pytest.mark.parametrize("size", [(8, 6, 1), (7, 5, 1), (9, 6, 1), (11, 5, 1), (23, 17, 1)])
+def test_nsin_oracle_equals_reference(size):
+    import scenarios as S
+    ref, orc = O.Backend("ref", 2), O.Backend("orc", 2)
+    if not ref.has("nsin_macro_collide"):
+        pytest.skip("oracle/_ref predates the NSin entry points: make -C oracle ref")
+    S.assert_same(S.nsin(ref, size, 4), S.nsin(orc, size, 4), f"NSin {size}")
