@@ -108,6 +108,18 @@ int pl_lattice_set_host(pl_lattice*, const double* f0_host, const double* f_host
 int pl_lattice_get_host(pl_lattice*, double* f0_host, double* f_host);
 /* Phase of the populations: 1 = pre-collision (after InitialCondition / Stream and its closures), 0 = just collided. */
 int pl_lattice_streamed(const pl_lattice*);
+/* Device-side checkpoint of a lattice's populations (with their layout and phase): the building block of checkpoint-recompute
+ * for transient adjoints.  The reference's transient drivers keep the macroscopic fields and the thermal snapshot of EVERY time
+ * step (production/heatsink3D_transient.cpp:50-57: 23 doubles per site and step) and walk them backwards (:190-215); with a
+ * checkpoint of both lattices every K steps the states in between can be recomputed segment by segment during the adjoint loop
+ * (panslbm2_b200/transient.py), which holds nt/K + K states instead of nt.  save / restore are stream-ordered device copies;
+ * restore invalidates what plans and the halo exchange derived from the old content.  On a decomposed lattice every rank must
+ * restore at the same point of its loop. */
+typedef struct pl_checkpoint pl_checkpoint;
+pl_checkpoint* pl_checkpoint_create(const pl_lattice*);
+int pl_checkpoint_save(pl_checkpoint*, const pl_lattice*);
+int pl_checkpoint_restore(const pl_checkpoint*, pl_lattice*);
+int pl_checkpoint_destroy(pl_checkpoint*);
 /* Device SoA view of the current populations: c-th plane at base + c*pitch (pitch in doubles). */
 int pl_lattice_device_view(pl_lattice*, double** base, size_t* pitch);
 /* Population memory.  A lattice owns ONE buffer of nc*pitch doubles (the reference keeps two, f and the hidden fnext, d3q15.h:41-45,

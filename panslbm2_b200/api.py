@@ -928,6 +928,12 @@ class StepPlan:
     def parity(self):
         return _lib.lib().pl_plan_parity(self._h)
 
+    def set_parity(self, parity):
+        """after the populations were put back to an earlier point of the loop (transient.Checkpoint.restore): the argument set that
+        point belongs to (the value `parity` had there)"""
+        check(_lib.lib().pl_plan_set_parity(self._h, int(parity)))
+        return self
+
     def free(self):
         if getattr(self, "_h", None):
             _lib.lib().pl_plan_destroy(self._h)

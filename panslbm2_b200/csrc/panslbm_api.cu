@@ -606,6 +606,53 @@ int pl_lattice_get_host(pl_lattice* l, double* f0, double* f) {
     return PL_OK;
 }
 int pl_lattice_streamed(const pl_lattice* l) { return l ? l->streamed : 0; }
+
+// ---- population checkpoints (checkpoint-recompute for transient adjoints) ----
+struct pl_checkpoint {
+    double* buf = nullptr;
+    size_t bytes = 0;
+    int kind = 0;
+    long long nxyz = 0;
+    int rep = 0, rep_inverse = 0, streamed = 1;
+    bool valid = false;
+};
+pl_checkpoint* pl_checkpoint_create(const pl_lattice* l) {
+    if (!l) { fail(PL_ERR_ARG, "pl_checkpoint_create: null"); return nullptr; }
+    pl_checkpoint* c = new pl_checkpoint();
+    c->bytes = l->bytes(); c->kind = l->kind; c->nxyz = l->g.nxyz;
+    if (cudaMalloc(&c->buf, c->bytes) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        fail(PL_ERR_CUDA, "pl_checkpoint_create: out of device memory");
+        return nullptr;
+    }
+    return c;
+}
+int pl_checkpoint_destroy(pl_checkpoint* c) {
+    if (!c) return PL_OK;
+    cudaStreamSynchronize(g_stream);
+    cudaFree(c->buf);
+    delete c;
+    return PL_OK;
+}
+// the buffer is copied as it is — in whichever layout the last pass left it — together with the layout and phase flags
+int pl_checkpoint_save(pl_checkpoint* c, const pl_lattice* l) {
+    if (!c || !l) return fail(PL_ERR_ARG, "pl_checkpoint_save: null");
+    if (c->kind != l->kind || c->nxyz != l->g.nxyz || c->bytes != l->bytes()) return fail(PL_ERR_ARG, "pl_checkpoint_save: the checkpoint was created for a lattice of another shape");
+    CU(cudaMemcpyAsync(c->buf, l->buf, c->bytes, cudaMemcpyDeviceToDevice, g_stream));
+    c->rep = l->rep; c->rep_inverse = l->rep_inverse; c->streamed = l->streamed;
+    c->valid = true;
+    return PL_OK;
+}
+int pl_checkpoint_restore(const pl_checkpoint* c, pl_lattice* l) {
+    if (!c || !l) return fail(PL_ERR_ARG, "pl_checkpoint_restore: null");
+    if (!c->valid) return fail(PL_ERR_ARG, "pl_checkpoint_restore: nothing has been saved into this checkpoint");
+    if (c->kind != l->kind || c->nxyz != l->g.nxyz || c->bytes != l->bytes()) return fail(PL_ERR_ARG, "pl_checkpoint_restore: the checkpoint belongs to a lattice of another shape");
+    CU(cudaMemcpyAsync(l->buf, c->buf, c->bytes, cudaMemcpyDeviceToDevice, g_stream));
+    l->rep = c->rep; l->rep_inverse = c->rep_inverse; l->streamed = c->streamed;
+    halo_touch(l);      // new content: plans refill their wall buffers, a decomposed block packs and exchanges again
+    return PL_OK;
+}
 int pl_memory_stats(uint64_t* out4) {
     if (!out4) return fail(PL_ERR_ARG, "pl_memory_stats: null");
     out4[0] = g_lattice_bytes; out4[1] = g_spares.held(); out4[2] = g_spares.borrows; out4[3] = g_conversions;
