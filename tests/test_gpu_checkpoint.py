@@ -72,6 +72,10 @@ def check(tag, res):
     assert len(keys) >= 25
     for k in keys:
         a = res[k] + 0.0
+        if k == "extra":        # the objective: a sum over the heat patch of every step, reduced on the device (other summation order)
+            want = z[f"{tag}/extra/s5"]
+            assert abs(a[0] - want[0]) <= 1e-12*abs(want[0]), (a, want)
+            continue
         assert np.array_equal(a[::5], z[f"{tag}/{k}/s5"]), f"{tag}: {k} differs from the reference fixture (max abs {np.max(np.abs(a[::5] - z[f'{tag}/{k}/s5'])):.3e})"
         assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() == bytes(z[f"{tag}/{k}/sha"]), f"{tag}: {k} digest"
 

@@ -55,7 +55,14 @@ def run_transient_cuda(size, nt, every, stats=None):
     res = {}
     tq = [1, nt//2, nt - 1]
 
+    import math
+    Lp = int(math.ceil(p["L"]))
+    objective = [0.0]
+
     def sample(t, s):
+        # objective: heat-patch temperature summed over every stored step (heatsink3D_transient.cpp:221-231) — taken on the device
+        # while the state is resident (pl_reduce_box_sum); the reference sums the same values on the host in another order
+        objective[0] += pl.box_sum(g, s["tem"], 0, Lp, 0, 1, 0, Lp)
         for q, tt in enumerate(tq):
             if tt == t:
                 for k in ("rho", "ux", "uz", "tem", "qy"):
@@ -93,6 +100,7 @@ def run_transient_cuda(size, nt, every, stats=None):
     aplan.advance(0, end_streamed=True)
     res.update({k: A[k].to_host() for k in H.ADJ})
     res["dfdss"] = dfdss.to_host()
+    res["extra"] = np.array([objective[0]])
     res["f.f0"], res["f.f"] = af.get_populations()
     res["g.f0"], res["g.f"] = ag.get_populations()
     if stats is not None:
