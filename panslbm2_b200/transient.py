@@ -51,10 +51,12 @@ class CheckpointSchedule:
     def forward_ops(self):
         """("save", c): checkpoint the populations in front of segment c (after step c*every; c = 0: after InitialCondition);
         ("step", t): forward step t"""
-        ops = [("save", 0)]
+        last = self.segment(self.T)       # its ring states are still there when the adjoint loop starts: never recomputed
+        need = lambda c: self.every >= 2 and c < last
+        ops = [("save", 0)] if need(0) else []
         for t in range(1, self.T + 1):
             ops.append(("step", t))
-            if t % self.every == 0 and t < self.T:
+            if t % self.every == 0 and need(t//self.every):
                 ops.append(("save", t//self.every))
         return ops
 

@@ -65,5 +65,8 @@ def test_memory_and_recompute_bounds():
     assert rec == 199 - 199//16 - (199 % 16)            # every ring state outside the last segment once
     s, rec = simulate(199, 1)
     assert s.n_ring == 0 and rec == 0                   # every = 1 is the store-all of the reference
+    assert not [op for op in s.forward_ops() if op[0] == "save"]          # ... and needs no population checkpoint
+    s = CheckpointSchedule(199, 16)
+    assert [v for op, v in s.forward_ops() if op == "save"] == list(range(12))      # the last segment is never recomputed
     s, rec = simulate(50, 400)
     assert s.n_perm == 1 and s.n_ring == 50 and rec == 0
