@@ -99,6 +99,8 @@ class HeatsinkSweep:
         class _L:
             nx, ny, nz, offx, offy, offz = f.nx, f.ny, f.nz, f.offsetx, f.offsety, f.offsetz
         self.host_design = [np.ascontiguousarray(a) for a in H.design_fields(p, *H.local_coords(_L))]   # alpha, kappa, dads, dkds
+        self.host_ss = np.ascontiguousarray(H.design_variable(p, *H.local_coords(_L)), dtype=np.float64)   # the (filtered) design they come from
+        self.ss = None
         self.alpha, self.kappa, self.dads, self.dkds = [pl.DeviceArray(n) for _ in range(4)]
         names = H.FWD + H.ADJ + ["uxp", "uyp", "uzp", "qxp", "qyp", "qzp", "iuxp", "iuyp", "iuzp", "iqxp", "iqyp", "iqzp"]
         self.A = {k: pl.DeviceArray(n, 0.0) for k in names}
@@ -115,6 +117,19 @@ class HeatsinkSweep:
         src = pinned if pinned is not None else self.host_design
         for d, h in zip((self.alpha, self.kappa, self.dads, self.dkds), src):
             d.upload(h) if pinned is None else self._up(d, h)
+
+    def design_map(self):
+        """alpha, kappa, dads, dkds from the design on the device (heatsink3D.cpp:114-119: pl_design_map, bit-identical to the host loop)"""
+        from panslbm2_b200 import _lib
+        p = self.p
+        _lib.check(_lib.lib().pl_design_map(self.ss.ptr, self.ss.n, float(p["diff_fluid"]), float(p["diff_solid"]), float(p["qg"]),
+                                            float(p["alphamax"]/float(p["ly"] - 1)), float(p["qf"]), self.kappa.ptr, self.alpha.ptr, self.dkds.ptr, self.dads.ptr))
+
+    def objective(self):
+        """mean temperature of the heat patch (heatsink3D.cpp:227-240) reduced on the device: 8 bytes come back"""
+        import math
+        Lp = int(math.ceil(self.p["L"]))
+        return self.api.box_sum(self.g, self.A["tem"], 0, Lp, 0, 1, 0, Lp if self.dim == 3 else 1)/float(Lp*(Lp if self.dim == 3 else 1))
 
     def _up(self, d, t):
         from panslbm2_b200 import _lib
@@ -471,30 +486,35 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers --------------------------------------------------
     # one optimisation-iteration shape (heatsink3D.cpp:114-246): design fields arrive from the host, the loops run, the
     # sensitivity and the temperature field go back to the host.
-    hdesign = [torch.from_numpy(a).pin_memory() for a in sw.host_design]
-    hout = [torch.empty(N, dtype=torch.float64).pin_memory() for _ in range(2)]
+    # The design variable arrives from the host (one field), its maps alpha, kappa, dalpha/ds, dkappa/ds are evaluated on the device
+    # (pl_design_map = heatsink3D.cpp:114-119, bit-identical to the host loop); the objective is reduced on the device
+    # (pl_reduce_box_sum = :227-240) and the sensitivity field goes back to the host.
+    import numpy as np
+    hss = torch.from_numpy(sw.host_ss).pin_memory()
+    hout = torch.empty(N, dtype=torch.float64).pin_memory()
+    sw.ss = pl.DeviceArray(N)
+    want = [a.to_host() for a in (sw.alpha, sw.kappa, sw.dads, sw.dkds)]      # what the host formulas gave (uploaded for the device-resident runs)
     sw.sensitivity()        # warm-up: bakes the heat-source planes once, as the first optimisation iteration of a run does
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    # alpha, kappa gate the first collide; dads, dkds are only read by the sensitivity: their copies run beside the loops
-    sw.alpha.upload_async(hdesign[0].data_ptr()); sw.kappa.upload_async(hdesign[1].data_ptr())
-    sw.init_forward()       # InitialCondition needs neither: it runs beside the first two copies
+    sw.ss.upload_async(hss.data_ptr())
+    sw.init_forward()       # InitialCondition does not need the design: it runs beside the copy
     api.copy_fence()
-    sw.dads.upload_async(hdesign[2].data_ptr()); sw.dkds.upload_async(hdesign[3].data_ptr())
+    sw.design_map()
     sw.fplan.advance(K, end_streamed=True, save_last=save_last)
-    sw.A["tem"].download_async(hout[1].data_ptr())      # final after the forward loop; the adjoint loop only reads it
+    objective = sw.objective()
     sw.init_adjoint()
     sw.aplan.advance(K, end_streamed=True, save_last=save_last)
-    api.copy_fence()
     sw.sensitivity()
-    sw.dfdss.download_async(hout[0].data_ptr())
+    sw.dfdss.download_async(hout.data_ptr())
     api.copy_wait()
     f1.record()
     barrier()
     e2e_ms = maxms(f0.elapsed_time(f1))
     e2e_value = 2*NG*K/(e2e_ms*1e-3)/1e6
-    checks = {"max_abs_dfdss": float(hout[0].abs().max()), "max_tem": float(hout[1].max())}
+    checks = {"max_abs_dfdss": float(hout.abs().max()), "objective_mean_patch_temperature": float(objective),
+              "device_design_map_equals_host_formulas": bool(all(np.array_equal(w, d.to_host()) for w, d in zip(want, (sw.alpha, sw.kappa, sw.dads, sw.dkds))))}
 
     # ---- secondary sweep: pure NS roofline case (BASELINE configs[2], test/cavityflow3D.cpp scaled) -------------
     extra = {}
@@ -550,10 +570,10 @@ def run_ours(args):
                    "library": os.path.basename(_lib.LIB_PATH)},
         "clocks": sampler.summary(),
         "sweeps": {"forward_mlups": NG*K/(fwd_ms*1e-3)/1e6, "adjoint_mlups": NG*K/(adj_ms*1e-3)/1e6, **extra},
-        "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": 4*N*8/K, "d2h_bytes_per_step": 2*N*8/K,
-                "note": "pinned host alpha,kappa -> H2D -> InitialCondition -> K forward (dads,dkds H2D beside it) -> adjoint InitialCondition -> "
-                        "K adjoint (tem D2H beside it) -> SensitivityTemperatureAtHeatSource -> D2H dfdss; copies on the library's copy stream, "
-                        "bytes amortised per step", **checks},
+        "e2e": {"value": e2e_value, "unit": "MLUPS", "h2d_bytes_per_step": N*8/K, "d2h_bytes_per_step": (N*8 + 8)/K,
+                "note": "pinned host design variable -> H2D (InitialCondition beside it) -> pl_design_map (alpha, kappa, dads, dkds on the device, "
+                        "heatsink3D.cpp:114-119) -> K forward -> objective by pl_reduce_box_sum (8 bytes D2H, :227-240) -> adjoint InitialCondition -> "
+                        "K adjoint -> SensitivityTemperatureAtHeatSource -> D2H dfdss; copies on the library's copy stream, bytes amortised per step", **checks},
         "gpu_launches": launches,
         "roofline": rf, "roofline_adjoint": ra,
     }

@@ -94,6 +94,20 @@ int pl_copy_fence(void);     /* the compute stream waits (on the device) for the
 int pl_copy_wait(void);      /* the host waits for the copies issued so far */
 int pl_array_fill(double* dev, double value, size_t n);
 
+/* Operation order.  The reference selects its arithmetic per program: with `#define _USE_AVX_DEFINES` before the includes
+ * (production/heatsink3D.cpp:2 and every other program but one) the __m256d overloads of src/equation_avx/*.h handle the first
+ * 4*(nxyz/4) sites and scalar tail code inside those files the rest; without it (production/nsopt.cpp:2) the scalar templates of
+ * src/equation/*.h handle every site.  The two differ in the association of a few sums (results agree to rounding) and in one
+ * place in what they store: the 2-D tail of NS::MacroBrinkmanCollide saves rho, u BEFORE the Brinkman force
+ * (navierstokes_avx.h:246-254), the scalar template after it (navierstokes.h:494-503).  The default here is the order of the
+ * _USE_AVX_DEFINES build; pl_set_scalar_order(1) — process-wide, before the first lattice is created; the drop-in headers call
+ * it when they are compiled without _USE_AVX_DEFINES — makes every site a scalar-order site (they all take the boundary-pass
+ * kernels: correct, bit-identical to the reference's scalar build, several times slower than the packed path).  One known
+ * exception: the reference's scalar 3-D SensitivityTemperatureAtHeatSource passes `_uz` and `_ig` to its face helpers in swapped
+ * order (adjointadvection.h:1536 vs :805) and reads out of bounds; the intended expression (= the AVX overload) is computed. */
+int pl_set_scalar_order(int on);
+int pl_scalar_order(void);
+
 /* ---- lattices: D2Q9<double> (src/particle/d2q9.h:24-158), D3Q15<double> (src/particle/d3q15.h:24-249) ---- */
 #define PL_D2Q9 2
 #define PL_D3Q15 3

@@ -22,10 +22,16 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORC_PATH = os.path.join(HERE, "liblbm_oracle.so")
 REF_PATH = {2: os.path.join(HERE, "_ref", "libpanslbm_ref2d.so"), 3: os.path.join(HERE, "_ref", "libpanslbm_ref3d.so")}
+# the same headers compiled WITHOUT _USE_AVX_DEFINES (scalar templates at every site, production/nsopt.cpp:2): Backend("ref_scalar", dim)
+REF_SCALAR_PATH = {2: os.path.join(HERE, "_ref", "libpanslbm_ref2d_scalar.so"), 3: os.path.join(HERE, "_ref", "libpanslbm_ref3d_scalar.so")}
 
 
 def have_ref(dim: int = 3) -> bool:
     return os.path.exists(REF_PATH[dim])
+
+
+def have_ref_scalar(dim: int = 3) -> bool:
+    return os.path.exists(REF_SCALAR_PATH[dim])
 
 
 def have_orc() -> bool:
@@ -61,11 +67,11 @@ class Lattice:
 
 
 class Backend:
-    """kind='orc' or 'ref'.  dim is 2 or 3 (the reference build has one library per lattice)."""
+    """kind='orc', 'ref' or 'ref_scalar'.  dim is 2 or 3 (the reference build has one library per lattice)."""
 
     def __init__(self, kind: str, dim: int = 3):
         self.kind, self.dim = kind, dim
-        path = ORC_PATH if kind == "orc" else REF_PATH[dim]
+        path = ORC_PATH if kind == "orc" else (REF_SCALAR_PATH[dim] if kind == "ref_scalar" else REF_PATH[dim])
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = C.CDLL(path)

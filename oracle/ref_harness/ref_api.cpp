@@ -17,7 +17,11 @@
 //     anonymous namespace, d2q9.h:19-22 / d3q15.h:19-22), so this file is compiled twice:
 //     -DDIM=2 -> libpanslbm_ref2d.so (D2Q9), -DDIM=3 -> libpanslbm_ref3d.so (D3Q15).
 //     For DIM 2 every *z pointer argument is ignored.
+// -DREF_SCALAR: the build of a program that leaves _USE_AVX_DEFINES out (production/nsopt.cpp:2): the scalar templates of
+// src/equation/*.h at every site -> libpanslbm_ref{2d,3d}_scalar.so (checker of pl_set_scalar_order).
+#ifndef REF_SCALAR
 #define _USE_AVX_DEFINES
+#endif
 #include <cmath>
 #include <cstring>
 #include <chrono>

@@ -66,6 +66,8 @@ _PROTOS = {
     "pl_lattice_get_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pl_lattice_device_view": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "pl_lattice_streamed": (C.c_int, [C.c_void_p]),
+    "pl_set_scalar_order": (C.c_int, [C.c_int]),
+    "pl_scalar_order": (C.c_int, []),
     "pl_checkpoint_create": (C.c_void_p, [C.c_void_p]),
     "pl_checkpoint_save": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pl_checkpoint_restore": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -804,6 +804,12 @@ class ConeFilter:
             pass
 
 
+def set_scalar_order(on=True):
+    """process-wide, before the first lattice: compute in the order of a reference build WITHOUT _USE_AVX_DEFINES (scalar templates at
+    every site, production/nsopt.cpp:2) instead of the AVX build's (include/panslbm_c.h, "Operation order")"""
+    check(_lib.lib().pl_set_scalar_order(1 if on else 0))
+
+
 def design_map(ss, diff_fluid, diff_solid, qg, alpha0, qf):
     """production/heatsink3D.cpp:114-119 on the device: filtered design -> (diffusivity, alpha, dkds, dads); alpha0 = alphamax/(ly - 1)"""
     out = [DeviceArray(ss.n) for _ in range(4)]

@@ -51,6 +51,8 @@ struct CollideParams {
     double *ip, *iux, *iuy, *iuz, *imx, *imy, *imz, *item, *iqx, *iqy, *iqz;
     double *snap;             // SoA [c][snap_pitch]
     size_t snap_pitch;
+    int scalar_build;         // the caller was built WITHOUT _USE_AVX_DEFINES: every site runs the scalar templates of src/equation/*.h
+                              // (all sites are "tail" sites, and the quirks of the tail code inside the *_avx.h files do not apply)
 };
 
 template <int D> PL_D double dot(double ax, double ay, double az, double bx, double by, double bz) {
@@ -320,8 +322,9 @@ PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Col
         fmacro();
         if constexpr (G) ad_macro<D>(g, ux, uy, uz, omegag, tem, qx, qy, qz);
         // quirk: the 2-D scalar tail of NS::MacroBrinkmanCollide stores the macros before the force (navierstokes_avx.h:246-254)
+        // (the scalar template proper stores them after the force like every other version, navierstokes.h:494-503)
         constexpr bool early = SC && D == 2 && FL == F_BRINK;
-        if constexpr (early) { if (save) { P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy; } }
+        if constexpr (early) { if (save && !P.scalar_build) { P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy; } }
         if constexpr ((FL & F_NATCONV) != 0) ad_natconv<D, SC>(f, tem, P);
         if constexpr ((FL & F_BRINK) != 0) ns_brinkman<D>(f, rho, ux, uy, uz, P.alpha[idx]);
         if constexpr ((FL & (F_NATCONV | F_BRINK)) != 0) fmacro();
@@ -331,6 +334,8 @@ PL_D void collide_site(double (&f)[LT<D>::nc], double (&g)[LT<D>::nc], const Col
             if constexpr (!early) {
                 P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy;
                 if constexpr (D == 3) P.uz[idx] = uz;
+            } else {
+                if (P.scalar_build) { P.rho[idx] = rho; P.ux[idx] = ux; P.uy[idx] = uy; }
             }
             if constexpr (G) {
                 P.tem[idx] = tem; P.qx[idx] = qx; P.qy[idx] = qy;

@@ -130,6 +130,8 @@ struct SparePool {
     // standalone Stream() every few steps keeps them (cudaMalloc / cudaFree of a 5 GB buffer inside a loop costs milliseconds)
     void inplace_pass() { if (!free_.empty() && ++streak >= 64) trim(); }
 } g_spares;
+int g_scalar_order = 0;      // pl_set_scalar_order: the caller is a build WITHOUT _USE_AVX_DEFINES (scalar templates at every site)
+inline long long packed_sites(long long nxyz) { return g_scalar_order ? 0 : 4*(nxyz/4); }
 uint64_t g_lattice_bytes = 0, g_conversions = 0;      // population buffers owned by live lattices; streamed -> natural conversions so far
 
 // grow-only device scratch for the reductions: cudaMalloc/cudaFree per call would cost milliseconds next to tens of GB of
@@ -427,6 +429,8 @@ extern "C" {
 const char* pl_last_error(void) { return g_err.c_str(); }
 int pl_in_call(void) { return g_in_call; }
 const char* pl_version(void) { return "panslbm_b200 0.1 (sm_100a, fp64, fmad=off)"; }
+int pl_set_scalar_order(int on) { g_scalar_order = on ? 1 : 0; return PL_OK; }
+int pl_scalar_order(void) { return g_scalar_order; }
 int pl_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -531,7 +535,7 @@ pl_lattice* pl_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx
     g.offz = kind == PL_D2Q9 ? 0 : (mz - l->pez > lz%mz ? l->pez*g.nz : lz - (mz - l->pez)*g.nz);
     g.nxyz = (long long)g.nx*g.ny*g.nz;
     if (g.nxyz <= 0 || g.nxyz >= (1LL << 31)) { delete l; fail(PL_ERR_ARG, "pl_lattice_create: block must hold 1..2^31-1 sites"); return nullptr; }
-    g.npacked = 4*(g.nxyz/4);
+    g.npacked = packed_sites(g.nxyz);
     g.pitch = (size_t)((g.nxyz + 15)/16*16);
     {
         cudaError_t e = cudaMalloc(&l->buf, l->bytes());
@@ -880,6 +884,7 @@ int make_params(const pl_lattice* f, const pl_lattice* g, const pl_collide_args*
     P.ip = a->ip; P.iux = a->iux; P.iuy = a->iuy; P.iuz = a->iuz; P.imx = a->imx; P.imy = a->imy; P.imz = a->imz;
     P.item = a->item; P.iqx = a->iqx; P.iqy = a->iqy; P.iqz = a->iqz;
     P.snap = (flags & F_SNAP) ? a->snapshot : nullptr; P.snap_pitch = (size_t)f->g.nxyz;
+    P.scalar_build = (f->g.npacked == 0 && g_scalar_order) ? 1 : 0;
     // argument validation: every array the selected model dereferences must be present
     auto need = [&](const void* p, const char* what) { if (!p) { g_err = std::string("pl_collide: missing array ") + what; return false; } return true; };
     bool ok = true;
@@ -1056,7 +1061,7 @@ int pl_snapshot_convert(int kind, long long nxyz, const double* in, double* out,
     if ((kind != PL_D2Q9 && kind != PL_D3Q15) || nxyz <= 0 || !in || !out) return fail(PL_ERR_ARG, "pl_snapshot_convert: bad arguments");
     Geom g;
     memset(&g, 0, sizeof(g));
-    g.nxyz = nxyz; g.npacked = 4*(nxyz/4);
+    g.nxyz = nxyz; g.npacked = packed_sites(nxyz);
     const size_t n = (size_t)nxyz*(kind == PL_D2Q9 ? 9 : 15);
     double* d = nullptr;
     CU(cudaMalloc(&d, n*sizeof(double)));

@@ -79,6 +79,10 @@ namespace b200 {
         static unsigned long long next_gen() { static unsigned long long g = 0; return ++g; }
         static std::vector<unsigned long long>& live() { static std::vector<unsigned long long> v; return v; }
         void create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz, double** f0, double** f) {
+#ifndef _USE_AVX_DEFINES
+            // this program is built like production/nsopt.cpp:2 — the reference would run its scalar templates at every site
+            pl_set_scalar_order(1);
+#endif
             h = pl_lattice_create(kind, lx, ly, lz, peid, mx, my, mz);
             if (!h) check(1, "pl_lattice_create");
             gen = next_gen();

@@ -1,9 +1,10 @@
 """Fixtures for tests/test_gpu_nsopt.py: tests/dropin/nsopt_dump.cpp (the loops of production/nsopt.cpp:82-150) built against the
 UNMODIFIED reference headers (-I/root/reference/src, README flags + -O2 -ffp-contract=off) and run on the CPU in this container,
-twice: with the AVX overloads (-DNSOPT_AVX: the operation order the drop-in computes in -> compared bit for bit) and as nsopt.cpp
-is committed, scalar templates at every site (-> compared within north_star's tolerances).
+twice: with the AVX overloads (-DNSOPT_AVX) and as nsopt.cpp is committed, scalar templates at every site ("<tag>.scalar/...").  The
+drop-in headers honour the same macro (pl_set_scalar_order), so each build of the test program is compared with its own fixture,
+bit for bit.
     python tests/golden/make_nsopt_golden.py        (needs /root/reference; writes tests/golden/nsopt.npz)
-Per case and output array: SHA-256 of the raw fp64 bytes, every 5th value; of the scalar build every 5th value (tolerance compare)."""
+Per case, build and output array: SHA-256 of the raw fp64 bytes and every 5th value."""
 import hashlib
 import os
 import subprocess
@@ -34,11 +35,9 @@ def main():
                 for f in sorted(os.listdir(w)):
                     if f.endswith(".out"):
                         a = np.fromfile(os.path.join(w, f)) + 0.0
-                        if build == "avx":
-                            res[f"{tag}/{f[:-4]}/sha"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
-                            res[f"{tag}/{f[:-4]}/s5"] = a if f == "extra.out" else a[::5]
-                        elif not f.startswith("f."):
-                            res[f"{tag}/{f[:-4]}/scalar5"] = a if f == "extra.out" else a[::5]
+                        key = f"{tag}/{f[:-4]}" if build == "avx" else f"{tag}.scalar/{f[:-4]}"
+                        res[key + "/sha"] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+                        res[key + "/s5"] = a if f == "extra.out" else a[::5]
     np.savez_compressed(os.path.join(HERE, "nsopt.npz"), **res)
     print(len(res), "entries", os.path.getsize(os.path.join(HERE, "nsopt.npz")), "bytes")
 

@@ -27,10 +27,15 @@ def params(dim, size):
     return p
 
 
+def design_variable(p, i, j, k):
+    """closed-form grey (filtered) design on global coordinates: what the filter stage hands to heatsink3D.cpp:114-119"""
+    inbox = (i < p["mx"]) & (j < p["my"]) & ((k < p["mz"]) if p["dim"] == 3 else True)
+    return np.where(inbox, 0.5 + 0.4*np.sin(0.37*i)*np.cos(0.23*j)*np.sin(0.31*k + 0.5), 1.0)
+
+
 def design_fields(p, i, j, k):
     """closed-form grey design on global coordinates -> alpha, diffusivity, dads, dkds (heatsink3D.cpp:114-119)"""
-    inbox = (i < p["mx"]) & (j < p["my"]) & ((k < p["mz"]) if p["dim"] == 3 else True)
-    ss = np.where(inbox, 0.5 + 0.4*np.sin(0.37*i)*np.cos(0.23*j)*np.sin(0.31*k + 0.5), 1.0)
+    ss = design_variable(p, i, j, k)
     qg, qf, ly = p["qg"], p["qf"], p["ly"]
     kappa = p["diff_solid"] + (p["diff_fluid"] - p["diff_solid"])*ss*(1.0 + qg)/(ss + qg)
     alpha = p["alphamax"]/float(ly - 1)*qf*(1.0 - ss)/(ss + qf)

@@ -110,6 +110,7 @@ CollideParams params(const Lat* f, double nu, double kconst, double gx, double g
     CollideParams P;
     memset(&P, 0, sizeof(P));
     P.issave = issave;
+    P.scalar_build = (f->npacked == 0 && f->nxyz >= 4) ? 1 : 0;      // hm_set_scalar_build(1): as pl_set_scalar_order does in the product
     P.omegaf = 1.0/(3.0*nu + 0.5); P.iomegaf = 1.0 - P.omegaf;
     P.omegag = 1.0/(3.0*kconst + 0.5); P.iomegag = 1.0 - P.omegag;
     const bool d3 = f->kind == 3;
@@ -125,8 +126,12 @@ CollideParams params(const Lat* f, double nu, double kconst, double gx, double g
 }
 }  // namespace
 
+// a program built WITHOUT _USE_AVX_DEFINES runs the reference's scalar templates at every site: no packed sites
+static int g_scalar_build = 0;
+
 extern "C" {
 
+void hm_set_scalar_build(int on) { g_scalar_build = on; }
 void* hm_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz) {
     Lat* l = new Lat();
     if (kind == 2) { lz = 1; mz = 1; }
@@ -137,7 +142,7 @@ void* hm_lattice_create(int kind, int lx, int ly, int lz, int peid, int mx, int 
     l->offx = mx - l->pex > lx%mx ? l->pex*l->nx : lx - (mx - l->pex)*l->nx;
     l->offy = my - l->pey > ly%my ? l->pey*l->ny : ly - (my - l->pey)*l->ny;
     l->offz = kind == 2 ? 0 : (mz - l->pez > lz%mz ? l->pez*l->nz : lz - (mz - l->pez)*l->nz);
-    l->nxyz = (long long)l->nx*l->ny*l->nz; l->npacked = 4*(l->nxyz/4);
+    l->nxyz = (long long)l->nx*l->ny*l->nz; l->npacked = g_scalar_build ? 0 : 4*(l->nxyz/4);
     l->f0.assign(l->nxyz, 0.0); l->f.assign((size_t)l->nxyz*(l->nc - 1), 0.0);
     return l;
 }

@@ -74,3 +74,60 @@ def test_nsin_site_math():
         pytest.skip("oracle/_ref predates the NSin entry points: make -C oracle ref")
     for n, size in enumerate(SIZES[2] + [(23, 17, 1)]):
         S.assert_same(S.nsin(ref, size, 4 + n, steps=0), S.nsin(hm, size, 4 + n, steps=0), f"NSin {size}")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pl_set_scalar_order: a caller built WITHOUT _USE_AVX_DEFINES (production/nsopt.cpp:2).  The product's site math with every site
+# taken as a scalar-order site, against the reference headers compiled without the macro (oracle/_ref/*_scalar.so).
+def _scalar_pair(dim):
+    import ctypes as C
+    if not O.have_ref_scalar(dim):
+        pytest.skip("oracle/_ref/*_scalar.so not built (make -C oracle ref)")
+    hm = hostmath_backend(dim)
+    hm._fn("set_scalar_build")(C.c_int(1))
+    return O.Backend("ref_scalar", dim), hm
+
+
+def _ns_collides(be, dim, size, seed):
+    from helpers import random_field, random_pops
+    import numpy as np
+    l = be.lattice(*size)
+    n = l.nxyz
+    l.set(*random_pops(n, l.nc, seed))
+    alpha = random_field(n, seed + 5, 0.0, 40.0)
+    res = []
+    for k, (issave, nu, al) in enumerate(((1, 0.07, None), (0, 0.02, None), (1, 0.1, alpha), (0, 0.03, alpha))):
+        m = [np.full(n, -7.0 - i) for i in range(4)]
+        if al is None:
+            be.ns_macro_collide(l, *m, nu, issave)
+        else:
+            be.ns_macro_brinkman_collide(l, *m, nu, al, issave)
+        if issave:
+            res += [(f"m{k}{i}", m[i].copy()) for i in range(dim + 1)]
+        res += S.pops(f"c{k}", l)
+    l.free()
+    return res
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_scalar_order_site_math_equals_the_scalar_build_of_the_reference(dim):
+    import ctypes as C
+    ref, hm = _scalar_pair(dim)
+    try:
+        for n, size in enumerate(SIZES[dim]):
+            S.assert_same(_ns_collides(ref, dim, size, 3 + n), _ns_collides(hm, dim, size, 3 + n), f"NS collides {size}")
+            for model in S.FORWARD_MODELS + S.ADJOINT_MODELS:
+                if model.endswith("massflow") and dim == 3:
+                    continue
+                S.assert_same(S.collide(ref, dim, model, size, 3 + n), S.collide(hm, dim, model, size, 3 + n), f"{model} {size}")
+            for kind in S.CLOSURES:
+                if kind == "aad_iset_rho" and dim == 3:
+                    continue
+                S.assert_same(S.closure(ref, dim, kind, size, 5 + n), S.closure(hm, dim, kind, size, 5 + n), f"{kind} {size}")
+            for kind in S.SENSITIVITIES:
+                if kind == "aad_temperature_at_heat_source" and dim == 3:
+                    continue    # the reference's scalar 3-D overload reads out of bounds (_uz / _ig swapped, adjointadvection.h:1536 vs :805)
+                S.assert_same(S.sensitivity(ref, dim, kind, size, 9 + n), S.sensitivity(hm, dim, kind, size, 9 + n), f"{kind} {size}")
+            S.assert_same(S.inits(ref, dim, size, 2 + n), S.inits(hm, dim, size, 2 + n), f"init {size}")
+    finally:
+        hm._fn("set_scalar_build")(C.c_int(0))
