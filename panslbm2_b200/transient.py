@@ -122,7 +122,8 @@ class CheckpointedSweep:
         self.sched = CheckpointSchedule(T, every)
         self.perm = [state0 if (c == 0 and state0 is not None) else make_state() for c in range(self.sched.n_perm)]
         self.ring = [make_state() for _ in range(self.sched.n_ring)]
-        self.cps = {}
+        # every population checkpoint the schedule will take, allocated up front (no device allocation inside the loops)
+        self.cps = {v: ([Checkpoint(l) for l in self.lattices], 0) for op, v in self.sched.forward_ops() if op == "save"}
         self.recomputed = 0
 
     def state(self, t):
@@ -137,7 +138,7 @@ class CheckpointedSweep:
         L = _lib.lib()
         for op, v in self.sched.forward_ops():
             if op == "save":
-                cps = self.cps[v][0] if v in self.cps else [Checkpoint(l) for l in self.lattices]
+                cps = self.cps[v][0]
                 for cp, l in zip(cps, self.lattices):
                     cp.save(l)
                 self.cps[v] = (cps, L.pl_plan_parity(self.plan._h))
