@@ -359,7 +359,7 @@ def parity_decomposed(pl, api, torch, dist, rank, m, world):
 
 
 def parity_golden(pl, api, torch, dist, rank, m, world, size):
-    """--config heatsink3d: 81x161x81 on the PE grid, 300 + 300 fused steps + sensitivity, against the fixture generated from the
+    """--config heatsink3d: 81x161x81 on the PE grid, 2000 + 2000 fused steps + sensitivity, against the fixture generated from the
     reference build at that size (tests/golden/heatsink_fullsize.npz: 1-in-997 samples + sha256 of every global field)"""
     import hashlib
     import numpy as np

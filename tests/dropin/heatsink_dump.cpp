@@ -4,7 +4,11 @@
 // reads afterwards), with the step budget and the design of tests/heatsink_case.py.  It dumps every field as raw fp64 so that
 // tests/test_gpu_dropin.py can compare them bit for bit with the fixtures generated from the reference build (tests/golden).
 //   heatsink_dump <dim> <lx> <ly> <lz> <nt> <dir>      reads <dir>/{alpha,kappa,dads,dkds}.bin, <dir>/params.bin; writes <dir>/*.out
+// -DHEATSINK_SCALAR: built like a program that leaves _USE_AVX_DEFINES out (production/nsopt.cpp:2) — the headers then select the
+// arithmetic of the reference's scalar templates (pl_set_scalar_order); fixtures: tests/golden/heatsink_scalar.npz.
+#ifndef HEATSINK_SCALAR
 #define _USE_AVX_DEFINES
+#endif
 #include <chrono>
 #include <cstdio>
 #include <string>

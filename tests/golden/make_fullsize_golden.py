@@ -1,7 +1,7 @@
 """Full-size fixture: the heatsink3D iteration of tests/heatsink_case.py at the production size of production/heatsink3D.cpp:42
-(81 x 161 x 81 = 1 056 321 sites: one scalar-tail site) on the REFERENCE build (oracle/_ref), 300 forward + 300 adjoint steps.
+(81 x 161 x 81 = 1 056 321 sites: one scalar-tail site) on the REFERENCE build (oracle/_ref), 2000 forward + 2000 adjoint steps (SURVEY §8d cfg 2/4).
 Stores sha256 digests and 1-in-997 samples of every field (the fields themselves are ~8 MB each).
-    make -C oracle ref && python tests/golden/make_fullsize_golden.py      (about two minutes on 8 cores)
+    make -C oracle ref && python tests/golden/make_fullsize_golden.py      (about a quarter of an hour on 8 cores)
 With the argument 2: the 2-D twin at the size of production/heatsink.cpp:41 (141 x 161 = 22 701 sites, BASELINE configs[1]),
 2000 forward + 2000 adjoint steps -> heatsink2d_fullsize.npz."""
 import hashlib
@@ -18,7 +18,7 @@ from oracle import oracle as O  # noqa: E402
 import heatsink_case as H  # noqa: E402
 
 DIM = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-SIZE, NT = ((81, 161, 81), 300) if DIM == 3 else ((141, 161, 1), 2000)
+SIZE, NT = ((81, 161, 81), 2000) if DIM == 3 else ((141, 161, 1), 2000)
 NAME = "heatsink_fullsize.npz" if DIM == 3 else "heatsink2d_fullsize.npz"
 t0 = time.time()
 r = H.run_oplevel(O.Backend("ref", DIM), DIM, SIZE, NT)

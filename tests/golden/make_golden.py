@@ -87,7 +87,29 @@ def heatsink():
     np.savez_compressed(os.path.join(HERE, "heatsink.npz"), **out)
 
 
+def heatsink_scalar():
+    """the same iteration on the reference headers compiled WITHOUT _USE_AVX_DEFINES (oracle/_ref/*_scalar.so: scalar templates at every
+    site, the build of production/nsopt.cpp:2) -> heatsink_scalar.npz: what a drop-in program built without the macro must reproduce
+    (pl_set_scalar_order).  dfdss is left out in 3-D: the reference's scalar 3-D SensitivityTemperatureAtHeatSource reads out of bounds
+    (_uz / _ig swapped between adjointadvection.h:1536 and :805)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import heatsink_case as H
+    out = {}
+    for tag in ("hs2d", "hs3d_tail"):
+        dim, size, nt = HEATSINK_CASES[tag]
+        r = H.run_oplevel(O.Backend("ref_scalar", dim), dim, size, nt)
+        for k, a in r.items():
+            if dim == 3 and k == "dfdss":
+                continue
+            out[f"{tag}/{k}/s5"] = (a + 0.0)[::5].copy()
+            out[f"{tag}/{k}/sha"] = np.frombuffer(bytes.fromhex(digest(a + 0.0)), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "heatsink_scalar.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "scalar" in sys.argv[1:]:
+        heatsink_scalar()
+        sys.exit(0)
     cavity3d()
     ops()
     heatsink()

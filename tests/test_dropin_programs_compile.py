@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(ROOT, "panslbm2_b200")
 
-PROGRAMS = [("heatsink_dump.cpp", []), ("transient_dump.cpp", ["-DTRANSIENT_DIM=3", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
+PROGRAMS = [("heatsink_dump.cpp", []), ("heatsink_dump.cpp", ["-DHEATSINK_SCALAR"]), ("transient_dump.cpp", ["-DTRANSIENT_DIM=3", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("transient_dump.cpp", ["-DTRANSIENT_DIM=2", "-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
             ("ncpump_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]), ("filter_dump.cpp", []),
             ("ncpump_periodic_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")]),
@@ -18,7 +18,7 @@ PROGRAMS = [("heatsink_dump.cpp", []), ("transient_dump.cpp", ["-DTRANSIENT_DIM=
             ("nsopt_dump.cpp", ["-DPANSLBM_B200_DROPIN", "-I" + os.path.join(LIB, "src")])]
 
 
-@pytest.mark.parametrize("src,flags", PROGRAMS, ids=[p[0] + "".join(f for f in p[1] if f.startswith("-DTRANSIENT")) for p in PROGRAMS])
+@pytest.mark.parametrize("src,flags", PROGRAMS, ids=[p[0] + "".join(f for f in p[1] if f.startswith(("-DTRANSIENT", "-DHEATSINK"))) for p in PROGRAMS])
 def test_parity_program_builds_against_dropin_headers(tmp_path, src, flags):
     if not os.path.exists(os.path.join(LIB, "libpanslbm_b200.so")):
         pytest.skip("libpanslbm_b200.so not built (python __graft_entry__.py)")

@@ -100,8 +100,41 @@ def test_cpp_surface_matches_reference_fixture(dump_exe, tmp_path, tag):
     assert abs(res["extra"][0] - want) <= 1e-14*max(1.0, abs(want))
 
 
+@pytest.fixture(scope="session")
+def dump_exe_scalar(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("dropin_scalar") / "heatsink_dump_scalar")
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    lib = os.path.join(ROOT, "panslbm2_b200")
+    subprocess.check_call(["g++", "-O2", "-mavx", "-ffp-contract=off", "-w", "-DHEATSINK_SCALAR", "-I" + os.path.join(ROOT, "include"), os.path.join(HERE, "dropin", "heatsink_dump.cpp"),
+                           "-o", out, "-L" + lib, "-lpanslbm_b200", "-Wl,-rpath," + lib], env=env)
+    return out
+
+
+@pytest.mark.parametrize("tag", ["hs2d", "hs3d_tail"])
+def test_cpp_surface_built_without_the_avx_macro_matches_the_scalar_build_of_the_reference(dump_exe_scalar, tmp_path, tag):
+    """a program that leaves _USE_AVX_DEFINES out (production/nsopt.cpp:2) gets the arithmetic of the reference's scalar templates at
+    every site (pl_set_scalar_order, called by the headers): the heatsink iteration — two lattices, SetT / SetQ closures, thermal
+    snapshots in the scalar build's [idx][c] layout, sensitivity — against the reference headers compiled without the macro
+    (tests/golden/heatsink_scalar.npz), bit for bit"""
+    dim, size, nt = heatsink_cases()[tag]
+    res, log = run_dump(dump_exe_scalar, str(tmp_path), dim, size, nt)
+    z = np.load(os.path.join(G, "heatsink_scalar.npz"))
+    keys = sorted(k.split("/")[1] for k in z.files if k.startswith(tag + "/") and k.endswith("/sha"))
+    assert len(keys) >= 18
+    for k in keys:
+        a = res[k] + 0.0
+        assert np.array_equal(a[::5], z[f"{tag}/{k}/s5"]), f"{tag} (scalar order): {k} differs from the reference fixture (max abs {np.max(np.abs(a[::5] - z[f'{tag}/{k}/s5'])):.3e})"
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() == bytes(z[f"{tag}/{k}/sha"]), f"{tag} (scalar order): {k} digest"
+    # ... and it differs from the AVX build's fixture in the last bits, as the reference's own two builds do
+    za = np.load(os.path.join(G, "heatsink.npz"))
+    assert not np.array_equal(res["ux"][::5], za[f"{tag}/ux/s5"])
+    n = size[0]*size[1]*size[2]
+    if n*8 >= 4096:
+        assert res["stats"][0] >= 2*(nt - 3), log
+
+
 def test_cpp_surface_production_size_matches_reference_fixture(dump_exe, tmp_path):
-    """the same program at 81 x 161 x 81 (production/heatsink3D.cpp:42), 300 + 300 steps: digests of the reference build"""
+    """the same program at 81 x 161 x 81 (production/heatsink3D.cpp:42), 2000 + 2000 steps: digests of the reference build"""
     z = np.load(os.path.join(G, "heatsink_fullsize.npz"))
     lx, ly, lz, nt = [int(v) for v in z["shape"]]
     res, log = run_dump(dump_exe, str(tmp_path), 3, (lx, ly, lz), nt)

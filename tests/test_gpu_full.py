@@ -144,7 +144,7 @@ def check_fullsize(res):
 
 
 def test_heatsink3d_production_size_matches_reference_fixture():
-    """81 x 161 x 81 (production/heatsink3D.cpp:42), 300 forward + 300 adjoint fused steps + sensitivity: every field bit-identical
+    """81 x 161 x 81 (production/heatsink3D.cpp:42), 2000 forward + 2000 adjoint fused steps + sensitivity: every field bit-identical
     to the reference build's (tests/golden/make_fullsize_golden.py)."""
     z = np.load(os.path.join(G, "heatsink_fullsize.npz"))
     lx, ly, lz, nt = [int(v) for v in z["shape"]]
