@@ -429,7 +429,13 @@ extern "C" {
 const char* pl_last_error(void) { return g_err.c_str(); }
 int pl_in_call(void) { return g_in_call; }
 const char* pl_version(void) { return "panslbm_b200 0.1 (sm_100a, fp64, fmad=off)"; }
-int pl_set_scalar_order(int on) { g_scalar_order = on ? 1 : 0; return PL_OK; }
+int pl_set_scalar_order(int on) {
+    const int v = on ? 1 : 0;
+    // lattices fix their packed / scalar split when they are created: one order per process, chosen before the first lattice
+    if (v != g_scalar_order && g_lattice_bytes != 0) return fail(PL_ERR_ARG, "pl_set_scalar_order: lattices exist already (the operation order is chosen once, before the first lattice)");
+    g_scalar_order = v;
+    return PL_OK;
+}
 int pl_scalar_order(void) { return g_scalar_order; }
 int pl_device_count(void) {
     int n = 0;

@@ -81,7 +81,9 @@ namespace b200 {
         void create(int kind, int lx, int ly, int lz, int peid, int mx, int my, int mz, double** f0, double** f) {
 #ifndef _USE_AVX_DEFINES
             // this program is built like production/nsopt.cpp:2 — the reference would run its scalar templates at every site
-            pl_set_scalar_order(1);
+            check(pl_set_scalar_order(1), "pl_set_scalar_order (translation units built with and without _USE_AVX_DEFINES in one program?)");
+#else
+            check(pl_set_scalar_order(0), "pl_set_scalar_order (translation units built with and without _USE_AVX_DEFINES in one program?)");
 #endif
             h = pl_lattice_create(kind, lx, ly, lz, peid, mx, my, mz);
             if (!h) check(1, "pl_lattice_create");
