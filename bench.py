@@ -495,6 +495,7 @@ def run_ours(args):
     sw.ss = pl.DeviceArray(N)
     want = [a.to_host() for a in (sw.alpha, sw.kappa, sw.dads, sw.dkds)]      # what the host formulas gave (uploaded for the device-resident runs)
     sw.sensitivity()        # warm-up: bakes the heat-source planes once, as the first optimisation iteration of a run does
+    sw.objective()          # ... and the first all-reduce of the communicator sets up its channels (N > 1): not part of an iteration
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
