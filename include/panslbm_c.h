@@ -95,9 +95,9 @@ int pl_copy_wait(void);      /* the host waits for the copies issued so far */
 int pl_array_fill(double* dev, double value, size_t n);
 
 /* Operation order.  The reference selects its arithmetic per program: with `#define _USE_AVX_DEFINES` before the includes
- * (production/heatsink3D.cpp:2 and every other program but one) the __m256d overloads of src/equation_avx/*.h handle the first
+ * (production/heatsink3D.cpp:2 and every other program but one) the __m256d overloads of the src/equation_avx headers handle the first
  * 4*(nxyz/4) sites and scalar tail code inside those files the rest; without it (production/nsopt.cpp:2) the scalar templates of
- * src/equation/*.h handle every site.  The two differ in the association of a few sums (results agree to rounding) and in one
+ * the src/equation headers handle every site.  The two differ in the association of a few sums (results agree to rounding) and in one
  * place in what they store: the 2-D tail of NS::MacroBrinkmanCollide saves rho, u BEFORE the Brinkman force
  * (navierstokes_avx.h:246-254), the scalar template after it (navierstokes.h:494-503).  The default here is the order of the
  * _USE_AVX_DEFINES build; pl_set_scalar_order(1) — process-wide, before the first lattice is created; the drop-in headers call
