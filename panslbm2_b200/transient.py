@@ -117,13 +117,14 @@ class CheckpointedSweep:
     forward() runs steps 1..T; backward(visit) calls visit(t, state_t, state_t_plus_1) for t = t_hi..t_lo with both states
     resident (state_t_plus_1 is None for t = T), recomputing segments as it goes."""
 
-    def __init__(self, plan, lattices, T, every, make_state, bind, state0=None):
+    def __init__(self, plan, lattices, T, every, make_state, bind, state0=None, checkpoint=None):
         self.plan, self.lattices, self.bind = plan, list(lattices), bind
+        Checkpoint_ = checkpoint if checkpoint is not None else Checkpoint      # (a test double stands in for the device copy on a CPU)
         self.sched = CheckpointSchedule(T, every)
         self.perm = [state0 if (c == 0 and state0 is not None) else make_state() for c in range(self.sched.n_perm)]
         self.ring = [make_state() for _ in range(self.sched.n_ring)]
         # every population checkpoint the schedule will take, allocated up front (no device allocation inside the loops)
-        self.cps = {v: ([Checkpoint(l) for l in self.lattices], 0) for op, v in self.sched.forward_ops() if op == "save"}
+        self.cps = {v: ([Checkpoint_(l) for l in self.lattices], 0) for op, v in self.sched.forward_ops() if op == "save"}
         self.recomputed = 0
 
     def state(self, t):
@@ -135,18 +136,16 @@ class CheckpointedSweep:
         self.plan.advance(1, end_streamed=last)
 
     def forward(self, end_streamed=True):
-        L = _lib.lib()
         for op, v in self.sched.forward_ops():
             if op == "save":
                 cps = self.cps[v][0]
                 for cp, l in zip(cps, self.lattices):
                     cp.save(l)
-                self.cps[v] = (cps, L.pl_plan_parity(self.plan._h))
+                self.cps[v] = (cps, self.plan.parity)
             else:
                 self._step(v, last=(end_streamed and v == self.sched.T))
 
     def backward(self, visit, t_hi=None, t_lo=0):
-        L = _lib.lib()
         T = self.sched.T
         for op, v in self.sched.backward_ops(t_hi, t_lo):
             if op == "restore":
