@@ -252,6 +252,35 @@ def test_unmodified_reference_nsadncsens(tmp_path):
     assert seen == len([k for k in z.files if k.startswith("nsadncsens.")]) and seen >= 10
 
 
+@pytest.mark.parametrize("prog,stem", [("nssens", "adjoint"), ("nssens3D", "adjoint3D"), ("nsadsens", "nsadsens"), ("naturalconvection", "naturalconvection")])
+def test_unmodified_reference_test_programs(tmp_path, prog, stem):
+    """test/nssens.cpp (NS + ANS on a 101 x 51 channel, closures capturing by reference), test/nssens3D.cpp (D3Q15 101 x 51 x 51),
+    test/nsadsens.cpp (the heat-exchange collides and AAD::SensitivityHeatExchange, 30 000 + 30 000 steps) and
+    test/naturalconvection.cpp (100 000 steps) unmodified, through the learned / fused replay: every array their VTK writer puts out
+    equals the reference build's to the 6 digits written (tests/golden/make_dropin_more_golden.py)."""
+    import re
+    fixture = os.path.join(G, "dropin_more.npz")
+    if not os.path.exists(fixture):
+        pytest.skip("tests/golden/dropin_more.npz absent")
+    z = np.load(fixture)
+    os.makedirs(tmp_path / "result")
+    r = subprocess.run([need(prog)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    txt = open(tmp_path / "result" / (stem + "_0.vts")).read()
+    seen = 0
+    for m in re.finditer(r'<DataArray type="Float64" Name="(\w+)" NumberOfComponents="(\d)" format="ascii">(.*?)</DataArray>', txt, re.S):
+        got = np.array(m.group(3).split(), dtype=np.float64).reshape(-1, int(m.group(2)))
+        key = f"{prog}.{m.group(1)}"
+        if key in z.files:
+            want = z[key]
+            assert np.array_equal(got, want), (prog, m.group(1), float(np.max(np.abs(got - want))), float(np.max(np.abs(want))))
+        else:       # large arrays: every 11th site and the digest of the whole array
+            assert np.array_equal(got[::11], z[key + "/s11"]), (prog, m.group(1), float(np.max(np.abs(got[::11] - z[key + "/s11"]))))
+            assert hashlib.sha256(np.ascontiguousarray(got + 0.0).tobytes()).digest() == bytes(z[key + "/sha"]), (prog, m.group(1))
+        seen += 1
+    assert seen == len({k.split("/")[0] for k in z.files if k.startswith(prog + ".")}) and seen >= 2
+
+
 # ---------------------------------------------------------------------------------------------------------
 def vts_pieces(result_dir, stem, names):
     """assemble the per-rank .vts pieces of a VTKXMLExport run into global arrays (pieces overlap by one layer)"""
