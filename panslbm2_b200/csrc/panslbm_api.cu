@@ -2300,7 +2300,10 @@ int pl_sensitivity(pl_lattice* l, const pl_sens_args* a) {
     if (!l || !a) return fail(PL_ERR_ARG, "pl_sensitivity: null");
     const bool d3 = l->kind == PL_D3Q15;
     if (a->kind < 1 || a->kind > 3) return fail(PL_ERR_ARG, "pl_sensitivity: unknown kind");
-    if (!a->dfds || !a->ux || !a->uy || !a->imx || !a->imy || !a->dads || (d3 && (!a->uz || !a->imz)))
+    // test/nssens3D.cpp:105 hands a D3Q15 lattice to the 2-D overload of ANS::SensitivityBrinkman (no uz, imz): the reference then
+    // evaluates the two-component expression at every site (adjointnavierstokes_avx.h:262-278) — so does this
+    const bool planar = d3 && a->kind == PL_SENS_ANS_BRINKMAN && !a->uz && !a->imz;
+    if (!a->dfds || !a->ux || !a->uy || !a->imx || !a->imy || !a->dads || (d3 && !planar && (!a->uz || !a->imz)))
         return fail(PL_ERR_ARG, "pl_sensitivity: missing dfds / u / im / dads arrays");
     if (a->kind == PL_SENS_AAD_HEATEX && (!a->tem || !a->item || !a->dbds)) return fail(PL_ERR_ARG, "pl_sensitivity: HeatExchange needs tem, item, dbds");
     if (a->kind == PL_SENS_AAD_BRINKMAN_DIFF &&
@@ -2310,8 +2313,8 @@ int pl_sensitivity(pl_lattice* l, const pl_sens_args* a) {
     A.kind = a->kind; A.dfds = a->dfds; A.ux = a->ux; A.uy = a->uy; A.uz = a->uz; A.imx = a->imx; A.imy = a->imy; A.imz = a->imz; A.dads = a->dads;
     A.tem = a->tem; A.item = a->item; A.iqx = a->iqx; A.iqy = a->iqy; A.iqz = a->iqz; A.gsnap = a->gsnap; A.igsnap = a->igsnap;
     A.kappa = a->diffusivity; A.dkds = a->dkds; A.dbds = a->dbds; A.pitch = (size_t)l->g.nxyz;
-    if (d3) LAUNCH(k_sensitivity<3>, blocks_for(l->g.nxyz, 256), 256, l->g, A);
-    else LAUNCH(k_sensitivity<2>, blocks_for(l->g.nxyz, 256), 256, l->g, A);
+    if (d3 && !planar) LAUNCH(k_sensitivity<3>, blocks_for(l->g.nxyz, 256), 256, l->g, A);
+    else LAUNCH(k_sensitivity<2>, blocks_for(l->g.nxyz, 256), 256, l->g, A);      // (the Brinkman kind reads nothing lattice-specific but nxyz / npacked)
     return PL_OK;
 }
 int pl_sensitivity_heat_source(pl_lattice* l, const pl_bc* plane, double* dfds, const double* ux, const double* uy, const double* uz,
