@@ -233,6 +233,11 @@ void ref_ans_sensitivity_brinkman(void* h, double* dfds, const double* ux, const
     ANS::SensitivityBrinkman(*L(h)->p, dfds, ux, uy, Z(uz) imx, imy, Z(imz) dads);
 }
 
+// the two-component overload on whatever lattice this library was built for: test/nssens3D.cpp:105 calls it with its D3Q15 lattice
+void ref_ans_sensitivity_brinkman_planar(void* h, double* dfds, const double* ux, const double* uy, const double* imx, const double* imy, const double* dads) {
+    ANS::SensitivityBrinkman(*L(h)->p, dfds, ux, uy, imx, imy, dads);
+}
+
 //---------------------------------------------------------------- AAD
 void ref_aad_init(void* hg, const double* ux, const double* uy, const double* uz, const double* item, const double* iqx, const double* iqy, const double* iqz) {
     AAD::InitialCondition(*L(hg)->p, ux, uy, Z(uz) item, iqx, iqy ZL(iqz));

@@ -305,6 +305,14 @@ void hm_ans_sensitivity_brinkman(void* h, double* dfds, const double* ux, const 
         else dfds[i] = tail ? sens_brinkman<3, true>(s) : sens_brinkman<3, false>(s);
     }
 }
+// test/nssens3D.cpp:105 — the two-component overload handed a D3Q15 lattice: what pl_sensitivity does when uz / imz are absent
+void hm_ans_sensitivity_brinkman_planar(void* h, double* dfds, const double* ux, const double* uy, const double* imx, const double* imy, const double* dads) {
+    Lat* l = L(h);
+    for (long long i = 0; i < l->nxyz; ++i) {
+        SensSite s = site(i, false, dfds, ux, uy, nullptr, imx, imy, nullptr, dads);
+        dfds[i] = i >= l->npacked ? sens_brinkman<2, true>(s) : sens_brinkman<2, false>(s);
+    }
+}
 void hm_aad_sensitivity_heat_exchange(void* h, double* dfds, const double* ux, const double* uy, const double* uz, const double* imx, const double* imy, const double* imz,
         const double* dads, const double* tem, const double* item, const double* dbds) {
     Lat* l = L(h);

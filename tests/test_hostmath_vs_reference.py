@@ -131,3 +131,25 @@ def test_scalar_order_site_math_equals_the_scalar_build_of_the_reference(dim):
             S.assert_same(S.inits(ref, dim, size, 2 + n), S.inits(hm, dim, size, 2 + n), f"init {size}")
     finally:
         hm._fn("set_scalar_build")(C.c_int(0))
+
+
+def test_planar_sensitivity_on_a_3d_lattice():
+    """test/nssens3D.cpp:105 hands its D3Q15 lattice to the two-component overload of ANS::SensitivityBrinkman; pl_sensitivity accepts
+    the call (uz / imz absent) and evaluates the two-component expression at every site, as the reference does"""
+    if 3 not in DIMS:
+        pytest.skip("oracle/_ref (3-D) not built")
+    import numpy as np
+    from helpers import random_field
+    ref, hm = both(3)
+    if not ref.has("ans_sensitivity_brinkman_planar"):
+        pytest.skip("oracle/_ref predates the entry point: make -C oracle ref")
+    for n, size in enumerate(SIZES[3]):
+        res = []
+        for be in (ref, hm):
+            l = be.lattice(*size)
+            F = S.Fields(l.nxyz, 9 + n)
+            dfds = random_field(l.nxyz, 40 + n, -1, 1)
+            be.ans_sensitivity_brinkman_planar(l, dfds, F.ux, F.uy, F.imx, F.imy, F.dads)
+            res.append(dfds)
+            l.free()
+        assert np.array_equal(res[0], res[1]), size
